@@ -1,0 +1,252 @@
+"""Generate golden input/output vectors by running the UNMODIFIED reference code.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):   python tests/golden/make_golden.py
+Writes tests/golden/*.npz (committed).  The reference ships no golden vectors for this
+path, so these pin the oracle (tests/test_oracle_golden.py) and,
+through the oracle and directly, the CUDA kernels (tests/test_*_gpu.py).
+
+Harness-side shims (reference files untouched):
+  * bare ``basicsr`` package object so basicsr/__init__.py (which imports every arch /
+    dataset and dies on missing deps) is skipped; stub ``basicsr.version``;
+  * ``mmcv.ops`` stub: ModulatedDeformConv2d base class + modulated_deform_conv2d routed to
+    torchvision.ops.deform_conv2d (same offset/mask channel layout as
+    basicsr/ops/dcn/src/deform_conv_cuda_kernel.cu:600-613); mmcv itself is un-vendored
+    and unpinned in the reference (requirements.txt has no mmcv line);
+  * torchvision vgg constructors patched to ignore ``pretrained=True`` (no network).
+"""
+import importlib.util
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF = '/root/reference'
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def install_shims():
+    pkg = types.ModuleType('basicsr')
+    pkg.__path__ = [os.path.join(REF, 'basicsr')]
+    sys.modules['basicsr'] = pkg
+    ver = types.ModuleType('basicsr.version')
+    ver.__version__ = '1.3.5'
+    ver.__gitsha__ = 'unknown'
+    sys.modules['basicsr.version'] = ver
+
+    import torchvision
+    from torchvision.ops import deform_conv2d
+    from torch.nn.modules.utils import _pair
+
+    class ModulatedDeformConv2d(nn.Module):
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                     groups=1, deform_groups=1, bias=True):
+            super().__init__()
+            self.in_channels, self.out_channels = in_channels, out_channels
+            self.kernel_size, self.stride = _pair(kernel_size), _pair(stride)
+            self.padding, self.dilation = _pair(padding), _pair(dilation)
+            self.groups, self.deform_groups = groups, deform_groups
+            self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+            self.bias = nn.Parameter(torch.Tensor(out_channels)) if bias else None
+            n = in_channels * self.kernel_size[0] * self.kernel_size[1]
+            self.weight.data.uniform_(-1. / math.sqrt(n), 1. / math.sqrt(n))
+            if self.bias is not None:
+                self.bias.data.zero_()
+
+    def modulated_deform_conv2d(x, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups):
+        return deform_conv2d(x, offset, weight, bias, stride, padding, dilation, mask)
+
+    mmcv = types.ModuleType('mmcv')
+    ops = types.ModuleType('mmcv.ops')
+    ops.ModulatedDeformConv2d = ModulatedDeformConv2d
+    ops.modulated_deform_conv2d = modulated_deform_conv2d
+    mmcv.ops = ops
+    sys.modules['mmcv'] = mmcv
+    sys.modules['mmcv.ops'] = ops
+
+    import torchvision.models.vgg as tvgg
+    for name in ('vgg16', 'vgg19'):
+        orig = getattr(tvgg, name)
+        setattr(tvgg, name, (lambda o: (lambda pretrained=False, **kw: o(weights=None)))(orig))
+        setattr(torchvision.models, name, getattr(tvgg, name))
+
+
+def load_ref_map_util():
+    spec = importlib.util.spec_from_file_location('ref_map_util', os.path.join(REF, 'basicsr/archs/ref_map_util.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def unit(c, h, w, gen):
+    return F.normalize(torch.randn(c, h * w, generator=gen), dim=0).view(c, h, w)
+
+
+def matcher_cases():
+    g = torch.Generator().manual_seed(1234)
+    cases = {}
+    # (a) independent unit-norm features, the configuration CorrespondenceGenerationArch uses
+    cases['rand'] = dict(fi=unit(64, 16, 18, g), fr=unit(64, 16, 18, g), kw=dict(is_norm=True, norm_input=True))
+    # (b) KAT: reference = input translated by (+3 rows, +2 cols): arg-max known analytically
+    base = unit(64, 20, 22, g)
+    cases['shift'] = dict(fi=base[:, :16, :18].contiguous(), fr=base[:, 3:19, 2:20].contiguous(),
+                          kw=dict(is_norm=True, norm_input=True))
+    # (c) zero-padded reference (CUFED val pads to 500^2): exact-tie plateau, first index must win
+    fr = unit(64, 16, 18, g)
+    fr[:, 9:, :] = 0
+    fr[:, :, 11:] = 0
+    fi = unit(64, 16, 18, g)
+    fi[:, 12:, :] = 0
+    cases['zeropad'] = dict(fi=fi, fr=fr, kw=dict(is_norm=True, norm_input=True))
+    # (d) defaults of the function signature (norm_input=False), un-normalised features, h != w
+    cases['raw'] = dict(fi=torch.randn(32, 11, 15, generator=g), fr=torch.randn(32, 11, 15, generator=g),
+                        kw=dict(is_norm=True, norm_input=False))
+    # (e) no normalisation at all
+    cases['nonorm'] = dict(fi=torch.randn(32, 10, 10, generator=g), fr=torch.randn(32, 10, 10, generator=g),
+                           kw=dict(is_norm=False, norm_input=False))
+    # (f) different input / reference sizes and non-unit strides (general signature)
+    cases['strided'] = dict(fi=torch.randn(16, 13, 12, generator=g), fr=torch.randn(16, 15, 17, generator=g),
+                            kw=dict(patch_size=3, input_stride=2, ref_stride=2, is_norm=True, norm_input=True))
+    # (g) production channel count
+    cases['c256'] = dict(fi=unit(256, 12, 12, g), fr=unit(256, 12, 12, g), kw=dict(is_norm=True, norm_input=True))
+    return cases
+
+
+def gen_matcher():
+    rmu = load_ref_map_util()
+    out = {}
+    for name, c in matcher_cases().items():
+        idx, val = rmu.feature_match_index(c['fi'], c['fr'], **c['kw'])
+        out[f'{name}.fi'] = c['fi'].numpy()
+        out[f'{name}.fr'] = c['fr'].numpy()
+        out[f'{name}.idx'] = idx.numpy()
+        out[f'{name}.val'] = val.numpy()
+        out[f'{name}.kw'] = np.array(repr(c['kw']))
+    # sample_patches layout
+    x = torch.arange(2 * 4 * 5, dtype=torch.float32).view(2, 4, 5)
+    out['patches.x'] = x.numpy()
+    out['patches.y'] = rmu.sample_patches(x, 3, 1).contiguous().numpy()
+    np.savez_compressed(os.path.join(OUT, 'matcher.npz'), **out)
+    print('matcher.npz', {k: v.shape for k, v in out.items() if k.endswith('.idx')})
+
+
+def gen_correspondence():
+    from basicsr.archs.corres_generation_arch import CorrespondenceGenerationArch
+    torch.manual_seed(10)
+    net = CorrespondenceGenerationArch(patch_size=3, stride=1, vgg_layer_list=['relu1_1', 'relu2_1', 'relu3_1'],
+                                       vgg_type='vgg19').eval()
+    g = torch.Generator().manual_seed(77)
+    b, c, h, w = 2, 64, 10, 12
+    f1 = torch.randn(b, c, h, w, generator=g)
+    f2 = torch.randn(b, c, h, w, generator=g)
+    img = torch.rand(b, 3, 4 * h, 4 * w, generator=g)
+    with torch.no_grad():
+        pre, feats = net({'dense_features1': f1, 'dense_features2': f2}, img)
+    rmu = load_ref_map_util()
+    idx = []
+    for i in range(b):
+        a = F.normalize(f1[i].reshape(c, -1), dim=0).view(c, h, w)
+        r = F.normalize(f2[i].reshape(c, -1), dim=0).view(c, h, w)
+        idx.append(rmu.feature_match_index(a, r, patch_size=3, input_stride=1, ref_stride=1, is_norm=True,
+                                           norm_input=True)[0])
+    out = dict(f1=f1.numpy(), f2=f2.numpy(), max_idx=torch.stack(idx).numpy(),
+               relu3_1=pre['relu3_1'].numpy(), relu2_1=pre['relu2_1'].numpy(), relu1_1=pre['relu1_1'].numpy())
+    np.savez_compressed(os.path.join(OUT, 'correspondence.npz'), **out)
+    print('correspondence.npz', {k: v.shape for k, v in out.items()})
+
+
+def gen_dynagg():
+    """DynAgg forward + gradients through the reference module (DCN = mmcv stub -> torchvision)."""
+    from basicsr.archs.ref_mrapa_restoration_arch import DynAgg
+    out = {}
+    for name, (b, c, h, w, dg) in {'small': (2, 32, 9, 10, 8), 'big_offsets': (1, 16, 12, 12, 4)}.items():
+        torch.manual_seed(5)
+        m = DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True)
+        # reference zero-inits conv_offset_mask (offsets integer, mask 0.5); randomise so bilinear paths run
+        g = torch.Generator().manual_seed(99)
+        m.conv_offset_mask.weight.data = torch.randn(m.conv_offset_mask.weight.shape, generator=g) * 0.05
+        m.conv_offset_mask.bias.data = torch.randn(m.conv_offset_mask.bias.shape, generator=g) * 0.5
+        m.bias.data = torch.randn(c, generator=g) * 0.1
+        x = torch.randn(b, c, h, w, generator=g)
+        feat = torch.randn(b, c, h, w, generator=g)
+        scale = 3.0 if name == 'small' else float(h)   # big_offsets: many samples leave the image
+        pre = torch.round(torch.randn(b, 9, h, w, 2, generator=g) * scale)
+        x.requires_grad_(True)
+        feat.requires_grad_(True)
+        y = m([x, feat], pre)
+        go = torch.randn(y.shape, generator=g)
+        # also capture the tensors that reach the DCN boundary
+        conv_out = m.conv_offset_mask(feat)
+        o1, o2, mk = torch.chunk(conv_out, 3, dim=1)
+        offset = torch.cat((o1, o2), 1)
+        pr = pre.repeat([1, dg, 1, 1, 1])
+        reo = torch.zeros_like(offset)
+        reo[:, 0::2] = pr[..., 1]
+        reo[:, 1::2] = pr[..., 0]
+        offset = (offset + reo).detach().requires_grad_(True)
+        mask = torch.sigmoid(mk).detach().requires_grad_(True)
+        xx = x.detach().clone().requires_grad_(True)
+        wgt = m.weight.detach().clone().requires_grad_(True)
+        bia = m.bias.detach().clone().requires_grad_(True)
+        from mmcv.ops import modulated_deform_conv2d
+        y2 = modulated_deform_conv2d(xx, offset, mask, wgt, bia, (1, 1), (1, 1), (1, 1), 1, dg)
+        assert torch.equal(y2, y)
+        y2.backward(go)
+        d = dict(x=x, feat=feat, pre=pre, com_w=m.conv_offset_mask.weight, com_b=m.conv_offset_mask.bias,
+                 weight=m.weight, bias=m.bias, conv_out=conv_out, offset=offset, mask=mask, y=y, go=go,
+                 gx=xx.grad, goffset=offset.grad, gmask=mask.grad, gweight=wgt.grad, gbias=bia.grad)
+        for k, v in d.items():
+            out[f'{name}.{k}'] = v.detach().numpy()
+        out[f'{name}.dg'] = np.array(dg)
+    np.savez_compressed(os.path.join(OUT, 'dynagg.npz'), **out)
+    print('dynagg.npz', [k for k in out if k.endswith('.y')])
+
+
+def gen_fusion():
+    """MRAPAFusion forward; hooks capture the attention core's inputs/outputs
+    (ref_mrapa_restoration_arch.py:321-335) without touching the reference."""
+    from basicsr.archs.ref_mrapa_restoration_arch import MRAPAFusion
+    out = {}
+    for name, (n, nf, ref_nf, h, w, t) in {'t5': (2, 8, 16, 8, 12, 5), 't1': (1, 8, 16, 4, 4, 1),
+                                           'pad': (1, 8, 8, 7, 9, 3)}.items():
+        torch.manual_seed(3)
+        m = MRAPAFusion(nf=nf, ref_nf=ref_nf).eval()
+        g = torch.Generator().manual_seed(21)
+        target = torch.randn(n, nf, h, w, generator=g)
+        refs = [torch.randn(n, ref_nf, h, w, generator=g) for _ in range(t)]
+        cap = {}
+        hs = [m.conv_emb1.register_forward_hook(lambda mod, i, o: cap.__setitem__('emb1', o.detach())),
+              m.conv_emb2.register_forward_hook(lambda mod, i, o: cap.__setitem__('emb', o.detach())),
+              m.conv_ass.register_forward_hook(lambda mod, i, o: cap.__setitem__('ass', o.detach())),
+              m.spatial_attn.register_forward_hook(lambda mod, i, o: cap.__setitem__('cat', i[0].detach()))]
+        with torch.no_grad():
+            y = m(target, refs)
+        for hk in hs:
+            hk.remove()
+        out[f'{name}.target'] = target.numpy()
+        out[f'{name}.refs'] = torch.stack(refs, 0).numpy()
+        out[f'{name}.emb_t'] = (cap['emb1'] * m.scale).numpy()
+        out[f'{name}.emb'] = cap['emb'].numpy()
+        out[f'{name}.ass'] = cap['ass'].numpy()
+        out[f'{name}.core_out'] = cap['cat'][:, nf:].contiguous().numpy()
+        out[f'{name}.y'] = y.numpy()
+        out[f'{name}.t'] = np.array(t)
+        for k, v in m.state_dict().items():
+            out[f'{name}.sd.{k}'] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, 'fusion.npz'), **out)
+    print('fusion.npz', [k for k in out if k.endswith('.y')])
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(8)
+    install_shims()
+    gen_matcher()
+    gen_correspondence()
+    gen_dynagg()
+    gen_fusion()
+    print('sizes:', {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT)) if f.endswith('.npz')})

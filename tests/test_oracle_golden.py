@@ -1,0 +1,109 @@
+"""Pin the CPU oracle against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import pytest
+import torch
+
+import oracle
+from oracle.dcn import modulated_deform_conv_c, modulated_deform_conv_backward_c
+
+MATCH_CASES = ['rand', 'shift', 'zeropad', 'raw', 'nonorm', 'strided', 'c256']
+
+
+@pytest.mark.parametrize('case', MATCH_CASES)
+@pytest.mark.parametrize('use_conv', [True, False])
+def test_matcher_oracle_matches_reference(golden, case, use_conv):
+    g = golden('matcher')
+    kw = eval(str(g(f'{case}.kw')))
+    idx, val, gap = oracle.feature_match_index_oracle(g(f'{case}.fi'), g(f'{case}.fr'), use_conv=use_conv,
+                                                      return_gap=True, **kw)
+    ref_idx, ref_val = g(f'{case}.idx'), g(f'{case}.val')
+    assert idx.shape == ref_idx.shape and idx.dtype == torch.int64
+    # values: 1e-5 abs on O(1) similarities (fp32 summation order differs between conv2d and matmul)
+    scale = max(1.0, ref_val.abs().max().item())
+    assert (val - ref_val).abs().max().item() <= 1e-5 * scale
+    # indices exact wherever the top-2 gap is resolvable (north star: gap >= 1e-5)
+    bad = (idx != ref_idx) & (gap >= 1e-5 * scale)
+    assert not bad.any()
+    if use_conv and case != 'zeropad':
+        assert torch.equal(idx, ref_idx)
+
+
+def test_matcher_shift_known_answer(golden):
+    g = golden('matcher')
+    idx = g('shift.idx')
+    hp, wp = idx.shape
+    ys, xs = torch.meshgrid(torch.arange(hp), torch.arange(wp), indexing='ij')
+    # ref = input shifted by (+3, +2): input patch (y, x) sits at ref (y-3, x-2) when that is inside
+    inside = (ys >= 3) & (xs >= 2)
+    assert torch.equal(idx[inside], ((ys - 3) * wp + (xs - 2))[inside])
+    assert (g('shift.val')[inside] > 0.999).all()
+
+
+def test_matcher_zero_plateau_first_index(golden):
+    g = golden('matcher')
+    idx, val = g('zeropad.idx'), g('zeropad.val')
+    # input rows >= 12 are zero => all similarities are exactly 0 => first reference index wins
+    assert (idx[12:] == 0).all() and (val[12:] == 0).all()
+    o_idx, _ = oracle.feature_match_index_oracle(g('zeropad.fi'), g('zeropad.fr'), is_norm=True, norm_input=True)
+    assert (o_idx[12:] == 0).all()
+
+
+def test_sample_patches_layout(golden):
+    g = golden('matcher')
+    assert torch.equal(oracle.sample_patches_oracle(g('patches.x'), 3, 1), g('patches.y'))
+
+
+def test_pre_offsets_oracle(golden):
+    g = golden('correspondence')
+    idx = g('max_idx')
+    for b in range(idx.shape[0]):
+        pre = oracle.pre_offsets_oracle(idx[b])
+        for name in ('relu3_1', 'relu2_1', 'relu1_1'):
+            assert torch.equal(pre[name], g(name)[b]), name
+    # and the matcher feeding it
+    import torch.nn.functional as F
+    f1, f2 = g('f1'), g('f2')
+    c, h, w = f1.shape[1:]
+    for b in range(idx.shape[0]):
+        a = F.normalize(f1[b].reshape(c, -1), dim=0).view(c, h, w)
+        r = F.normalize(f2[b].reshape(c, -1), dim=0).view(c, h, w)
+        oi, _, gap = oracle.feature_match_index_oracle(a, r, is_norm=True, norm_input=True, return_gap=True)
+        assert not ((oi != idx[b]) & (gap >= 1e-5)).any()
+
+
+@pytest.mark.parametrize('case', ['small', 'big_offsets'])
+@pytest.mark.parametrize('impl', ['torch', 'c'])
+def test_dcn_oracle_forward_backward(golden, case, impl):
+    g = golden('dynagg')
+    dg = int(g(f'{case}.dg'))
+    x, off, mask, w, b = (g(f'{case}.{k}') for k in ('x', 'offset', 'mask', 'weight', 'bias'))
+    fwd = oracle.modulated_deform_conv_oracle if impl == 'torch' else modulated_deform_conv_c
+    bwd = oracle.modulated_deform_conv_backward_oracle if impl == 'torch' else modulated_deform_conv_backward_c
+    y = fwd(x, off, mask, w, b, 1, 1, 1, 1, dg)
+    ref = g(f'{case}.y')
+    assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    grads = bwd(x, off, mask, w, b, g(f'{case}.go'), 1, 1, 1, 1, dg)
+    for got, key in zip(grads, ('gx', 'goffset', 'gmask', 'gweight', 'gbias')):
+        r = g(f'{case}.{key}')
+        assert (got - r).abs().max().item() <= 2e-5 * max(1.0, r.abs().max().item()), key
+
+
+@pytest.mark.parametrize('case', ['small', 'big_offsets'])
+def test_dynagg_glue_oracle(golden, case):
+    g = golden('dynagg')
+    dg = int(g(f'{case}.dg'))
+    off, mask = oracle.dynagg_offsets_oracle(g(f'{case}.conv_out'), g(f'{case}.pre'), dg)
+    assert torch.equal(off, g(f'{case}.offset'))
+    assert torch.allclose(mask, g(f'{case}.mask'), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize('case', ['t5', 't1', 'pad'])
+def test_fusion_oracle(golden, case):
+    g = golden('fusion')
+    t = int(g(f'{case}.t'))
+    out = oracle.mrapa_attention_oracle(g(f'{case}.emb_t'), g(f'{case}.emb'), g(f'{case}.ass'), t)
+    ref = g(f'{case}.core_out')
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    if t == 1:   # single reference: softmax == 1, core is the identity on ass
+        assert torch.allclose(out, g(f'{case}.ass'), atol=1e-7)
