@@ -1,0 +1,188 @@
+/*
+ * mrefsr_b200.h -- C ABI of libmrefsr_b200.so: the B200-native (sm_100a) implementation of
+ * MRefSR's reference-alignment hot path.
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes only; no torch / ATen types.
+ *   - All tensor pointers are DEVICE pointers to contiguous row-major (NCHW) buffers unless the
+ *     function name ends in _host.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Calls are asynchronous with respect to the host, like the reference's kernels
+ *     (basicsr/ops/dcn/src/deform_conv_cuda_kernel.cu:788 launches on the current stream).
+ *   - The caller owns every buffer, including the scratch `workspace` whose size the matching
+ *     *_workspace_bytes() function reports (the reference's `ones` / `columns` scratch tensors,
+ *     basicsr/ops/dcn/deform_conv.py:148, play the same role).
+ *   - Return value: 0 on success, negative on error; mrefsr_last_error() returns the message of
+ *     the last failing call on this thread.  There is no CPU fallback anywhere: a missing GPU or
+ *     an unsupported configuration is an error, never a silent slow path.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef MREFSR_B200_H_
+#define MREFSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MREFSR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MREFSR_API __attribute__((visibility("default")))
+#else
+#define MREFSR_API
+#endif
+
+MREFSR_API int mrefsr_abi_version(void);
+MREFSR_API const char* mrefsr_last_error(void);
+/* number of SMs of the current device (148 on B200); negative on error */
+MREFSR_API int mrefsr_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Correspondence matcher
+ *     replaces  basicsr/archs/ref_map_util.py:26-86  feature_match_index(feat_input, feat_ref,
+ *               patch_size, input_stride, ref_stride, is_norm, norm_input)
+ *     batched over the (image, reference) pairs that basicsr/archs/corres_generation_arch.py:53
+ *     and basicsr/models/multi_ref_restoration_model.py:287 loop over in Python.
+ *
+ * feat_in  [n_in,  C, h_in,  w_in ]  fp32     feat_ref [n_pairs, C, h_ref, w_ref] fp32
+ * pair p is matched against input  (p / in_div) % n_in   (pairs laid out [B,R]: in_div = R;
+ * laid out [R,B]: in_div = 1).
+ * normalize_pixels != 0 first applies F.normalize(x.reshape(C,-1), dim=0) (eps 1e-12) to both,
+ * i.e. corres_generation_arch.py:57-59.
+ * max_idx [n_pairs, h', w'] int64 (value y_ref * w'_ref + x_ref), max_val [n_pairs, h', w'] fp32,
+ * h' = (h_in - patch_size) / input_stride + 1 etc.  Ties resolve to the lowest reference index
+ * (torch.max semantics, ref_map_util.py:69-76).
+ *
+ * mode: MREFSR_MATCH_AUTO picks the tcgen05 path when patch_size == 3, both strides == 1 and
+ *       C % 64 == 0, else the fp32 CUDA-core path.
+ *       MREFSR_MATCH_TC_BF16X3: tcgen05 with 3-pass split-bf16 operands (fp32-grade similarities);
+ *       MREFSR_MATCH_TC_BF16:   tcgen05 single bf16 pass (fast, similarity error ~1e-4);
+ *       MREFSR_MATCH_FP32:      exact-fp32 CUDA-core kernel, any patch_size / stride.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    MREFSR_MATCH_AUTO = 0,
+    MREFSR_MATCH_TC_BF16X3 = 1,
+    MREFSR_MATCH_TC_BF16 = 2,
+    MREFSR_MATCH_FP32 = 3,
+};
+/* tuning flags OR-ed into `mode` (bits 8..): see DESIGN.md "matcher kernel" */
+#define MREFSR_MATCH_FLAG_NO_STRIP 0x100      /* one tap per pipeline stage (no row-shifted descriptors) */
+#define MREFSR_MATCH_FLAG_BASE_OFFSET 0x200   /* encode (addr>>7)&7 in the descriptor base-offset field */
+
+MREFSR_API size_t mrefsr_match_workspace_bytes(int n_in, int n_pairs, int C, int h_in, int w_in, int h_ref, int w_ref,
+                                    int mode);
+MREFSR_API int mrefsr_feature_match_batched(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div,
+                                 int C, int h_in, int w_in, int h_ref, int w_ref, int patch_size, int input_stride,
+                                 int ref_stride, int is_norm, int norm_input, int normalize_pixels, int mode,
+                                 int64_t* max_idx, float* max_val, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
+/* idx -> flow -> nine zero-filled shifts at three scales.
+ *     replaces  basicsr/archs/corres_generation_arch.py:30-47 (index_to_flow) and :70-105,
+ *               basicsr/archs/arch_util.py:386-410 (tensor_shift)
+ * max_idx [n, h-2, w-2] int64  ->  out_s1 [n,9,h,w,2], out_s2 [n,9,2h,2w,2], out_s4 [n,9,4h,4w,2]
+ * fp32, last dim (x, y).  Any of the outputs may be NULL. */
+MREFSR_API int mrefsr_pre_offsets(const int64_t* max_idx, int n, int h, int w, float* out_s1, float* out_s2, float* out_s4,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Modulated deformable convolution (DCNv2)
+ *     replaces  basicsr/ops/dcn/src/deform_conv_ext.cpp:107-147 (pybind exports
+ *               modulated_deform_conv_forward / modulated_deform_conv_backward) and the host code
+ *               basicsr/ops/dcn/src/deform_conv_cuda.cpp:490-685.
+ * input  [B, C, H, W]   weight [Co, C/group, kh, kw]   bias [Co] or NULL (with_bias = 0)
+ * offset [B, 2*dg*kh*kw, Ho, Wo]  (channel 2*(g*K+k) = dy, +1 = dx)   mask [B, dg*kh*kw, Ho, Wo]
+ * output [B, Co, Ho, Wo], overwritten.  The reference's `ones` / `columns` scratch tensors are
+ * replaced by `workspace`.
+ * mode: MREFSR_DCN_AUTO / MREFSR_DCN_FP32 (CUDA-core, exact fp32) / MREFSR_DCN_TF32 (tcgen05).
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    MREFSR_DCN_AUTO = 0,
+    MREFSR_DCN_FP32 = 1,
+    MREFSR_DCN_TF32 = 2,
+};
+MREFSR_API size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                  int pad_h, int pad_w, int dil_h, int dil_w, int group, int deformable_group,
+                                  int mode, int backward);
+MREFSR_API int mrefsr_modulated_deform_conv_forward(const float* input, const float* weight, const float* bias,
+                                         const float* offset, const float* mask, float* output, int B, int C, int H,
+                                         int W, int Co, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                         int pad_w, int dil_h, int dil_w, int group, int deformable_group,
+                                         int with_bias, int mode, void* workspace, size_t workspace_bytes,
+                                         void* stream);
+/* grad_input / grad_offset / grad_mask are overwritten; grad_weight / grad_bias are ACCUMULATED
+ * into (the reference accumulates with addmm_ beta = 1 into caller-zeroed tensors,
+ * deform_conv_cuda.cpp:659-671).  grad_input may be NULL (skipped). */
+MREFSR_API int mrefsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset,
+                                          const float* mask, const float* grad_output, float* grad_input,
+                                          float* grad_weight, float* grad_bias, float* grad_offset, float* grad_mask,
+                                          int B, int C, int H, int W, int Co, int kh, int kw, int stride_h,
+                                          int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int group,
+                                          int deformable_group, int with_bias, int mode, void* workspace,
+                                          size_t workspace_bytes, void* stream);
+
+/* DynAgg glue, fused: conv_out [B, 3*dg*9, H, W] (raw conv_offset_mask output) + pre_offset
+ * [B, 9, H, W, 2] (x, y)  ->  offset [B, 2*dg*9, H, W], mask [B, dg*9, H, W] (sigmoid), and the
+ * mean |learned offset| accumulated into *abs_sum (device float, may be NULL) instead of the
+ * reference's host sync.
+ *     replaces  basicsr/archs/ref_mrapa_restoration_arch.py:55-73 */
+MREFSR_API int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float* offset, float* mask,
+                          float* abs_sum, int B, int dg, int K, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Multi-reference attention fusion core
+ *     replaces  basicsr/archs/ref_mrapa_restoration_arch.py:321-335
+ * emb_t [n, C, h, w] (already scaled by C^-0.5), emb [n*t, C, h, w], ass [n*t, Cv, h, w]
+ * out [n, Cv, h, w] = sum_t softmax_t(<emb_t, emb_t'>)[t] * ass[t];  prob [n, t, h, w] optional
+ * (saved for backward; may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+MREFSR_API int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const float* ass, float* out, float* prob,
+                                   int n, int t, int C, int Cv, int h, int w, void* stream);
+MREFSR_API int mrefsr_mrapa_attention_backward(const float* emb_t, const float* emb, const float* ass, const float* prob,
+                                    const float* grad_out, float* grad_emb_t, float* grad_emb, float* grad_ass,
+                                    int n, int t, int C, int Cv, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer variants (end-to-end path): copy inputs host->device, run, copy results back, and
+ * synchronise the stream before returning.  Device scratch comes from an internal arena that
+ * grows on demand (mrefsr_arena_release() frees it).
+ * ------------------------------------------------------------------------------------------ */
+MREFSR_API int mrefsr_feature_match_batched_host(const float* feat_in, const float* feat_ref, int n_in, int n_pairs,
+                                      int in_div, int C, int h_in, int w_in, int h_ref, int w_ref, int patch_size,
+                                      int input_stride, int ref_stride, int is_norm, int norm_input,
+                                      int normalize_pixels, int mode, int64_t* max_idx, float* max_val,
+                                      void* stream);
+MREFSR_API int mrefsr_modulated_deform_conv_forward_host(const float* input, const float* weight, const float* bias,
+                                              const float* offset, const float* mask, float* output, int B, int C,
+                                              int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                              int pad_h, int pad_w, int dil_h, int dil_w, int group,
+                                              int deformable_group, int with_bias, int mode, void* stream);
+MREFSR_API int mrefsr_mrapa_attention_forward_host(const float* emb_t, const float* emb, const float* ass, float* out, int n,
+                                        int t, int C, int Cv, int h, int w, void* stream);
+MREFSR_API void mrefsr_arena_release(void);
+
+/* Per-kernel device timing for the roofline report (bench.py).  When enabled, the main kernel of each piece
+ * is bracketed by CUDA events recorded on the launching stream; mrefsr_timing_read() synchronises those
+ * events and returns the accumulated milliseconds and launch count per kernel id, then resets. */
+enum {
+    MREFSR_K_MATCH_MAIN = 0, /* correlation + arg-max kernel (tcgen05 or fp32) */
+    MREFSR_K_MATCH_PREP = 1, /* layout / split / norms / finalize around it */
+    MREFSR_K_DCN_FWD = 2,    /* DCN forward main kernel */
+    MREFSR_K_DCN_AUX = 3,    /* DCN layout / weight repack kernels */
+    MREFSR_K_FUSION_FWD = 4, /* attention core */
+    MREFSR_K_GLUE = 5,       /* pre-offsets, DynAgg offset/mask assembly */
+    MREFSR_K_COUNT = 6
+};
+MREFSR_API void mrefsr_timing_enable(int on);
+MREFSR_API int mrefsr_timing_read(double* ms_out, unsigned long long* launches_out, int n);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+MREFSR_API unsigned long long mrefsr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MREFSR_B200_H_ */

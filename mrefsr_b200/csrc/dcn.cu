@@ -1,0 +1,549 @@
+// mrefsr_b200/csrc/dcn.cu -- modulated deformable convolution (DCNv2): exact-fp32 CUDA-core forward, backward,
+// and the DynAgg offset/mask glue.  The tcgen05 (TF32) forward lives in dcn_tc.cu.
+//
+// Replaces basicsr/ops/dcn/src/deform_conv_cuda.cpp:490-685 and the kernels of
+// basicsr/ops/dcn/src/deform_conv_cuda_kernel.cu:468-767.  Differences in structure (not in results):
+//   * forward: no columns buffer and no per-sample loop -- the bilinear gather feeds the GEMM tile directly
+//     from shared memory, batched over B in one launch (the reference launches im2col + addmm_ per sample,
+//     deform_conv_cuda.cpp:539-555);
+//   * backward: the reference's per-sample {addmm_, col2im_coord, col2im, im2col, addmm_ x2} sequence
+//     (deform_conv_cuda.cpp:612-672) is batched over chunks of samples sized to a bounded workspace.
+#include "common.cuh"
+#include "dcn_common.cuh"
+#include "../../include/mrefsr_b200.h"
+
+namespace mrefsr {
+
+constexpr int DT = 64;  // tile edge of the CUDA-core GEMM tiles
+constexpr int DK = 16;  // K step
+
+// =====================================================================================================
+// forward, exact fp32: tile = 64 output positions x 64 output channels, K = (tap, 16 input channels)
+// grid (ceil(P/64), G * ceil(Co/G/64), B), block 256
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+dcn_fwd_simt_kernel(const float* __restrict__ x, const float* __restrict__ offset, const float* __restrict__ mask,
+                    const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ out,
+                    const DcnShape s) {
+    __shared__ float As[DK][DT + 4];
+    __shared__ float Bs[DK][DT + 4];
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cpg = s.C / s.G, opg = s.Co / s.G, cdg = s.C / s.DG;
+    const int oct = cdiv_d(opg, DT);
+    const int b = blockIdx.z, gi = blockIdx.y / oct, ot = blockIdx.y % oct;
+    const int p0 = blockIdx.x * DT, oc0 = ot * DT;  // oc0 is group-local
+    const int t = threadIdx.x;
+    const int lpos = t & 63, lkq = (t >> 6) * 4;
+    const int ty = t >> 4, tx = t & 15;
+    const int p = p0 + lpos;
+    const bool pvalid = p < P;
+    const int oy = pvalid ? p / s.Wo : 0, ox = pvalid ? p % s.Wo : 0;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < K; ++tap) {
+        const int ti = tap / s.kw, tj = tap % s.kw;
+        const float ybase = (float)(oy * s.sh - s.ph + ti * s.dh), xbase = (float)(ox * s.sw - s.pw + tj * s.dw);
+        for (int c0 = 0; c0 < cpg; c0 += DK) {
+            // ---- A tile: gathered, modulated samples
+            int last_dg = -1;
+            float sy = 0.f, sx = 0.f, sm = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int cl = c0 + lkq + e;
+                float v = 0.f;
+                if (pvalid && cl < cpg) {
+                    const int ch = gi * cpg + cl;
+                    const int dgi = ch / cdg;
+                    if (dgi != last_dg) {
+                        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+                        sy = ybase + __ldg(offset + ob);
+                        sx = xbase + __ldg(offset + ob + P);
+                        sm = __ldg(mask + ((size_t)(b * s.DG + dgi) * K + tap) * P + p);
+                        last_dg = dgi;
+                    }
+                    v = dcn_sample(x + ((size_t)b * s.C + ch) * s.H * s.W, s.H, s.W, sy, sx) * sm;
+                }
+                As[lkq + e][lpos] = v;
+            }
+            // ---- B tile: weights W[oc][c][tap]
+            {
+                const int oc = oc0 + lpos;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int cl = c0 + lkq + e;
+                    float v = 0.f;
+                    if (oc < opg && cl < cpg) v = __ldg(weight + ((size_t)(gi * opg + oc) * cpg + cl) * K + tap);
+                    Bs[lkq + e][lpos] = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < DK; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ocl = oc0 + tx * 4 + j;
+        if (ocl >= opg) continue;
+        const int oc = gi * opg + ocl;
+        const float bv = bias ? __ldg(bias + oc) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pp = p0 + ty * 4 + i;
+            if (pp < P) out[((size_t)b * s.Co + oc) * P + pp] = acc[i][j] + bv;
+        }
+    }
+}
+
+// =====================================================================================================
+// backward
+// =====================================================================================================
+// (1) gcol[bl][(ch*K+tap)][p] = sum_oc W[oc][(c*K+tap)] * gout[b][oc][p]     (deform_conv_cuda.cpp:623-626)
+// grid (ceil(P/64), G * ceil(cpg*K/64), nb), block 256
+__global__ void __launch_bounds__(256)
+dcn_bwd_gcol_kernel(const float* __restrict__ weight, const float* __restrict__ gout, float* __restrict__ gcol,
+                    const DcnShape s, int b0) {
+    __shared__ float As[DK][DT + 4];
+    __shared__ float Bs[DK][DT + 4];
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cpg = s.C / s.G, opg = s.Co / s.G, MK = cpg * K;
+    const int mt_per = cdiv_d(MK, DT);
+    const int bl = blockIdx.z, b = b0 + bl, gi = blockIdx.y / mt_per, mt = blockIdx.y % mt_per;
+    const int p0 = blockIdx.x * DT, m0 = mt * DT;
+    const int t = threadIdx.x, lidx = t & 63, lkq = (t >> 6) * 4, ty = t >> 4, tx = t & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < opg; k0 += DK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + lkq + e;
+            const int m = m0 + lidx, pp = p0 + lidx;
+            As[lkq + e][lidx] = (k < opg && m < MK) ? __ldg(weight + (size_t)(gi * opg + k) * MK + m) : 0.f;
+            Bs[lkq + e][lidx] = (k < opg && pp < P) ? __ldg(gout + ((size_t)b * s.Co + gi * opg + k) * P + pp) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < DK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= MK) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pp = p0 + tx * 4 + j;
+            if (pp < P) gcol[((size_t)bl * s.C * K + (size_t)gi * MK + m) * P + pp] = acc[i][j];
+        }
+    }
+}
+
+// (2) grad_offset / grad_mask  (.cu:695-767): one thread per (bl, deform group, tap, position)
+__global__ void dcn_bwd_coord_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+                                     const float* __restrict__ mask, const float* __restrict__ gcol,
+                                     float* __restrict__ goff, float* __restrict__ gmask, const DcnShape s, int b0,
+                                     int nb) {
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG;
+    const size_t total = (size_t)nb * s.DG * K * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int tap = (idx / P) % K;
+        const int dgi = (idx / ((size_t)P * K)) % s.DG;
+        const int bl = idx / ((size_t)P * K * s.DG);
+        const int b = b0 + bl;
+        const int oy = p / s.Wo, ox = p % s.Wo, ti = tap / s.kw, tj = tap % s.kw;
+        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+        const size_t mb = ((size_t)(b * s.DG + dgi) * K + tap) * P + p;
+        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + offset[ob];
+        const float xx = (float)(ox * s.sw - s.pw + tj * s.dw) + offset[ob + P];
+        const float m = mask[mb];
+        float dy = 0.f, dx = 0.f, dm = 0.f;
+        if (y > -1.f && xx > -1.f && y < (float)s.H && xx < (float)s.W) {
+            const int y0 = (int)floorf(y), x0 = (int)floorf(xx), y1 = y0 + 1, x1 = x0 + 1;
+            const float ly = y - y0, lx = xx - x0;
+            const bool va = y0 >= 0 && x0 >= 0, vb = y0 >= 0 && x1 <= s.W - 1, vc = y1 <= s.H - 1 && x0 >= 0,
+                       vd = y1 <= s.H - 1 && x1 <= s.W - 1;
+            for (int cc = 0; cc < cdg; ++cc) {
+                const int ch = dgi * cdg + cc;
+                const float* pl = x + ((size_t)b * s.C + ch) * s.H * s.W;
+                const float a = va ? __ldg(pl + y0 * s.W + x0) : 0.f;
+                const float bq = vb ? __ldg(pl + y0 * s.W + x1) : 0.f;
+                const float cq = vc ? __ldg(pl + y1 * s.W + x0) : 0.f;
+                const float d = vd ? __ldg(pl + y1 * s.W + x1) : 0.f;
+                const float gc = gcol[((size_t)bl * s.C * K + (size_t)ch * K + tap) * P + p];
+                const float v = (1.f - ly) * (1.f - lx) * a + (1.f - ly) * lx * bq + ly * (1.f - lx) * cq + ly * lx * d;
+                dm += gc * v;
+                dy += gc * m * ((1.f - lx) * (cq - a) + lx * (d - bq));
+                dx += gc * m * ((1.f - ly) * (bq - a) + ly * (d - cq));
+            }
+        }
+        goff[ob] = dy;
+        goff[ob + P] = dx;
+        gmask[mb] = dm;
+    }
+}
+
+// (3) grad_input: bilinear scatter of gcol * mask (.cu:635-693), one thread per (bl, channel, tap, position)
+__global__ void dcn_bwd_input_kernel(const float* __restrict__ offset, const float* __restrict__ mask,
+                                     const float* __restrict__ gcol, float* __restrict__ gx, const DcnShape s, int b0,
+                                     int nb) {
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG;
+    const size_t total = (size_t)nb * s.C * K * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int tap = (idx / P) % K;
+        const int ch = (idx / ((size_t)P * K)) % s.C;
+        const int bl = idx / ((size_t)P * K * s.C);
+        const int b = b0 + bl, dgi = ch / cdg;
+        const int oy = p / s.Wo, ox = p % s.Wo, ti = tap / s.kw, tj = tap % s.kw;
+        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + offset[ob];
+        const float xx = (float)(ox * s.sw - s.pw + tj * s.dw) + offset[ob + P];
+        if (!(y > -1.f && xx > -1.f && y < (float)s.H && xx < (float)s.W)) continue;
+        const float tval = gcol[idx] * mask[((size_t)(b * s.DG + dgi) * K + tap) * P + p];
+        const int y0 = (int)floorf(y), x0 = (int)floorf(xx), y1 = y0 + 1, x1 = x0 + 1;
+        const float ly = y - y0, lx = xx - x0;
+        float* pl = gx + ((size_t)b * s.C + ch) * s.H * s.W;
+        if (y0 >= 0 && x0 >= 0) atomicAdd(pl + y0 * s.W + x0, (1.f - ly) * (1.f - lx) * tval);
+        if (y0 >= 0 && x1 <= s.W - 1) atomicAdd(pl + y0 * s.W + x1, (1.f - ly) * lx * tval);
+        if (y1 <= s.H - 1 && x0 >= 0) atomicAdd(pl + y1 * s.W + x0, ly * (1.f - lx) * tval);
+        if (y1 <= s.H - 1 && x1 <= s.W - 1) atomicAdd(pl + y1 * s.W + x1, ly * lx * tval);
+    }
+}
+
+// (4a) columns[bl][(ch*K+tap)][p]  (.cu:571-633), recomputed for grad_weight like deform_conv_cuda.cpp:647-650
+__global__ void dcn_im2col_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+                                  const float* __restrict__ mask, float* __restrict__ col, const DcnShape s, int b0,
+                                  int nb) {
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG;
+    const size_t total = (size_t)nb * s.C * K * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int tap = (idx / P) % K;
+        const int ch = (idx / ((size_t)P * K)) % s.C;
+        const int bl = idx / ((size_t)P * K * s.C);
+        const int b = b0 + bl, dgi = ch / cdg;
+        const int oy = p / s.Wo, ox = p % s.Wo, ti = tap / s.kw, tj = tap % s.kw;
+        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + offset[ob];
+        const float xx = (float)(ox * s.sw - s.pw + tj * s.dw) + offset[ob + P];
+        const float m = mask[((size_t)(b * s.DG + dgi) * K + tap) * P + p];
+        col[idx] = dcn_sample(x + ((size_t)b * s.C + ch) * s.H * s.W, s.H, s.W, y, xx) * m;
+    }
+}
+
+// (4b) grad_weight[oc][m] += sum_{bl, p} gout[b][oc][p] * col[bl][m][p]   (deform_conv_cuda.cpp:659-664)
+// grid (G * ceil(MK/64), ceil(opg/64), nb * pchunks), block 256; split-K partial sums merged with atomicAdd.
+constexpr int WCHUNK = 2048;
+__global__ void __launch_bounds__(256)
+dcn_bwd_weight_kernel(const float* __restrict__ gout, const float* __restrict__ col, float* __restrict__ gw,
+                      const DcnShape s, int b0, int pchunks) {
+    __shared__ float As[DK][DT + 4];
+    __shared__ float Bs[DK][DT + 4];
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cpg = s.C / s.G, opg = s.Co / s.G, MK = cpg * K;
+    const int mt_per = cdiv_d(MK, DT);
+    const int gi = blockIdx.x / mt_per, m0 = (blockIdx.x % mt_per) * DT, oc0 = blockIdx.y * DT;
+    const int bl = blockIdx.z / pchunks, pc = blockIdx.z % pchunks, b = b0 + bl;
+    const int pbeg = pc * WCHUNK, pend = min(P, pbeg + WCHUNK);
+    const int t = threadIdx.x, lr = t >> 2, lk = (t & 3) * 4, ty = t >> 4, tx = t & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int oc = oc0 + lr, m = m0 + lr;
+    const float* arow = (oc < opg) ? gout + ((size_t)b * s.Co + gi * opg + oc) * P : nullptr;
+    const float* brow = (m < MK) ? col + ((size_t)bl * s.C * K + (size_t)gi * MK + m) * P : nullptr;
+    for (int k0 = pbeg; k0 < pend; k0 += DK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int pp = k0 + lk + e;
+            As[lk + e][lr] = (arow && pp < pend) ? __ldg(arow + pp) : 0.f;
+            Bs[lk + e][lr] = (brow && pp < pend) ? __ldg(brow + pp) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < DK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = oc0 + ty * 4 + i;
+        if (o >= opg) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int mm = m0 + tx * 4 + j;
+            if (mm < MK) atomicAdd(gw + (size_t)(gi * opg + o) * MK + mm, acc[i][j]);
+        }
+    }
+}
+
+// (5) grad_bias[oc] += sum_{b, p} gout[b][oc][p]   (deform_conv_cuda.cpp:665-671); one block per channel
+__global__ void dcn_bwd_bias_kernel(const float* __restrict__ gout, float* __restrict__ gb, int B, int Co, int P) {
+    __shared__ float red[32];
+    const int oc = blockIdx.x;
+    float sum = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float* g = gout + ((size_t)b * Co + oc) * P;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) sum += g[p];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) gb[oc] += v;
+    }
+}
+
+// =====================================================================================================
+// DynAgg glue (ref_mrapa_restoration_arch.py:55-73): chunk / cat / pre-offset add / sigmoid in one pass
+// =====================================================================================================
+__global__ void dynagg_offsets_kernel(const float* __restrict__ conv_out, const float* __restrict__ pre,
+                                      float* __restrict__ offset, float* __restrict__ mask,
+                                      float* __restrict__ abs_sum, int B, int dg, int K, int P) {
+    const int OC = 2 * dg * K, MC = dg * K, TC = OC + MC;
+    const size_t total = (size_t)B * TC * P;
+    float local = 0.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int ch = (idx / P) % TC;
+        const int b = idx / ((size_t)P * TC);
+        const float v = conv_out[idx];
+        if (ch < OC) {
+            // offset channel ch: tap k = (ch/2) % K; even = y (pre[...,1]), odd = x (pre[...,0])
+            const int k = (ch >> 1) % K;
+            const float pv = pre[(((size_t)b * K + k) * P + p) * 2 + ((ch & 1) ? 0 : 1)];
+            offset[((size_t)b * OC + ch) * P + p] = v + pv;
+            local += fabsf(v);
+        } else {
+            mask[((size_t)b * MC + (ch - OC)) * P + p] = 1.f / (1.f + expf(-v));
+        }
+    }
+    if (abs_sum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(abs_sum, local);
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+int dcn_make_shape(DcnShape* s, int B, int C, int H, int W, int Co, int kh, int kw, int sh, int sw, int ph, int pw,
+                   int dh, int dw, int G, int DG) {
+    MREFSR_CHECK(B > 0 && C > 0 && H > 0 && W > 0 && Co > 0 && kh > 0 && kw > 0, ERR_BAD_ARG, "dcn: bad sizes");
+    MREFSR_CHECK(sh > 0 && sw > 0 && dh > 0 && dw > 0 && ph >= 0 && pw >= 0, ERR_BAD_ARG, "dcn: bad stride/pad/dilation");
+    MREFSR_CHECK(G > 0 && DG > 0 && C % G == 0 && Co % G == 0, ERR_BAD_ARG,
+                 "dcn: input shape and kernel channels won't match: (%d vs %d groups)", C, G);
+    MREFSR_CHECK(C % DG == 0, ERR_BAD_ARG, "dcn: channels %d not divisible by deformable_group %d", C, DG);
+    s->B = B; s->C = C; s->H = H; s->W = W; s->Co = Co; s->kh = kh; s->kw = kw; s->sh = sh; s->sw = sw;
+    s->ph = ph; s->pw = pw; s->dh = dh; s->dw = dw; s->G = G; s->DG = DG;
+    s->Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
+    s->Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+    MREFSR_CHECK(s->Ho > 0 && s->Wo > 0, ERR_BAD_ARG, "dcn: empty output %d x %d", s->Ho, s->Wo);
+    return 0;
+}
+
+static int bwd_chunk(const DcnShape& s) {
+    const size_t per = (size_t)s.C * s.kh * s.kw * s.Ho * s.Wo * 4;
+    size_t nb = ((size_t)256 << 20) / per;
+    if (nb < 1) nb = 1;
+    if (nb > (size_t)s.B) nb = s.B;
+    return (int)nb;
+}
+
+static int grid_for(size_t total) {
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 32;
+    return (int)(blocks > cap ? cap : blocks);
+}
+
+int dcn_forward_fp32(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
+                     const DcnShape& s, cudaStream_t st) {
+    const int P = s.Ho * s.Wo, opg = s.Co / s.G;
+    dim3 grid(cdiv(P, DT), s.G * cdiv(opg, DT), s.B);
+    ScopedTiming tm(MREFSR_K_DCN_FWD, st);
+    dcn_fwd_simt_kernel<<<grid, 256, 0, st>>>(x, off, mask, w, bias, out, s);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace mrefsr
+
+using namespace mrefsr;
+
+extern "C" {
+
+size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                  int pad_h, int pad_w, int dil_h, int dil_w, int group, int deformable_group, int mode,
+                                  int backward) {
+    DcnShape s;
+    if (dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
+                       deformable_group))
+        return 0;
+    if (backward) return 2 * (size_t)bwd_chunk(s) * C * kh * kw * s.Ho * s.Wo * 4 + 1024;
+    return dcn_tc_workspace_bytes(s, mode) + 1024;
+}
+
+int mrefsr_modulated_deform_conv_forward(const float* input, const float* weight, const float* bias,
+                                         const float* offset, const float* mask, float* output, int B, int C, int H,
+                                         int W, int Co, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                                         int dil_h, int dil_w, int group, int deformable_group, int with_bias, int mode,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+    MREFSR_CHECK(input && weight && offset && mask && output, ERR_BAD_ARG, "dcn forward: null pointer argument");
+    MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dcn forward: with_bias set but bias is NULL");
+    DcnShape s;
+    int rc = dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
+                            deformable_group);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* bp = with_bias ? bias : nullptr;
+    int m = mode;
+    if (m == MREFSR_DCN_AUTO) m = dcn_tc_eligible(s) ? MREFSR_DCN_TF32 : MREFSR_DCN_FP32;
+    if (m == MREFSR_DCN_FP32) return dcn_forward_fp32(input, weight, bp, offset, mask, output, s, st);
+    MREFSR_CHECK(m == MREFSR_DCN_TF32, ERR_BAD_ARG, "dcn forward: unknown mode %d", mode);
+    MREFSR_CHECK(dcn_tc_eligible(s), ERR_UNSUPPORTED,
+                 "dcn forward: tcgen05 path needs group 1, 3x3 kernel, C %% 32 == 0, Co %% 16 == 0, Co <= 256, "
+                 "(C/deformable_group) %% 4 == 0");
+    return dcn_forward_tc(input, weight, bp, offset, mask, output, s, workspace, workspace_bytes, st);
+}
+
+int mrefsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset,
+                                          const float* mask, const float* grad_output, float* grad_input,
+                                          float* grad_weight, float* grad_bias, float* grad_offset, float* grad_mask,
+                                          int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                          int pad_h, int pad_w, int dil_h, int dil_w, int group, int deformable_group,
+                                          int with_bias, int mode, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+    (void)mode;
+    MREFSR_CHECK(input && weight && offset && mask && grad_output && grad_weight && grad_offset && grad_mask, ERR_BAD_ARG,
+                 "dcn backward: null pointer argument");
+    MREFSR_CHECK(!with_bias || grad_bias, ERR_BAD_ARG, "dcn backward: with_bias set but grad_bias is NULL");
+    DcnShape s;
+    int rc = dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
+                            deformable_group);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = kh * kw, P = s.Ho * s.Wo, cpg = C / group, opg = Co / group, MK = cpg * K;
+    const int nbmax = bwd_chunk(s);
+    const size_t buf = (size_t)nbmax * C * K * P * 4;
+    MREFSR_CHECK(workspace && workspace_bytes >= 2 * buf, ERR_WORKSPACE, "dcn backward: workspace too small (%zu < %zu)",
+                 workspace_bytes, 2 * buf);
+    float* gcol = static_cast<float*>(workspace);
+    float* col = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + buf);
+    if (grad_input) MREFSR_CUDA(cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * 4, st));
+    for (int b0 = 0; b0 < B; b0 += nbmax) {
+        const int nb = (B - b0 < nbmax) ? B - b0 : nbmax;
+        dcn_bwd_gcol_kernel<<<dim3(cdiv(P, DT), group * cdiv(MK, DT), nb), 256, 0, st>>>(weight, grad_output, gcol, s, b0);
+        MREFSR_LAUNCH_CHECK();
+        dcn_bwd_coord_kernel<<<grid_for((size_t)nb * deformable_group * K * P), 256, 0, st>>>(
+            input, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(2);
+        if (grad_input) {
+            dcn_bwd_input_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(offset, mask, gcol, grad_input, s, b0, nb);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
+        }
+        dcn_im2col_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(input, offset, mask, col, s, b0, nb);
+        MREFSR_LAUNCH_CHECK();
+        const int pchunks = cdiv(P, WCHUNK);
+        dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
+            grad_output, col, grad_weight, s, b0, pchunks);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(2);
+    }
+    if (with_bias) {
+        dcn_bwd_bias_kernel<<<Co, 256, 0, st>>>(grad_output, grad_bias, B, Co, P);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+    }
+    return 0;
+}
+
+int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float* offset, float* mask, float* abs_sum,
+                          int B, int dg, int K, int H, int W, void* stream) {
+    MREFSR_CHECK(conv_out && pre_offset && offset && mask && B > 0 && dg > 0 && K > 0 && H > 0 && W > 0, ERR_BAD_ARG,
+                 "dynagg_offsets: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t total = (size_t)B * 3 * dg * K * H * W;
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    dynagg_offsets_kernel<<<grid_for(total), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, B, dg, K, H * W);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_modulated_deform_conv_forward_host(const float* input, const float* weight, const float* bias,
+                                              const float* offset, const float* mask, float* output, int B, int C,
+                                              int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                              int pad_h, int pad_w, int dil_h, int dil_w, int group,
+                                              int deformable_group, int with_bias, int mode, void* stream) {
+    DcnShape s;
+    int rc = dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
+                            deformable_group);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = kh * kw, P = s.Ho * s.Wo;
+    const size_t ws = align_up(mrefsr_dcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w,
+                                                          dil_h, dil_w, group, deformable_group, mode, 0), 1024);
+    const size_t n_in = (size_t)B * C * H * W, n_w = (size_t)Co * (C / group) * K, n_off = (size_t)B * 2 * deformable_group * K * P,
+                 n_mask = n_off / 2, n_out = (size_t)B * Co * P;
+    size_t o = ws;
+    auto take = [&](size_t elems) { size_t r = o; o += align_up(elems * 4, 1024); return r; };
+    const size_t o_in = take(n_in), o_w = take(n_w), o_b = take(Co), o_off = take(n_off), o_mask = take(n_mask), o_out = take(n_out);
+    void* base = nullptr;
+    rc = arena_get(o, &base);
+    if (rc) return rc;
+    uint8_t* p = static_cast<uint8_t*>(base);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(p + off); };
+    MREFSR_CUDA(cudaMemcpyAsync(F(o_in), input, n_in * 4, cudaMemcpyHostToDevice, st));
+    MREFSR_CUDA(cudaMemcpyAsync(F(o_w), weight, n_w * 4, cudaMemcpyHostToDevice, st));
+    if (with_bias) MREFSR_CUDA(cudaMemcpyAsync(F(o_b), bias, (size_t)Co * 4, cudaMemcpyHostToDevice, st));
+    MREFSR_CUDA(cudaMemcpyAsync(F(o_off), offset, n_off * 4, cudaMemcpyHostToDevice, st));
+    MREFSR_CUDA(cudaMemcpyAsync(F(o_mask), mask, n_mask * 4, cudaMemcpyHostToDevice, st));
+    rc = mrefsr_modulated_deform_conv_forward(F(o_in), F(o_w), with_bias ? F(o_b) : nullptr, F(o_off), F(o_mask), F(o_out),
+                                              B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
+                                              deformable_group, with_bias, mode, p, ws, st);
+    if (rc) return rc;
+    MREFSR_CUDA(cudaMemcpyAsync(output, F(o_out), n_out * 4, cudaMemcpyDeviceToHost, st));
+    MREFSR_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// mrefsr_b200/csrc/fusion.cu -- multi-reference attention core of MRAPAFusion.
+//
+// Replaces basicsr/archs/ref_mrapa_restoration_arch.py:321-335: three permute().contiguous() copies, a batched
+// [1 x C] . [C x t] matmul per pixel, softmax over t, and a [1 x t] . [t x 2C] matmul per pixel, then a
+// permute back.  Here it is one pass over the NCHW tensors exactly as the convolutions left them:
+//   CTA = 32 consecutive pixels of one image x 8 warps; lane = pixel (so every global access is a full
+//   128-byte line), warp = channel slice.
+//   phase 1: per-warp partial logits  l[t] += q[c] * k[t][c]  over its slice of C  -> shared memory
+//   phase 2: every thread sums the 8 partials of its pixel, softmax over t in registers
+//   phase 3: per-warp slice of the 2C value channels:  out[cv] = sum_t p[t] * v[t][cv]
+// HBM-bound: 4*(C + t*C + t*Cv + Cv) bytes per pixel, each byte touched once.
+#include "common.cuh"
+#include "../../include/mrefsr_b200.h"
+
+namespace mrefsr {
+
+constexpr int FW = 8;  // warps per CTA
+
+template <int TMAX>
+__global__ void __launch_bounds__(FW * 32)
+mrapa_fwd_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb, const float* __restrict__ ass,
+                 float* __restrict__ out, float* __restrict__ prob, int t, int C, int Cv, int HW) {
+    __shared__ float part[FW][TMAX][32];
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const bool ok = p < HW;
+    const int pc = ok ? p : HW - 1;  // clamp: out-of-range lanes read a valid address and never write
+    float l[TMAX];
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) l[i] = 0.f;
+    const float* q = emb_t + (size_t)n * C * HW + pc;
+    const float* k = emb + (size_t)n * t * C * HW + pc;
+    const int cper = (C + FW - 1) / FW;
+    const int cbeg = warp * cper, cend = min(C, cbeg + cper);
+#pragma unroll 4
+    for (int c = cbeg; c < cend; ++c) {
+        const float qv = __ldg(q + (size_t)c * HW);
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) l[i] = fmaf(qv, __ldg(k + ((size_t)i * C + c) * HW), l[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) part[warp][i][lane] = l[i];
+    __syncthreads();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < FW; ++w) s += part[w][i][lane];
+        l[i] = s;
+        if (i < t) mx = fmaxf(mx, s);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        l[i] = (i < t) ? expf(l[i] - mx) : 0.f;
+        den += l[i];
+    }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) l[i] *= inv;
+    if (prob && warp == 0 && ok) {
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) prob[((size_t)n * t + i) * HW + p] = l[i];
+    }
+    const float* v = ass + (size_t)n * t * Cv * HW + pc;
+    float* o = out + (size_t)n * Cv * HW + p;
+    const int vper = (Cv + FW - 1) / FW;
+    const int vbeg = warp * vper, vend = min(Cv, vbeg + vper);
+#pragma unroll 4
+    for (int c = vbeg; c < vend; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) acc = fmaf(l[i], __ldg(v + ((size_t)i * Cv + c) * HW), acc);
+        if (ok) o[(size_t)c * HW] = acc;
+    }
+}
+
+// backward:
+//   g_ass[t][cv] = p[t] * go[cv];   dp[t] = sum_cv go[cv] * v[t][cv];   dl[t] = p[t] * (dp[t] - sum_s p[s] dp[s])
+//   g_q[c] = sum_t dl[t] * k[t][c];   g_k[t][c] = dl[t] * q[c]
+template <int TMAX>
+__global__ void __launch_bounds__(FW * 32)
+mrapa_bwd_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb, const float* __restrict__ ass,
+                 const float* __restrict__ prob, const float* __restrict__ gout, float* __restrict__ g_emb_t,
+                 float* __restrict__ g_emb, float* __restrict__ g_ass, int t, int C, int Cv, int HW) {
+    __shared__ float part[FW][TMAX][32];
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const bool ok = p < HW;
+    const int pc = ok ? p : HW - 1;
+    float pr[TMAX], dp[TMAX];
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        pr[i] = (i < t) ? __ldg(prob + ((size_t)n * t + i) * HW + pc) : 0.f;
+        dp[i] = 0.f;
+    }
+    const float* v = ass + (size_t)n * t * Cv * HW + pc;
+    const float* go = gout + (size_t)n * Cv * HW + pc;
+    float* gv = g_ass + (size_t)n * t * Cv * HW + p;
+    const int vper = (Cv + FW - 1) / FW;
+    const int vbeg = warp * vper, vend = min(Cv, vbeg + vper);
+#pragma unroll 2
+    for (int c = vbeg; c < vend; ++c) {
+        const float g = __ldg(go + (size_t)c * HW);
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) {
+                dp[i] = fmaf(g, __ldg(v + ((size_t)i * Cv + c) * HW), dp[i]);
+                if (ok) gv[((size_t)i * Cv + c) * HW] = pr[i] * g;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) part[warp][i][lane] = dp[i];
+    __syncthreads();
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < FW; ++w) s += part[w][i][lane];
+        dp[i] = s;
+        dot = fmaf(pr[i], s, dot);
+    }
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) dp[i] = pr[i] * (dp[i] - dot);  // dl
+    const float* q = emb_t + (size_t)n * C * HW + pc;
+    const float* k = emb + (size_t)n * t * C * HW + pc;
+    float* gq = g_emb_t + (size_t)n * C * HW + p;
+    float* gk = g_emb + (size_t)n * t * C * HW + p;
+    const int cper = (C + FW - 1) / FW;
+    const int cbeg = warp * cper, cend = min(C, cbeg + cper);
+#pragma unroll 2
+    for (int c = cbeg; c < cend; ++c) {
+        const float qv = __ldg(q + (size_t)c * HW);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) {
+                acc = fmaf(dp[i], __ldg(k + ((size_t)i * C + c) * HW), acc);
+                if (ok) gk[((size_t)i * C + c) * HW] = dp[i] * qv;
+            }
+        if (ok) gq[(size_t)c * HW] = acc;
+    }
+}
+
+static int check_args(int n, int t, int C, int Cv, int h, int w) {
+    MREFSR_CHECK(n > 0 && t > 0 && C > 0 && Cv > 0 && h > 0 && w > 0, ERR_BAD_ARG, "mrapa attention: bad sizes");
+    MREFSR_CHECK(t <= 16, ERR_UNSUPPORTED, "mrapa attention: at most 16 references are supported (got %d)", t);
+    return 0;
+}
+
+}  // namespace mrefsr
+
+using namespace mrefsr;
+
+extern "C" {
+
+int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const float* ass, float* out, float* prob,
+                                   int n, int t, int C, int Cv, int h, int w, void* stream) {
+    MREFSR_CHECK(emb_t && emb && ass && out, ERR_BAD_ARG, "mrapa attention forward: null pointer argument");
+    int rc = check_args(n, t, C, Cv, h, w);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HW = h * w;
+    dim3 grid(cdiv(HW, 32), n);
+    ScopedTiming tm(MREFSR_K_FUSION_FWD, st);
+    if (t <= 8)
+        mrapa_fwd_kernel<8><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
+    else
+        mrapa_fwd_kernel<16><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_mrapa_attention_backward(const float* emb_t, const float* emb, const float* ass, const float* prob,
+                                    const float* grad_out, float* grad_emb_t, float* grad_emb, float* grad_ass, int n,
+                                    int t, int C, int Cv, int h, int w, void* stream) {
+    MREFSR_CHECK(emb_t && emb && ass && prob && grad_out && grad_emb_t && grad_emb && grad_ass, ERR_BAD_ARG,
+                 "mrapa attention backward: null pointer argument");
+    int rc = check_args(n, t, C, Cv, h, w);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int HW = h * w;
+    dim3 grid(cdiv(HW, 32), n);
+    if (t <= 8)
+        mrapa_bwd_kernel<8><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, prob, grad_out, grad_emb_t, grad_emb, grad_ass, t,
+                                                      C, Cv, HW);
+    else
+        mrapa_bwd_kernel<16><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, prob, grad_out, grad_emb_t, grad_emb, grad_ass,
+                                                       t, C, Cv, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_mrapa_attention_forward_host(const float* emb_t, const float* emb, const float* ass, float* out, int n, int t,
+                                        int C, int Cv, int h, int w, void* stream) {
+    int rc = check_args(n, t, C, Cv, h, w);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t HW = (size_t)h * w;
+    const size_t b_q = align_up(n * C * HW * 4, 1024), b_k = align_up((size_t)n * t * C * HW * 4, 1024),
+                 b_v = align_up((size_t)n * t * Cv * HW * 4, 1024), b_o = align_up((size_t)n * Cv * HW * 4, 1024);
+    void* base = nullptr;
+    rc = arena_get(b_q + b_k + b_v + b_o, &base);
+    if (rc) return rc;
+    uint8_t* p = static_cast<uint8_t*>(base);
+    float *dq = reinterpret_cast<float*>(p), *dk = reinterpret_cast<float*>(p + b_q),
+          *dv = reinterpret_cast<float*>(p + b_q + b_k), *d_o = reinterpret_cast<float*>(p + b_q + b_k + b_v);
+    MREFSR_CUDA(cudaMemcpyAsync(dq, emb_t, (size_t)n * C * HW * 4, cudaMemcpyHostToDevice, st));
+    MREFSR_CUDA(cudaMemcpyAsync(dk, emb, (size_t)n * t * C * HW * 4, cudaMemcpyHostToDevice, st));
+    MREFSR_CUDA(cudaMemcpyAsync(dv, ass, (size_t)n * t * Cv * HW * 4, cudaMemcpyHostToDevice, st));
+    rc = mrefsr_mrapa_attention_forward(dq, dk, dv, d_o, nullptr, n, t, C, Cv, h, w, st);
+    if (rc) return rc;
+    MREFSR_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n * Cv * HW * 4, cudaMemcpyDeviceToHost, st));
+    MREFSR_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,768 @@
+// mrefsr_b200/csrc/match.cu -- correspondence matcher (feature_match_index), batched over (image, ref) pairs.
+//
+// Replaces basicsr/archs/ref_map_util.py:26-86 (and the per-pixel F.normalize of
+// basicsr/archs/corres_generation_arch.py:57-59 when normalize_pixels is set).
+//
+// Pipeline (all on one stream):
+//   1. match_prep_kernel      NCHW fp32 -> pixel-major [HW, C] copy (fp32, or split bf16 hi/lo), optional
+//                             per-pixel L2 normalisation, per-pixel sum of squares.
+//   2. match_norms_kernel     3x3 (ps x ps) box sums of the pixel sums -> reference-patch 1/(norm+1e-5) as a
+//                             per-column (scale, bias) pair (bias = -inf masks columns that are not a
+//                             valid patch origin), input-patch (norm+1e-5) per row.
+//   3. match_tc_kernel        the correlation as a TMA-fed tcgen05/TMEM GEMM with implicit im2col by row
+//      (or match_simt_kernel)  shift, arg-max fused into the epilogue: the similarity volume never leaves
+//                             the SM.  Partial (max, argmax) per N tile are merged with one 64-bit
+//                             atomicMax per row on a packed key (ordered value << 32 | ~column).
+//   4. match_finalize_kernel  key -> (int64 index on the reference patch grid, fp32 value / input norm).
+//
+// Implicit im2col: with pixel-major features F[HW, C], the K = 9*C patch vector of the patch whose origin is
+// pixel-linear index p is the concatenation over taps (i, j) of row p + i*w + j.  So the A tile of tap (i, j)
+// for rows [m0, m0+128) is simply rows [m0 + i*w + j, ...) of F: a plain 2-D TMA box, no unfold copy.
+// Rows whose origin is not a valid patch origin (x > w-3 or y > h-3) are computed and discarded (10 % at 40x40).
+#include "common.cuh"
+#include "../../include/mrefsr_b200.h"
+
+namespace mrefsr {
+
+typedef __nv_bfloat16 bf16;
+
+// =====================================================================================================
+// 1. prep
+// =====================================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// grid (ceil(HW/32), n_img), block 256, dynamic smem C*33 floats.
+__global__ void __launch_bounds__(256)
+match_prep_kernel(const float* __restrict__ src, int C, int HW, int normalize, float* __restrict__ dst_f32,
+                  bf16* __restrict__ dst_hi, bf16* __restrict__ dst_lo, float* __restrict__ pix_sumsq) {
+    extern __shared__ float tile[];  // [C][33]
+    const int img = blockIdx.y, p0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float* s = src + (size_t)img * C * HW;
+    const int p = p0 + lane;
+    for (int c = warp; c < C; c += nwarps) tile[c * 33 + lane] = (p < HW) ? __ldg(s + (size_t)c * HW + p) : 0.f;
+    __syncthreads();
+    for (int pp = warp; pp < 32; pp += nwarps) {
+        float ss = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float v = tile[c * 33 + pp];
+            ss += v * v;
+        }
+        ss = warp_sum(ss);
+        if (normalize) {
+            // F.normalize(dim=0): x / max(||x||_2, 1e-12)  (corres_generation_arch.py:57-59)
+            const float denom = fmaxf(sqrtf(ss), 1e-12f);
+            float ss2 = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                float v = tile[c * 33 + pp] / denom;
+                tile[c * 33 + pp] = v;
+                ss2 += v * v;
+            }
+            ss = warp_sum(ss2);
+        }
+        const int q = p0 + pp;
+        if (q < HW) {
+            if (lane == 0) pix_sumsq[(size_t)img * HW + q] = ss;
+            const size_t row = ((size_t)img * HW + q) * C;
+            if (dst_f32) {
+                for (int c = lane; c < C; c += 32) dst_f32[row + c] = tile[c * 33 + pp];
+            }
+            if (dst_hi) {
+                for (int c = lane * 2; c < C; c += 64) {
+                    const float v0 = tile[c * 33 + pp], v1 = tile[(c + 1) * 33 + pp];
+                    const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                    __nv_bfloat162 hh;
+                    hh.x = h0;
+                    hh.y = h1;
+                    *reinterpret_cast<__nv_bfloat162*>(dst_hi + row + c) = hh;
+                    if (dst_lo) {
+                        __nv_bfloat162 ll;
+                        ll.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                        ll.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                        *reinterpret_cast<__nv_bfloat162*>(dst_lo + row + c) = ll;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// 2. patch norms
+// =====================================================================================================
+// One thread per pixel-linear position of one image.  A position is a valid patch origin when it lies on the
+// stride grid and the ps x ps window fits.  ref side: colsb[img][n] = (scale, bias); input side: rownorm.
+__global__ void match_norms_kernel(const float* __restrict__ pix_sumsq, int n_img, int h, int w, int ps, int stride,
+                                   int padded, int is_ref, int use_norm, float2* __restrict__ colsb,
+                                   float* __restrict__ rownorm) {
+    const int img = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= padded) return;
+    const int HW = h * w;
+    bool valid = n < HW;
+    float ss = 0.f;
+    if (valid) {
+        const int y = n / w, x = n % w;
+        valid = (y % stride == 0) && (x % stride == 0) && (y + ps <= h) && (x + ps <= w);
+        if (valid) {
+            const float* s = pix_sumsq + (size_t)img * HW;
+            for (int i = 0; i < ps; ++i)
+                for (int j = 0; j < ps; ++j) ss += s[(y + i) * w + x + j];
+        }
+    }
+    const float nrm = sqrtf(ss) + 1e-5f;  // ref_map_util.py:63 / :79
+    if (is_ref) {
+        float2 v;
+        v.x = valid ? (use_norm ? 1.f / nrm : 1.f) : 0.f;
+        v.y = valid ? 0.f : -INFINITY;
+        colsb[(size_t)img * padded + n] = v;
+    } else {
+        if (n < HW) rownorm[(size_t)img * HW + n] = use_norm ? nrm : 1.f;
+    }
+}
+
+// =====================================================================================================
+// 4. finalize
+// =====================================================================================================
+__global__ void match_finalize_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ rownorm,
+                                      int n_pairs, int in_div, int n_in, int h_in, int w_in, int w_ref, int ho,
+                                      int wo, int wo_ref, int s_in, int s_ref, int key_stride,
+                                      long long* __restrict__ max_idx, float* __restrict__ max_val) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = ho * wo;
+    if (t >= n_pairs * per) return;
+    const int pair = t / per, r = t % per;
+    const int yo = r / wo, xo = r % wo;
+    const int m = (yo * s_in) * w_in + xo * s_in;
+    const unsigned long long key = keys[(size_t)pair * key_stride + m];
+    const int img = (pair / in_div) % n_in;
+    float val;
+    long long idx;
+    if (key == 0ull) {  // no finite similarity was ever recorded for this row
+        val = __int_as_float(0x7fc00000);
+        idx = 0;
+    } else {
+        val = ordered_to_float((uint32_t)(key >> 32));
+        const uint32_t n = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+        const int yq = n / w_ref, xq = n % w_ref;
+        idx = (long long)(yq / s_ref) * wo_ref + xq / s_ref;
+        val = val / rownorm[(size_t)img * (h_in * w_in) + m];  // ref_map_util.py:84 (rownorm == 1 if !norm_input)
+    }
+    max_idx[t] = idx;
+    max_val[t] = val;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(float v, uint32_t n) {
+    return ((unsigned long long)float_to_ordered(v) << 32) | (unsigned long long)(0xFFFFFFFFu - n);
+}
+
+// =====================================================================================================
+// 3a. exact-fp32 CUDA-core matcher (any patch size / stride): 64x64 tile, 4x4 micro-tile per thread
+// =====================================================================================================
+constexpr int ST = 64;   // tile edge
+constexpr int SK = 16;   // channels per K step
+
+__global__ void __launch_bounds__(256)
+match_simt_kernel(const float* __restrict__ fin, const float* __restrict__ fref, const float2* __restrict__ colsb,
+                  unsigned long long* __restrict__ keys, int in_div, int n_in, int C, int h_in, int w_in, int h_ref,
+                  int w_ref, int ps, int s_in, int s_ref, int ho, int wo, int ho_ref, int wo_ref, int key_stride,
+                  int colsb_stride) {
+    __shared__ float As[SK][ST + 4];
+    __shared__ float Bs[SK][ST + 4];
+    __shared__ int rowbase[ST], colbase[ST];
+    __shared__ unsigned long long skeys[ST];
+    const int pair = blockIdx.z, img = (pair / in_div) % n_in;
+    const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST;
+    const int Nin = ho * wo, Nref = ho_ref * wo_ref;
+    const int t = threadIdx.x;
+    if (t < ST) {
+        const int m = m0 + t;
+        rowbase[t] = (m < Nin) ? ((m / wo) * s_in) * w_in + (m % wo) * s_in : -1;
+        const int n = n0 + t;
+        colbase[t] = (n < Nref) ? ((n / wo_ref) * s_ref) * w_ref + (n % wo_ref) * s_ref : -1;
+        skeys[t] = 0ull;
+    }
+    __syncthreads();
+    const float* A = fin + (size_t)img * h_in * w_in * C;
+    const float* B = fref + (size_t)pair * h_ref * w_ref * C;
+    const int lr = t >> 2, lk = (t & 3) * 4;       // loader: row, first of 4 channels
+    const int ty = t >> 4, tx = t & 15;            // compute: 4 rows ty*4.., 4 cols tx*4..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int rb = rowbase[lr], cb = colbase[lr];
+    for (int tap = 0; tap < ps * ps; ++tap) {
+        const int ti = tap / ps, tj = tap % ps;
+        const float* ar = (rb >= 0) ? A + (size_t)(rb + ti * w_in + tj) * C : nullptr;
+        const float* br = (cb >= 0) ? B + (size_t)(cb + ti * w_ref + tj) * C : nullptr;
+        for (int c0 = 0; c0 < C; c0 += SK) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = c0 + lk + e;
+                As[lk + e][lr] = (ar && c < C) ? __ldg(ar + c) : 0.f;
+                Bs[lk + e][lr] = (br && c < C) ? __ldg(br + c) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < SK; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    const float2* sb = colsb + (size_t)pair * colsb_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float best = -INFINITY;
+        uint32_t bestn = 0;
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cbp = colbase[tx * 4 + j];
+            if (cbp < 0) continue;
+            const float2 s = sb[cbp];
+            const float v = fmaf(acc[i][j], s.x, s.y);
+            if (v > best) {
+                best = v;
+                bestn = (uint32_t)cbp;
+                any = true;
+            }
+        }
+        if (any) atomicMax(&skeys[ty * 4 + i], pack_key(best, bestn));
+    }
+    __syncthreads();
+    if (t < ST && rowbase[t] >= 0 && skeys[t] != 0ull)
+        atomicMax(keys + (size_t)pair * key_stride + rowbase[t], skeys[t]);
+}
+
+// =====================================================================================================
+// 3b. tcgen05 / TMEM / TMA matcher
+// =====================================================================================================
+// Tile: 128 input rows x 256 reference columns, K step 64 channels (128-byte bf16 rows, SWIZZLE_128B).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Two 256-column fp32 accumulators in TMEM so the
+// epilogue of item k overlaps the MMAs of item k+1.  Persistent grid; work item = (pair, m_tile, n_tile).
+//
+// STRIP = 3: one pipeline stage holds the rows of a whole tap row (i, 0..2): 128+8 rows of A and 256+8 rows of
+// B per slab; the three taps are three MMAs groups whose descriptors start j rows (j*128 bytes) into the
+// strip.  This cuts L2->SMEM traffic 3x (the bf16x3 kernel would otherwise need ~62 B/clk/SM, above the
+// ~42 B/clk/SM the L2 can feed all 148 SMs).  STRIP = 1 is the plain one-tap-per-stage layout.
+// NPASS = 3: split-bf16 (hi*hi + hi*lo + lo*hi) for fp32-grade similarities; NPASS = 1: single bf16 pass.
+template <int STRIP, int NPASS>
+struct TcCfg {
+    static constexpr int BM = 128, BN = 256, BK = 64;
+    static constexpr int A_ROWS = (STRIP == 1) ? BM : BM + 8;
+    static constexpr int B_ROWS = (STRIP == 1) ? BN : BN + 8;
+    static constexpr int A_BYTES = A_ROWS * 128, B_BYTES = B_ROWS * 128;
+    static constexpr int NSPLIT = (NPASS == 1) ? 1 : 2;  // hi only, or hi + lo
+    static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+    static constexpr int GROUPS = 9 / STRIP;  // pipeline stages per channel slab
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 8 /*scale,bias*/ + 256 /*barriers*/ + 1024;
+};
+
+struct TcParams {
+    int n_pairs, in_div, n_in, C;
+    int hw_in, w_in, hw_ref, w_ref;
+    int m_tiles, n_tiles, total_items;
+    int key_stride, colsb_stride;
+    int base_offset_mode;
+};
+
+template <int STRIP, int NPASS>
+__global__ void __launch_bounds__(192, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                const __grid_constant__ CUtensorMap mapB2_hi, const __grid_constant__ CUtensorMap mapB2_lo,
+                const float2* __restrict__ colsb, unsigned long long* __restrict__ keys, const TcParams prm) {
+    using Cfg = TcCfg<STRIP, NPASS>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_sb) + 2 * BN * 8);
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* empty = bars + STAGES;       // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;   // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slabs = prm.C / Cfg::BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA_hi);
+        tma_prefetch_desc(&mapB_hi);
+        if (NPASS > 1) {
+            tma_prefetch_desc(&mapA_lo);
+            tma_prefetch_desc(&mapB_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x) {
+                const int nt = item % prm.n_tiles;
+                const int mt = (item / prm.n_tiles) % prm.m_tiles;
+                const int pair = item / (prm.n_tiles * prm.m_tiles);
+                const int img = (pair / prm.in_div) % prm.n_in;
+                const int m0 = mt * BM, n0 = nt * BN;
+                for (int slab = 0; slab < n_slabs; ++slab) {
+                    for (int g = 0; g < Cfg::GROUPS; ++g) {
+                        const int ti = (STRIP == 3) ? g : g / 3, tj = (STRIP == 3) ? 0 : g % 3;
+                        const int ra = m0 + ti * prm.w_in + tj, rb = n0 + ti * prm.w_ref + tj;
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sbm = sa + Cfg::NSPLIT * Cfg::A_BYTES;
+                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_3d(sa, &mapA_hi, &full[stage], slab * Cfg::BK, ra, img);
+                        tma_load_3d(sbm, &mapB_hi, &full[stage], slab * Cfg::BK, rb, pair);
+                        if (STRIP == 3) tma_load_3d(sbm + BN * 128, &mapB2_hi, &full[stage], slab * Cfg::BK, rb + BN, pair);
+                        if (NPASS > 1) {
+                            tma_load_3d(sa + Cfg::A_BYTES, &mapA_lo, &full[stage], slab * Cfg::BK, ra, img);
+                            tma_load_3d(sbm + Cfg::B_BYTES, &mapB_lo, &full[stage], slab * Cfg::BK, rb, pair);
+                            if (STRIP == 3)
+                                tma_load_3d(sbm + Cfg::B_BYTES + BN * 128, &mapB2_lo, &full[stage], slab * Cfg::BK,
+                                            rb + BN, pair);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
+                const int nt = item % prm.n_tiles;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                int ncols = prm.hw_ref - nt * BN;
+                ncols = ncols > BN ? BN : ((ncols + 31) & ~31);
+                const uint32_t idesc = umma_idesc(1, BM, ncols);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int slab = 0; slab < n_slabs; ++slab) {
+                    for (int g = 0; g < Cfg::GROUPS; ++g) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
+#pragma unroll
+                        for (int j = 0; j < STRIP; ++j) {
+#pragma unroll
+                            for (int pass = 0; pass < NPASS; ++pass) {
+                                // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
+                                const uint32_t a0 = sa + ((pass == 2) ? Cfg::A_BYTES : 0) + j * 128;
+                                const uint32_t b0 = sb + ((pass == 1) ? Cfg::B_BYTES : 0) + j * 128;
+                                const uint32_t bo = prm.base_offset_mode ? (uint32_t)j : 0u;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    umma_f16(tacc, umma_desc_sw128(a0 + kk * 32, bo), umma_desc_sw128(b0 + kk * 32, bo),
+                                             idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;            // 0..127
+        int it = 0;
+        for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
+            const int nt = item % prm.n_tiles;
+            const int mt = (item / prm.n_tiles) % prm.m_tiles;
+            const int pair = item / (prm.n_tiles * prm.m_tiles);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n0 = nt * BN;
+            int ncols = prm.hw_ref - n0;
+            ncols = ncols > BN ? BN : ((ncols + 31) & ~31);
+            float2* sbuf = s_sb + acc * BN;
+            const float2* gsb = colsb + (size_t)pair * prm.colsb_stride + n0;
+            for (int i = et; i < ncols; i += 128) sbuf[i] = gsb[i];
+            named_bar_sync(1, 128);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            float best = -INFINITY;
+            int bestn = 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float2 s = sbuf[c0 + e];
+                    const float val = fmaf(__uint_as_float(v[e]), s.x, s.y);
+                    if (val > best) {
+                        best = val;
+                        bestn = c0 + e;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            const int m = mt * BM + row;
+            if (m < prm.hw_in && best > -INFINITY)
+                atomicMax(keys + (size_t)pair * prm.key_stride + m, pack_key(best, (uint32_t)(n0 + bestn)));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct MatchPlan {
+    int mode, strip, base_offset_mode;
+    int hw_in, hw_ref, ho, wo, ho_ref, wo_ref;
+    int key_stride, colsb_stride;
+    size_t off_keys, off_sumsq_in, off_sumsq_ref, off_rownorm, off_colsb, off_a0, off_a1, off_b0, off_b1, total;
+};
+
+static bool tc_eligible(int C, int ps, int s_in, int s_ref) { return ps == 3 && s_in == 1 && s_ref == 1 && C % 64 == 0; }
+
+static int make_plan(MatchPlan* pl, int n_in, int n_pairs, int C, int h_in, int w_in, int h_ref, int w_ref, int ps,
+                     int s_in, int s_ref, int mode_flags) {
+    int mode = mode_flags & 0xff;
+    if (mode == MREFSR_MATCH_AUTO) mode = tc_eligible(C, ps, s_in, s_ref) ? MREFSR_MATCH_TC_BF16X3 : MREFSR_MATCH_FP32;
+    MREFSR_CHECK(mode >= 1 && mode <= 3, ERR_BAD_ARG, "matcher: unknown mode %d", mode);
+    if (mode != MREFSR_MATCH_FP32)
+        MREFSR_CHECK(tc_eligible(C, ps, s_in, s_ref), ERR_UNSUPPORTED,
+                     "matcher: tcgen05 path needs patch_size 3, strides 1, C %% 64 == 0 (got ps=%d, strides %d/%d, C=%d)",
+                     ps, s_in, s_ref, C);
+    pl->mode = mode;
+    pl->strip = (mode_flags & MREFSR_MATCH_FLAG_NO_STRIP) ? 1 : 3;
+    pl->base_offset_mode = (mode_flags & MREFSR_MATCH_FLAG_BASE_OFFSET) ? 1 : 0;
+    pl->hw_in = h_in * w_in;
+    pl->hw_ref = h_ref * w_ref;
+    pl->ho = (h_in - ps) / s_in + 1;
+    pl->wo = (w_in - ps) / s_in + 1;
+    pl->ho_ref = (h_ref - ps) / s_ref + 1;
+    pl->wo_ref = (w_ref - ps) / s_ref + 1;
+    pl->key_stride = (int)align_up(pl->hw_in, 128);
+    pl->colsb_stride = (int)align_up(pl->hw_ref, 256) + 256;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += align_up(bytes, 1024);
+        return r;
+    };
+    pl->off_keys = take((size_t)n_pairs * pl->key_stride * 8);
+    pl->off_sumsq_in = take((size_t)n_in * pl->hw_in * 4);
+    pl->off_sumsq_ref = take((size_t)n_pairs * pl->hw_ref * 4);
+    pl->off_rownorm = take((size_t)n_in * pl->hw_in * 4);
+    pl->off_colsb = take((size_t)n_pairs * pl->colsb_stride * 8);
+    const size_t ein = (size_t)n_in * pl->hw_in * C, eref = (size_t)n_pairs * pl->hw_ref * C;
+    if (mode == MREFSR_MATCH_FP32) {
+        pl->off_a0 = take(ein * 4);
+        pl->off_b0 = take(eref * 4);
+        pl->off_a1 = pl->off_b1 = 0;
+    } else {
+        pl->off_a0 = take(ein * 2);
+        pl->off_b0 = take(eref * 2);
+        pl->off_a1 = (mode == MREFSR_MATCH_TC_BF16X3) ? take(ein * 2) : 0;
+        pl->off_b1 = (mode == MREFSR_MATCH_TC_BF16X3) ? take(eref * 2) : 0;
+    }
+    pl->total = o;
+    return 0;
+}
+
+template <int STRIP, int NPASS>
+static int launch_tc(const MatchPlan& pl, uint8_t* ws, int n_in, int n_pairs, int in_div, int C, int w_in, int w_ref,
+                     cudaStream_t st) {
+    using Cfg = TcCfg<STRIP, NPASS>;
+    static_assert(Cfg::STAGES >= 2, "need at least a double-buffered pipeline");
+    CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mB2_hi, mB2_lo;
+    const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    int rc;
+    void* a_hi = ws + pl.off_a0;
+    void* b_hi = ws + pl.off_b0;
+    void* a_lo = (NPASS > 1) ? ws + pl.off_a1 : a_hi;
+    void* b_lo = (NPASS > 1) ? ws + pl.off_b1 : b_hi;
+    if ((rc = make_tensor_map_3d(&mA_hi, dt, 2, a_hi, C, pl.hw_in, n_in, 64, Cfg::A_ROWS, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mA_lo, dt, 2, a_lo, C, pl.hw_in, n_in, 64, Cfg::A_ROWS, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB_hi, dt, 2, b_hi, C, pl.hw_ref, n_pairs, 64, Cfg::BN, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB_lo, dt, 2, b_lo, C, pl.hw_ref, n_pairs, 64, Cfg::BN, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB2_hi, dt, 2, b_hi, C, pl.hw_ref, n_pairs, 64, 8, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB2_lo, dt, 2, b_lo, C, pl.hw_ref, n_pairs, 64, 8, sw))) return rc;
+    TcParams prm;
+    prm.n_pairs = n_pairs;
+    prm.in_div = in_div;
+    prm.n_in = n_in;
+    prm.C = C;
+    prm.hw_in = pl.hw_in;
+    prm.w_in = w_in;
+    prm.hw_ref = pl.hw_ref;
+    prm.w_ref = w_ref;
+    prm.m_tiles = cdiv(pl.hw_in, Cfg::BM);
+    prm.n_tiles = cdiv(pl.hw_ref, Cfg::BN);
+    prm.total_items = n_pairs * prm.m_tiles * prm.n_tiles;
+    prm.key_stride = pl.key_stride;
+    prm.colsb_stride = pl.colsb_stride;
+    prm.base_offset_mode = pl.base_offset_mode;
+    auto kern = match_tc_kernel<STRIP, NPASS>;
+    MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int grid = sm_count();
+    if (grid > prm.total_items) grid = prm.total_items;
+    kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, mB2_hi, mB2_lo,
+                                              reinterpret_cast<const float2*>(ws + pl.off_colsb),
+                                              reinterpret_cast<unsigned long long*>(ws + pl.off_keys), prm);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+static int run_match(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div, int C, int h_in,
+                     int w_in, int h_ref, int w_ref, int ps, int s_in, int s_ref, int is_norm, int norm_input,
+                     int normalize_pixels, int mode_flags, long long* max_idx, float* max_val, void* workspace,
+                     size_t ws_bytes, cudaStream_t st) {
+    MREFSR_CHECK(feat_in && feat_ref && max_idx && max_val, ERR_BAD_ARG, "matcher: null pointer argument");
+    MREFSR_CHECK(n_in > 0 && n_pairs > 0 && in_div > 0 && C > 0, ERR_BAD_ARG, "matcher: bad sizes");
+    MREFSR_CHECK(ps >= 1 && s_in >= 1 && s_ref >= 1, ERR_BAD_ARG, "matcher: bad patch_size / stride");
+    MREFSR_CHECK(h_in >= ps && w_in >= ps && h_ref >= ps && w_ref >= ps, ERR_BAD_ARG,
+                 "matcher: feature map smaller than the patch (%dx%d / %dx%d, patch %d)", h_in, w_in, h_ref, w_ref, ps);
+    MatchPlan pl;
+    int rc = make_plan(&pl, n_in, n_pairs, C, h_in, w_in, h_ref, w_ref, ps, s_in, s_ref, mode_flags);
+    if (rc) return rc;
+    MREFSR_CHECK(workspace && ws_bytes >= pl.total, ERR_WORKSPACE, "matcher: workspace too small (%zu < %zu)", ws_bytes,
+                 pl.total);
+    MREFSR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, ERR_WORKSPACE,
+                 "matcher: workspace must be 1024-byte aligned");
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    MREFSR_CUDA(cudaMemsetAsync(ws + pl.off_keys, 0, (size_t)n_pairs * pl.key_stride * 8, st));
+
+    // 1. prep
+    timing_begin(MREFSR_K_MATCH_PREP, st);
+    const size_t prep_smem = (size_t)C * 33 * sizeof(float);
+    MREFSR_CHECK(prep_smem <= 200 * 1024, ERR_UNSUPPORTED, "matcher: C = %d too large for the prep tile", C);
+    if (prep_smem > 48 * 1024)
+        MREFSR_CUDA(cudaFuncSetAttribute(match_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    const bool f32 = pl.mode == MREFSR_MATCH_FP32, x3 = pl.mode == MREFSR_MATCH_TC_BF16X3;
+    match_prep_kernel<<<dim3(cdiv(pl.hw_in, 32), n_in), 256, prep_smem, st>>>(
+        feat_in, C, pl.hw_in, normalize_pixels, f32 ? reinterpret_cast<float*>(ws + pl.off_a0) : nullptr,
+        f32 ? nullptr : reinterpret_cast<bf16*>(ws + pl.off_a0), x3 ? reinterpret_cast<bf16*>(ws + pl.off_a1) : nullptr,
+        reinterpret_cast<float*>(ws + pl.off_sumsq_in));
+    MREFSR_LAUNCH_CHECK();
+    match_prep_kernel<<<dim3(cdiv(pl.hw_ref, 32), n_pairs), 256, prep_smem, st>>>(
+        feat_ref, C, pl.hw_ref, normalize_pixels, f32 ? reinterpret_cast<float*>(ws + pl.off_b0) : nullptr,
+        f32 ? nullptr : reinterpret_cast<bf16*>(ws + pl.off_b0), x3 ? reinterpret_cast<bf16*>(ws + pl.off_b1) : nullptr,
+        reinterpret_cast<float*>(ws + pl.off_sumsq_ref));
+    MREFSR_LAUNCH_CHECK();
+    // 2. norms
+    match_norms_kernel<<<dim3(cdiv(pl.hw_in, 256), n_in), 256, 0, st>>>(
+        reinterpret_cast<const float*>(ws + pl.off_sumsq_in), n_in, h_in, w_in, ps, s_in, pl.hw_in, 0, norm_input,
+        nullptr, reinterpret_cast<float*>(ws + pl.off_rownorm));
+    MREFSR_LAUNCH_CHECK();
+    match_norms_kernel<<<dim3(cdiv(pl.colsb_stride, 256), n_pairs), 256, 0, st>>>(
+        reinterpret_cast<const float*>(ws + pl.off_sumsq_ref), n_pairs, h_ref, w_ref, ps, s_ref, pl.colsb_stride, 1,
+        is_norm, reinterpret_cast<float2*>(ws + pl.off_colsb), nullptr);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(4);
+    timing_end(MREFSR_K_MATCH_PREP, st);
+    // 3. correlation + arg-max
+    timing_begin(MREFSR_K_MATCH_MAIN, st);
+    if (f32) {
+        dim3 grid(cdiv(pl.ho_ref * pl.wo_ref, ST), cdiv(pl.ho * pl.wo, ST), n_pairs);
+        match_simt_kernel<<<grid, 256, 0, st>>>(
+            reinterpret_cast<const float*>(ws + pl.off_a0), reinterpret_cast<const float*>(ws + pl.off_b0),
+            reinterpret_cast<const float2*>(ws + pl.off_colsb), reinterpret_cast<unsigned long long*>(ws + pl.off_keys),
+            in_div, n_in, C, h_in, w_in, h_ref, w_ref, ps, s_in, s_ref, pl.ho, pl.wo, pl.ho_ref, pl.wo_ref,
+            pl.key_stride, pl.colsb_stride);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+    } else {
+        if (pl.strip == 3) {
+            rc = x3 ? launch_tc<3, 3>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st)
+                    : launch_tc<3, 1>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st);
+        } else {
+            rc = x3 ? launch_tc<1, 3>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st)
+                    : launch_tc<1, 1>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st);
+        }
+        if (rc) return rc;
+    }
+    timing_end(MREFSR_K_MATCH_MAIN, st);
+    // 4. finalize
+    const int total = n_pairs * pl.ho * pl.wo;
+    match_finalize_kernel<<<cdiv(total, 256), 256, 0, st>>>(
+        reinterpret_cast<const unsigned long long*>(ws + pl.off_keys), reinterpret_cast<const float*>(ws + pl.off_rownorm),
+        n_pairs, in_div, n_in, h_in, w_in, w_ref, pl.ho, pl.wo, pl.wo_ref, s_in, s_ref, pl.key_stride, max_idx, max_val);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+// =====================================================================================================
+// pre-offsets: idx -> flow -> nine zero-filled shifts at scales 1, 2, 4
+// (corres_generation_arch.py:30-47, :70-105; arch_util.py:386-410)
+//   pre_s[n, 3i+j, Y, X, :] = s * flow[Y/s - i, X/s - j] if Y/s >= i and X/s >= j (flow = 0 on the 2-wide border)
+// =====================================================================================================
+__global__ void pre_offsets_kernel(const long long* __restrict__ max_idx, int n_img, int h, int w, int s,
+                                   float2* __restrict__ out) {
+    const int H = h * s, W = w * s;
+    const size_t total = (size_t)n_img * 9 * H * W;
+    const int hp = h - 2, wp = w - 2;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int X = t % W;
+        const int Y = (t / W) % H;
+        const int k = (t / ((size_t)W * H)) % 9;
+        const int img = t / ((size_t)W * H * 9);
+        const int y = Y / s - k / 3, x = X / s - k % 3;
+        float2 v = make_float2(0.f, 0.f);
+        if (y >= 0 && x >= 0 && y < hp && x < wp) {
+            const long long idx = max_idx[((size_t)img * hp + y) * wp + x];
+            v.x = (float)((int)(idx % wp) - x) * (float)s;
+            v.y = (float)((int)(idx / wp) - y) * (float)s;
+        }
+        out[t] = v;
+    }
+}
+
+}  // namespace mrefsr
+
+using namespace mrefsr;
+
+extern "C" {
+
+size_t mrefsr_match_workspace_bytes(int n_in, int n_pairs, int C, int h_in, int w_in, int h_ref, int w_ref, int mode) {
+    MatchPlan pl;
+    // patch 3 / stride 1 sizes the scratch for every mode (other patch sizes only change ho/wo, not the scratch)
+    int m = mode & 0xff;
+    if (m == MREFSR_MATCH_AUTO) m = (C % 64 == 0) ? MREFSR_MATCH_TC_BF16X3 : MREFSR_MATCH_FP32;
+    const int ps = 3;
+    if (h_in < ps || w_in < ps || h_ref < ps || w_ref < ps) return 0;
+    // the fp32 scratch (4 B/elem) is never smaller than the bf16 hi+lo scratch, so size for the larger of the
+    // requested mode and the AUTO fallback
+    size_t best = 0;
+    for (int mm : {m, (int)MREFSR_MATCH_FP32}) {
+        if (mm != MREFSR_MATCH_FP32 && C % 64 != 0) continue;
+        if (make_plan(&pl, n_in, n_pairs, C, h_in, w_in, h_ref, w_ref, ps, 1, 1, mm | (mode & ~0xff)) == 0 && pl.total > best)
+            best = pl.total;
+    }
+    return best;
+}
+
+int mrefsr_feature_match_batched(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div, int C,
+                                 int h_in, int w_in, int h_ref, int w_ref, int patch_size, int input_stride,
+                                 int ref_stride, int is_norm, int norm_input, int normalize_pixels, int mode,
+                                 int64_t* max_idx, float* max_val, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    return run_match(feat_in, feat_ref, n_in, n_pairs, in_div, C, h_in, w_in, h_ref, w_ref, patch_size, input_stride,
+                     ref_stride, is_norm, norm_input, normalize_pixels, mode, reinterpret_cast<long long*>(max_idx),
+                     max_val, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mrefsr_pre_offsets(const int64_t* max_idx, int n, int h, int w, float* out_s1, float* out_s2, float* out_s4,
+                       void* stream) {
+    MREFSR_CHECK(max_idx && n > 0 && h > 2 && w > 2, ERR_BAD_ARG, "pre_offsets: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* outs[3] = {out_s1, out_s2, out_s4};
+    const int scales[3] = {1, 2, 4};
+    for (int i = 0; i < 3; ++i) {
+        if (!outs[i]) continue;
+        const size_t total = (size_t)n * 9 * h * scales[i] * w * scales[i];
+        int blocks = (int)((total + 255) / 256);
+        const int cap = sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        ScopedTiming tm(MREFSR_K_GLUE, st);
+        pre_offsets_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(max_idx), n, h, w, scales[i],
+                                                   reinterpret_cast<float2*>(outs[i]));
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+    }
+    return 0;
+}
+
+int mrefsr_feature_match_batched_host(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div,
+                                      int C, int h_in, int w_in, int h_ref, int w_ref, int patch_size, int input_stride,
+                                      int ref_stride, int is_norm, int norm_input, int normalize_pixels, int mode,
+                                      int64_t* max_idx, float* max_val, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MREFSR_CHECK(patch_size >= 1 && input_stride >= 1 && ref_stride >= 1 && h_in >= patch_size && w_in >= patch_size &&
+                     h_ref >= patch_size && w_ref >= patch_size,
+                 ERR_BAD_ARG, "matcher: bad sizes");
+    const size_t ws = mrefsr_match_workspace_bytes(n_in, n_pairs, C, h_in, w_in, h_ref, w_ref, mode);
+    const size_t b_in = align_up((size_t)n_in * C * h_in * w_in * 4, 1024);
+    const size_t b_ref = align_up((size_t)n_pairs * C * h_ref * w_ref * 4, 1024);
+    const int ho = (h_in - patch_size) / input_stride + 1, wo = (w_in - patch_size) / input_stride + 1;
+    const size_t b_idx = align_up((size_t)n_pairs * ho * wo * 8, 1024), b_val = align_up((size_t)n_pairs * ho * wo * 4, 1024);
+    void* base = nullptr;
+    int rc = arena_get(ws + b_in + b_ref + b_idx + b_val, &base);
+    if (rc) return rc;
+    uint8_t* p = static_cast<uint8_t*>(base);
+    uint8_t* d_ws = p;
+    float* d_in = reinterpret_cast<float*>(p + align_up(ws, 1024));
+    float* d_ref = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_in) + b_in);
+    long long* d_idx = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(d_ref) + b_ref);
+    float* d_val = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d_idx) + b_idx);
+    MREFSR_CUDA(cudaMemcpyAsync(d_in, feat_in, (size_t)n_in * C * h_in * w_in * 4, cudaMemcpyHostToDevice, st));
+    MREFSR_CUDA(cudaMemcpyAsync(d_ref, feat_ref, (size_t)n_pairs * C * h_ref * w_ref * 4, cudaMemcpyHostToDevice, st));
+    rc = run_match(d_in, d_ref, n_in, n_pairs, in_div, C, h_in, w_in, h_ref, w_ref, patch_size, input_stride, ref_stride,
+                   is_norm, norm_input, normalize_pixels, mode, d_idx, d_val, d_ws, align_up(ws, 1024), st);
+    if (rc) return rc;
+    MREFSR_CUDA(cudaMemcpyAsync(max_idx, d_idx, (size_t)n_pairs * ho * wo * 8, cudaMemcpyDeviceToHost, st));
+    MREFSR_CUDA(cudaMemcpyAsync(max_val, d_val, (size_t)n_pairs * ho * wo * 4, cudaMemcpyDeviceToHost, st));
+    MREFSR_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// mrefsr_b200/csrc/runtime.cu -- error plumbing, device queries, TMA descriptor encoding, device arena.
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/mrefsr_b200.h"
+
+namespace mrefsr {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached = n;
+    return n;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
+                       uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {
+    PFN_encodeTiled fn = encode_fn();
+    MREFSR_CHECK(fn != nullptr, ERR_NOT_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * elem_bytes, d0 * d1 * elem_bytes};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MREFSR_CHECK(r == CUDA_SUCCESS, ERR_BAD_ARG,
+                 "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu box %u x %u", (int)r,
+                 (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1);
+    return 0;
+}
+
+// ---------------------------------------------------------------- per-kernel timing
+static std::atomic<int> g_timing_on{0};
+struct EvPair {
+    cudaEvent_t a, b;
+    int id;
+};
+static std::mutex g_timing_mu;
+static std::vector<EvPair> g_ev_live;   // recorded, not yet read
+static std::vector<EvPair> g_ev_free;   // recycled
+static thread_local EvPair g_ev_open[MREFSR_K_COUNT];
+static thread_local bool g_ev_is_open[MREFSR_K_COUNT] = {false};
+
+void timing_begin(int id, cudaStream_t st) {
+    if (!g_timing_on.load(std::memory_order_relaxed) || id < 0 || id >= MREFSR_K_COUNT) return;
+    EvPair p;
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        if (!g_ev_free.empty()) {
+            p = g_ev_free.back();
+            g_ev_free.pop_back();
+        } else {
+            if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+        }
+    }
+    p.id = id;
+    cudaEventRecord(p.a, st);
+    g_ev_open[id] = p;
+    g_ev_is_open[id] = true;
+}
+
+void timing_end(int id, cudaStream_t st) {
+    if (id < 0 || id >= MREFSR_K_COUNT || !g_ev_is_open[id]) return;
+    g_ev_is_open[id] = false;
+    cudaEventRecord(g_ev_open[id].b, st);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_ev_live.push_back(g_ev_open[id]);
+}
+
+// ---------------------------------------------------------------- device arena for the *_host entry points
+static std::mutex g_arena_mu;
+static void* g_arena = nullptr;
+static size_t g_arena_bytes = 0;
+
+int arena_get(size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (bytes > g_arena_bytes) {
+        if (g_arena) {
+            cudaDeviceSynchronize();
+            cudaFree(g_arena);
+            g_arena = nullptr;
+            g_arena_bytes = 0;
+        }
+        size_t want = align_up(bytes + bytes / 8, (size_t)1 << 21);
+        MREFSR_CUDA(cudaMalloc(&g_arena, want));
+        g_arena_bytes = want;
+    }
+    *out = g_arena;
+    return 0;
+}
+
+}  // namespace mrefsr
+
+extern "C" {
+int mrefsr_abi_version(void) { return MREFSR_ABI_VERSION; }
+const char* mrefsr_last_error(void) { return mrefsr::get_error(); }
+int mrefsr_sm_count(void) { return mrefsr::sm_count(); }
+unsigned long long mrefsr_launch_count(void) { return mrefsr::g_launches.load(); }
+void mrefsr_timing_enable(int on) { mrefsr::g_timing_on.store(on ? 1 : 0); }
+int mrefsr_timing_read(double* ms_out, unsigned long long* launches_out, int n) {
+    using namespace mrefsr;
+    if (!ms_out || !launches_out || n < MREFSR_K_COUNT) {
+        set_error("timing_read: need arrays of at least %d entries", (int)MREFSR_K_COUNT);
+        return ERR_BAD_ARG;
+    }
+    for (int i = 0; i < n; ++i) {
+        ms_out[i] = 0.0;
+        launches_out[i] = 0;
+    }
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (auto& p : g_ev_live) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ms_out[p.id] += ms;
+            launches_out[p.id] += 1;
+        }
+        g_ev_free.push_back(p);
+    }
+    g_ev_live.clear();
+    return 0;
+}
+void mrefsr_arena_release(void) {
+    std::lock_guard<std::mutex> lk(mrefsr::g_arena_mu);
+    if (mrefsr::g_arena) {
+        cudaDeviceSynchronize();
+        cudaFree(mrefsr::g_arena);
+        mrefsr::g_arena = nullptr;
+        mrefsr::g_arena_bytes = 0;
+    }
+}
+}

@@ -1,0 +1,84 @@
+"""DynAgg: DCNv2 whose offsets are initialised with the matcher's pre-offsets.
+
+Drop-in for basicsr.archs.ref_mrapa_restoration_arch.DynAgg (:11-76): same constructor, same parameters
+(weight, bias, conv_offset_mask.{weight,bias}), same forward(x, pre_offset).  The chunk / cat / repeat /
+zeros_like / strided scatter / add / sigmoid sequence (:55-68) is one kernel, and the reference's host-syncing
+``if offset_mean > 100`` check (:69-73, which also references an undefined ``logger``) is replaced by an
+asynchronous device-side accumulator readable through ``last_offset_abs_mean()``.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .mmcv_ops import ModulatedDeformConv2d, modulated_deform_conv2d
+
+
+class DynAggOffsetsFunction(Function):
+    """(conv_out [B,3*dg*K,H,W], pre_offset [B,K,H,W,2]) -> (offset [B,2*dg*K,H,W], mask [B,dg*K,H,W])."""
+
+    @staticmethod
+    def forward(ctx, conv_out, pre_offset, dg, stats):
+        _lib.require_cuda(conv_out, pre_offset)
+        ctx.in_dtype = conv_out.dtype
+        co = conv_out.contiguous().float()
+        pre = pre_offset.contiguous().float()
+        b, ch, h, w = co.shape
+        k = pre.shape[1]
+        if ch != 3 * dg * k or tuple(pre.shape) != (b, k, h, w, 2):
+            raise ValueError('expected conv_out [B,3*dg*K,H,W] and pre_offset [B,K,H,W,2]')
+        offset = torch.empty(b, 2 * dg * k, h, w, dtype=torch.float32, device=co.device)
+        mask = torch.empty(b, dg * k, h, w, dtype=torch.float32, device=co.device)
+        with torch.cuda.device(co.device):
+            rc = _lib.lib().mrefsr_dynagg_offsets(_lib.ptr(co), _lib.ptr(pre), _lib.ptr(offset), _lib.ptr(mask),
+                                                  _lib.ptr(stats), b, dg, k, h, w, _lib.stream_ptr(co.device))
+        _lib.check(rc, 'mrefsr_dynagg_offsets')
+        ctx.save_for_backward(mask)
+        return offset.to(conv_out.dtype), mask.to(conv_out.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_offset, g_mask):
+        (mask,) = ctx.saved_tensors
+        # d offset / d conv_out = 1 on the first 2*dg*K channels; d sigmoid = m (1 - m) on the rest
+        g = torch.cat((g_offset.float(), g_mask.float() * mask * (1 - mask)), dim=1)
+        return g.to(ctx.in_dtype), None, None, None
+
+
+class DynAgg(ModulatedDeformConv2d):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, groups=1,
+                 deform_groups=1, extra_offset_mask=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, deform_groups)
+        self.extra_offset_mask = extra_offset_mask
+        channels_ = self.deform_groups * 3 * self.kernel_size[0] * self.kernel_size[1]
+        self.conv_offset_mask = nn.Conv2d(self.in_channels, channels_, kernel_size=self.kernel_size,
+                                          stride=self.stride, padding=self.padding, bias=True)
+        self.init_offset()
+        self._stats = None
+        self._stats_count = 0
+
+    def init_offset(self):
+        self.conv_offset_mask.weight.data.zero_()
+        self.conv_offset_mask.bias.data.zero_()
+
+    def last_offset_abs_mean(self):
+        """mean |learned offset| of the last forward (one device->host read, only when asked)."""
+        if self._stats is None or self._stats_count == 0:
+            return None
+        return float(self._stats.item()) / self._stats_count
+
+    def forward(self, x, pre_offset):
+        if self.extra_offset_mask:
+            out = self.conv_offset_mask(x[1])
+            x = x[0]
+        else:
+            out = self.conv_offset_mask(x)
+        if self._stats is None or self._stats.device != out.device:
+            self._stats = torch.zeros(1, dtype=torch.float32, device=out.device)
+        self._stats.zero_()
+        offset, mask = DynAggOffsetsFunction.apply(out, pre_offset, self.deform_groups, self._stats)
+        self._stats_count = offset.numel()
+        return modulated_deform_conv2d(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                       self.dilation, self.groups, self.deform_groups)

@@ -1,0 +1,108 @@
+"""Multi-reference attention fusion: host-side mirror of MRAPAFusion
+(basicsr/archs/ref_mrapa_restoration_arch.py:262-348) with the attention core (:321-335) on csrc/fusion.cu.
+
+``MRAPAFusion`` keeps the reference's constructor, parameter names (state-dict keys conv_emb1.0.*,
+conv_emb1.1.weight, conv_emb2.*, conv_ass.*, feat_fusion.*, spatial_attn*.*) and forward signature
+``forward(target, refs: list[Tensor])``; the plain convolutions stay cuDNN library calls.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+
+class MRAPAAttentionFunction(Function):
+    """out[n,Cv,h,w] = sum_t softmax_t(<emb_t[n,:,y,x], emb[n,t,:,y,x]>) * ass[n,t,:,y,x]."""
+
+    @staticmethod
+    def forward(ctx, emb_t, emb, ass, t):
+        _lib.require_cuda(emb_t, emb, ass)
+        ctx.in_dtype = emb_t.dtype
+        q, k, v = (x.contiguous().float() for x in (emb_t, emb, ass))
+        n, c, h, w = q.shape
+        if k.shape[0] != n * t or k.shape[1] != c or v.shape[0] != n * t or k.shape[2:] != q.shape[2:] \
+                or v.shape[2:] != q.shape[2:]:
+            raise ValueError('expected emb_t [n,C,h,w], emb [n*t,C,h,w], ass [n*t,Cv,h,w]')
+        cv = v.shape[1]
+        out = torch.empty(n, cv, h, w, dtype=torch.float32, device=q.device)
+        need = any(ctx.needs_input_grad[:3])
+        prob = torch.empty(n, t, h, w, dtype=torch.float32, device=q.device) if need else None
+        with torch.cuda.device(q.device):
+            rc = _lib.lib().mrefsr_mrapa_attention_forward(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out),
+                                                           _lib.ptr(prob), n, t, c, cv, h, w,
+                                                           _lib.stream_ptr(q.device))
+        _lib.check(rc, 'mrefsr_mrapa_attention_forward')
+        if need:
+            ctx.save_for_backward(q, k, v, prob)
+        ctx.t = t
+        return out.to(emb_t.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        q, k, v, prob = ctx.saved_tensors
+        go = grad_out.contiguous().float()
+        n, c, h, w = q.shape
+        cv = v.shape[1]
+        gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        with torch.cuda.device(q.device):
+            rc = _lib.lib().mrefsr_mrapa_attention_backward(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(prob),
+                                                            _lib.ptr(go), _lib.ptr(gq), _lib.ptr(gk), _lib.ptr(gv), n,
+                                                            ctx.t, c, cv, h, w, _lib.stream_ptr(q.device))
+        _lib.check(rc, 'mrefsr_mrapa_attention_backward')
+        dt = ctx.in_dtype
+        return gq.to(dt), gk.to(dt), gv.to(dt), None
+
+
+def mrapa_attention(emb_t, emb, ass, t):
+    """emb_t [n,C,h,w] (already scaled by C**-0.5), emb [n*t,C,h,w], ass [n*t,Cv,h,w] -> [n,Cv,h,w]."""
+    return MRAPAAttentionFunction.apply(emb_t, emb, ass, t)
+
+
+class MRAPAFusion(nn.Module):
+    """Drop-in for basicsr.archs.ref_mrapa_restoration_arch.MRAPAFusion (same parameters and forward)."""
+
+    def __init__(self, nf=64, ref_nf=256):
+        super().__init__()
+        self.patch_size = 3
+        channels = ref_nf
+        self.conv_emb1 = nn.Sequential(nn.Conv2d(nf, channels, 1), nn.PReLU())
+        self.conv_emb2 = nn.Sequential(nn.Conv2d(ref_nf, channels, self.patch_size, 1, self.patch_size // 2),
+                                       nn.PReLU())
+        self.conv_ass = nn.Conv2d(ref_nf, channels * 2, self.patch_size, 1, self.patch_size // 2)
+        self.scale = channels ** -0.5
+        self.feat_fusion = nn.Conv2d(nf + channels * 2, nf, 1)
+        self.spatial_attn = nn.Conv2d(nf + channels * 2, channels * 2, 1)
+        self.spatial_attn_mul1 = nn.Conv2d(channels * 2, channels * 2, 3, padding=1)
+        self.spatial_attn_mul2 = nn.Conv2d(channels * 2, channels * 2, 3, padding=1)
+        self.spatial_attn_add1 = nn.Conv2d(channels * 2, channels * 2, 3, padding=1)
+        self.spatial_attn_add2 = nn.Conv2d(channels * 2, channels * 2, 3, padding=1)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def spatial_padding(self, feats):
+        _, _, h, w = feats.size()
+        pad_h = (4 - h % 4) % 4
+        pad_w = (4 - w % 4) % 4
+        return F.pad(feats, [0, pad_w, 0, pad_h], mode='reflect')
+
+    def forward(self, target, refs):
+        n, _, h_input, w_input = target.size()
+        t = len(refs)
+        target = self.spatial_padding(target)
+        refs = self.spatial_padding(torch.stack(refs, dim=1).flatten(0, 1))
+        # multi-ref attention: one fused kernel instead of 3 permute copies + 2 batched matmuls (:321-335)
+        emb_t = self.conv_emb1(target) * self.scale
+        emb = self.conv_emb2(refs)
+        ass = self.conv_ass(refs)
+        refs = mrapa_attention(emb_t, emb, ass, t)
+        # spatial attention (:338-344)
+        attn = self.lrelu(self.spatial_attn(torch.cat([target, refs], dim=1)))
+        attn_mul = self.spatial_attn_mul2(self.lrelu(self.spatial_attn_mul1(attn)))
+        attn_add = self.spatial_attn_add2(self.lrelu(self.spatial_attn_add1(attn)))
+        attn_mul = torch.sigmoid(attn_mul)
+        refs = refs * attn_mul * 2 + attn_add
+        feat = self.lrelu(self.feat_fusion(torch.cat([target, refs], dim=1)))
+        return feat[:, :, :h_input, :w_input]

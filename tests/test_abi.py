@@ -1,0 +1,89 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/mrefsr_b200.h declares;
+host-side argument validation; the product package never imports the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'mrefsr_b200.h')).read()
+    return sorted(set(re.findall(r'MREFSR_API[^;(]*?\b(mrefsr_\w+)\s*\(', text)))
+
+
+def test_header_symbols_exported():
+    from mrefsr_b200 import _lib, build
+    build.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(handle, s), s
+    # the ctypes table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_abi_version_and_errors_without_gpu():
+    from mrefsr_b200 import _lib
+    lib = _lib.lib()
+    assert lib.mrefsr_abi_version() == 1
+    # argument validation happens before any CUDA call
+    rc = lib.mrefsr_pre_offsets(None, 0, 0, 0, None, None, None, None)
+    assert rc < 0 and b'pre_offsets' in lib.mrefsr_last_error()
+    rc = lib.mrefsr_mrapa_attention_forward(None, None, None, None, None, 1, 1, 1, 1, 1, 1, None)
+    assert rc < 0
+
+
+def test_cpu_tensors_raise():
+    import mrefsr_b200 as M
+    with pytest.raises(NotImplementedError):
+        M.feature_match_index(torch.randn(8, 6, 6), torch.randn(8, 6, 6))
+    with pytest.raises(NotImplementedError):
+        M.modulated_deform_conv(torch.randn(1, 4, 5, 5), torch.randn(1, 18, 5, 5), torch.rand(1, 9, 5, 5),
+                                torch.randn(4, 4, 3, 3), None, 1, 1, 1, 1, 1)
+    with pytest.raises(NotImplementedError):
+        M.mrapa_attention(torch.randn(1, 4, 2, 2), torch.randn(2, 4, 2, 2), torch.randn(2, 8, 2, 2), 2)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'mrefsr_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, re.M), f
+                assert 'oracle/' not in text, f
+
+
+def test_module_state_dict_keys_match_reference(golden):
+    """Drop-in contract: identical parameter names (checkpoint/resume row)."""
+    import mrefsr_b200 as M
+    g = golden('fusion')
+    ref_keys = sorted(k.split('.sd.', 1)[1] for k in g.keys() if k.startswith('t5.sd.'))
+    m = M.MRAPAFusion(nf=8, ref_nf=16)
+    assert sorted(m.state_dict().keys()) == ref_keys
+    d = M.DynAgg(16, 16, 3, stride=1, padding=1, deform_groups=4)
+    assert sorted(d.state_dict().keys()) == ['bias', 'conv_offset_mask.bias', 'conv_offset_mask.weight', 'weight']
+    assert d.kernel_size == (3, 3) and d.stride == (1, 1) and d.padding == (1, 1) and d.deform_groups == 4
+    p = M.ModulatedDeformConvPack(8, 8, 3, padding=1, deformable_groups=2)
+    assert sorted(p.state_dict().keys()) == ['bias', 'conv_offset.bias', 'conv_offset.weight', 'weight']
+
+
+def test_mmcv_shim_install():
+    import sys
+    from mrefsr_b200 import mmcv_ops
+    saved = {k: sys.modules.get(k) for k in ('mmcv', 'mmcv.ops')}
+    try:
+        ops = mmcv_ops.install(force=True)
+        from mmcv.ops import ModulatedDeformConv2d, modulated_deform_conv2d  # noqa: F401
+        assert ops.ModulatedDeformConv2d is mmcv_ops.ModulatedDeformConv2d
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

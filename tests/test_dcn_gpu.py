@@ -1,0 +1,163 @@
+"""Parity of the CUDA DCNv2 (through the C ABI) against the oracle, the golden vectors generated from the
+reference's DynAgg, and -- when oracle/_ref holds the reference's own CUDA extension -- the reference kernels."""
+import os
+
+import pytest
+import torch
+
+import mrefsr_b200 as M
+import oracle
+from mrefsr_b200 import dcn as D
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = 1e-3   # north star: DCN outputs within 1e-3 relative error in fp32
+
+
+def _rand_problem(b, c, h, w, co, dg, seed, off_scale=2.0, groups=1, k=3, stride=1, pad=1, dil=1):
+    g = torch.Generator().manual_seed(seed)
+    ho = (h + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    wo = (w + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    x = torch.randn(b, c, h, w, generator=g)
+    off = torch.randn(b, 2 * dg * k * k, ho, wo, generator=g) * off_scale
+    mask = torch.rand(b, dg * k * k, ho, wo, generator=g)
+    wgt = torch.randn(co, c // groups, k, k, generator=g) * (1.0 / (c * k * k) ** 0.5)
+    bias = torch.randn(co, generator=g) * 0.1
+    return x, off, mask, wgt, bias
+
+
+@pytest.mark.parametrize('case', ['small', 'big_offsets'])
+@pytest.mark.parametrize('mode', ['fp32', 'auto'])
+def test_golden_forward_backward(golden, case, mode):
+    g = golden('dynagg')
+    dg = int(g(f'{case}.dg'))
+    D.set_default_mode(mode)
+    try:
+        ts = [g(f'{case}.{k}').to(DEV).requires_grad_(True) for k in ('x', 'offset', 'mask', 'weight', 'bias')]
+        y = M.modulated_deform_conv(ts[0], ts[1], ts[2], ts[3], ts[4], 1, 1, 1, 1, dg)
+        assert rel_err(y, g(f'{case}.y')) <= TOL
+        y.backward(g(f'{case}.go').to(DEV))
+        for t, key in zip(ts, ('gx', 'goffset', 'gmask', 'gweight', 'gbias')):
+            assert rel_err(t.grad, g(f'{case}.{key}')) <= TOL, key
+    finally:
+        D.set_default_mode('auto')
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(b=2, c=64, h=20, w=24, co=64, dg=8),                       # relu1_1-like
+    dict(b=1, c=128, h=16, w=16, co=128, dg=8),                     # relu2_1-like
+    dict(b=1, c=256, h=10, w=12, co=256, dg=8),                     # relu3_1-like
+    dict(b=2, c=16, h=9, w=7, co=24, dg=2, off_scale=6.0),          # ragged sizes, many samples out of range
+    dict(b=1, c=8, h=6, w=6, co=8, dg=1, groups=2),                 # grouped conv
+    dict(b=1, c=8, h=11, w=13, co=4, dg=2, stride=2, pad=2, dil=2),  # stride / dilation
+])
+@pytest.mark.parametrize('mode', ['fp32', 'auto'])
+def test_forward_vs_oracle(cfg, mode):
+    cfg = dict(cfg)
+    b, c, h, w, co, dg = (cfg.pop(k) for k in ('b', 'c', 'h', 'w', 'co', 'dg'))
+    groups, stride, pad, dil = cfg.get('groups', 1), cfg.get('stride', 1), cfg.get('pad', 1), cfg.get('dil', 1)
+    x, off, mask, wgt, bias = _rand_problem(b, c, h, w, co, dg, 5, **cfg)
+    ref = oracle.modulated_deform_conv_oracle(x, off, mask, wgt, bias, stride, pad, dil, groups, dg, dtype=torch.float64)
+    out = D.dcn_forward_raw(x.to(DEV), off.to(DEV), mask.to(DEV), wgt.to(DEV), bias.to(DEV), (stride,) * 2, (pad,) * 2,
+                            (dil,) * 2, groups, dg, mode=mode)
+    assert rel_err(out, ref) <= TOL
+    out_nb = D.dcn_forward_raw(x.to(DEV), off.to(DEV), mask.to(DEV), wgt.to(DEV), None, (stride,) * 2, (pad,) * 2,
+                               (dil,) * 2, groups, dg, mode=mode)
+    assert rel_err(out_nb, ref - bias.double().view(1, -1, 1, 1)) <= TOL
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(b=2, c=32, h=10, w=12, co=32, dg=8),
+    dict(b=3, c=16, h=9, w=7, co=24, dg=2, off_scale=6.0),
+    dict(b=1, c=8, h=6, w=6, co=8, dg=1, groups=2),
+    dict(b=1, c=8, h=11, w=13, co=4, dg=2, stride=2, pad=2, dil=2),
+])
+def test_backward_vs_oracle(cfg):
+    cfg = dict(cfg)
+    b, c, h, w, co, dg = (cfg.pop(k) for k in ('b', 'c', 'h', 'w', 'co', 'dg'))
+    groups, stride, pad, dil = cfg.get('groups', 1), cfg.get('stride', 1), cfg.get('pad', 1), cfg.get('dil', 1)
+    x, off, mask, wgt, bias = _rand_problem(b, c, h, w, co, dg, 9, **cfg)
+    ts = [t.to(DEV).requires_grad_(True) for t in (x, off, mask, wgt, bias)]
+    y = M.modulated_deform_conv(ts[0], ts[1], ts[2], ts[3], ts[4], stride, pad, dil, groups, dg)
+    go = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
+    y.backward(go.to(DEV))
+    ref = oracle.modulated_deform_conv_backward_oracle(x, off, mask, wgt, bias, go, stride, pad, dil, groups, dg,
+                                                       dtype=torch.float64)
+    for t, r, name in zip(ts, ref, ('input', 'offset', 'mask', 'weight', 'bias')):
+        assert rel_err(t.grad, r) <= TOL, name
+
+
+def test_zero_offset_is_plain_conv():
+    """Known answer: zero offsets and mask 1 reduce DCNv2 to F.conv2d."""
+    x, off, mask, wgt, bias = _rand_problem(2, 32, 12, 12, 16, 4, 3)
+    out = D.dcn_forward_raw(x.to(DEV), torch.zeros_like(off).to(DEV), torch.ones_like(mask).to(DEV), wgt.to(DEV),
+                            bias.to(DEV), (1, 1), (1, 1), (1, 1), 1, 4)
+    ref = torch.nn.functional.conv2d(x.double(), wgt.double(), bias.double(), 1, 1)
+    assert rel_err(out, ref) <= TOL
+
+
+def test_full_size_linearity():
+    """BASELINE config 2 large scale (C=64, 160x160): DCN is linear in the input for fixed offsets/mask."""
+    b, c, h, w, dg = 2, 64, 160, 160, 8
+    x, off, mask, wgt, bias = _rand_problem(b, c, h, w, c, dg, 21, off_scale=8.0)
+    x2 = torch.randn(x.shape, generator=torch.Generator().manual_seed(22))
+    args = (off.to(DEV), mask.to(DEV), wgt.to(DEV), None, (1, 1), (1, 1), (1, 1), 1, dg)
+    ya = D.dcn_forward_raw(x.to(DEV), *args)
+    yb = D.dcn_forward_raw(x2.to(DEV), *args)
+    yc = D.dcn_forward_raw((2 * x - 3 * x2).to(DEV), *args)
+    assert rel_err(yc, 2 * ya - 3 * yb) <= TOL
+
+
+def test_dynagg_module_golden(golden):
+    g = golden('dynagg')
+    for case in ('small', 'big_offsets'):
+        dg = int(g(f'{case}.dg'))
+        c = g(f'{case}.x').shape[1]
+        m = M.DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True).to(DEV)
+        m.load_state_dict({'weight': g(f'{case}.weight'), 'bias': g(f'{case}.bias'),
+                           'conv_offset_mask.weight': g(f'{case}.com_w'), 'conv_offset_mask.bias': g(f'{case}.com_b')})
+        x = g(f'{case}.x').to(DEV).requires_grad_(True)
+        feat = g(f'{case}.feat').to(DEV).requires_grad_(True)
+        y = m([x, feat], g(f'{case}.pre').to(DEV))
+        assert rel_err(y, g(f'{case}.y')) <= TOL
+        assert m.last_offset_abs_mean() is not None
+
+
+def test_dynagg_glue_golden(golden):
+    from mrefsr_b200.dynagg import DynAggOffsetsFunction
+    g = golden('dynagg')
+    for case in ('small', 'big_offsets'):
+        dg = int(g(f'{case}.dg'))
+        off, mask = DynAggOffsetsFunction.apply(g(f'{case}.conv_out').to(DEV), g(f'{case}.pre').to(DEV), dg, None)
+        assert torch.equal(off.cpu(), g(f'{case}.offset'))
+        assert (mask.cpu() - g(f'{case}.mask')).abs().max() <= 1e-6
+
+
+def test_errors():
+    x, off, mask, wgt, bias = _rand_problem(1, 8, 6, 6, 8, 2, 1)
+    with pytest.raises(NotImplementedError):
+        M.modulated_deform_conv(x, off, mask, wgt, bias, 1, 1, 1, 1, 2)           # CPU tensors
+    with pytest.raises(RuntimeError):
+        M.modulated_deform_conv(x.to(DEV), off.to(DEV), mask.to(DEV), wgt[:, :4].contiguous().to(DEV), bias.to(DEV),
+                                1, 1, 1, 1, 2)                                     # channel mismatch
+
+
+_REF_SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref',
+                       'deform_conv_ext_ref.so')
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_SO), reason='reference CUDA extension not prebuilt (oracle/build.py --ref)')
+def test_against_reference_cuda_extension():
+    """The reference's own deform_conv_ext, compiled unmodified for sm_100a into oracle/_ref/ (checker only)."""
+    torch.ops.load_library(_REF_SO) if False else None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('deform_conv_ext_ref', _REF_SO)
+    ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ext)
+    x, off, mask, wgt, bias = (t.to(DEV) for t in _rand_problem(2, 64, 24, 20, 64, 8, 31, off_scale=4.0))
+    out_ref = x.new_empty(2, 64, 24, 20)
+    ext.modulated_deform_conv_forward(x, wgt, bias, x.new_empty(0), off, mask, out_ref, x.new_empty(0), 3, 3, 1, 1, 1, 1,
+                                      1, 1, 1, 8, True)
+    out = D.dcn_forward_raw(x, off, mask, wgt, bias, (1, 1), (1, 1), (1, 1), 1, 8)
+    assert rel_err(out, out_ref) <= TOL

@@ -1,0 +1,74 @@
+"""Parity of the CUDA multi-reference attention core (through the C ABI) against the oracle and golden vectors."""
+import pytest
+import torch
+
+import mrefsr_b200 as M
+import oracle
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = 1e-3
+
+
+@pytest.mark.parametrize('case', ['t5', 't1', 'pad'])
+def test_core_golden(golden, case):
+    g = golden('fusion')
+    t = int(g(f'{case}.t'))
+    out = M.mrapa_attention(g(f'{case}.emb_t').to(DEV), g(f'{case}.emb').to(DEV), g(f'{case}.ass').to(DEV), t)
+    assert rel_err(out, g(f'{case}.core_out')) <= 1e-5
+
+
+@pytest.mark.parametrize('case', ['t5', 't1', 'pad'])
+def test_module_golden(golden, case):
+    g = golden('fusion')
+    t = int(g(f'{case}.t'))
+    target, refs = g(f'{case}.target'), g(f'{case}.refs')
+    m = M.MRAPAFusion(nf=target.shape[1], ref_nf=refs.shape[2]).to(DEV).eval()
+    sd = {k.split('.sd.', 1)[1]: g(k) for k in g.keys() if k.startswith(f'{case}.sd.')}
+    m.load_state_dict(sd)          # identical state-dict keys to the reference module
+    with torch.no_grad():
+        y = m(target.to(DEV), [refs[i].to(DEV) for i in range(t)])
+    assert rel_err(y, g(f'{case}.y')) <= TOL
+
+
+@pytest.mark.parametrize('shape', [(2, 5, 64, 128, 19, 33), (1, 8, 256, 512, 8, 8), (1, 2, 30, 7, 5, 3),
+                                   (1, 12, 16, 32, 6, 6)])
+def test_forward_backward_vs_oracle(shape):
+    n, t, c, cv, h, w = shape
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(n, c, h, w, generator=g) * 0.3
+    k = torch.randn(n * t, c, h, w, generator=g)
+    v = torch.randn(n * t, cv, h, w, generator=g)
+    go = torch.randn(n, cv, h, w, generator=g)
+    ts = [x.to(DEV).requires_grad_(True) for x in (q, k, v)]
+    out = M.mrapa_attention(ts[0], ts[1], ts[2], t)
+    out.backward(go.to(DEV))
+    rs = [x.double().requires_grad_(True) for x in (q, k, v)]
+    ref = oracle.mrapa_attention_oracle(rs[0], rs[1], rs[2], t)
+    ref.backward(go.double())
+    assert rel_err(out, ref) <= 1e-5
+    for a, b, name in zip(ts, rs, ('emb_t', 'emb', 'ass')):
+        assert rel_err(a.grad, b.grad) <= 1e-4, name
+
+
+def test_full_size_convexity():
+    """BASELINE config 2 large scale: the output is a convex combination of the t value maps, so it lies
+    between their per-pixel min and max; with identical references it equals them."""
+    n, t, c, h, w = 2, 5, 64, 160, 160
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(n, c, h, w, generator=g).to(DEV)
+    k = torch.randn(n * t, c, h, w, generator=g).to(DEV)
+    v = torch.randn(n * t, 2 * c, h, w, generator=g).to(DEV)
+    out = M.mrapa_attention(q, k, v, t)
+    vv = v.view(n, t, 2 * c, h, w)
+    assert (out <= vv.max(1).values + 1e-5).all() and (out >= vv.min(1).values - 1e-5).all()
+    same = vv[:, :1].expand(-1, t, -1, -1, -1).reshape(n * t, 2 * c, h, w).contiguous()
+    out2 = M.mrapa_attention(q, k, same, t)
+    assert rel_err(out2, vv[:, 0]) <= 1e-5
+
+
+def test_too_many_refs_errors():
+    q = torch.randn(1, 8, 4, 4, device=DEV)
+    with pytest.raises(RuntimeError):
+        M.mrapa_attention(q, torch.randn(17, 8, 4, 4, device=DEV), torch.randn(17, 8, 4, 4, device=DEV), 17)

@@ -1,0 +1,137 @@
+"""Parity of the CUDA matcher (through the C ABI) against the oracle and the reference-generated golden vectors."""
+import pytest
+import torch
+
+import mrefsr_b200 as M
+from mrefsr_b200 import matcher as MM
+from tests.util import match_parity, unit_features
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+CASES = ['rand', 'shift', 'zeropad', 'raw', 'nonorm', 'strided', 'c256']
+TC_MODES = [MM.MATCH_TC_BF16X3, MM.MATCH_TC_BF16X3 | MM.FLAG_NO_STRIP]
+
+
+def _run(fi, fr, kw, mode):
+    idx, val = M.feature_match_index(fi.to(DEV), fr.to(DEV), mode=mode, **kw)
+    torch.cuda.synchronize()
+    return idx, val
+
+
+@pytest.mark.parametrize('case', CASES)
+@pytest.mark.parametrize('mode', ['auto', 'fp32'])
+def test_golden(golden, case, mode):
+    g = golden('matcher')
+    kw = eval(str(g(f'{case}.kw')))
+    fi, fr = g(f'{case}.fi'), g(f'{case}.fr')
+    idx, val = _run(fi, fr, kw, mode)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == tuple(g(f'{case}.idx').shape)
+    r = match_parity(idx, val, fi, fr, kw)
+    assert r['n_bad'] == 0 and r['val_err'] <= 1e-3, r
+    # against the reference's own output: exact wherever the gap is resolvable
+    ref_idx = g(f'{case}.idx')
+    if case != 'zeropad':
+        assert (idx.cpu() != ref_idx).sum().item() <= r['n_lowgap']
+    else:
+        assert torch.equal(idx.cpu()[12:], ref_idx[12:])   # exact-tie plateau: lowest index wins
+
+
+@pytest.mark.parametrize('case', ['rand', 'shift', 'zeropad', 'c256'])
+@pytest.mark.parametrize('mode', TC_MODES)
+def test_tensor_core_modes(golden, case, mode):
+    g = golden('matcher')
+    kw = eval(str(g(f'{case}.kw')))
+    fi, fr = g(f'{case}.fi'), g(f'{case}.fr')
+    idx, val = _run(fi, fr, kw, mode)
+    r = match_parity(idx, val, fi, fr, kw)
+    assert r['n_bad'] == 0 and r['val_err'] <= 1e-3, r
+
+
+def test_bf16_fast_mode_tolerance():
+    """Single-pass bf16: stated tolerance 2e-3 absolute on the similarity; indices may differ where the gap is
+    below that tolerance."""
+    fi, fr = unit_features(1, 256, 40, 40, 1)[0], unit_features(1, 256, 40, 40, 2)[0]
+    kw = dict(is_norm=True, norm_input=True)
+    idx, val = _run(fi, fr, kw, 'bf16')
+    r = match_parity(idx, val, fi, fr, kw, gap_tol=2e-3)
+    assert r['n_bad'] == 0, r
+    r2 = match_parity(idx, val, fi, fr, kw)
+    assert r2['val_err'] < 0.05, r2
+
+
+@pytest.mark.parametrize('shape', [(256, 40, 40), (256, 75, 75), (64, 3, 3), (64, 3, 40), (128, 17, 23), (64, 5, 130)])
+def test_shapes_vs_oracle(shape):
+    c, h, w = shape
+    fi, fr = unit_features(1, c, h, w, 11)[0], unit_features(1, c, h, w, 12)[0]
+    kw = dict(is_norm=True, norm_input=True)
+    idx, val = _run(fi, fr, kw, 'auto')
+    r = match_parity(idx, val, fi, fr, kw, dtype=torch.float32 if h * w > 3000 else torch.float64)
+    assert r['n_bad'] == 0 and r['val_err'] <= 1e-3, r
+
+
+def test_different_input_and_ref_sizes():
+    fi, fr = unit_features(1, 64, 12, 20, 5)[0], unit_features(1, 64, 30, 17, 6)[0]
+    kw = dict(is_norm=True, norm_input=True)
+    for mode in ('auto', 'fp32'):
+        idx, val = _run(fi, fr, kw, mode)
+        r = match_parity(idx, val, fi, fr, kw)
+        assert r['n_bad'] == 0 and r['val_err'] <= 1e-3, (mode, r)
+
+
+@pytest.mark.parametrize('layout', ['BR', 'RB'])
+def test_batched_pairs(layout):
+    b, r, c, h, w = 2, 3, 256, 20, 24
+    fin = torch.randn(b, c, h, w, generator=torch.Generator().manual_seed(3))
+    fref = torch.randn(b * r, c, h, w, generator=torch.Generator().manual_seed(4))
+    in_div = r if layout == 'BR' else 1
+    idx, val = M.feature_match_index_batched(fin.to(DEV), fref.to(DEV), is_norm=True, norm_input=True,
+                                             normalize_pixels=True, in_div=in_div)
+    import torch.nn.functional as F
+    kw = dict(is_norm=True, norm_input=True)
+    for p in range(b * r):
+        i = (p // in_div) % b
+        a = F.normalize(fin[i].reshape(c, -1), dim=0).view(c, h, w)
+        rr = F.normalize(fref[p].reshape(c, -1), dim=0).view(c, h, w)
+        res = match_parity(idx[p], val[p], a, rr, kw)
+        assert res['n_bad'] == 0 and res['val_err'] <= 1e-3, (p, res)
+
+
+def test_full_size_shift_property():
+    """BASELINE config 2 shape (16 images x 5 refs, 256 x 40 x 40): each reference is the input translated by a
+    known integer shift, so arg-max and similarity (= 1) are known analytically -- no oracle needed."""
+    b, r, c, h, w = 16, 5, 256, 40, 40
+    big = unit_features(b, c, h + 8, w + 8, 77)
+    shifts = [(0, 0), (1, 3), (4, 2), (6, 6), (8, 1)]
+    fin = big[:, :, 4:4 + h, 4:4 + w].contiguous()
+    refs = torch.stack([big[:, :, dy:dy + h, dx:dx + w] for dy, dx in shifts], dim=1)   # [B,R,C,h,w]
+    idx, val = M.feature_match_index_batched(fin.to(DEV), refs.flatten(0, 1).contiguous().to(DEV), is_norm=True,
+                                             norm_input=True)
+    idx, val = idx.cpu().view(b, r, h - 2, w - 2), val.cpu().view(b, r, h - 2, w - 2)
+    ys, xs = torch.meshgrid(torch.arange(h - 2), torch.arange(w - 2), indexing='ij')
+    for k, (dy, dx) in enumerate(shifts):
+        # input pixel (y, x) = big (y+4, x+4) = ref_k (y+4-dy, x+4-dx)
+        ry, rx = ys + 4 - dy, xs + 4 - dx
+        ok = (ry >= 0) & (ry < h - 2) & (rx >= 0) & (rx < w - 2)
+        exp = ry * (w - 2) + rx
+        assert torch.equal(idx[:, k][:, ok], exp[ok].expand(b, -1)), k
+        assert (val[:, k][:, ok] - 1).abs().max() < 1e-4
+
+
+def test_pre_offsets_golden(golden):
+    g = golden('correspondence')
+    o1, o2, o4 = M.pre_offsets(g('max_idx').to(DEV))
+    assert torch.equal(o1.cpu(), g('relu3_1')) and torch.equal(o2.cpu(), g('relu2_1')) and torch.equal(o4.cpu(), g('relu1_1'))
+
+
+def test_correspondence_golden(golden):
+    g = golden('correspondence')
+    pre = M.correspondence(g('f1').to(DEV), g('f2').to(DEV))
+    for k in ('relu3_1', 'relu2_1', 'relu1_1'):
+        # flows are integers: equality up to the (rare) unresolvable near-ties
+        diff = (pre[k].cpu() != g(k)).any(-1).float().mean().item()
+        assert diff < 0.02, (k, diff)
+
+
+def test_cpu_tensor_raises():
+    with pytest.raises(NotImplementedError):
+        M.feature_match_index(torch.randn(8, 6, 6), torch.randn(8, 6, 6))
