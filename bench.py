@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of MRefSR's reference-alignment hot path on B200 (this repo) or on host cores
+(--impl reference: the CPU oracle port of the reference algorithm).
+
+One "step" = one pass of the hot path over one batch of synthetic CUFED5-shaped input, BASELINE.json config 2:
+B images per GPU (default 16), R = 5 references, 160x160 HR (feature grids 40/80/160, C = 256/128/64):
+  (1) correspondence matcher over the B*R (image, reference) pairs (+ per-pixel normalisation, + pre-offsets
+      at three scales),
+  (2) DynAgg offset/mask assembly + DCNv2 forward at three scales over the B*R samples,
+  (3) multi-reference attention fusion at three scales.
+metric = x4 SR images/sec through that path (images = B per step).  Multi-GPU: images are independent, so the
+batch is sharded across ranks with no data-path collective ("weak" scaling: B per GPU fixed).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the definitions of every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'x4 SR images/sec through the reference-alignment hot path (match + DCNv2 + fusion), 5 refs @160^2 HR'
+UNIT = 'images/s'
+SCALES = ((256, 40), (128, 80), (64, 160))   # (channels, feature grid) at relu3_1 / relu2_1 / relu1_1
+DG = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
+    ap.add_argument('--refs', type=int, default=5)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-images', type=int, default=2, help='images in the bounded CPU-baseline sample')
+    ap.add_argument('--match-mode', default='auto')
+    ap.add_argument('--dcn-mode', default='auto')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ----------------------------------------------------------------------------------------------------------
+def make_inputs(b, r, seed, device, pin=False):
+    """Seeded synthetic tensors of the config-2 shapes.  Returned on `device` ('cpu' tensors are pinned if pin)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def rnd(*shape, scale=1.0):
+        t = torch.randn(*shape, generator=g) * scale
+        if device != 'cpu':
+            return t.to(device)
+        return t.pin_memory() if pin else t
+
+    d = {'feat_in': rnd(b, 256, 40, 40), 'feat_ref': rnd(b * r, 256, 40, 40)}
+    for c, hw in SCALES:
+        d[f'x{c}'] = rnd(b * r, c, hw, hw)                          # reference VGG features (DCN input)
+        d[f'conv_out{c}'] = rnd(b * r, 3 * DG * 9, hw, hw, scale=0.5)  # raw conv_offset_mask output
+        d[f'w{c}'] = rnd(c, c, 3, 3, scale=(c * 9) ** -0.5)
+        d[f'b{c}'] = rnd(c, scale=0.1)
+        d[f'emb_t{c}'] = rnd(b, c, hw, hw, scale=0.2)
+        d[f'emb{c}'] = rnd(b * r, c, hw, hw)
+        d[f'ass{c}'] = rnd(b * r, 2 * c, hw, hw)
+    return d
+
+
+def input_bytes(d):
+    return sum(t.numel() * t.element_size() for t in d.values())
+
+
+def hot_path_step(M, d, b, r, match_mode, dcn_mode, to_host=False):
+    """One pass over the batch on the current stream.  Returns the list of outputs."""
+    from mrefsr_b200.dynagg import DynAggOffsetsFunction
+    from mrefsr_b200.dcn import dcn_forward_raw
+    outs = []
+    idx, val = M.feature_match_index_batched(d['feat_in'], d['feat_ref'], is_norm=True, norm_input=True,
+                                             normalize_pixels=True, in_div=r, mode=match_mode)
+    pre = M.pre_offsets(idx)                                   # [B*R,9,s*40,s*40,2] for s = 1, 2, 4
+    outs += [idx, val]
+    for (c, hw), pre_s in zip(SCALES, pre):
+        off, mask = DynAggOffsetsFunction.apply(d[f'conv_out{c}'], pre_s, DG, None)
+        y = dcn_forward_raw(d[f'x{c}'], off, mask, d[f'w{c}'], d[f'b{c}'], (1, 1), (1, 1), (1, 1), 1, DG, mode=dcn_mode)
+        f = M.mrapa_attention(d[f'emb_t{c}'], d[f'emb{c}'], d[f'ass{c}'], r)
+        outs += [y, f]
+    return outs
+
+
+# ----------------------------------------------------------------------------------------------------------
+# algorithmic work (DESIGN.md "Measurement")
+# ----------------------------------------------------------------------------------------------------------
+def algorithmic(b, r):
+    n = 38 * 38
+    w = {'match_main': {'flops': 2.0 * n * n * 2304 * b * r, 'bytes': (2 * 256 * 1600 * 4 + 12 * n) * b * r}}
+    dcn_f = sum(2.0 * c * c * 9 * hw * hw for c, hw in SCALES) * b * r
+    dcn_b = sum(4.0 * hw * hw * (c + 27 * DG + c) + 4.0 * c * c * 9 + 4 * c for c, hw in SCALES) * b * r
+    w['dcn_fwd'] = {'flops': dcn_f, 'bytes': dcn_b}
+    w['fusion_fwd'] = {'flops': 0.0, 'bytes': sum(4.0 * hw * hw * c * (3 + 3 * r) for c, hw in SCALES) * b}
+    return w
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {'hbm_gbs': j['hbm_gbs'], 'bf16_tflops': j['bf16_tflops'],
+                'bf16_tflops_sustained': j.get('bf16_tflops_sustained', j['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        sm.sort()
+        # median of the samples in the upper half = clocks under load (idle samples before/after drag it down)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {'sm_mhz': med, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference algorithm, all host threads
+# ----------------------------------------------------------------------------------------------------------
+def cpu_hot_path(n_images, r, seed=4321):
+    """One pass of the same hot path for n_images images on the host (oracle port; see oracle/__init__.py)."""
+    import torch.nn.functional as F
+    import oracle
+    from oracle.dcn import modulated_deform_conv_c
+    d = make_inputs(n_images, r, seed, 'cpu')
+    t0 = time.perf_counter()
+    idxs = []
+    for p in range(n_images * r):
+        a = F.normalize(d['feat_in'][p // r].reshape(256, -1), dim=0).view(256, 40, 40)
+        q = F.normalize(d['feat_ref'][p].reshape(256, -1), dim=0).view(256, 40, 40)
+        idx, _ = oracle.feature_match_index_oracle(a, q, is_norm=True, norm_input=True, use_conv=True)
+        idxs.append(idx)
+    t1 = time.perf_counter()
+    pres = [oracle.pre_offsets_oracle(i) for i in idxs]
+    t_dcn = t_fus = 0.0
+    for (c, hw), key in zip(SCALES, ('relu3_1', 'relu2_1', 'relu1_1')):
+        ta = time.perf_counter()
+        pre = torch.stack([p[key] for p in pres], 0)
+        off, mask = oracle.dynagg_offsets_oracle(d[f'conv_out{c}'], pre, DG)
+        modulated_deform_conv_c(d[f'x{c}'], off, mask, d[f'w{c}'], d[f'b{c}'], 1, 1, 1, 1, DG)
+        tb = time.perf_counter()
+        oracle.mrapa_attention_oracle(d[f'emb_t{c}'], d[f'emb{c}'], d[f'ass{c}'], r)
+        tc = time.perf_counter()
+        t_dcn += tb - ta
+        t_fus += tc - tb
+    t2 = time.perf_counter()
+    return {'total_s': t2 - t0, 'match_s': t1 - t0, 'dcn_s': t_dcn, 'fusion_s': t_fus}
+
+
+def cpu_baseline(n_images, r):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    cpu_hot_path(1, r)                                  # warm-up (thread pools, page faults)
+    best = min((cpu_hot_path(n_images, r) for _ in range(2)), key=lambda x: x['total_s'])
+    return {'value': n_images / best['total_s'], 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d image(s) x %d refs @160^2 through the oracle port (torch CPU matcher + OpenMP C DCN + '
+                      'torch CPU fusion), best of 2' % (n_images, r),
+            'split_s': {k: round(v, 4) for k, v in best.items()}}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; /root/reference is a Python
+    tree that cannot travel to the GPU box) on all host cores; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_img = 1
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_hot_path(n_img, args.refs)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_hot_path(n_img, args.refs)
+    dt = time.perf_counter() - t0
+    v = n_img * steps / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': 1, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'MRefSR x4 alignment hot path, %d refs @160^2 HR (BASELINE config 2 shapes), '
+                                   'bounded sample: %d image per step on host cores' % (args.refs, n_img)},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d image x %d refs per step, %d steps' % (n_img, args.refs, steps)},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback '
+                         '(use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group('nccl', device_id=dev)
+
+    import mrefsr_b200 as M
+    from mrefsr_b200 import _lib
+    b, r = args.batch, args.refs
+    d = make_inputs(b, r, 1234 + rank, dev)
+    in_gb = input_bytes(d) / 1e9
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(3, args.warmup)):
+        hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode)
+    barrier()
+
+    # ---- timed region: K steps, device-timed, inputs resident in HBM (several GB/step of inputs >> 126 MB L2)
+    _lib.timing_enable(True)
+    _lib.timing_read()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count() - launches0
+    ktimes = _lib.timing_read()
+    _lib.timing_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = b * world * args.steps / (ms_max / 1e3)
+
+    # ---- e2e: same step through the operator API with HOST (pinned) buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hd = make_inputs(b, r, 1234 + rank, 'cpu', pin=True)
+        h2d = input_bytes(hd)
+        d2h = [0]
+
+        def e2e_step():
+            dd = {k: v.to(dev, non_blocking=True) for k, v in hd.items()}
+            outs = hot_path_step(M, dd, b, r, args.match_mode, args.dcn_mode)
+            host = [o.to('cpu', non_blocking=True) for o in outs]
+            torch.cuda.synchronize()
+            d2h[0] = sum(o.numel() * o.element_size() for o in host)
+        del d
+        torch.cuda.empty_cache()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {'value': b * world * n_e2e / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h[0], 'steps': n_e2e,
+               'note': 'pinned host tensors -> operator API -> host; PCIe-bound at this operator boundary'}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (by measured device time inside the timed region)
+    pk = peaks()
+    work = algorithmic(b, r)
+    per_kernel = {}
+    for k, (tot_ms, n) in ktimes.items():
+        if n:
+            per_kernel[k] = {'ms_per_step': tot_ms / args.steps, 'launches_per_step': n / args.steps}
+    dom = max((k for k in per_kernel if k in work), key=lambda k: per_kernel[k]['ms_per_step'])
+
+    def roof(k):
+        t_s = per_kernel[k]['ms_per_step'] / 1e3
+        wk = work[k]
+        t_flop = wk['flops'] / (pk['bf16_tflops_sustained'] * 1e12)
+        t_byte = wk['bytes'] / (pk['hbm_gbs'] * 1e9)
+        if t_flop >= t_byte:
+            a = wk['flops'] / t_s / 1e12
+            return {'kernel': k, 'bound': 'tensor', 'achieved': a, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                    'frac': a / pk['bf16_tflops_sustained'], 'traffic': None,
+                    'peak_source': pk['source'] + ' (cuBLAS bf16, sustained)'}
+        a = wk['bytes'] / t_s / 1e9
+        return {'kernel': k, 'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': a / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'] + ' (copy)'}
+
+    roofline = roof(dom)
+    roofline['ms_per_launch'] = per_kernel[dom]['ms_per_step'] / per_kernel[dom]['launches_per_step']
+    roof_all = {k: roof(k) for k in per_kernel if k in work}
+
+    cpu = None if args.no_cpu_baseline else cpu_baseline(args.cpu_images, r)
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (matcher: split-bf16 x3 on tcgen05, fp32 accumulate)',
+            'data': 'synthetic',
+            'config': {'workload': 'MRefSR x4 inference alignment hot path, batch %d per GPU, %d refs at 160x160 '
+                                   '(BASELINE config 2): %d matcher pairs, DynAgg+DCNv2 x3 scales over %d samples, '
+                                   'fusion x3 scales' % (b, r, b * r, b * r),
+                       'images_per_step': b * world, 'l2': 'inputs (%.1f GB/step/GPU) larger than the 126 MB L2' % in_gb,
+                       'parallelism': 'batch-sharded x%d, no collective' % world,
+                       'match_mode': args.match_mode, 'dcn_mode': args.dcn_mode},
+            'roofline': roofline, 'roofline_all': roof_all, 'kernel_ms_per_step': per_kernel,
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
