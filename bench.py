@@ -46,6 +46,9 @@ def parse():
     ap.add_argument('--cpu-images', type=int, default=2, help='images in the bounded CPU-baseline sample')
     ap.add_argument('--match-mode', default='auto')
     ap.add_argument('--dcn-mode', default='auto')
+    ap.add_argument('--no-fused', action='store_true',
+                    help='materialise pre-offsets / offset / mask (reference operator boundaries) instead of the '
+                         'fused DynAgg gather')
     return ap.parse_args()
 
 
@@ -78,18 +81,22 @@ def input_bytes(d):
     return sum(t.numel() * t.element_size() for t in d.values())
 
 
-def hot_path_step(M, d, b, r, match_mode, dcn_mode, to_host=False):
+def hot_path_step(M, d, b, r, match_mode, dcn_mode, fused=True):
     """One pass over the batch on the current stream.  Returns the list of outputs."""
     from mrefsr_b200.dynagg import DynAggOffsetsFunction
-    from mrefsr_b200.dcn import dcn_forward_raw
+    from mrefsr_b200.dcn import dcn_forward_raw, dynagg_dcn_forward
     outs = []
     idx, val = M.feature_match_index_batched(d['feat_in'], d['feat_ref'], is_norm=True, norm_input=True,
                                              normalize_pixels=True, in_div=r, mode=match_mode)
-    pre = M.pre_offsets(idx)                                   # [B*R,9,s*40,s*40,2] for s = 1, 2, 4
     outs += [idx, val]
-    for (c, hw), pre_s in zip(SCALES, pre):
-        off, mask = DynAggOffsetsFunction.apply(d[f'conv_out{c}'], pre_s, DG, None)
-        y = dcn_forward_raw(d[f'x{c}'], off, mask, d[f'w{c}'], d[f'b{c}'], (1, 1), (1, 1), (1, 1), 1, DG, mode=dcn_mode)
+    pre = None if fused else M.pre_offsets(idx)                # [B*R,9,s*40,s*40,2] for s = 1, 2, 4
+    for k, (c, hw) in enumerate(SCALES):
+        if fused:   # offsets / masks / pre-offsets assembled inside the DCN gather
+            y = dynagg_dcn_forward(d[f'x{c}'], d[f'conv_out{c}'], idx, hw // 40, d[f'w{c}'], d[f'b{c}'], DG)
+        else:       # the reference's operator boundaries, one kernel each
+            off, mask = DynAggOffsetsFunction.apply(d[f'conv_out{c}'], pre[k], DG, None)
+            y = dcn_forward_raw(d[f'x{c}'], off, mask, d[f'w{c}'], d[f'b{c}'], (1, 1), (1, 1), (1, 1), 1, DG,
+                                mode=dcn_mode)
         f = M.mrapa_attention(d[f'emb_t{c}'], d[f'emb{c}'], d[f'ass{c}'], r)
         outs += [y, f]
     return outs
@@ -266,6 +273,7 @@ def main():
     import mrefsr_b200 as M
     from mrefsr_b200 import _lib
     b, r = args.batch, args.refs
+    fused = not args.no_fused
     d = make_inputs(b, r, 1234 + rank, dev)
     in_gb = input_bytes(d) / 1e9
 
@@ -276,7 +284,7 @@ def main():
 
     # ---- warm-up
     for _ in range(max(3, args.warmup)):
-        hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode)
+        hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode, fused)
     barrier()
 
     # ---- timed region: K steps, device-timed, inputs resident in HBM (several GB/step of inputs >> 126 MB L2)
@@ -288,7 +296,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode)
+        hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode, fused)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -311,7 +319,7 @@ def main():
 
         def e2e_step():
             dd = {k: v.to(dev, non_blocking=True) for k, v in hd.items()}
-            outs = hot_path_step(M, dd, b, r, args.match_mode, args.dcn_mode)
+            outs = hot_path_step(M, dd, b, r, args.match_mode, args.dcn_mode, fused)
             host = [o.to('cpu', non_blocking=True) for o in outs]
             torch.cuda.synchronize()
             d2h[0] = sum(o.numel() * o.element_size() for o in host)
@@ -375,7 +383,8 @@ def main():
                                    'fusion x3 scales' % (b, r, b * r, b * r),
                        'images_per_step': b * world, 'l2': 'inputs (%.1f GB/step/GPU) larger than the 126 MB L2' % in_gb,
                        'parallelism': 'batch-sharded x%d, no collective' % world,
-                       'match_mode': args.match_mode, 'dcn_mode': args.dcn_mode},
+                       'match_mode': args.match_mode, 'dcn_mode': args.dcn_mode,
+                       'dynagg': 'fused gather (conv_out + arg-max map)' if fused else 'materialised offset/mask'},
             'roofline': roofline, 'roofline_all': roof_all, 'kernel_ms_per_step': per_kernel,
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
     print(json.dumps(line), flush=True)

@@ -132,6 +132,21 @@ MREFSR_API int mrefsr_modulated_deform_conv_backward(const float* input, const f
 MREFSR_API int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float* offset, float* mask,
                           float* abs_sum, int B, int dg, int K, int H, int W, void* stream);
 
+/* Fused DynAgg forward (inference): DCNv2 whose offsets / masks are assembled inside the gather from the raw
+ * conv_offset_mask output and the matcher's arg-max map, so neither the pre-offset tensors nor offset / mask
+ * are ever written to HBM:
+ *   offset[:, 2(g*9+k)  ] = conv_out[:, 2(g*9+k)  ] + s * flow_y[Y/s - i, X/s - j]      (k = 3i + j)
+ *   offset[:, 2(g*9+k)+1] = conv_out[:, 2(g*9+k)+1] + s * flow_x[Y/s - i, X/s - j]
+ *   mask = sigmoid(conv_out[:, 2*dg*9 + g*9 + k]),  flow = index_to_flow(max_idx) (0 outside the grid)
+ *     replaces  basicsr/archs/ref_mrapa_restoration_arch.py:45-76 (DynAgg.forward) together with
+ *               basicsr/archs/corres_generation_arch.py:30-47, :70-105 for one scale.
+ * input [B,C,H,W], conv_out [B,3*dg*9,H,W], max_idx [B,H/s-2,W/s-2] int64, 3x3 kernel, stride 1, pad 1, dil 1.
+ * Requires the tcgen05 path (C % 32 == 0, (C/dg) % 4 == 0, Co % 32 == 0, Co <= 256). */
+MREFSR_API int mrefsr_dynagg_dcn_forward(const float* input, const float* weight, const float* bias, const float* conv_out,
+                              const int64_t* max_idx, int flow_scale, float* output, int B, int C, int H, int W,
+                              int Co, int deformable_group, int with_bias, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) Multi-reference attention fusion core
  *     replaces  basicsr/archs/ref_mrapa_restoration_arch.py:321-335

@@ -27,6 +27,7 @@ SIGNATURES = {
     'mrefsr_dcn_workspace_bytes': (c_size_t, [_I] * 17),
     'mrefsr_modulated_deform_conv_forward': (c_int, [_P] * 6 + [_I] * 17 + [_P, c_size_t, _P]),
     'mrefsr_modulated_deform_conv_backward': (c_int, [_P] * 10 + [_I] * 17 + [_P, c_size_t, _P]),
+    'mrefsr_dynagg_dcn_forward': (c_int, [_P] * 5 + [_I] + [_P] + [_I] * 7 + [_P, c_size_t, _P]),
     'mrefsr_dynagg_offsets': (c_int, [_P] * 5 + [_I] * 5 + [_P]),
     'mrefsr_mrapa_attention_forward': (c_int, [_P] * 5 + [_I] * 6 + [_P]),
     'mrefsr_mrapa_attention_backward': (c_int, [_P] * 8 + [_I] * 6 + [_P]),

@@ -120,6 +120,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// For waits that are expected to be long (a whole tile): back off so the spinning warp does not steal issue
+// slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ---- TMA (cp.async.bulk.tensor), 3-D tiled load, completion on an mbarrier
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,

@@ -438,7 +438,7 @@ int mrefsr_modulated_deform_conv_forward(const float* input, const float* weight
     if (m == MREFSR_DCN_FP32) return dcn_forward_fp32(input, weight, bp, offset, mask, output, s, st);
     MREFSR_CHECK(m == MREFSR_DCN_TF32, ERR_BAD_ARG, "dcn forward: unknown mode %d", mode);
     MREFSR_CHECK(dcn_tc_eligible(s), ERR_UNSUPPORTED,
-                 "dcn forward: tcgen05 path needs group 1, 3x3 kernel, C %% 32 == 0, Co %% 16 == 0, Co <= 256, "
+                 "dcn forward: tcgen05 path needs group 1, C %% 32 == 0, Co %% 32 == 0, Co <= 256, "
                  "(C/deformable_group) %% 4 == 0");
     return dcn_forward_tc(input, weight, bp, offset, mask, output, s, workspace, workspace_bytes, st);
 }
@@ -494,6 +494,22 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
         count_launches(1);
     }
     return 0;
+}
+
+int mrefsr_dynagg_dcn_forward(const float* input, const float* weight, const float* bias, const float* conv_out,
+                              const int64_t* max_idx, int flow_scale, float* output, int B, int C, int H, int W, int Co,
+                              int deformable_group, int with_bias, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    MREFSR_CHECK(input && weight && conv_out && max_idx && output, ERR_BAD_ARG, "dynagg forward: null pointer argument");
+    MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dynagg forward: with_bias set but bias is NULL");
+    DcnShape s;
+    int rc = dcn_make_shape(&s, B, C, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, deformable_group);
+    if (rc) return rc;
+    MREFSR_CHECK(dcn_tc_eligible(s), ERR_UNSUPPORTED,
+                 "dynagg forward: needs C %% 32 == 0, (C/deformable_group) %% 4 == 0, Co %% 32 == 0, Co <= 256");
+    return dcn_forward_tc_impl(input, weight, with_bias ? bias : nullptr, conv_out, nullptr,
+                               reinterpret_cast<const long long*>(max_idx), flow_scale, output, s, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float* offset, float* mask, float* abs_sum,

@@ -35,6 +35,9 @@ int dcn_forward_fp32(const float* x, const float* w, const float* bias, const fl
 // tcgen05 (TF32) forward, dcn_tc.cu
 bool dcn_tc_eligible(const DcnShape& s);
 size_t dcn_tc_workspace_bytes(const DcnShape& s, int mode);
+int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const float* off, const float* mask,
+                        const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st);
 int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                    const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

@@ -1,13 +1,555 @@
-// mrefsr_b200/csrc/dcn_tc.cu -- tcgen05 (TF32) DCNv2 forward.  Placeholder until the kernel lands: reports
-// "not eligible" so MREFSR_DCN_AUTO resolves to the exact-fp32 CUDA-core kernel and MREFSR_DCN_TF32 errors out.
+// mrefsr_b200/csrc/dcn_tc.cu -- DCNv2 forward on tcgen05 (TF32 operands, fp32 accumulation in TMEM).
+//
+// Replaces the reference's per-sample {im2col kernel -> columns buffer in HBM -> cuBLAS addmm_}
+// (basicsr/ops/dcn/src/deform_conv_cuda.cpp:539-555, deform_conv_cuda_kernel.cu:571-633) with ONE launch over
+// the whole batch in which the deformable im2col tile never leaves the SM:
+//
+//   CTA tile   : 256 consecutive output positions (of the B*Ho*Wo concatenation) x all Co output channels
+//   K loop     : (32-channel slab) x (tap); per step the A tile [256 x 32] fp32 is produced by 8 gather warps
+//                straight into 128B-swizzled shared memory (bilinear 4-corner gather from an NHWC copy of the
+//                input: one float4 per corner per 4 channels, mask multiply and tf32 rounding fused), the B
+//                tile [Co x 32] of the repacked weights arrives by TMA, and one elected thread issues
+//                2 (M halves) x 4 (K=8 steps) tcgen05.mma.kind::tf32 into TMEM.
+//   epilogue   : 4 warps read TMEM (tcgen05.ld 32x32b), add the bias and store NCHW with position-major lanes
+//                (128-byte coalesced stores).
+//   pipelines  : smem ring full/empty mbarriers (gather + TMA -> MMA), TMEM full/empty (MMA -> epilogue).
+//
+// Offsets / masks come either as materialised tensors (the reference operator API) or -- fused DynAgg mode --
+// straight from the raw conv_offset_mask output plus the matcher's arg-max map: offset = conv + s*flow shifted
+// by the tap, mask = sigmoid(conv) (basicsr/archs/ref_mrapa_restoration_arch.py:55-68 and
+// corres_generation_arch.py:70-105 folded into the gather), which removes two full passes over the
+// 216-plane tensor.
 #include "dcn_common.cuh"
+#include "../../include/mrefsr_b200.h"
 
 namespace mrefsr {
-bool dcn_tc_eligible(const DcnShape&) { return false; }
-size_t dcn_tc_workspace_bytes(const DcnShape&, int) { return 0; }
-int dcn_forward_tc(const float*, const float*, const float*, const float*, const float*, float*, const DcnShape&,
-                   void*, size_t, cudaStream_t) {
-    set_error("dcn forward: tcgen05 path not built");
-    return ERR_UNSUPPORTED;
+
+constexpr int TBM = 256;            // rows (output positions) per CTA tile
+constexpr int TBK = 32;             // fp32 channels per K step (128-byte rows)
+constexpr int T_A_BYTES = TBM * 128;
+#ifndef MREFSR_DCN_PW
+#define MREFSR_DCN_PW 8
+#endif
+constexpr int T_PW = MREFSR_DCN_PW;  // producer warps: sample table (2 K steps ahead) + gather, mbarrier dataflow
+constexpr int T_RSTEP = T_PW * 4;    // row stride between a thread's gather items
+constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items per thread per K step
+constexpr int T_BATCH = 4;                         // items whose loads are issued together
+constexpr int T_ENT = 4 * TBM / (T_PW * 32);       // max table entries per thread (gs = 4)
+constexpr int T_PRODUCERS = T_PW * 32;
+constexpr int T_MMA_WARP = T_PW, T_TMA_WARP = T_PW + 1, T_EPI_WARP0 = T_PW + 2;
+constexpr int T_THREADS = T_PRODUCERS + 64 + 128;   // + MMA warp + TMA warp + 4 epilogue warps
+constexpr int T_NTAB = 4;                           // sample-table ring depth
+constexpr int T_AHEAD = 2;                          // tables are decoded this many K steps before their gather
+constexpr int T_SMEM_BUDGET = 150 * 1024;           // stage ring; the rest of the 228 KB stays L1 for the gather
+
+struct DcnTcParams {
+    DcnShape s;
+    int P, total_rows, tiles, n_slabs, taps, cdg, gs, stages, nbuf, stage_bytes;
+    // fused DynAgg mode
+    int fused, flow_scale, hp, wp;
+};
+
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
 }
+
+// round-to-nearest (ties away) to tf32 in one integer add: the tensor core ignores the low 13 mantissa bits
+__device__ __forceinline__ float tf32_round_bits(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// NCHW -> NHWC (fp32) through a 32x32 shared-memory tile; grid (ceil(HW/32), ceil(C/32), B), block (32, 8)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* s = src + (size_t)b * C * HW;
+    float* d = dst + (size_t)b * C * HW;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? __ldg(s + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) d[(size_t)p * C + c] = tile[threadIdx.x][i];
+    }
+}
+
+// W[co][c][tap] -> Wt[co][tap*C + c], rounded to tf32 (round-to-nearest, so the MMA's operand truncation is exact)
+__global__ void dcn_weight_repack_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int C, int K) {
+    const int total = Co * C * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % C, tap = (i / C) % K, co = i / (C * K);
+        wt[i] = to_tf32(__ldg(w + ((size_t)co * C + c) * K + tap));
+    }
+}
+
+constexpr int TAB_STRIDE = TBM + 4;   // per-group row stride of the sample table (+4: no bank conflicts)
+
+// One table entry = one (row, deform-group-in-slab).  Raw inputs are loaded one K step before they are decoded.
+struct RowCoord {
+    int b, p, oy, ox;   // b < 0: row outside the problem
+};
+struct RawParam {
+    float dy, dx, mk;
+    int b, yx, tij;   // yx = oy << 16 | ox, tij = ti << 8 | tj
+};
+
+template <bool FUSED>
+__device__ __forceinline__ RawParam load_raw_param(const DcnTcParams& prm, const float* __restrict__ offset,
+                                                   const float* __restrict__ mask,
+                                                   const long long* __restrict__ max_idx, const RowCoord& rc, int dgi,
+                                                   int tap, int ti, int tj) {
+    const DcnShape& s = prm.s;
+    RawParam r;
+    r.dy = r.dx = r.mk = 0.f;
+    r.b = rc.b;
+    r.yx = (rc.oy << 16) | rc.ox;
+    r.tij = (ti << 8) | tj;
+    if (rc.b < 0) return r;
+    const int K = prm.taps, P = prm.P;
+    if (!FUSED) {
+        const size_t ob = ((size_t)(rc.b * s.DG + dgi) * 2 * K + 2 * tap) * P + rc.p;
+        r.dy = __ldg(offset + ob);
+        r.dx = __ldg(offset + ob + P);
+        r.mk = __ldg(mask + ((size_t)(rc.b * s.DG + dgi) * K + tap) * P + rc.p);
+    } else {
+        const size_t cb = (size_t)rc.b * 3 * s.DG * K * P + rc.p;
+        r.dy = __ldg(offset + cb + (size_t)(2 * (dgi * K + tap)) * P);
+        r.dx = __ldg(offset + cb + (size_t)(2 * (dgi * K + tap) + 1) * P);
+        r.mk = __ldg(offset + cb + (size_t)(2 * s.DG * K + dgi * K + tap) * P);   // raw; sigmoid at decode
+        // pre-offset: s * flow[Y/s - i, X/s - j], zero outside the (h-2) x (w-2) flow grid
+        const int fy = rc.oy / prm.flow_scale - ti, fx = rc.ox / prm.flow_scale - tj;
+        if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
+            const int mi = (int)__ldg(max_idx + ((size_t)rc.b * prm.hp + fy) * prm.wp + fx);
+            const int my = mi / prm.wp, mx = mi - my * prm.wp;
+            r.dy += (float)((my - fy) * prm.flow_scale);
+            r.dx += (float)((mx - fx) * prm.flow_scale);
+        }
+    }
+    return r;
+}
+
+// Decode into the shared-memory sample table: element offset of the (clamped) top-left corner into the NHWC
+// input with two flag bits (bit0: +1 pixel in x is addressable, bit1: +1 row is addressable) and the four
+// bilinear weights with the modulation mask and corner validity folded in
+// (deform_conv_cuda_kernel.cu:468-497, :618-627).
+template <bool FUSED>
+__device__ __forceinline__ void store_param(const DcnTcParams& prm, const RawParam& r, int* __restrict__ tbase,
+                                            float* __restrict__ tw, int e, int wstride) {
+    const DcnShape& s = prm.s;
+    int base = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+    if (r.b >= 0) {
+        const int ti = r.tij >> 8, tj = r.tij & 255;
+        const float y = (float)((r.yx >> 16) * s.sh - s.ph + ti * s.dh) + r.dy;
+        const float x = (float)((r.yx & 0xffff) * s.sw - s.pw + tj * s.dw) + r.dx;
+        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+            const float mk = FUSED ? 1.f / (1.f + __expf(-r.mk)) : r.mk;
+            const int y0 = (int)floorf(y), x0 = (int)floorf(x);
+            const float ly = y - (float)y0, lx = x - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+            base = ((r.b * s.H + yc) * s.W + xc) * s.C;
+            if (tx0 && tx1) base |= 1;
+            if (ty0 && ty1) base |= 2;
+            // when the low corner is clamped away (y0 = -1 or x0 = -1) the "high" corner sits at the base itself
+            w0 = (ty0 && tx0) ? hy * hx * mk : 0.f;
+            w1 = (ty0 && tx1) ? hy * lx * mk : 0.f;
+            w2 = (ty1 && tx0) ? ly * hx * mk : 0.f;
+            w3 = (ty1 && tx1) ? ly * lx * mk : 0.f;
+        }
+    }
+    tbase[e] = base;
+    tw[e] = w0;
+    tw[e + wstride] = w1;
+    tw[e + 2 * wstride] = w2;
+    tw[e + 3 * wstride] = w3;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(T_THREADS, 1)
+dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ xt,
+              const float* __restrict__ offset,   // !FUSED: offset [B,2*DG*K,P];  FUSED: conv_out [B,3*DG*K,P]
+              const float* __restrict__ mask,     // !FUSED: mask [B,DG*K,P];      FUSED: unused
+              const long long* __restrict__ max_idx,  // FUSED: [B, hp, wp]
+              const float* __restrict__ bias, float* __restrict__ out, const DcnTcParams prm) {
+    // 1024-byte aligned dynamic shared memory (SWIZZLE_128B atoms); no pointer<->integer round trip, so the
+    // compiler keeps every access in the shared address space (LDS/STS, 32-bit addressing)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    const DcnShape& s = prm.s;
+    const int S = prm.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * prm.stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* tab_full = tempty + 2;          // [T_NTAB]
+    uint64_t* tab_empty = tab_full + T_NTAB;  // [T_NTAB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_empty + T_NTAB);
+    // sample-table ring: [T_NTAB][gs*TAB_STRIDE] ints + [T_NTAB][4][gs*TAB_STRIDE] floats
+    const int tab_n = prm.gs * TAB_STRIDE;
+    int* tab_base = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* tab_w = reinterpret_cast<float*>(tab_base + T_NTAB * tab_n);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Co = s.Co, C = s.C, K = prm.taps, P = prm.P;
+    const int nkb_tile = prm.n_slabs * K;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapW);
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], T_PW + 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        for (int a = 0; a < T_NTAB; ++a) {
+            mbar_init(&tab_full[a], T_PW);
+            mbar_init(&tab_empty[a], T_PW);
+        }
+        fence_mbar_init();
+    }
+    if (warp == T_MMA_WARP) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_tiles = (prm.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_kb = my_tiles * nkb_tile;   // K steps of this CTA, flattened over its tiles: (tile, slab, tap)
+
+    if (warp < T_PW) {
+        // ------------------------------------------------------------------ producer warps
+        // Iteration kb:  (L) issue the raw offset/mask loads of table kb+3,  (D) decode table kb+2 into the
+        // ring,  (G) gather K step kb from table kb into a free A stage.  Everything is mbarrier dataflow
+        // (one elected arrive per warp), so warps drift by up to two K steps and hide each other's latency.
+        const int tid = threadIdx.x;
+        const int ch = tid & 7;                    // 16-byte chunk (4 channels) within the 32-channel slab
+        const int r0 = tid >> 3;                   // rows r0 + T_RSTEP*i, i < T_ITEMS
+        const int gsub = (ch * 4) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
+        const int gslab = TBK / prm.cdg;           // deform groups per slab when cdg < 32 (else 0)
+        // table entries owned by this thread: row = tid (T_PRODUCERS == TBM), deform-group-in-slab j < gs
+        static_assert(T_PRODUCERS == TBM, "one table row per producer thread");
+        // load cursor (runs T_AHEAD + 1 steps ahead of the gather)
+        int l_kb = 0, l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0;
+        RowCoord rc;
+        auto decode_rows = [&](int tile) {
+            const int m = tile * TBM + tid;
+            rc.b = -1;
+            rc.p = rc.oy = rc.ox = 0;
+            if (m < prm.total_rows) {
+                rc.b = m / P;
+                rc.p = m - rc.b * P;
+                rc.oy = rc.p / s.Wo;
+                rc.ox = rc.p - rc.oy * s.Wo;
+            }
+        };
+        RawParam raw[4];
+        auto load_next = [&]() {      // raw <- inputs of table l_kb, then advance the load cursor
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < prm.gs) {
+                    const int dgi = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * gslab + j;
+                    raw[j] = load_raw_param<FUSED>(prm, offset, mask, max_idx, rc, dgi, l_tap, l_ti, l_tj);
+                }
+            }
+            ++l_kb;
+            if (++l_tj == s.kw) {
+                l_tj = 0;
+                ++l_ti;
+            }
+            if (++l_tap == K) {
+                l_tap = l_ti = l_tj = 0;
+                if (++l_slab == prm.n_slabs) {
+                    l_slab = 0;
+                    l_tile += gridDim.x;
+                    if (l_kb < total_kb) decode_rows(l_tile);
+                }
+            }
+        };
+        int d_slot = 0;
+        uint32_t d_phase = 0;
+        auto decode_store = [&]() {   // raw -> ring slot d_slot (table index = number of tables decoded so far)
+            mbar_wait(&tab_empty[d_slot], d_phase ^ 1);
+            int* tb = tab_base + d_slot * tab_n;
+            float* tw = tab_w + d_slot * 4 * tab_n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < prm.gs) store_param<FUSED>(prm, raw[j], tb, tw, j * TAB_STRIDE + tid, tab_n);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tab_full[d_slot]);
+            if (++d_slot == T_NTAB) {
+                d_slot = 0;
+                d_phase ^= 1;
+            }
+        };
+        // prologue: tables 0 .. T_AHEAD-1 decoded, table T_AHEAD loaded
+        if (total_kb > 0) decode_rows(l_tile);
+        for (int i = 0; i < T_AHEAD && i < total_kb; ++i) {
+            load_next();
+            decode_store();
+        }
+        if (T_AHEAD < total_kb) load_next();
+
+        int stage = 0, c_slab = 0, c_tap = 0, g_slot = 0;
+        uint32_t phase = 0, g_phase = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            // (D) table kb + T_AHEAD from the raw values loaded one iteration ago, (L) loads of the one after
+            if (kb + T_AHEAD < total_kb) decode_store();
+            if (kb + T_AHEAD + 1 < total_kb) load_next();
+            // (G)
+            const int c0 = c_slab * TBK + ch * 4;
+            const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE;
+            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE;
+            mbar_wait(&tab_full[g_slot], g_phase);
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
+#pragma unroll
+            for (int bt = 0; bt < T_ITEMS / T_BATCH; ++bt) {
+                float4 v[T_BATCH][4];
+                float w[T_BATCH][4];
+#pragma unroll
+                for (int ii = 0; ii < T_BATCH; ++ii) {
+                    const int r = r0 + T_RSTEP * (bt * T_BATCH + ii);
+                    const int bf = tb[r];
+                    w[ii][0] = tw[r];
+                    w[ii][1] = tw[r + tab_n];
+                    w[ii][2] = tw[r + 2 * tab_n];
+                    w[ii][3] = tw[r + 3 * tab_n];
+                    const float* base = xt + (size_t)(bf & ~3) + c0;
+                    const int dxo = (bf & 1) ? C : 0, dyo = (bf & 2) ? s.W * C : 0;
+                    v[ii][0] = ldg4(base);
+                    v[ii][1] = ldg4(base + dxo);
+                    v[ii][2] = ldg4(base + dyo);
+                    v[ii][3] = ldg4(base + dyo + dxo);
+                }
+#pragma unroll
+                for (int ii = 0; ii < T_BATCH; ++ii) {
+                    const int r = r0 + T_RSTEP * (bt * T_BATCH + ii);
+                    float4 o;
+                    o.x = tf32_round_bits(w[ii][0] * v[ii][0].x + w[ii][1] * v[ii][1].x + w[ii][2] * v[ii][2].x + w[ii][3] * v[ii][3].x);
+                    o.y = tf32_round_bits(w[ii][0] * v[ii][0].y + w[ii][1] * v[ii][1].y + w[ii][2] * v[ii][2].y + w[ii][3] * v[ii][3].y);
+                    o.z = tf32_round_bits(w[ii][0] * v[ii][0].z + w[ii][1] * v[ii][1].z + w[ii][2] * v[ii][2].z + w[ii][3] * v[ii][3].z);
+                    o.w = tf32_round_bits(w[ii][0] * v[ii][0].w + w[ii][1] * v[ii][1].w + w[ii][2] * v[ii][2].w + w[ii][3] * v[ii][3].w);
+                    const int rr = r & 127;
+                    uint8_t* dst = A + (r >> 7) * (128 * 128) + rr * 128 + ((ch ^ (rr & 7)) << 4);
+                    *reinterpret_cast<float4*>(dst) = o;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[stage]);
+                mbar_arrive(&tab_empty[g_slot]);
+            }
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+            if (++g_slot == T_NTAB) {
+                g_slot = 0;
+                g_phase ^= 1;
+            }
+            if (++c_tap == K) {
+                c_tap = 0;
+                if (++c_slab == prm.n_slabs) c_slab = 0;
+            }
+        }
+    } else if (warp == T_MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(2, 128, Co);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
+                const int buf = it % prm.nbuf;
+                const uint32_t bphase = (it / prm.nbuf) & 1;
+                mbar_wait_backoff(&tempty[buf], bphase ^ 1, 64);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * 2 * Co;
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < nkb_tile; ++kb) {
+                    mbar_wait_backoff(&full[stage], phase, 20);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
+                    const uint32_t sb = sa + T_A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t db = umma_desc_sw128(sb + kk * 32, 0);
+                        umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), db, idesc, accumulate);
+                        umma_tf32(tacc + Co, umma_desc_sw128(sa + 128 * 128 + kk * 32, 0), db, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == T_TMA_WARP) {
+        // ------------------------------------------------------------------ TMA producer for the weight tiles
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x) {
+                for (int slab = 0; slab < prm.n_slabs; ++slab) {
+                    for (int tap = 0; tap < K; ++tap) {
+                        mbar_wait_backoff(&empty[stage], phase ^ 1, 32);
+                        mbar_expect_tx(&full[stage], Co * 128);
+                        tma_load_3d(smem + (size_t)stage * prm.stage_bytes + T_A_BYTES, &mapW, &full[stage],
+                                    tap * C + slab * TBK, 0, 0);
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps)
+        const int q = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
+            const int buf = it % prm.nbuf;
+            const uint32_t bphase = (it / prm.nbuf) & 1;
+            mbar_wait_backoff(&tfull[buf], bphase, 256);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int m = tile * TBM + half * 128 + q * 32 + lane;
+                const bool ok = m < prm.total_rows;
+                const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
+                float* o = out + (size_t)b * Co * P + p;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * Co + half * Co;
+                for (int c0 = 0; c0 < Co; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            if (c0 + e < Co) {
+                                const float bv = bias ? __ldg(bias + c0 + e) : 0.f;
+                                o[(size_t)(c0 + e) * P] = __uint_as_float(v[e]) + bv;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+bool dcn_tc_eligible(const DcnShape& s) {
+    const int cdg = s.C / s.DG;
+    // a 32-channel slab must cover whole deform groups (cdg | 32) or lie inside one (32 | cdg)
+    const bool slab_ok = (cdg >= TBK) ? (cdg % TBK == 0) : (TBK % cdg == 0 && cdg % 4 == 0 && TBK / cdg <= 4);
+    return s.G == 1 && s.C % TBK == 0 && slab_ok && s.Co % 32 == 0 && s.Co >= 32 && s.Co <= 256 &&
+           (size_t)s.B * s.C * s.H * s.W < ((size_t)1 << 31) && s.Ho < 32768 && s.Wo < 65536;
+}
+
+size_t dcn_tc_workspace_bytes(const DcnShape& s, int mode) {
+    if (mode == MREFSR_DCN_FP32 || !dcn_tc_eligible(s)) return 0;
+    return align_up((size_t)s.B * s.C * s.H * s.W * 4, 1024) + align_up((size_t)s.Co * s.C * s.kh * s.kw * 4, 1024);
+}
+
+static int make_weight_map(CUtensorMap* map, const float* wt, int Co, int Ktot) {
+    // 2-D tensor [Co rows][Ktot cols] fp32, box = 32 cols x Co rows, 128-byte swizzle; encoded as 3-D with d2 = 1
+    return make_tensor_map_3d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wt, (uint64_t)Ktot, (uint64_t)Co, 1, TBK,
+                              (uint32_t)Co, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const float* off, const float* mask,
+                        const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+    const size_t need = dcn_tc_workspace_bytes(s, MREFSR_DCN_TF32);
+    MREFSR_CHECK(workspace && workspace_bytes >= need, ERR_WORKSPACE, "dcn forward: workspace too small (%zu < %zu)",
+                 workspace_bytes, need);
+    MREFSR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, ERR_WORKSPACE,
+                 "dcn forward: workspace must be 1024-byte aligned");
+    float* xt = static_cast<float*>(workspace);
+    float* wt = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align_up((size_t)s.B * s.C * s.H * s.W * 4, 1024));
+    const int K = s.kh * s.kw, HW = s.H * s.W;
+    {
+        ScopedTiming tm(MREFSR_K_DCN_AUX, st);
+        nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(s.C, 32), s.B), dim3(32, 8), 0, st>>>(x, xt, s.C, HW);
+        MREFSR_LAUNCH_CHECK();
+        dcn_weight_repack_kernel<<<cdiv(s.Co * s.C * K, 256), 256, 0, st>>>(w, wt, s.Co, s.C, K);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(2);
+    }
+    CUtensorMap mapW;
+    int rc = make_weight_map(&mapW, wt, s.Co, K * s.C);
+    if (rc) return rc;
+    DcnTcParams prm;
+    prm.s = s;
+    prm.P = s.Ho * s.Wo;
+    prm.total_rows = s.B * prm.P;
+    prm.tiles = cdiv(prm.total_rows, TBM);
+    prm.n_slabs = s.C / TBK;
+    prm.taps = K;
+    prm.cdg = s.C / s.DG;
+    prm.gs = prm.cdg >= TBK ? 1 : TBK / prm.cdg;
+    prm.stage_bytes = T_A_BYTES + s.Co * 128;
+    const size_t table_bytes = (size_t)T_NTAB * 5 * prm.gs * (TBM + 4) * 4;
+    prm.stages = (int)((T_SMEM_BUDGET - (int)table_bytes) / prm.stage_bytes);
+    if (prm.stages > 4) prm.stages = 4;
+    if (prm.stages < 2) prm.stages = 2;
+    prm.nbuf = (2 * s.Co * 2 <= 512) ? 2 : 1;
+    prm.fused = max_idx != nullptr;
+
+    prm.flow_scale = flow_scale;
+    prm.hp = prm.wp = 0;
+    if (prm.fused) {
+        MREFSR_CHECK(flow_scale >= 1 && s.Ho % flow_scale == 0 && s.Wo % flow_scale == 0, ERR_BAD_ARG,
+                     "fused DynAgg: output %dx%d not a multiple of the flow scale %d", s.Ho, s.Wo, flow_scale);
+        prm.hp = s.Ho / flow_scale - 2;
+        prm.wp = s.Wo / flow_scale - 2;
+        MREFSR_CHECK(prm.hp > 0 && prm.wp > 0, ERR_BAD_ARG, "fused DynAgg: feature grid too small");
+    }
+    const size_t smem = (size_t)prm.stages * prm.stage_bytes + 256 + table_bytes + 1024;
+    int grid = sm_count();
+    if (grid > prm.tiles) grid = prm.tiles;
+    ScopedTiming tm(MREFSR_K_DCN_FWD, st);
+    if (prm.fused) {
+        auto kern = dcn_tc_kernel<true>;
+        MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, nullptr, max_idx, bias, out, prm);
+    } else {
+        auto kern = dcn_tc_kernel<false>;
+        MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, mask, nullptr, bias, out, prm);
+    }
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
+                   const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    return dcn_forward_tc_impl(x, w, bias, off, mask, nullptr, 1, out, s, workspace, workspace_bytes, st);
+}
+
 }  // namespace mrefsr

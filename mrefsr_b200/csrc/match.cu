@@ -289,8 +289,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 const float2* __restrict__ colsb, unsigned long long* __restrict__ keys, const TcParams prm) {
     using Cfg = TcCfg<STRIP, NPASS>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte aligned dynamic shared memory (SWIZZLE_128B atoms); no pointer<->integer round trip, so the
+    // compiler keeps every access in the shared address space (LDS/STS, 32-bit addressing)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* stage_base = smem;
     float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BN]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_sb) + 2 * BN * 8);
@@ -341,7 +343,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     for (int g = 0; g < Cfg::GROUPS; ++g) {
                         const int ti = (STRIP == 3) ? g : g / 3, tj = (STRIP == 3) ? 0 : g % 3;
                         const int ra = m0 + ti * prm.w_in + tj, rb = n0 + ti * prm.w_ref + tj;
-                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_wait_backoff(&empty[stage], phase ^ 1, 64);
                         uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
                         uint8_t* sbm = sa + Cfg::NSPLIT * Cfg::A_BYTES;
                         mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
@@ -377,7 +379,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 int ncols = prm.hw_ref - nt * BN;
                 ncols = ncols > BN ? BN : ((ncols + 31) & ~31);
                 const uint32_t idesc = umma_idesc(1, BM, ncols);
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait_backoff(&tempty[acc], acc_phase ^ 1, 64);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + acc * BN;
                 uint32_t accumulate = 0;
@@ -433,7 +435,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             const float2* gsb = colsb + (size_t)pair * prm.colsb_stride + n0;
             for (int i = et; i < ncols; i += 128) sbuf[i] = gsb[i];
             named_bar_sync(1, 128);
-            mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait_backoff(&tfull[acc], acc_phase, 512);
             tc_fence_after();
             float best = -INFINITY;
             int bestn = 0;

@@ -69,6 +69,34 @@ def dcn_forward_raw(input, offset, mask, weight, bias, stride, padding, dilation
     return out
 
 
+def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups):
+    """Fused DynAgg forward for inference (no autograd): DCNv2 (3x3, stride 1, pad 1) whose offsets and masks are
+    assembled inside the gather from the raw conv_offset_mask output and the matcher's arg-max map
+    (ref_mrapa_restoration_arch.py:45-76 + corres_generation_arch.py:30-47, :70-105 for one scale).
+    input [B,C,H,W], conv_out [B,3*dg*9,H,W], max_idx int64 [B,H/s-2,W/s-2] -> [B,Co,H,W]."""
+    _lib.require_cuda(input, conv_out, max_idx, weight, bias)
+    lib = _lib.lib()
+    x, co_, wgt = (t.contiguous().float() for t in (input, conv_out, weight))
+    bs = bias.contiguous().float() if bias is not None else None
+    mi = max_idx.contiguous()
+    b, c, h, w = x.shape
+    co = wgt.shape[0]
+    dg = deformable_groups
+    if tuple(co_.shape) != (b, 3 * dg * 9, h, w):
+        raise RuntimeError('conv_out shape %s, expected %s' % (tuple(co_.shape), (b, 3 * dg * 9, h, w)))
+    if mi.dtype != torch.int64 or tuple(mi.shape) != (b, h // flow_scale - 2, w // flow_scale - 2):
+        raise RuntimeError('max_idx must be int64 [%d,%d,%d]' % (b, h // flow_scale - 2, w // flow_scale - 2))
+    out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, DCN_TF32, 0)
+        ws, ws_bytes = _lib.workspace(nbytes, x.device)
+        rc = lib.mrefsr_dynagg_dcn_forward(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
+                                           int(flow_scale), _lib.ptr(out), b, c, h, w, co, dg, int(bs is not None), ws,
+                                           ws_bytes, _lib.stream_ptr(x.device))
+    _lib.check(rc, 'mrefsr_dynagg_dcn_forward')
+    return out
+
+
 class ModulatedDeformConvFunction(Function):
 
     @staticmethod

@@ -69,6 +69,17 @@ class DynAgg(ModulatedDeformConv2d):
             return None
         return float(self._stats.item()) / self._stats_count
 
+    def forward_fused(self, x, max_idx, flow_scale):
+        """Inference fast path (no autograd): same result as forward(x, pre_offset) where pre_offset is the
+        matcher's shifted flow at this scale, but offsets / masks / pre-offsets never touch HBM."""
+        from .dcn import dynagg_dcn_forward
+        if self.extra_offset_mask:
+            out = self.conv_offset_mask(x[1])
+            x = x[0]
+        else:
+            out = self.conv_offset_mask(x)
+        return dynagg_dcn_forward(x, out, max_idx, flow_scale, self.weight, self.bias, self.deform_groups)
+
     def forward(self, x, pre_offset):
         if self.extra_offset_mask:
             out = self.conv_offset_mask(x[1])

@@ -88,6 +88,57 @@ def test_backward_vs_oracle(cfg):
         assert rel_err(t.grad, r) <= TOL, name
 
 
+@pytest.mark.parametrize('cfg', [dict(b=3, c=64, h=16, w=24, s=4), dict(b=2, c=128, h=12, w=12, s=2),
+                                 dict(b=2, c=256, h=10, w=14, s=1), dict(b=1, c=32, h=8, w=8, s=1, dg=2)])
+def test_fused_dynagg_vs_oracle(cfg):
+    """Fused DynAgg (conv_out + max_idx -> DCN) against the oracle composition pre_offsets -> glue -> DCN."""
+    b, c, h, w, s = (cfg[k] for k in ('b', 'c', 'h', 'w', 's'))
+    dg = cfg.get('dg', 8)
+    g = torch.Generator().manual_seed(17)
+    hc, wc = h // s, w // s
+    max_idx = torch.randint(0, (hc - 2) * (wc - 2), (b, hc - 2, wc - 2), generator=g)
+    x = torch.randn(b, c, h, w, generator=g)
+    conv_out = torch.randn(b, 3 * dg * 9, h, w, generator=g) * 0.7
+    wgt = torch.randn(c, c, 3, 3, generator=g) * (c * 9) ** -0.5
+    bias = torch.randn(c, generator=g) * 0.1
+    key = {1: 'relu3_1', 2: 'relu2_1', 4: 'relu1_1'}[s]
+    pre = torch.stack([oracle.pre_offsets_oracle(max_idx[i])[key] for i in range(b)], 0)
+    off, mask = oracle.dynagg_offsets_oracle(conv_out, pre, dg)
+    ref = oracle.modulated_deform_conv_oracle(x, off, mask, wgt, bias, 1, 1, 1, 1, dg, dtype=torch.float64)
+    out = D.dynagg_dcn_forward(x.to(DEV), conv_out.to(DEV), max_idx.to(DEV), s, wgt.to(DEV), bias.to(DEV), dg)
+    assert rel_err(out, ref) <= TOL
+    # and the module-level fast path agrees with the reference-API path
+    m = M.DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True).to(DEV)
+    m.conv_offset_mask.weight.data.normal_(0, 0.02)
+    m.conv_offset_mask.bias.data.normal_(0, 0.3)
+    feat = torch.randn(b, c, h, w, generator=g).to(DEV)
+    with torch.no_grad():
+        y1 = m([x.to(DEV), feat], pre.to(DEV))
+        y2 = m.forward_fused([x.to(DEV), feat], max_idx.to(DEV), s)
+    assert rel_err(y2, y1) <= TOL
+
+
+@pytest.mark.parametrize('cfg', [dict(b=2, c=64, h=20, w=24, co=64, dg=8), dict(b=1, c=256, h=10, w=12, co=256, dg=8),
+                                 dict(b=3, c=32, h=7, w=5, co=96, dg=2, off_scale=5.0),
+                                 dict(b=1, c=64, h=9, w=9, co=32, dg=4, stride=2, pad=1, dil=1)])
+def test_tf32_mode_explicit(cfg):
+    cfg = dict(cfg)
+    b, c, h, w, co, dg = (cfg.pop(k) for k in ('b', 'c', 'h', 'w', 'co', 'dg'))
+    stride, pad, dil = cfg.get('stride', 1), cfg.get('pad', 1), cfg.get('dil', 1)
+    x, off, mask, wgt, bias = _rand_problem(b, c, h, w, co, dg, 5, **cfg)
+    ref = oracle.modulated_deform_conv_oracle(x, off, mask, wgt, bias, stride, pad, dil, 1, dg, dtype=torch.float64)
+    out = D.dcn_forward_raw(x.to(DEV), off.to(DEV), mask.to(DEV), wgt.to(DEV), bias.to(DEV), (stride,) * 2, (pad,) * 2,
+                            (dil,) * 2, 1, dg, mode='tf32')
+    assert rel_err(out, ref) <= TOL
+
+
+def test_tf32_mode_rejects_ineligible():
+    x, off, mask, wgt, bias = _rand_problem(1, 8, 6, 6, 8, 2, 1)
+    with pytest.raises(RuntimeError):
+        D.dcn_forward_raw(x.to(DEV), off.to(DEV), mask.to(DEV), wgt.to(DEV), bias.to(DEV), (1, 1), (1, 1), (1, 1), 1, 2,
+                          mode='tf32')
+
+
 def test_zero_offset_is_plain_conv():
     """Known answer: zero offsets and mask 1 reduce DCNv2 to F.conv2d."""
     x, off, mask, wgt, bias = _rand_problem(2, 32, 12, 12, 16, 4, 3)

@@ -89,14 +89,14 @@ def matcher_timing():
 
 def dcn_timing():
     for (c, hw) in [(256, 40), (128, 80), (64, 160)]:
-        n = 16
+        n = 80
         g = torch.Generator().manual_seed(0)
         x = torch.randn(n, c, hw, hw, generator=g).to(DEV)
         off = (torch.randn(n, 144, hw, hw, generator=g) * 3).to(DEV)
         mask = torch.rand(n, 72, hw, hw, generator=g).to(DEV)
         wgt = (torch.randn(c, c, 3, 3, generator=g) * 0.02).to(DEV)
         bias = torch.zeros(c).to(DEV)
-        for mode in ('fp32', 'auto'):
+        for mode in ('tf32',):
             try:
                 ms = timeit(lambda: D.dcn_forward_raw(x, off, mask, wgt, bias, (1, 1), (1, 1), (1, 1), 1, 8, mode=mode), iters=3)
                 flops = 2.0 * c * c * 9 * hw * hw * n
@@ -104,6 +104,16 @@ def dcn_timing():
                 emit(test='dcn_timing', C=c, hw=hw, mode=mode, ms=ms, tflops=flops / ms / 1e9, gbs=byt / ms / 1e6)
             except Exception as e:  # noqa: BLE001
                 emit(test='dcn_timing', C=c, hw=hw, mode=mode, error=repr(e)[:300])
+        try:
+            _lib.timing_enable(True); _lib.timing_read()
+            conv_out = (torch.randn(n, 216, hw, hw, generator=g) * 0.5).to(DEV)
+            mi = torch.randint(0, 38 * 38, (n, 38, 38), generator=g).to(DEV)
+            ms = timeit(lambda: D.dynagg_dcn_forward(x, conv_out, mi, hw // 40, wgt, bias, 8), iters=5)
+            t = _lib.timing_read(); _lib.timing_enable(False)
+            emit(test='dcn_fused_timing', C=c, hw=hw, ms=ms, ms_main=t['dcn_fwd'][0] / max(1, t['dcn_fwd'][1]),
+                 ms_aux=t['dcn_aux'][0] / max(1, t['dcn_aux'][1]), gbs=4.0 * hw * hw * (c + 216 + c) * n / ms / 1e6)
+        except Exception as e:  # noqa: BLE001
+            emit(test='dcn_fused_timing', C=c, hw=hw, error=repr(e)[:300])
         # spot parity on sample 0 against the C oracle
         try:
             out = D.dcn_forward_raw(x[:1], off[:1], mask[:1], wgt, bias, (1, 1), (1, 1), (1, 1), 1, 8, mode='auto')
