@@ -65,7 +65,33 @@ def make_inputs(b, r, seed, device, pin=False):
             return t.to(device)
         return t.pin_memory() if pin else t
 
-    d = {'feat_in': rnd(b, 256, 40, 40), 'feat_ref': rnd(b * r, 256, 40, 40)}
+    # matcher features: each image gets references that are integer translations of itself
+    # (known arg-max, similarity ~ 1), independent references (near-tie stress) and one zero-padded reference
+    # (exact-tie plateau, like CUFED5's pad-to-500^2)
+    big = torch.randn(b, 256, 48, 48, generator=g)
+    fin = big[:, :, 4:44, 4:44].contiguous()
+    refs = []
+    for k in range(r):
+        kind = k % 5
+        if kind == 0:
+            ref = big[:, :, 3:43, 2:42]
+        elif kind == 1:
+            ref = big[:, :, 7:47, 5:45]
+        elif kind == 4:
+            ref = big[:, :, 2:42, 6:46].clone()
+            ref[:, :, 30:, :] = 0
+            ref[:, :, :, 32:] = 0
+        else:
+            ref = torch.randn(b, 256, 40, 40, generator=g)
+        refs.append(ref)
+    fref = torch.stack(refs, 1).reshape(b * r, 256, 40, 40).contiguous()
+
+    def place(t):
+        if device != 'cpu':
+            return t.to(device)
+        return t.pin_memory() if pin else t
+
+    d = {'feat_in': place(fin), 'feat_ref': place(fref)}
     for c, hw in SCALES:
         d[f'x{c}'] = rnd(b * r, c, hw, hw)                          # reference VGG features (DCN input)
         d[f'conv_out{c}'] = rnd(b * r, 3 * DG * 9, hw, hw, scale=0.5)  # raw conv_offset_mask output

@@ -79,6 +79,96 @@ mrapa_fwd_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb,
     }
 }
 
+// Vectorised forward: each lane owns 4 consecutive pixels (one 16-byte load per plane and lane, 512 bytes per
+// warp-level load), CTA = 128 pixels x 8 warps.  Needs HW % 4 == 0 and 16-byte aligned tensors.
+__device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(FW * 32)
+mrapa_fwd_vec4_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb, const float* __restrict__ ass,
+                      float* __restrict__ out, float* __restrict__ prob, int t, int C, int Cv, int HW) {
+    constexpr int TMAX = 8;
+    __shared__ float4 part[FW][TMAX][32];
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = (blockIdx.x * 32 + lane) * 4;
+    const bool ok = p < HW;
+    const int pc = ok ? p : 0;
+    float4 l[TMAX];
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) l[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* q = emb_t + (size_t)n * C * HW + pc;
+    const float* k = emb + (size_t)n * t * C * HW + pc;
+    const int cper = (C + FW - 1) / FW;
+    const int cbeg = warp * cper, cend = min(C, cbeg + cper);
+#pragma unroll 2
+    for (int c = cbeg; c < cend; ++c) {
+        const float4 qv = ldcs4(q + (size_t)c * HW);
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) {
+                const float4 kv = ldcs4(k + ((size_t)i * C + c) * HW);
+                l[i].x = fmaf(qv.x, kv.x, l[i].x);
+                l[i].y = fmaf(qv.y, kv.y, l[i].y);
+                l[i].z = fmaf(qv.z, kv.z, l[i].z);
+                l[i].w = fmaf(qv.w, kv.w, l[i].w);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) part[warp][i][lane] = l[i];
+    __syncthreads();
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < FW; ++w) {
+            const float4 pv = part[w][i][lane];
+            sacc.x += pv.x; sacc.y += pv.y; sacc.z += pv.z; sacc.w += pv.w;
+        }
+        l[i] = sacc;
+        if (i < t) {
+            mx.x = fmaxf(mx.x, sacc.x); mx.y = fmaxf(mx.y, sacc.y); mx.z = fmaxf(mx.z, sacc.z); mx.w = fmaxf(mx.w, sacc.w);
+        }
+    }
+    float4 den = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        if (i < t) {
+            l[i].x = expf(l[i].x - mx.x); l[i].y = expf(l[i].y - mx.y); l[i].z = expf(l[i].z - mx.z); l[i].w = expf(l[i].w - mx.w);
+        } else {
+            l[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        den.x += l[i].x; den.y += l[i].y; den.z += l[i].z; den.w += l[i].w;
+    }
+    const float4 inv = make_float4(1.f / den.x, 1.f / den.y, 1.f / den.z, 1.f / den.w);
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+        l[i].x *= inv.x; l[i].y *= inv.y; l[i].z *= inv.z; l[i].w *= inv.w;
+    }
+    if (prob && warp == 0 && ok) {
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) *reinterpret_cast<float4*>(prob + ((size_t)n * t + i) * HW + p) = l[i];
+    }
+    const float* v = ass + (size_t)n * t * Cv * HW + pc;
+    float* o = out + (size_t)n * Cv * HW + p;
+    const int vper = (Cv + FW - 1) / FW;
+    const int vbeg = warp * vper, vend = min(Cv, vbeg + vper);
+#pragma unroll 2
+    for (int c = vbeg; c < vend; ++c) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < TMAX; ++i)
+            if (i < t) {
+                const float4 vv = ldcs4(v + ((size_t)i * Cv + c) * HW);
+                acc.x = fmaf(l[i].x, vv.x, acc.x);
+                acc.y = fmaf(l[i].y, vv.y, acc.y);
+                acc.z = fmaf(l[i].z, vv.z, acc.z);
+                acc.w = fmaf(l[i].w, vv.w, acc.w);
+            }
+        if (ok) __stcs(reinterpret_cast<float4*>(o + (size_t)c * HW), acc);
+    }
+}
+
 // backward:
 //   g_ass[t][cv] = p[t] * go[cv];   dp[t] = sum_cv go[cv] * v[t][cv];   dl[t] = p[t] * (dp[t] - sum_s p[s] dp[s])
 //   g_q[c] = sum_t dl[t] * k[t][c];   g_k[t][c] = dl[t] * q[c]
@@ -168,6 +258,13 @@ int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const f
     const int HW = h * w;
     dim3 grid(cdiv(HW, 32), n);
     ScopedTiming tm(MREFSR_K_FUSION_FWD, st);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (t <= 8 && HW % 4 == 0 && al16(emb_t) && al16(emb) && al16(ass) && al16(out) && (!prob || al16(prob))) {
+        mrapa_fwd_vec4_kernel<<<dim3(cdiv(HW, 128), n), FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+        return 0;
+    }
     if (t <= 8)
         mrapa_fwd_kernel<8><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
     else

@@ -552,12 +552,14 @@ static int launch_tc(const MatchPlan& pl, uint8_t* ws, int n_in, int n_pairs, in
     prm.in_div = in_div;
     prm.n_in = n_in;
     prm.C = C;
-    prm.hw_in = pl.hw_in;
+    // only pixel-linear indices up to the last valid 3x3 patch origin, (h-3)*w + (w-3), need computing: the two
+    // bottom rows can never be an origin (the right-hand columns inside the range are masked by colsb / finalize)
+    prm.hw_in = (pl.hw_in / w_in - 3) * w_in + (w_in - 2);
     prm.w_in = w_in;
-    prm.hw_ref = pl.hw_ref;
+    prm.hw_ref = (pl.hw_ref / w_ref - 3) * w_ref + (w_ref - 2);
     prm.w_ref = w_ref;
-    prm.m_tiles = cdiv(pl.hw_in, Cfg::BM);
-    prm.n_tiles = cdiv(pl.hw_ref, Cfg::BN);
+    prm.m_tiles = cdiv(prm.hw_in, Cfg::BM);
+    prm.n_tiles = cdiv(prm.hw_ref, Cfg::BN);
     prm.total_items = n_pairs * prm.m_tiles * prm.n_tiles;
     prm.key_stride = pl.key_stride;
     prm.colsb_stride = pl.colsb_stride;
