@@ -27,20 +27,16 @@ namespace mrefsr {
 constexpr int TBM = 256;            // rows (output positions) per CTA tile
 constexpr int TBK = 32;             // fp32 channels per K step (128-byte rows)
 constexpr int T_A_BYTES = TBM * 128;
-#ifndef MREFSR_DCN_PW
-#define MREFSR_DCN_PW 8
-#endif
-constexpr int T_PW = MREFSR_DCN_PW;  // producer warps: sample table (2 K steps ahead) + gather, mbarrier dataflow
+constexpr int T_PW = 16;             // producer warps: sample table (2 K steps ahead) + gather; warps 0..3 also drain TMEM
 constexpr int T_RSTEP = T_PW * 4;    // row stride between a thread's gather items
-constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items per thread per K step
-constexpr int T_BATCH = 4;                         // items whose loads are issued together
-constexpr int T_ENT = 4 * TBM / (T_PW * 32);       // max table entries per thread (gs = 4)
+constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items per thread per K step (4)
+constexpr int T_BATCH = 2;                         // items whose loads are issued together
 constexpr int T_PRODUCERS = T_PW * 32;
-constexpr int T_MMA_WARP = T_PW, T_TMA_WARP = T_PW + 1, T_EPI_WARP0 = T_PW + 2;
-constexpr int T_THREADS = T_PRODUCERS + 64 + 128;   // + MMA warp + TMA warp + 4 epilogue warps
-constexpr int T_NTAB = 4;                           // sample-table ring depth
-constexpr int T_AHEAD = 2;                          // tables are decoded this many K steps before their gather
-constexpr int T_SMEM_BUDGET = 150 * 1024;           // stage ring; the rest of the 228 KB stays L1 for the gather
+constexpr int T_MMA_WARP = T_PW;
+constexpr int T_THREADS = T_PRODUCERS + 32;        // + the MMA warp (17 warps: register budget 100/thread)
+constexpr int T_NTAB = 4;                          // sample-table ring depth
+constexpr int T_AHEAD = 2;                         // tables are decoded this many K steps before their gather
+constexpr int T_SMEM_BUDGET = 150 * 1024;          // stage ring; the rest of the 228 KB stays L1 for the gather
 
 struct DcnTcParams {
     DcnShape s;
@@ -53,6 +49,19 @@ __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
+}
+
+// Loads whose issue point matters (software pipelining): volatile asm keeps program order with respect to the
+// mbarrier waits, so the compiler cannot sink them down to their first use one K step later.
+__device__ __forceinline__ float ldg_early(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ long long ldg_early_s64(const long long* p) {
+    long long v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
 }
 
 // round-to-nearest (ties away) to tf32 in one integer add: the tensor core ignores the low 13 mantissa bits
@@ -95,6 +104,7 @@ struct RowCoord {
 struct RawParam {
     float dy, dx, mk;
     int b, yx, tij;   // yx = oy << 16 | ox, tij = ti << 8 | tj
+    int mi, fyx;      // fused mode: matched index and flow-grid cell (fy << 16 | fx), fyx < 0: no pre-offset
 };
 
 template <bool FUSED>
@@ -105,6 +115,8 @@ __device__ __forceinline__ RawParam load_raw_param(const DcnTcParams& prm, const
     const DcnShape& s = prm.s;
     RawParam r;
     r.dy = r.dx = r.mk = 0.f;
+    r.mi = 0;
+    r.fyx = -1;
     r.b = rc.b;
     r.yx = (rc.oy << 16) | rc.ox;
     r.tij = (ti << 8) | tj;
@@ -112,21 +124,21 @@ __device__ __forceinline__ RawParam load_raw_param(const DcnTcParams& prm, const
     const int K = prm.taps, P = prm.P;
     if (!FUSED) {
         const size_t ob = ((size_t)(rc.b * s.DG + dgi) * 2 * K + 2 * tap) * P + rc.p;
-        r.dy = __ldg(offset + ob);
-        r.dx = __ldg(offset + ob + P);
-        r.mk = __ldg(mask + ((size_t)(rc.b * s.DG + dgi) * K + tap) * P + rc.p);
+        r.dy = ldg_early(offset + ob);
+        r.dx = ldg_early(offset + ob + P);
+        r.mk = ldg_early(mask + ((size_t)(rc.b * s.DG + dgi) * K + tap) * P + rc.p);
     } else {
         const size_t cb = (size_t)rc.b * 3 * s.DG * K * P + rc.p;
-        r.dy = __ldg(offset + cb + (size_t)(2 * (dgi * K + tap)) * P);
-        r.dx = __ldg(offset + cb + (size_t)(2 * (dgi * K + tap) + 1) * P);
-        r.mk = __ldg(offset + cb + (size_t)(2 * s.DG * K + dgi * K + tap) * P);   // raw; sigmoid at decode
-        // pre-offset: s * flow[Y/s - i, X/s - j], zero outside the (h-2) x (w-2) flow grid
+        r.dy = ldg_early(offset + cb + (size_t)(2 * (dgi * K + tap)) * P);
+        r.dx = ldg_early(offset + cb + (size_t)(2 * (dgi * K + tap) + 1) * P);
+        r.mk = ldg_early(offset + cb + (size_t)(2 * s.DG * K + dgi * K + tap) * P);   // raw; sigmoid at decode
+        // pre-offset: s * flow[Y/s - i, X/s - j], zero outside the (h-2) x (w-2) flow grid; the arg-max value
+        // is kept raw (r.mi) and turned into a flow at decode time so that this load is not waited on here
         const int fy = rc.oy / prm.flow_scale - ti, fx = rc.ox / prm.flow_scale - tj;
+        r.fyx = -1;
         if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
-            const int mi = (int)__ldg(max_idx + ((size_t)rc.b * prm.hp + fy) * prm.wp + fx);
-            const int my = mi / prm.wp, mx = mi - my * prm.wp;
-            r.dy += (float)((my - fy) * prm.flow_scale);
-            r.dx += (float)((mx - fx) * prm.flow_scale);
+            r.mi = (int)ldg_early_s64(max_idx + ((size_t)rc.b * prm.hp + fy) * prm.wp + fx);
+            r.fyx = (fy << 16) | fx;
         }
     }
     return r;
@@ -144,8 +156,14 @@ __device__ __forceinline__ void store_param(const DcnTcParams& prm, const RawPar
     float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
     if (r.b >= 0) {
         const int ti = r.tij >> 8, tj = r.tij & 255;
-        const float y = (float)((r.yx >> 16) * s.sh - s.ph + ti * s.dh) + r.dy;
-        const float x = (float)((r.yx & 0xffff) * s.sw - s.pw + tj * s.dw) + r.dx;
+        float dy = r.dy, dx = r.dx;
+        if (FUSED && r.fyx >= 0) {
+            const int my = r.mi / prm.wp, mx = r.mi - my * prm.wp;
+            dy += (float)((my - (r.fyx >> 16)) * prm.flow_scale);
+            dx += (float)((mx - (r.fyx & 0xffff)) * prm.flow_scale);
+        }
+        const float y = (float)((r.yx >> 16) * s.sh - s.ph + ti * s.dh) + dy;
+        const float x = (float)((r.yx & 0xffff) * s.sw - s.pw + tj * s.dw) + dx;
         if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
             const float mk = FUSED ? 1.f / (1.f + __expf(-r.mk)) : r.mk;
             const int y0 = (int)floorf(y), x0 = (int)floorf(x);
@@ -202,7 +220,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapW);
         for (int i = 0; i < S; ++i) {
-            mbar_init(&full[i], T_PW + 1);
+            mbar_init(&full[i], T_PW + 1);   // one elected arrive per producer warp + the TMA expect_tx arrive
             mbar_init(&empty[i], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -220,27 +238,74 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
     const int my_tiles = (prm.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * nkb_tile;   // K steps of this CTA, flattened over its tiles: (tile, slab, tap)
 
     if (warp < T_PW) {
         // ------------------------------------------------------------------ producer warps
-        // Iteration kb:  (L) issue the raw offset/mask loads of table kb+3,  (D) decode table kb+2 into the
-        // ring,  (G) gather K step kb from table kb into a free A stage.  Everything is mbarrier dataflow
-        // (one elected arrive per warp), so warps drift by up to two K steps and hide each other's latency.
+        // Iteration kb:  (D) decode table kb+2 into the ring,  (L) issue the raw offset/mask loads of table kb+3,
+        // (G) gather K step kb from table kb into a free A stage (warp 0 also starts the weight-tile TMA).
+        // Everything is mbarrier dataflow with one elected arrive per warp, so warps drift by up to two K steps
+        // and hide each other's latency.  Warps 0..3 additionally drain finished accumulators (epilogue): they
+        // poll the TMEM-full barrier while they wait and at every K step.
         const int tid = threadIdx.x;
         const int ch = tid & 7;                    // 16-byte chunk (4 channels) within the 32-channel slab
         const int r0 = tid >> 3;                   // rows r0 + T_RSTEP*i, i < T_ITEMS
         const int gsub = (ch * 4) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
         const int gslab = TBK / prm.cdg;           // deform groups per slab when cdg < 32 (else 0)
-        // table entries owned by this thread: row = tid (T_PRODUCERS == TBM), deform-group-in-slab j < gs
-        static_assert(T_PRODUCERS == TBM, "one table row per producer thread");
-        // load cursor (runs T_AHEAD + 1 steps ahead of the gather)
-        int l_kb = 0, l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0;
+        // table entries owned by this thread: e = tid + 512 j -> row = tid % 256, group-in-slab = tid / 256 + 2 j
+        const int erow = tid & (TBM - 1), eg0 = tid >> 8;
+
+        // ---- epilogue duty (warps 0..3): tiles fully produced but not yet drained
+        const bool is_epi = warp < 4;
+        int ep_done = 0, prod_done = 0;            // tiles drained / tiles whose K steps this warp has all produced
+        auto epilogue_tile = [&](int it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int buf = it % prm.nbuf;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int m = tile * TBM + half * 128 + warp * 32 + lane;
+                const bool ok = m < prm.total_rows;
+                const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
+                float* o = out + (size_t)b * Co * P + p;
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * Co + half * Co;
+#pragma unroll 1
+                for (int c0 = 0; c0 < Co; c0 += 8) {
+                    uint32_t v[8];
+                    tmem_ld_32x8(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float bv = bias ? __ldg(bias + c0 + e) : 0.f;
+                            o[(size_t)(c0 + e) * P] = __uint_as_float(v[e]) + bv;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        };
+        auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
+            if (is_epi && ep_done < prod_done) {
+                const int buf = ep_done % prm.nbuf;
+                if (mbar_try_wait(&tfull[buf], (ep_done / prm.nbuf) & 1)) {
+                    tc_fence_after();
+                    epilogue_tile(ep_done);
+                    ++ep_done;
+                }
+            }
+        };
+        auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
+            while (!mbar_try_wait(bar, parity)) poll_epilogue();
+        };
+
+        // ---- table pipeline
+        int l_kb = 0, l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0;   // load cursor
         RowCoord rc;
         auto decode_rows = [&](int tile) {
-            const int m = tile * TBM + tid;
+            const int m = tile * TBM + erow;
             rc.b = -1;
             rc.p = rc.oy = rc.ox = 0;
             if (m < prm.total_rows) {
@@ -250,12 +315,13 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
                 rc.ox = rc.p - rc.oy * s.Wo;
             }
         };
-        RawParam raw[4];
+        RawParam raw[2];
         auto load_next = [&]() {      // raw <- inputs of table l_kb, then advance the load cursor
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < prm.gs) {
-                    const int dgi = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * gslab + j;
+            for (int j = 0; j < 2; ++j) {
+                const int g = eg0 + 2 * j;
+                if (g < prm.gs) {
+                    const int dgi = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * gslab + g;
                     raw[j] = load_raw_param<FUSED>(prm, offset, mask, max_idx, rc, dgi, l_tap, l_ti, l_tj);
                 }
             }
@@ -275,13 +341,15 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         };
         int d_slot = 0;
         uint32_t d_phase = 0;
-        auto decode_store = [&]() {   // raw -> ring slot d_slot (table index = number of tables decoded so far)
-            mbar_wait(&tab_empty[d_slot], d_phase ^ 1);
+        auto decode_store = [&]() {   // raw -> ring slot d_slot
+            wait_poll(&tab_empty[d_slot], d_phase ^ 1);
             int* tb = tab_base + d_slot * tab_n;
             float* tw = tab_w + d_slot * 4 * tab_n;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < prm.gs) store_param<FUSED>(prm, raw[j], tb, tw, j * TAB_STRIDE + tid, tab_n);
+            for (int j = 0; j < 2; ++j) {
+                const int g = eg0 + 2 * j;
+                if (g < prm.gs) store_param<FUSED>(prm, raw[j], tb, tw, g * TAB_STRIDE + erow, tab_n);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&tab_full[d_slot]);
             if (++d_slot == T_NTAB) {
@@ -300,16 +368,19 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         int stage = 0, c_slab = 0, c_tap = 0, g_slot = 0;
         uint32_t phase = 0, g_phase = 0;
         for (int kb = 0; kb < total_kb; ++kb) {
-            // (D) table kb + T_AHEAD from the raw values loaded one iteration ago, (L) loads of the one after
             if (kb + T_AHEAD < total_kb) decode_store();
             if (kb + T_AHEAD + 1 < total_kb) load_next();
-            // (G)
+            poll_epilogue();
             const int c0 = c_slab * TBK + ch * 4;
             const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE;
             const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE;
-            mbar_wait(&tab_full[g_slot], g_phase);
-            mbar_wait(&empty[stage], phase ^ 1);
+            wait_poll(&tab_full[g_slot], g_phase);
+            wait_poll(&empty[stage], phase ^ 1);
             uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
+            if (tid == 0) {       // weight tile of this K step (TMA, lands on the same full barrier)
+                mbar_expect_tx(&full[stage], Co * 128);
+                tma_load_3d(A + T_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
+            }
 #pragma unroll
             for (int bt = 0; bt < T_ITEMS / T_BATCH; ++bt) {
                 float4 v[T_BATCH][4];
@@ -358,10 +429,21 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             }
             if (++c_tap == K) {
                 c_tap = 0;
-                if (++c_slab == prm.n_slabs) c_slab = 0;
+                if (++c_slab == prm.n_slabs) {
+                    c_slab = 0;
+                    ++prod_done;      // every K step of this tile has been produced by this warp
+                }
             }
         }
-    } else if (warp == T_MMA_WARP) {
+        // drain the remaining accumulators
+        while (is_epi && ep_done < prod_done) {
+            const int buf = ep_done % prm.nbuf;
+            mbar_wait_backoff(&tfull[buf], (ep_done / prm.nbuf) & 1, 64);
+            tc_fence_after();
+            epilogue_tile(ep_done);
+            ++ep_done;
+        }
+    } else {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(2, 128, Co);
@@ -370,7 +452,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
                 const int buf = it % prm.nbuf;
                 const uint32_t bphase = (it / prm.nbuf) & 1;
-                mbar_wait_backoff(&tempty[buf], bphase ^ 1, 64);
+                mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + buf * 2 * Co;
                 uint32_t accumulate = 0;
@@ -396,62 +478,6 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             }
         }
         __syncwarp();
-    } else if (warp == T_TMA_WARP) {
-        // ------------------------------------------------------------------ TMA producer for the weight tiles
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x) {
-                for (int slab = 0; slab < prm.n_slabs; ++slab) {
-                    for (int tap = 0; tap < K; ++tap) {
-                        mbar_wait_backoff(&empty[stage], phase ^ 1, 32);
-                        mbar_expect_tx(&full[stage], Co * 128);
-                        tma_load_3d(smem + (size_t)stage * prm.stage_bytes + T_A_BYTES, &mapW, &full[stage],
-                                    tap * C + slab * TBK, 0, 0);
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------------------------ epilogue (4 warps)
-        const int q = warp & 3;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
-            const int buf = it % prm.nbuf;
-            const uint32_t bphase = (it / prm.nbuf) & 1;
-            mbar_wait_backoff(&tfull[buf], bphase, 256);
-            tc_fence_after();
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int m = tile * TBM + half * 128 + q * 32 + lane;
-                const bool ok = m < prm.total_rows;
-                const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
-                float* o = out + (size_t)b * Co * P + p;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * Co + half * Co;
-                for (int c0 = 0; c0 < Co; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (ok) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            if (c0 + e < Co) {
-                                const float bv = bias ? __ldg(bias + c0 + e) : 0.f;
-                                o[(size_t)(c0 + e) * P] = __uint_as_float(v[e]) + bv;
-                            }
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
-        }
     }
     tc_fence_before();
     __syncthreads();
