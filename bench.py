@@ -292,6 +292,9 @@ def main():
     dev = torch.device('cuda', local_rank)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line (NCCL_DEBUG=VERSION/WARN/INFO prints a version banner on stdout)
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN', 'INFO'):
+            os.environ.pop('NCCL_DEBUG')
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group('nccl', device_id=dev)
