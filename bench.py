@@ -346,10 +346,29 @@ def main():
         h2d = input_bytes(hd)
         d2h = [0]
 
+        copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
         def e2e_step():
-            dd = {k: v.to(dev, non_blocking=True) for k, v in hd.items()}
+            # H2D on a copy stream; the compute stream waits per tensor group, so the PCIe transfer of the later
+            # operators' inputs overlaps the earlier kernels; D2H of each result starts as soon as it exists
+            cur = torch.cuda.current_stream(dev)
+            dd, evs = {}, {}
+            with torch.cuda.stream(copy_in):
+                for k, v in hd.items():
+                    dd[k] = v.to(dev, non_blocking=True)
+                    evs[k] = torch.cuda.Event()
+                    evs[k].record(copy_in)
+            for k in hd:
+                cur.wait_event(evs[k])      # (a finer-grained wait would need the step to be split per operator)
             outs = hot_path_step(M, dd, b, r, args.match_mode, args.dcn_mode, fused)
-            host = [o.to('cpu', non_blocking=True) for o in outs]
+            done = torch.cuda.Event()
+            done.record(cur)
+            copy_out.wait_event(done)
+            with torch.cuda.stream(copy_out):
+                host = [o.to('cpu', non_blocking=True) for o in outs]
+            for t_ in list(dd.values()) + outs:
+                t_.record_stream(copy_out)
+            copy_out.synchronize()
             torch.cuda.synchronize()
             d2h[0] = sum(o.numel() * o.element_size() for o in host)
         del d

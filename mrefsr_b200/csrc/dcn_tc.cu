@@ -69,20 +69,31 @@ __device__ __forceinline__ float tf32_round_bits(float v) { return __uint_as_flo
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// NCHW -> NHWC (fp32) through a 32x32 shared-memory tile; grid (ceil(HW/32), ceil(C/32), B), block (32, 8)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+// NCHW -> NHWC (fp32): tile = 32 pixels x up to 128 channels per CTA (256 threads).  Loads: lane = pixel (128-byte
+// coalesced, 16 independent loads per thread in flight); stores: one float4 (4 channels) per lane, 512 bytes
+// contiguous per warp.  grid (ceil(HW/32), ceil(C/128), B)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[128][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* s = src + (size_t)b * C * HW;
     float* d = dst + (size_t)b * C * HW;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, p = p0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < C && p < HW) ? __ldg(s + (size_t)c * HW + p) : 0.f;
+    const int p = p0 + lane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int cl = warp + 8 * i, c = c0 + cl;
+        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int p = p0 + i, c = c0 + threadIdx.x;
-        if (p < HW && c < C) d[(size_t)p * C + c] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+        if (pp < HW && c < C) {   // C % 4 == 0 on this path (C % 32 == 0 is an eligibility condition)
+            const float4 v = make_float4(tile[lane * 4][pl], tile[lane * 4 + 1][pl], tile[lane * 4 + 2][pl],
+                                         tile[lane * 4 + 3][pl]);
+            *reinterpret_cast<float4*>(d + (size_t)pp * C + c) = v;
+        }
     }
 }
 
@@ -520,7 +531,7 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     const int K = s.kh * s.kw, HW = s.H * s.W;
     {
         ScopedTiming tm(MREFSR_K_DCN_AUX, st);
-        nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(s.C, 32), s.B), dim3(32, 8), 0, st>>>(x, xt, s.C, HW);
+        nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(s.C, 128), s.B), 256, 0, st>>>(x, xt, s.C, HW);
         MREFSR_LAUNCH_CHECK();
         dcn_weight_repack_kernel<<<cdiv(s.Co * s.C * K, 256), 256, 0, st>>>(w, wt, s.Co, s.C, K);
         MREFSR_LAUNCH_CHECK();

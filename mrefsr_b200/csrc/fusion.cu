@@ -83,10 +83,10 @@ mrapa_fwd_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb,
 // warp-level load), CTA = 128 pixels x 8 warps.  Needs HW % 4 == 0 and 16-byte aligned tensors.
 __device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
-__global__ void __launch_bounds__(FW * 32)
+template <int TMAX>   // TMAX == t exactly: no dead accumulators, so 3 CTAs (24 warps) fit per SM
+__global__ void __launch_bounds__(FW * 32, 3)
 mrapa_fwd_vec4_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb, const float* __restrict__ ass,
                       float* __restrict__ out, float* __restrict__ prob, int t, int C, int Cv, int HW) {
-    constexpr int TMAX = 8;
     __shared__ float4 part[FW][TMAX][32];
     const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = (blockIdx.x * 32 + lane) * 4;
@@ -260,7 +260,19 @@ int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const f
     ScopedTiming tm(MREFSR_K_FUSION_FWD, st);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (t <= 8 && HW % 4 == 0 && al16(emb_t) && al16(emb) && al16(ass) && al16(out) && (!prob || al16(prob))) {
-        mrapa_fwd_vec4_kernel<<<dim3(cdiv(HW, 128), n), FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
+        const dim3 g4(cdiv(HW, 128), n);
+#define MREFSR_FWD4(T) mrapa_fwd_vec4_kernel<T><<<g4, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW)
+        switch (t) {
+            case 1: MREFSR_FWD4(1); break;
+            case 2: MREFSR_FWD4(2); break;
+            case 3: MREFSR_FWD4(3); break;
+            case 4: MREFSR_FWD4(4); break;
+            case 5: MREFSR_FWD4(5); break;
+            case 6: MREFSR_FWD4(6); break;
+            case 7: MREFSR_FWD4(7); break;
+            default: MREFSR_FWD4(8); break;
+        }
+#undef MREFSR_FWD4
         MREFSR_LAUNCH_CHECK();
         count_launches(1);
         return 0;
