@@ -11,5 +11,6 @@ from .dcn import (ModulatedDeformConvFunction, modulated_deform_conv, ModulatedD
 from .mmcv_ops import ModulatedDeformConv2d, modulated_deform_conv2d  # noqa: F401
 from .fusion import MRAPAFusion, mrapa_attention  # noqa: F401
 from .dynagg import DynAgg  # noqa: F401
+from .archs import CorrespondenceGenerationArch, VGGFeatureExtractor  # noqa: F401
 
 __version__ = '0.1.0'

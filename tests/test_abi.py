@@ -87,3 +87,17 @@ def test_mmcv_shim_install():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_correspondence_arch_mirrors_reference_keys():
+    """CorrespondenceGenerationArch owns `vgg.vgg_net.<layer>` parameters and mean/std buffers like the reference
+    (basicsr/archs/vgg_arch.py:118-139), truncated at the deepest requested layer (relu3_1 -> conv3_1)."""
+    import mrefsr_b200 as M
+    net = M.CorrespondenceGenerationArch(patch_size=3, stride=1, vgg_layer_list=['relu1_1', 'relu2_1', 'relu3_1'])
+    keys = sorted(net.state_dict().keys())
+    assert keys == sorted(['vgg.mean', 'vgg.std'] + ['vgg.vgg_net.%s.%s' % (n, p) for n in
+                                                      ('conv1_1', 'conv1_2', 'conv2_1', 'conv2_2', 'conv3_1')
+                                                      for p in ('weight', 'bias')])
+    feats = net.vgg(torch.rand(1, 3, 16, 16))
+    assert {k: tuple(v.shape) for k, v in feats.items()} == {'relu1_1': (1, 64, 16, 16), 'relu2_1': (1, 128, 8, 8),
+                                                            'relu3_1': (1, 256, 4, 4)}

@@ -132,6 +132,20 @@ def test_correspondence_golden(golden):
         assert diff < 0.02, (k, diff)
 
 
+def test_correspondence_arch_module(golden):
+    """Module-level drop-in: same forward contract as the reference CorrespondenceGenerationArch."""
+    g = golden('correspondence')
+    net = M.CorrespondenceGenerationArch(patch_size=3, stride=1, vgg_layer_list=['relu1_1', 'relu2_1', 'relu3_1']).to(DEV)
+    f1, f2 = g('f1').to(DEV), g('f2').to(DEV)
+    img = torch.rand(f1.shape[0], 3, 4 * f1.shape[2], 4 * f1.shape[3], device=DEV)
+    with torch.no_grad():
+        pre, feats = net({'dense_features1': f1, 'dense_features2': f2}, img)
+    for k in ('relu3_1', 'relu2_1', 'relu1_1'):
+        assert pre[k].shape == g(k).shape
+        assert (pre[k].cpu() != g(k)).any(-1).float().mean().item() < 0.02
+    assert feats['relu3_1'].shape == (f1.shape[0], 256, f1.shape[2], f1.shape[3])
+
+
 def test_cpu_tensor_raises():
     with pytest.raises(NotImplementedError):
         M.feature_match_index(torch.randn(8, 6, 6), torch.randn(8, 6, 6))
