@@ -10,7 +10,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libmrefsr_b200.so')
+LIB_PATH = os.environ.get('MREFSR_LIB') or os.path.join(_HERE, 'lib', 'libmrefsr_b200.so')   # MREFSR_LIB: tuning builds
 
 c_int, c_size_t, c_void_p = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
 

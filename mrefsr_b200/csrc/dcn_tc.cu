@@ -5,14 +5,25 @@
 // the whole batch in which the deformable im2col tile never leaves the SM:
 //
 //   CTA tile   : 256 consecutive output positions (of the B*Ho*Wo concatenation) x all Co output channels
-//   K loop     : (32-channel slab) x (tap); per step the A tile [256 x 32] fp32 is produced by 8 gather warps
-//                straight into 128B-swizzled shared memory (bilinear 4-corner gather from an NHWC copy of the
-//                input: one float4 per corner per 4 channels, mask multiply and tf32 rounding fused), the B
-//                tile [Co x 32] of the repacked weights arrives by TMA, and one elected thread issues
-//                2 (M halves) x 4 (K=8 steps) tcgen05.mma.kind::tf32 into TMEM.
-//   epilogue   : 4 warps read TMEM (tcgen05.ld 32x32b), add the bias and store NCHW with position-major lanes
-//                (128-byte coalesced stores).
-//   pipelines  : smem ring full/empty mbarriers (gather + TMA -> MMA), TMEM full/empty (MMA -> epilogue).
+//   K loop     : (32-channel slab) x (tap).  Per step the A tile [256 x 32] fp32 is produced on the SM by 16
+//                producer warps and stored straight into 128B-swizzled shared memory; the B tile [Co x 32] of the
+//                repacked (tf32-rounded) weights arrives by TMA; one elected thread of a 17th warp issues
+//                2 (M halves) x 4 (K = 8 steps) tcgen05.mma.kind::tf32 into TMEM.
+//   producers  : (a) two K steps ahead, decode a shared-memory sample table -- per (row, deform group): corner
+//                offset into an NHWC copy of the input + the four bilinear weights with mask and corner validity
+//                folded in -- from position-major (coalesced) offset / mask reads issued one step earlier;
+//                (b) gather: per (row, 4-channel chunk) four float4 corner loads, blend, round to tf32, one
+//                16-byte swizzled store.  All hand-offs are mbarriers with ONE elected arrive per warp (table
+//                ring full/empty, stage ring full/empty); there is no CTA-wide barrier in the loop, so warps
+//                drift by up to two K steps and hide each other's latency.
+//   epilogue   : producer warps 0..3 also drain finished accumulators (tcgen05.ld 32x32b, bias add,
+//                position-major coalesced NCHW stores); they poll the TMEM-full barrier while they wait.
+//
+// Measured limits (profiles/r01_dcn_gather_microbench.txt): the bilinear gather alone needs 0.35 / 0.79 / 2.07 ms
+// per 80-sample call at 32+ warps/SM and 0.60 / 1.31 / 2.75 ms at the 16 gather warps this kernel can afford
+// (register-bound); this kernel takes 0.82 / 1.57 / 4.2 ms.  Variants tried and rejected on B200 this round:
+// separate table warps, register-resident decode with 256-bit loads, a group-major zero-bordered layout, two
+// 128-row CTAs per SM (spills at 56 registers) -- none beat this version.
 //
 // Offsets / masks come either as materialised tensors (the reference operator API) or -- fused DynAgg mode --
 // straight from the raw conv_offset_mask output plus the matcher's arg-max map: offset = conv + s*flow shifted

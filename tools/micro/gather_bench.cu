@@ -45,7 +45,8 @@ __global__ void gather_kernel(const float* __restrict__ x, const float* __restri
     }
     if (acc == 1234.5678f) out[0] = acc;
 }
-int main() {
+int main(int argc, char** argv) {
+    const int bps = argc > 1 ? atoi(argv[1]) : 8, threads = argc > 2 ? atoi(argv[2]) : 256;
     const int B = 80;
     const int cfgs[3][2] = {{256, 40}, {128, 80}, {64, 160}};
     for (int ci = 0; ci < 3; ++ci) {
@@ -58,18 +59,18 @@ int main() {
         for (size_t i = 0; i < no; ++i) { float u = 0; for (int k = 0; k < 4; ++k) u += rand() / (float)RAND_MAX - 0.5f; h[i] = u * 5.2f; }  // ~N(0, 3^2)
         cudaMemcpy(off, h.data(), no * 4, cudaMemcpyHostToDevice);
         cudaMemset(x, 0, nx * 4); cudaMemset(msk, 0, nm * 4);
-        for (int variant = 0; variant < 4; ++variant) {
+        for (int variant = 0; variant < 1; ++variant) {
             for (int smooth = 0; smooth < 2; ++smooth) {
                 if (smooth) cudaMemset(off, 0, no * 4); else cudaMemcpy(off, h.data(), no * 4, cudaMemcpyHostToDevice);
                 cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
                 float best = 1e9;
                 for (int rep = 0; rep < 4; ++rep) {
                     cudaEventRecord(e0);
-                    const int grid = 148 * 8;
-                    if (variant == 0) gather_kernel<0, 0><<<grid, 256>>>(x, off, msk, out, B, C, H, W, DG);
-                    if (variant == 1) gather_kernel<0, 1><<<grid, 256>>>(x, off, msk, out, B, C, H, W, DG);
-                    if (variant == 2) gather_kernel<1, 0><<<grid, 256>>>(x, off, msk, out, B, C, H, W, DG);
-                    if (variant == 3) gather_kernel<1, 1><<<grid, 256>>>(x, off, msk, out, B, C, H, W, DG);
+                    const int grid = 148 * bps;
+                    if (variant == 0) gather_kernel<0, 0><<<grid, threads>>>(x, off, msk, out, B, C, H, W, DG);
+                    if (variant == 1) gather_kernel<0, 1><<<grid, threads>>>(x, off, msk, out, B, C, H, W, DG);
+                    if (variant == 2) gather_kernel<1, 0><<<grid, threads>>>(x, off, msk, out, B, C, H, W, DG);
+                    if (variant == 3) gather_kernel<1, 1><<<grid, threads>>>(x, off, msk, out, B, C, H, W, DG);
                     cudaEventRecord(e1); cudaEventSynchronize(e1);
                     float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0 && ms < best) best = ms;
                 }
