@@ -97,6 +97,8 @@ MREFSR_API int mrefsr_pre_offsets(const int64_t* max_idx, int n, int h, int w, f
  * offset [B, 2*dg*kh*kw, Ho, Wo]  (channel 2*(g*K+k) = dy, +1 = dx)   mask [B, dg*kh*kw, Ho, Wo]
  * output [B, Co, Ho, Wo], overwritten.  The reference's `ones` / `columns` scratch tensors are
  * replaced by `workspace`.
+ * mask == NULL means an all-ones mask: with bias == NULL that is DCNv1 (deform_conv_forward,
+ * deform_conv_ext.cpp:52-66; same sampling rule, deform_conv_cuda_kernel.cu:84-112, 190-243).
  * mode: MREFSR_DCN_AUTO / MREFSR_DCN_FP32 (CUDA-core, exact fp32) / MREFSR_DCN_TF32 (tcgen05).
  * ------------------------------------------------------------------------------------------ */
 enum {
@@ -115,7 +117,9 @@ MREFSR_API int mrefsr_modulated_deform_conv_forward(const float* input, const fl
                                          void* stream);
 /* grad_input / grad_offset / grad_mask are overwritten; grad_weight / grad_bias are ACCUMULATED
  * into (the reference accumulates with addmm_ beta = 1 into caller-zeroed tensors,
- * deform_conv_cuda.cpp:659-671).  grad_input may be NULL (skipped). */
+ * deform_conv_cuda.cpp:659-671).  grad_input, grad_weight, grad_offset (+ grad_mask) may each be NULL (that
+ * part is skipped); mask == NULL = all-ones mask, which gives DCNv1's deform_conv_backward_input /
+ * deform_conv_backward_parameters (deform_conv_ext.cpp:68-105). */
 MREFSR_API int mrefsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset,
                                           const float* mask, const float* grad_output, float* grad_input,
                                           float* grad_weight, float* grad_bias, float* grad_offset, float* grad_mask,

@@ -7,7 +7,7 @@ from . import _lib  # noqa: F401
 from .matcher import (sample_patches, feature_match_index, feature_match_index_batched, pre_offsets,  # noqa: F401
                       correspondence)
 from .dcn import (ModulatedDeformConvFunction, modulated_deform_conv, ModulatedDeformConv,  # noqa: F401
-                  ModulatedDeformConvPack, DeformConv, DeformConvPack, deform_conv)
+                  ModulatedDeformConvPack, DeformConvFunction, DeformConv, DeformConvPack, deform_conv)
 from .mmcv_ops import ModulatedDeformConv2d, modulated_deform_conv2d  # noqa: F401
 from .fusion import MRAPAFusion, mrapa_attention  # noqa: F401
 from .dynagg import DynAgg  # noqa: F401

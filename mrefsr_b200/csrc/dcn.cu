@@ -61,7 +61,7 @@ dcn_fwd_simt_kernel(const float* __restrict__ x, const float* __restrict__ offse
                         const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
                         sy = ybase + __ldg(offset + ob);
                         sx = xbase + __ldg(offset + ob + P);
-                        sm = __ldg(mask + ((size_t)(b * s.DG + dgi) * K + tap) * P + p);
+                        sm = mask ? __ldg(mask + ((size_t)(b * s.DG + dgi) * K + tap) * P + p) : 1.f;
                         last_dg = dgi;
                     }
                     v = dcn_sample(x + ((size_t)b * s.C + ch) * s.H * s.W, s.H, s.W, sy, sx) * sm;
@@ -178,7 +178,7 @@ __global__ void dcn_bwd_coord_kernel(const float* __restrict__ x, const float* _
         const size_t mb = ((size_t)(b * s.DG + dgi) * K + tap) * P + p;
         const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + offset[ob];
         const float xx = (float)(ox * s.sw - s.pw + tj * s.dw) + offset[ob + P];
-        const float m = mask[mb];
+        const float m = mask ? mask[mb] : 1.f;
         float dy = 0.f, dx = 0.f, dm = 0.f;
         if (y > -1.f && xx > -1.f && y < (float)s.H && xx < (float)s.W) {
             const int y0 = (int)floorf(y), x0 = (int)floorf(xx), y1 = y0 + 1, x1 = x0 + 1;
@@ -201,7 +201,7 @@ __global__ void dcn_bwd_coord_kernel(const float* __restrict__ x, const float* _
         }
         goff[ob] = dy;
         goff[ob + P] = dx;
-        gmask[mb] = dm;
+        if (gmask) gmask[mb] = dm;
     }
 }
 
@@ -222,7 +222,7 @@ __global__ void dcn_bwd_input_kernel(const float* __restrict__ offset, const flo
         const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + offset[ob];
         const float xx = (float)(ox * s.sw - s.pw + tj * s.dw) + offset[ob + P];
         if (!(y > -1.f && xx > -1.f && y < (float)s.H && xx < (float)s.W)) continue;
-        const float tval = gcol[idx] * mask[((size_t)(b * s.DG + dgi) * K + tap) * P + p];
+        const float tval = gcol[idx] * (mask ? mask[((size_t)(b * s.DG + dgi) * K + tap) * P + p] : 1.f);
         const int y0 = (int)floorf(y), x0 = (int)floorf(xx), y1 = y0 + 1, x1 = x0 + 1;
         const float ly = y - y0, lx = xx - x0;
         float* pl = gx + ((size_t)b * s.C + ch) * s.H * s.W;
@@ -249,7 +249,7 @@ __global__ void dcn_im2col_kernel(const float* __restrict__ x, const float* __re
         const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
         const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + offset[ob];
         const float xx = (float)(ox * s.sw - s.pw + tj * s.dw) + offset[ob + P];
-        const float m = mask[((size_t)(b * s.DG + dgi) * K + tap) * P + p];
+        const float m = mask ? mask[((size_t)(b * s.DG + dgi) * K + tap) * P + p] : 1.f;
         col[idx] = dcn_sample(x + ((size_t)b * s.C + ch) * s.H * s.W, s.H, s.W, y, xx) * m;
     }
 }
@@ -425,7 +425,7 @@ int mrefsr_modulated_deform_conv_forward(const float* input, const float* weight
                                          int W, int Co, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
                                          int dil_h, int dil_w, int group, int deformable_group, int with_bias, int mode,
                                          void* workspace, size_t workspace_bytes, void* stream) {
-    MREFSR_CHECK(input && weight && offset && mask && output, ERR_BAD_ARG, "dcn forward: null pointer argument");
+    MREFSR_CHECK(input && weight && offset && output, ERR_BAD_ARG, "dcn forward: null pointer argument");
     MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dcn forward: with_bias set but bias is NULL");
     DcnShape s;
     int rc = dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
@@ -451,8 +451,8 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
                                           int with_bias, int mode, void* workspace, size_t workspace_bytes,
                                           void* stream) {
     (void)mode;
-    MREFSR_CHECK(input && weight && offset && mask && grad_output && grad_weight && grad_offset && grad_mask, ERR_BAD_ARG,
-                 "dcn backward: null pointer argument");
+    MREFSR_CHECK(input && weight && offset && grad_output, ERR_BAD_ARG, "dcn backward: null pointer argument");
+    MREFSR_CHECK(grad_offset || !grad_mask, ERR_BAD_ARG, "dcn backward: grad_mask requires grad_offset");
     MREFSR_CHECK(!with_bias || grad_bias, ERR_BAD_ARG, "dcn backward: with_bias set but grad_bias is NULL");
     DcnShape s;
     int rc = dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
@@ -469,24 +469,31 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
     if (grad_input) MREFSR_CUDA(cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * 4, st));
     for (int b0 = 0; b0 < B; b0 += nbmax) {
         const int nb = (B - b0 < nbmax) ? B - b0 : nbmax;
-        dcn_bwd_gcol_kernel<<<dim3(cdiv(P, DT), group * cdiv(MK, DT), nb), 256, 0, st>>>(weight, grad_output, gcol, s, b0);
-        MREFSR_LAUNCH_CHECK();
-        dcn_bwd_coord_kernel<<<grid_for((size_t)nb * deformable_group * K * P), 256, 0, st>>>(
-            input, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
-        MREFSR_LAUNCH_CHECK();
-        count_launches(2);
+        if (grad_input || grad_offset) {
+            dcn_bwd_gcol_kernel<<<dim3(cdiv(P, DT), group * cdiv(MK, DT), nb), 256, 0, st>>>(weight, grad_output, gcol, s, b0);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
+        }
+        if (grad_offset) {
+            dcn_bwd_coord_kernel<<<grid_for((size_t)nb * deformable_group * K * P), 256, 0, st>>>(
+                input, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
+        }
         if (grad_input) {
             dcn_bwd_input_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(offset, mask, gcol, grad_input, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }
-        dcn_im2col_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(input, offset, mask, col, s, b0, nb);
-        MREFSR_LAUNCH_CHECK();
-        const int pchunks = cdiv(P, WCHUNK);
-        dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
-            grad_output, col, grad_weight, s, b0, pchunks);
-        MREFSR_LAUNCH_CHECK();
-        count_launches(2);
+        if (grad_weight) {
+            dcn_im2col_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(input, offset, mask, col, s, b0, nb);
+            MREFSR_LAUNCH_CHECK();
+            const int pchunks = cdiv(P, WCHUNK);
+            dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
+                grad_output, col, grad_weight, s, b0, pchunks);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(2);
+        }
     }
     if (with_bias) {
         dcn_bwd_bias_kernel<<<Co, 256, 0, st>>>(grad_output, grad_bias, B, Co, P);

@@ -148,7 +148,7 @@ __device__ __forceinline__ RawParam load_raw_param(const DcnTcParams& prm, const
         const size_t ob = ((size_t)(rc.b * s.DG + dgi) * 2 * K + 2 * tap) * P + rc.p;
         r.dy = ldg_early(offset + ob);
         r.dx = ldg_early(offset + ob + P);
-        r.mk = ldg_early(mask + ((size_t)(rc.b * s.DG + dgi) * K + tap) * P + rc.p);
+        r.mk = mask ? ldg_early(mask + ((size_t)(rc.b * s.DG + dgi) * K + tap) * P + rc.p) : 1.f;
     } else {
         const size_t cb = (size_t)rc.b * 3 * s.DG * K * P + rc.p;
         r.dy = ldg_early(offset + cb + (size_t)(2 * (dgi * K + tap)) * P);

@@ -7,8 +7,8 @@ Same operator API as the reference (deform_conv.py:121-188, :289-379):
     modulated_deform_conv = ModulatedDeformConvFunction.apply
     ModulatedDeformConv, ModulatedDeformConvPack  (same parameters / state-dict keys / init)
 stride / padding / dilation may be ints (basicsr) or pairs (mmcv.ops, see mmcv_ops.py).
-DCNv1 (DeformConv, deform_conv) is exported by the reference package but is not on the MRefSR path; the
-names exist here and raise NotImplementedError.
+DCNv1 (DeformConv, DeformConvPack, deform_conv; deform_conv.py:33-118, :191-286) is exported by the reference
+package but unused by MRefSR; it runs on the same kernels with an implicit all-ones mask.
 """
 import math
 
@@ -44,12 +44,12 @@ def _check_shapes(input, offset, mask, weight, groups, dg, ho, wo):
         raise RuntimeError("Input shape and kernel channels won't match: (%d vs %d)." % (c, cg * groups))
     if tuple(offset.shape) != (b, 2 * dg * kh * kw, ho, wo):
         raise RuntimeError('offset shape %s, expected %s' % (tuple(offset.shape), (b, 2 * dg * kh * kw, ho, wo)))
-    if tuple(mask.shape) != (b, dg * kh * kw, ho, wo):
+    if mask is not None and tuple(mask.shape) != (b, dg * kh * kw, ho, wo):
         raise RuntimeError('mask shape %s, expected %s' % (tuple(mask.shape), (b, dg * kh * kw, ho, wo)))
 
 
 def dcn_forward_raw(input, offset, mask, weight, bias, stride, padding, dilation, groups, dg, mode=None):
-    """Forward on contiguous fp32 CUDA tensors -> output [B,Co,Ho,Wo] (no autograd)."""
+    """Forward on contiguous fp32 CUDA tensors -> output [B,Co,Ho,Wo] (no autograd).  mask=None: all-ones (DCNv1)."""
     lib = _lib.lib()
     b, c, h, w = input.shape
     co, _, kh, kw = weight.shape
@@ -123,27 +123,9 @@ class ModulatedDeformConvFunction(Function):
         if not grad_output.is_cuda:
             raise NotImplementedError
         x, off, msk, wgt = ctx.saved_tensors
-        go = grad_output.contiguous().float()
-        lib = _lib.lib()
-        b, c, h, w = x.shape
-        co, _, kh, kw = wgt.shape
-        need_gi = ctx.needs_input_grad[0]
-        grad_input = torch.empty_like(x) if need_gi else None
-        grad_offset = torch.empty_like(off)
-        grad_mask = torch.empty_like(msk)
-        grad_weight = torch.zeros_like(wgt)
-        grad_bias = torch.zeros(co, dtype=torch.float32, device=x.device) if ctx.with_bias else None
-        s, p, d = ctx.stride, ctx.padding, ctx.dilation
-        with torch.cuda.device(x.device):
-            nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, kh, kw, s[0], s[1], p[0], p[1], d[0], d[1],
-                                                    ctx.groups, ctx.deformable_groups, _default_mode, 1)
-            ws, ws_bytes = _lib.workspace(nbytes, x.device)
-            rc = lib.mrefsr_modulated_deform_conv_backward(
-                _lib.ptr(x), _lib.ptr(wgt), _lib.ptr(off), _lib.ptr(msk), _lib.ptr(go), _lib.ptr(grad_input),
-                _lib.ptr(grad_weight), _lib.ptr(grad_bias), _lib.ptr(grad_offset), _lib.ptr(grad_mask), b, c, h, w, co,
-                kh, kw, s[0], s[1], p[0], p[1], d[0], d[1], ctx.groups, ctx.deformable_groups, int(ctx.with_bias),
-                _default_mode, ws, ws_bytes, _lib.stream_ptr(x.device))
-        _lib.check(rc, 'mrefsr_modulated_deform_conv_backward')
+        grad_input, grad_offset, grad_mask, grad_weight, grad_bias = dcn_backward_raw(
+            x, off, msk, wgt, grad_output.contiguous().float(), ctx.stride, ctx.padding, ctx.dilation, ctx.groups,
+            ctx.deformable_groups, ctx.with_bias, need_input=ctx.needs_input_grad[0])
         dt = ctx.in_dtype
         cast = (lambda t: None if t is None else t.to(dt))
         return (cast(grad_input), cast(grad_offset), cast(grad_mask), cast(grad_weight), cast(grad_bias), None, None,
@@ -161,16 +143,141 @@ class ModulatedDeformConvFunction(Function):
 modulated_deform_conv = ModulatedDeformConvFunction.apply
 
 
-def deform_conv(*args, **kwargs):
-    raise NotImplementedError('DCNv1 (deform_conv) is not on the MRefSR alignment path and is not built here')
+def dcn_backward_raw(input, offset, mask, weight, grad_output, stride, padding, dilation, groups, dg, with_bias,
+                     need_input=True, need_offset=True, need_weight=True):
+    """Backward on contiguous fp32 CUDA tensors -> (grad_input, grad_offset, grad_mask, grad_weight, grad_bias);
+    entries that were not requested (or do not exist: mask None, no bias) are None."""
+    lib = _lib.lib()
+    b, c, h, w = input.shape
+    co, _, kh, kw = weight.shape
+    gi = torch.empty_like(input) if need_input else None
+    go = torch.empty_like(offset) if need_offset else None
+    gm = torch.empty_like(mask) if (need_offset and mask is not None) else None
+    gw = torch.zeros_like(weight) if need_weight else None
+    gb = torch.zeros(co, dtype=torch.float32, device=input.device) if with_bias else None
+    s, p, d = stride, padding, dilation
+    with torch.cuda.device(input.device):
+        nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, kh, kw, s[0], s[1], p[0], p[1], d[0], d[1], groups, dg,
+                                                _default_mode, 1)
+        ws, ws_bytes = _lib.workspace(nbytes, input.device)
+        rc = lib.mrefsr_modulated_deform_conv_backward(
+            _lib.ptr(input), _lib.ptr(weight), _lib.ptr(offset), _lib.ptr(mask), _lib.ptr(grad_output), _lib.ptr(gi),
+            _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(go), _lib.ptr(gm), b, c, h, w, co, kh, kw, s[0], s[1], p[0], p[1], d[0],
+            d[1], groups, dg, int(with_bias), _default_mode, ws, ws_bytes, _lib.stream_ptr(input.device))
+    _lib.check(rc, 'mrefsr_modulated_deform_conv_backward')
+    return gi, go, gm, gw, gb
+
+
+class DeformConvFunction(Function):
+    """DCNv1 (basicsr/ops/dcn/deform_conv.py:33-118): the same kernels with an implicit all-ones mask and no bias.
+    `im2col_step` is accepted for signature compatibility; the whole batch is one launch here."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError(f'Expected 4D tensor as input, got {input.dim()}D tensor instead.')
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        ctx.groups = groups
+        ctx.deformable_groups = deformable_groups
+        ctx.im2col_step = im2col_step
+        if not input.is_cuda:
+            raise NotImplementedError
+        _lib.require_cuda(offset, weight)
+        cur = min(im2col_step, input.shape[0])
+        assert (input.shape[0] % cur) == 0, 'im2col step must divide batchsize'
+        kh, kw = weight.shape[2:4]
+        ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, ctx.stride, ctx.padding, ctx.dilation)
+        if ho <= 0 or wo <= 0:
+            raise ValueError('convolution input is too small (output would be %dx%d)' % (ho, wo))
+        ctx.in_dtype = input.dtype
+        x, off, wgt = (t.contiguous().float() for t in (input, offset, weight))
+        ctx.save_for_backward(x, off, wgt)
+        out = dcn_forward_raw(x, off, None, wgt, None, ctx.stride, ctx.padding, ctx.dilation, groups, deformable_groups)
+        return out.to(input.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        x, off, wgt = ctx.saved_tensors
+        need_io = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gi, go, _, gw, _ = dcn_backward_raw(x, off, None, wgt, grad_output.contiguous().float(), ctx.stride, ctx.padding,
+                                            ctx.dilation, ctx.groups, ctx.deformable_groups, False, need_input=need_io,
+                                            need_offset=need_io, need_weight=ctx.needs_input_grad[2])
+        dt = ctx.in_dtype
+        cast = (lambda t: None if t is None else t.to(dt))
+        return (cast(gi), cast(go), cast(gw), None, None, None, None, None, None)
+
+
+deform_conv = DeformConvFunction.apply
 
 
 class DeformConv(nn.Module):
+    """Same constructor, parameter (weight) and init as deform_conv.py:191-245."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super().__init__()
+        assert not bias
+        assert in_channels % groups == 0, f'in_channels {in_channels} is not divisible by groups {groups}'
+        assert out_channels % groups == 0, f'out_channels {out_channels} is not divisible by groups {groups}'
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride)
+        self.padding = _pair(padding)
+        self.dilation = _pair(dilation)
+        self.groups = groups
+        self.deformable_groups = deformable_groups
+        self.transposed = False
+        self.output_padding = _single(0)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // self.groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, offset):
+        input_pad = (x.size(2) < self.kernel_size[0] or x.size(3) < self.kernel_size[1])
+        if input_pad:
+            pad_h = max(self.kernel_size[0] - x.size(2), 0)
+            pad_w = max(self.kernel_size[1] - x.size(3), 0)
+            x = torch.nn.functional.pad(x, (0, pad_w, 0, pad_h), 'constant', 0).contiguous()
+            offset = torch.nn.functional.pad(offset, (0, pad_w, 0, pad_h), 'constant', 0).contiguous()
+        out = deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                          self.deformable_groups)
+        if input_pad:
+            out = out[:, :, :out.size(2) - pad_h, :out.size(3) - pad_w].contiguous()
+        return out
+
+
+class DeformConvPack(DeformConv):
+    """deform_conv.py:248-286: adds the zero-initialised conv_offset that predicts the offsets."""
+
+    _version = 2
+
     def __init__(self, *args, **kwargs):
-        raise NotImplementedError('DCNv1 (DeformConv) is not on the MRefSR alignment path and is not built here')
+        super().__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels,
+                                     self.deformable_groups * 2 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride),
+                                     padding=_pair(self.padding), dilation=_pair(self.dilation), bias=True)
+        self.init_offset()
 
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
 
-DeformConvPack = DeformConv
+    def forward(self, x):
+        offset = self.conv_offset(x)
+        return deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
 
 
 class ModulatedDeformConv(nn.Module):
@@ -287,12 +394,43 @@ class _Ext:
                 ws_bytes, _lib.stream_ptr(input.device))
         _lib.check(rc, 'mrefsr_modulated_deform_conv_backward')
 
+    # DCNv1 exports (deform_conv_ext.cpp:52-105); note the reference's (W, H) argument order
     @staticmethod
-    def deform_conv_forward(*a, **k):
-        raise NotImplementedError('DCNv1 is not on the MRefSR alignment path and is not built here')
+    def deform_conv_forward(input, weight, offset, output, columns, ones, kW, kH, dW, dH, padW, padH, dilationW,
+                            dilationH, group, deformable_group, im2col_step):
+        if not input.is_cuda:
+            raise RuntimeError('deform conv is not implemented on CPU')          # deform_conv_ext.cpp:63
+        out = dcn_forward_raw(input.contiguous().float(), offset.contiguous().float(), None, weight.contiguous().float(),
+                              None, (dH, dW), (padH, padW), (dilationH, dilationW), group, deformable_group)
+        output.view(out.shape).copy_(out)
+        return 1
 
-    deform_conv_backward_input = deform_conv_forward
-    deform_conv_backward_parameters = deform_conv_forward
+    @staticmethod
+    def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset, weight, columns, kW, kH, dW, dH,
+                                   padW, padH, dilationW, dilationH, group, deformable_group, im2col_step):
+        if not input.is_cuda:
+            raise RuntimeError('deform conv is not implemented on CPU')
+        gi, go, _, _, _ = dcn_backward_raw(input.contiguous().float(), offset.contiguous().float(), None,
+                                           weight.contiguous().float(), gradOutput.contiguous().float(), (dH, dW),
+                                           (padH, padW), (dilationH, dilationW), group, deformable_group, False,
+                                           need_weight=False)
+        gradInput.copy_(gi)
+        gradOffset.copy_(go)
+        return 1
+
+    @staticmethod
+    def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, columns, ones, kW, kH, dW, dH, padW,
+                                        padH, dilationW, dilationH, group, deformable_group, scale, im2col_step):
+        if not input.is_cuda:
+            raise RuntimeError('deform conv is not implemented on CPU')
+        kshape = (gradWeight.shape[0], input.shape[1] // group, kH, kW)
+        wdummy = torch.empty(kshape, dtype=torch.float32, device=input.device)
+        _, _, _, gw, _ = dcn_backward_raw(input.contiguous().float(), offset.contiguous().float(), None, wdummy,
+                                          gradOutput.contiguous().float(), (dH, dW), (padH, padW),
+                                          (dilationH, dilationW), group, deformable_group, False, need_input=False,
+                                          need_offset=False)
+        gradWeight.add_(gw.view_as(gradWeight), alpha=scale)        # accumulates, like the reference
+        return 1
 
 
 ext = _Ext()

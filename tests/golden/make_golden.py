@@ -242,6 +242,24 @@ def gen_fusion():
     print('fusion.npz', [k for k in out if k.endswith('.y')])
 
 
+def gen_dcnv1():
+    """DCNv1 (no mask, no bias): torchvision.ops.deform_conv2d implements the rule of
+    basicsr/ops/dcn/src/deform_conv_cuda_kernel.cu:84-112, 190-243 (the reference's own DCNv1 kernels need a GPU)."""
+    from torchvision.ops import deform_conv2d
+    g = torch.Generator().manual_seed(41)
+    b, c, h, w, co, dg, groups = 2, 8, 9, 10, 12, 2, 2
+    x = torch.randn(b, c, h, w, generator=g, requires_grad=True)
+    off = (torch.randn(b, 2 * dg * 9, h, w, generator=g) * 2.5).requires_grad_(True)
+    wgt = (torch.randn(co, c // groups, 3, 3, generator=g) * 0.2).requires_grad_(True)
+    y = deform_conv2d(x, off, wgt, None, 1, 1, 1, None)
+    go = torch.randn(y.shape, generator=g)
+    y.backward(go)
+    out = dict(x=x, offset=off, weight=wgt, y=y, go=go, gx=x.grad, goffset=off.grad, gweight=wgt.grad)
+    np.savez_compressed(os.path.join(OUT, 'dcnv1.npz'), dg=np.array(dg), groups=np.array(groups),
+                        **{k: v.detach().numpy() for k, v in out.items()})
+    print('dcnv1.npz', tuple(y.shape))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
     install_shims()
@@ -249,4 +267,5 @@ if __name__ == '__main__':
     gen_correspondence()
     gen_dynagg()
     gen_fusion()
+    gen_dcnv1()
     print('sizes:', {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT)) if f.endswith('.npz')})

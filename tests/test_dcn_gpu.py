@@ -185,6 +185,33 @@ def test_dynagg_glue_golden(golden):
         assert (mask.cpu() - g(f'{case}.mask')).abs().max() <= 1e-6
 
 
+def test_dcnv1_golden(golden):
+    """DCNv1 mirror (DeformConvFunction / deform_conv) against vectors from torchvision's implementation of the
+    reference rule, and the three DCNv1 exports of the replaced extension."""
+    g = golden('dcnv1')
+    dg, groups = int(g('dg')), int(g('groups'))
+    ts = [g(k).to(DEV).requires_grad_(True) for k in ('x', 'offset', 'weight')]
+    y = M.deform_conv(ts[0], ts[1], ts[2], 1, 1, 1, groups, dg)
+    assert rel_err(y, g('y')) <= TOL
+    y.backward(g('go').to(DEV))
+    for t, key in zip(ts, ('gx', 'goffset', 'gweight')):
+        assert rel_err(t.grad, g(key)) <= TOL, key
+    x, off, w = (g(k).to(DEV) for k in ('x', 'offset', 'weight'))
+    out = torch.empty_like(y)
+    e = x.new_empty(0)
+    assert D.ext.deform_conv_forward(x, w, off, out, e, e, 3, 3, 1, 1, 1, 1, 1, 1, groups, dg, 2) == 1
+    assert rel_err(out, g('y')) <= TOL
+    gi, go_ = torch.zeros_like(x), torch.zeros_like(off)
+    D.ext.deform_conv_backward_input(x, off, g('go').to(DEV), gi, go_, w, e, 3, 3, 1, 1, 1, 1, 1, 1, groups, dg, 2)
+    assert rel_err(gi, g('gx')) <= TOL and rel_err(go_, g('goffset')) <= TOL
+    gw = torch.zeros_like(w)
+    D.ext.deform_conv_backward_parameters(x, off, g('go').to(DEV), gw, e, e, 3, 3, 1, 1, 1, 1, 1, 1, groups, dg, 1.0, 2)
+    assert rel_err(gw, g('gweight')) <= TOL
+    m = M.DeformConvPack(8, 12, 3, padding=1, groups=groups, deformable_groups=dg).to(DEV)
+    assert sorted(m.state_dict().keys()) == ['conv_offset.bias', 'conv_offset.weight', 'weight']
+    assert m(x).shape == (2, 12, 9, 10)
+
+
 def test_errors():
     x, off, mask, wgt, bias = _rand_problem(1, 8, 6, 6, 8, 2, 1)
     with pytest.raises(NotImplementedError):
@@ -201,7 +228,6 @@ _REF_SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 @pytest.mark.skipif(not os.path.exists(_REF_SO), reason='reference CUDA extension not prebuilt (oracle/build.py --ref)')
 def test_against_reference_cuda_extension():
     """The reference's own deform_conv_ext, compiled unmodified for sm_100a into oracle/_ref/ (checker only)."""
-    torch.ops.load_library(_REF_SO) if False else None
     import importlib.util
     spec = importlib.util.spec_from_file_location('deform_conv_ext_ref', _REF_SO)
     ext = importlib.util.module_from_spec(spec)
@@ -212,3 +238,17 @@ def test_against_reference_cuda_extension():
                                       1, 1, 1, 8, True)
     out = D.dcn_forward_raw(x, off, mask, wgt, bias, (1, 1), (1, 1), (1, 1), 1, 8)
     assert rel_err(out, out_ref) <= TOL
+    # backward through the reference's own kernels
+    go = torch.randn_like(out_ref)
+    gr = [torch.zeros_like(t) for t in (x, wgt, bias, off, mask)]
+    ext.modulated_deform_conv_backward(x, wgt, bias, x.new_empty(0), off, mask, x.new_empty(0), gr[0], gr[1], gr[2],
+                                       gr[3], gr[4], go, 3, 3, 1, 1, 1, 1, 1, 1, 1, 8, True)
+    gi, goff, gm, gw, gb = D.dcn_backward_raw(x, off, mask, wgt, go, (1, 1), (1, 1), (1, 1), 1, 8, True)
+    for got, ref, name in ((gi, gr[0], 'input'), (gw, gr[1], 'weight'), (gb, gr[2], 'bias'), (goff, gr[3], 'offset'),
+                           (gm, gr[4], 'mask')):
+        assert rel_err(got, ref) <= TOL, name
+    # DCNv1 forward of the reference extension
+    out1 = x.new_empty(2, 64, 24, 20)
+    ext.deform_conv_forward(x, wgt, off, out1, x.new_empty(0), x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 8, 2)
+    mine = M.deform_conv(x, off, wgt, 1, 1, 1, 1, 8)
+    assert rel_err(mine, out1) <= TOL

@@ -107,3 +107,16 @@ def test_fusion_oracle(golden, case):
     assert (out - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
     if t == 1:   # single reference: softmax == 1, core is the identity on ass
         assert torch.allclose(out, g(f'{case}.ass'), atol=1e-7)
+
+
+def test_dcnv1_oracle(golden):
+    """DCNv1 = the same sampling rule with an all-ones mask and no bias."""
+    g = golden('dcnv1')
+    dg, groups = int(g('dg')), int(g('groups'))
+    x, off, w = g('x'), g('offset'), g('weight')
+    ones = torch.ones(x.shape[0], dg * 9, x.shape[2], x.shape[3])
+    y = oracle.modulated_deform_conv_oracle(x, off, ones, w, None, 1, 1, 1, groups, dg)
+    assert (y - g('y')).abs().max().item() <= 1e-5 * g('y').abs().max().item()
+    gi, goff, _, gw, _ = oracle.modulated_deform_conv_backward_oracle(x, off, ones, w, None, g('go'), 1, 1, 1, groups, dg)
+    for got, key in ((gi, 'gx'), (goff, 'goffset'), (gw, 'gweight')):
+        assert (got - g(key)).abs().max().item() <= 2e-5 * max(1.0, g(key).abs().max().item()), key

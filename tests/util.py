@@ -28,5 +28,5 @@ def match_parity(idx, val, fi, fr, kw, val_rtol=1e-3, gap_tol=1e-5, dtype=torch.
 
 
 def rel_err(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
