@@ -1,0 +1,235 @@
+"""The MRefSR network around the hot path ("next" row of SURVEY.md section 8f: the callers either side).
+
+Mirrors, with identical module / parameter names (so reference checkpoints load):
+  * ContrasMultiExtractorSep      basicsr/archs/contras_multi_extractor_arch.py:10-64   (VGG16 -> conv3_1)
+  * MRAPARestorationNet           basicsr/archs/ref_mrapa_restoration_arch.py:79-259
+    (ContentExtractor, DynamicAggregationRestoration with DynAgg x3 and MRAPAFusion x3)
+and `MRefSRPipeline`, the inference flow of MultiRefRestorationModel.test()
+(basicsr/models/multi_ref_restoration_model.py:281-294) with the Python loops over references and batch items
+replaced by batched calls: one matcher launch for all B*R pairs, the R references of a scale stacked into the batch
+dimension of the offset convolutions and of ONE fused DynAgg launch (offsets / masks / pre-offsets assembled in the
+DCN gather), one fusion launch per scale.  The plain convolutions stay cuDNN library calls.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+
+from .archs import CorrespondenceGenerationArch
+from .dynagg import DynAgg
+from .fusion import MRAPAFusion
+from .matcher import feature_match_index_batched, pre_offsets
+
+_VGG16_TO_CONV3_1 = [('conv1_1', (3, 64)), ('relu1_1', None), ('conv1_2', (64, 64)), ('relu1_2', None), ('pool1', 'M'),
+                     ('conv2_1', (64, 128)), ('relu2_1', None), ('conv2_2', (128, 128)), ('relu2_2', None),
+                     ('pool2', 'M'), ('conv3_1', (128, 256))]
+
+
+@torch.no_grad()
+def default_init_weights(module_list, scale=1, bias_fill=0, **kwargs):
+    """arch_util.py:43-70 (conv / linear branch)."""
+    if not isinstance(module_list, list):
+        module_list = [module_list]
+    for module in module_list:
+        for m in module.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                init.kaiming_normal_(m.weight, **kwargs)
+                m.weight.data *= scale
+                if m.bias is not None:
+                    m.bias.data.fill_(bias_fill)
+
+
+def srntt_init_weights(net, init_gain=0.02):
+    """arch_util.py:18-40 with init_type='normal'."""
+    def init_func(m):
+        name = m.__class__.__name__
+        if hasattr(m, 'weight') and ('Conv' in name or 'Linear' in name):
+            init.normal_(m.weight.data, 0.0, init_gain)
+            if hasattr(m, 'bias') and m.bias is not None:
+                init.constant_(m.bias.data, 0.0)
+    net.apply(init_func)
+
+
+def make_layer(basic_block, num_basic_block, **kwarg):
+    return nn.Sequential(*[basic_block(**kwarg) for _ in range(num_basic_block)])
+
+
+class ResidualBlockNoBN(nn.Module):
+    """arch_util.py:88-117."""
+
+    def __init__(self, num_feat=64, res_scale=1, pytorch_init=False):
+        super().__init__()
+        self.res_scale = res_scale
+        self.conv1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1, bias=True)
+        self.conv2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1, bias=True)
+        self.relu = nn.ReLU(inplace=True)
+        if not pytorch_init:
+            default_init_weights([self.conv1, self.conv2], 0.1)
+
+    def forward(self, x):
+        return x + self.conv2(self.relu(self.conv1(x))) * self.res_scale
+
+
+class ContrasExtractorLayer(nn.Module):
+    """VGG16 features up to conv3_1 (no ReLU after it), parameters under `model.<layer>`."""
+
+    def __init__(self):
+        super().__init__()
+        layers = OrderedDict()
+        for name, spec in _VGG16_TO_CONV3_1:
+            if spec is None:
+                layers[name] = nn.ReLU(inplace=True)
+            elif spec == 'M':
+                layers[name] = nn.MaxPool2d(kernel_size=2, stride=2)
+            else:
+                layers[name] = nn.Conv2d(spec[0], spec[1], 3, padding=1)
+        self.model = nn.Sequential(layers)
+        self.register_buffer('mean', torch.Tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer('std', torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+
+    def forward(self, batch):
+        return self.model((batch - self.mean) / self.std)
+
+
+class ContrasMultiExtractorSep(nn.Module):
+    """Same forward contract as the reference (list of {'dense_features1','dense_features2'} dicts) plus
+    `forward_batched` which runs all references through the second tower in one call."""
+
+    def __init__(self):
+        super().__init__()
+        self.feature_extraction_image1 = ContrasExtractorLayer()
+        self.feature_extraction_image2 = ContrasExtractorLayer()
+
+    def forward(self, image1, image_list):
+        f1 = self.feature_extraction_image1(image1)
+        return [{'dense_features1': f1, 'dense_features2': self.feature_extraction_image2(im)} for im in image_list]
+
+    def forward_batched(self, image1, refs):
+        """image1 [B,3,H,W], refs [B,R,3,H,W] -> (f1 [B,256,h,w], f2 [B*R,256,h,w])."""
+        return self.feature_extraction_image1(image1), self.feature_extraction_image2(refs.flatten(0, 1))
+
+
+class ContentExtractor(nn.Module):
+    def __init__(self, in_nc=3, out_nc=3, nf=64, n_blocks=16):
+        super().__init__()
+        self.conv_first = nn.Conv2d(in_nc, nf, 3, 1, 1)
+        self.body = make_layer(ResidualBlockNoBN, n_blocks, num_feat=nf)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        default_init_weights([self.conv_first], 0.1)
+
+    def forward(self, x):
+        return self.body(self.lrelu(self.conv_first(x)))
+
+
+class DynamicAggregationRestoration(nn.Module):
+    """ref_mrapa_restoration_arch.py:140-259, same attribute names."""
+
+    def __init__(self, ngf=64, n_blocks=16, groups=8):
+        super().__init__()
+        for name, c in (('small', 256), ('medium', 128), ('large', 64)):
+            setattr(self, f'{name}_offset_conv1', nn.Conv2d(ngf + c, c, 3, 1, 1, bias=True))
+            setattr(self, f'{name}_offset_conv2', nn.Conv2d(c, c, 3, 1, 1, bias=True))
+            setattr(self, f'{name}_dyn_agg', DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=groups,
+                                                     extra_offset_mask=True))
+            setattr(self, f'head_{name}', MRAPAFusion(nf=ngf, ref_nf=c))
+            setattr(self, f'body_{name}', make_layer(ResidualBlockNoBN, n_blocks, num_feat=ngf))
+        self.tail_small = nn.Sequential(nn.Conv2d(ngf, ngf * 4, 3, 1, 1), nn.PixelShuffle(2), nn.LeakyReLU(0.1, True))
+        self.tail_medium = nn.Sequential(nn.Conv2d(ngf, ngf * 4, 3, 1, 1), nn.PixelShuffle(2), nn.LeakyReLU(0.1, True))
+        self.tail_large = nn.Sequential(nn.Conv2d(ngf, ngf // 2, 3, 1, 1), nn.LeakyReLU(0.1, True),
+                                        nn.Conv2d(ngf // 2, 3, 3, 1, 1))
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    _SCALES = (('small', 'relu3_1'), ('medium', 'relu2_1'), ('large', 'relu1_1'))
+
+    def forward(self, x, pre_offset_list, img_ref_feat_list):
+        """Reference contract: lists over references of pre_offset / VGG feature dicts."""
+        for name, key in self._SCALES:
+            conv1, conv2 = getattr(self, f'{name}_offset_conv1'), getattr(self, f'{name}_offset_conv2')
+            agg = getattr(self, f'{name}_dyn_agg')
+            swapped = []
+            for pre_offset, feat in zip(pre_offset_list, img_ref_feat_list):
+                o = self.lrelu(conv1(torch.cat([x, feat[key]], 1)))
+                o = self.lrelu(conv2(o))
+                swapped.append(self.lrelu(agg([feat[key], o], pre_offset[key])))
+            h = getattr(self, f'head_{name}')(x, swapped)
+            h = getattr(self, f'body_{name}')(h) + x
+            x = getattr(self, f'tail_{name}')(h)
+        return x
+
+    def forward_batched(self, x, max_idx, ref_feats, n_refs):
+        """Inference fast path.  max_idx int64 [B*R,h-2,w-2] (pairs laid out [B,R]); ref_feats {layer: [B*R,C,H,W]}.
+        The R references are stacked into the batch of the offset convolutions and of ONE fused DynAgg launch."""
+        r = n_refs
+        for s, (name, key) in zip((1, 2, 4), self._SCALES):
+            conv1, conv2 = getattr(self, f'{name}_offset_conv1'), getattr(self, f'{name}_offset_conv2')
+            agg = getattr(self, f'{name}_dyn_agg')
+            feat = ref_feats[key]                                           # [B*R, C, H, W]
+            xr = x.repeat_interleave(r, dim=0)                              # [B*R, ngf, H, W]
+            o = self.lrelu(conv1(torch.cat([xr, feat], 1)))
+            o = self.lrelu(conv2(o))
+            y = self.lrelu(agg.forward_fused([feat, o], max_idx, s))        # [B*R, C, H, W]
+            b = x.shape[0]
+            swapped = list(y.view(b, r, *y.shape[1:]).unbind(1))
+            h = getattr(self, f'head_{name}')(x, swapped)
+            h = getattr(self, f'body_{name}')(h) + x
+            x = getattr(self, f'tail_{name}')(h)
+        return x
+
+
+class MRAPARestorationNet(nn.Module):
+    """ref_mrapa_restoration_arch.py:99-137."""
+
+    def __init__(self, ngf=64, n_blocks=16, groups=8):
+        super().__init__()
+        self.content_extractor = ContentExtractor(in_nc=3, out_nc=3, nf=ngf, n_blocks=n_blocks)
+        self.dyn_agg_restore = DynamicAggregationRestoration(ngf, n_blocks, groups)
+        srntt_init_weights(self, init_gain=0.02)
+        for name in ('small', 'medium', 'large'):
+            getattr(self.dyn_agg_restore, f'{name}_dyn_agg').init_offset()
+
+    def forward(self, x, pre_offset_list, img_ref_feat_list):
+        base = F.interpolate(x, None, 4, 'bilinear', False)
+        return self.dyn_agg_restore(self.content_extractor(x), pre_offset_list, img_ref_feat_list) + base
+
+    def forward_batched(self, x, max_idx, ref_feats, n_refs):
+        base = F.interpolate(x, None, 4, 'bilinear', False)
+        return self.dyn_agg_restore.forward_batched(self.content_extractor(x), max_idx, ref_feats, n_refs) + base
+
+
+class MRefSRPipeline(nn.Module):
+    """net_extractor -> net_map -> net_g as MultiRefRestorationModel.test() wires them
+    (multi_ref_restoration_model.py:281-294), batched over references."""
+
+    def __init__(self, ngf=64, n_blocks=16, groups=8, match_mode='auto'):
+        super().__init__()
+        self.net_extractor = ContrasMultiExtractorSep()
+        self.net_map = CorrespondenceGenerationArch(patch_size=3, stride=1,
+                                                    vgg_layer_list=['relu1_1', 'relu2_1', 'relu3_1'], vgg_type='vgg19',
+                                                    match_mode=match_mode)
+        self.net_g = MRAPARestorationNet(ngf=ngf, n_blocks=n_blocks, groups=groups)
+        self.match_mode = match_mode
+
+    @torch.no_grad()
+    def forward(self, img_in_lq, img_in_up, img_refs):
+        """img_in_lq [B,3,H/4,W/4], img_in_up [B,3,H,W] (the LR input upsampled x4), img_refs [B,R,3,H,W] -> SR [B,3,H,W]."""
+        b, r = img_refs.shape[:2]
+        f1, f2 = self.net_extractor.forward_batched(img_in_up, img_refs)
+        max_idx, _ = feature_match_index_batched(f1, f2, 3, 1, 1, True, True, normalize_pixels=True, in_div=r,
+                                                 mode=self.match_mode)
+        ref_feats = self.net_map.vgg(img_refs.flatten(0, 1))
+        return self.net_g.forward_batched(img_in_lq, max_idx, ref_feats, r)
+
+    @torch.no_grad()
+    def forward_reference_order(self, img_in_lq, img_in_up, img_refs):
+        """The reference's own operator order (one net_map call per reference, materialised pre-offsets, DynAgg through
+        the modulated_deform_conv boundary): slower, used to cross-check `forward`."""
+        refs = list(img_refs.unbind(1))
+        feats = self.net_extractor(img_in_up, refs)
+        pres, rfs = [], []
+        for f, ref in zip(feats, refs):
+            pre, rf = self.net_map(f, ref)
+            pres.append(pre)
+            rfs.append(rf)
+        return self.net_g(img_in_lq, pres, rfs)

@@ -260,6 +260,45 @@ def gen_dcnv1():
     print('dcnv1.npz', tuple(y.shape))
 
 
+def gen_full_model():
+    """End-to-end reference forward (extractor -> net_map per reference -> net_g), exactly as
+    basicsr/models/multi_ref_restoration_model.py:284-293 wires it, with key-seeded weights (tests/util.py)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from tests.util import refill_parameters
+    from basicsr.archs.contras_multi_extractor_arch import ContrasMultiExtractorSep
+    from basicsr.archs.corres_generation_arch import CorrespondenceGenerationArch
+    from basicsr.archs.ref_mrapa_restoration_arch import MRAPARestorationNet
+    ext = refill_parameters(ContrasMultiExtractorSep().eval(), 1)
+    nmap = refill_parameters(CorrespondenceGenerationArch(patch_size=3, stride=1,
+                                                          vgg_layer_list=['relu1_1', 'relu2_1', 'relu3_1'],
+                                                          vgg_type='vgg19').eval(), 2)
+    netg = refill_parameters(MRAPARestorationNet(ngf=64, n_blocks=16, groups=8).eval(), 3)
+    g = torch.Generator().manual_seed(2024)
+    b, r, H, W = 2, 2, 48, 56
+    gt = torch.rand(b, 3, H, W, generator=g)
+    gt = F.avg_pool2d(F.pad(gt, (2, 2, 2, 2), mode='reflect'), 5, 1)            # band-limited image
+    lq = F.interpolate(gt, scale_factor=0.25, mode='bicubic', align_corners=False).clamp(0, 1)
+    up = F.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    refs = []
+    for k in range(r):
+        img = torch.roll(gt, shifts=(4 * (k + 1), -8 * (k + 1)), dims=(2, 3)) if k == 0 else torch.rand(b, 3, H, W, generator=g)
+        refs.append(img)
+    with torch.no_grad():
+        feats = ext(up, refs)
+        pres, rfs = [], []
+        for f, ref in zip(feats, refs):
+            pre, rf = nmap(f, ref)
+            pres.append(pre)
+            rfs.append(rf)
+        sr = netg(lq, pres, rfs)
+    out = dict(lq=lq.numpy(), up=up.numpy(), refs=torch.stack(refs, 1).numpy(), sr=sr.numpy(),
+               keys_ext=np.array(sorted(ext.state_dict().keys())), keys_map=np.array(sorted(nmap.state_dict().keys())),
+               keys_g=np.array(sorted(netg.state_dict().keys())),
+               shapes_g=np.array([str(tuple(v.shape)) for k, v in sorted(netg.state_dict().items())]))
+    np.savez_compressed(os.path.join(OUT, 'full_model.npz'), **out)
+    print('full_model.npz sr', tuple(sr.shape), 'mean', float(sr.mean()), 'std', float(sr.std()), 'n_keys', len(out['keys_g']))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
     install_shims()
@@ -268,4 +307,5 @@ if __name__ == '__main__':
     gen_dynagg()
     gen_fusion()
     gen_dcnv1()
+    gen_full_model()
     print('sizes:', {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT)) if f.endswith('.npz')})

@@ -101,3 +101,16 @@ def test_correspondence_arch_mirrors_reference_keys():
     feats = net.vgg(torch.rand(1, 3, 16, 16))
     assert {k: tuple(v.shape) for k, v in feats.items()} == {'relu1_1': (1, 64, 16, 16), 'relu2_1': (1, 128, 8, 8),
                                                             'relu3_1': (1, 256, 4, 4)}
+
+
+def test_full_model_state_dict_keys_match_reference(golden):
+    """The mirrors of the three MRefSR nets carry exactly the reference's parameter names and shapes (350 keys in
+    net_g), so reference checkpoints load unchanged."""
+    from mrefsr_b200.models import MRefSRPipeline
+    g = golden('full_model')
+    m = MRefSRPipeline()
+    assert sorted(m.net_extractor.state_dict().keys()) == list(g('keys_ext'))
+    assert sorted(m.net_map.state_dict().keys()) == list(g('keys_map'))
+    sd = m.net_g.state_dict()
+    assert sorted(sd.keys()) == list(g('keys_g')) and len(sd) == 350
+    assert [str(tuple(v.shape)) for k, v in sorted(sd.items())] == list(g('shapes_g'))

@@ -30,3 +30,26 @@ def match_parity(idx, val, fi, fr, kw, val_rtol=1e-3, gap_tol=1e-5, dtype=torch.
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def refill_parameters(module, seed=0):
+    """Deterministic, init-order-independent weights: every state-dict entry (except the fixed mean/std buffers) is
+    re-drawn from a generator seeded by its KEY, so a reference module and its mirror with equal key names get equal
+    weights.  Used by tests/golden/make_golden.py (reference side) and the full-model parity test (our side)."""
+    import zlib
+    sd = module.state_dict()
+    with torch.no_grad():
+        for key in sorted(sd):
+            t = sd[key]
+            if key.endswith('mean') or key.endswith('std') or not t.dtype.is_floating_point:
+                continue
+            g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + seed) & 0x7fffffff)
+            if t.dim() == 4:
+                fan_in = t.shape[1] * t.shape[2] * t.shape[3]
+                scale = (0.25 if 'conv_offset_mask' in key else 0.7) / fan_in ** 0.5
+                t.copy_(torch.randn(t.shape, generator=g) * scale)
+            elif t.numel() == 1:
+                t.fill_(0.25)                       # PReLU slope
+            else:
+                t.copy_(torch.randn(t.shape, generator=g) * 0.02)
+    return module
