@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--cpu-images', type=int, default=2, help='images in the bounded CPU-baseline sample')
     ap.add_argument('--match-mode', default='auto')
     ap.add_argument('--dcn-mode', default='auto')
+    ap.add_argument('--no-full-model', action='store_true', help='skip the whole-network (images in -> SR out) leg')
     ap.add_argument('--no-fused', action='store_true',
                     help='materialise pre-offsets / offset / mask (reference operator boundaries) instead of the '
                          'fused DynAgg gather')
@@ -286,6 +287,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def full_model_leg(dev, b, r, rank, world, dist, barrier, steps=5):
+    from mrefsr_b200.models import MRefSRPipeline
+    torch.manual_seed(10)
+    net = MRefSRPipeline().eval().to(dev)
+    g = torch.Generator().manual_seed(99 + rank)
+    lq = torch.rand(b, 3, 40, 40, generator=g).pin_memory()
+    up = torch.nn.functional.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1).pin_memory()
+    refs = torch.rand(b, r, 3, 160, 160, generator=g).pin_memory()
+
+    def step():
+        sr = net(lq.to(dev, non_blocking=True), up.to(dev, non_blocking=True), refs.to(dev, non_blocking=True))
+        return sr.to('cpu', non_blocking=True)
+    for _ in range(3):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    h2d = sum(t.numel() * 4 for t in (lq, up, refs))
+    return {'value': b * world * steps / float(dt.item()), 'unit': UNIT, 'ms_per_step': float(dt.item()) / steps * 1e3,
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': out.numel() * 4, 'steps': steps,
+            'note': 'whole x4 MRefSR network, random-init weights, host images in -> SR images out; '
+                    'convolutions = cuDNN (TF32 allowed)'}
+
+
 # ----------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -398,6 +428,16 @@ def main():
                'd2h_bytes_per_step': d2h[0], 'steps': n_e2e,
                'note': 'pinned host tensors -> operator API -> host; PCIe-bound at this operator boundary'}
 
+    # ---- full model: the whole x4 MRefSR network (extractor -> matcher -> VGG19 -> MRAPARestorationNet) from pinned
+    # host images to SR images on the host; plain convolutions are cuDNN (TF32 allowed, torch default), the alignment
+    # path is this repo's kernels.  Extra information next to the contract keys: the literal "x4 SR images/sec".
+    full = None
+    if not args.no_full_model:
+        try:
+            full = full_model_leg(dev, b, r, rank, world, dist, barrier)
+        except Exception as e:  # noqa: BLE001
+            full = {'error': repr(e)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -444,7 +484,7 @@ def main():
                        'match_mode': args.match_mode, 'dcn_mode': args.dcn_mode,
                        'dynagg': 'fused gather (conv_out + arg-max map)' if fused else 'materialised offset/mask'},
             'roofline': roofline, 'roofline_all': roof_all, 'kernel_ms_per_step': per_kernel,
-            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks}
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'full_model': full}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
