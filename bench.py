@@ -452,6 +452,11 @@ def main():
             per_kernel[k] = {'ms_per_step': tot_ms / args.steps, 'launches_per_step': n / args.steps}
     dom = max((k for k in per_kernel if k in work), key=lambda k: per_kernel[k]['ms_per_step'])
 
+    traffic = {}
+    tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tp) and b == 16 and r == 5 and fused:     # measured for exactly this workload
+        traffic = json.load(open(tp)).get('bytes_per_step', {})
+
     def roof(k):
         t_s = per_kernel[k]['ms_per_step'] / 1e3
         wk = work[k]
@@ -460,11 +465,12 @@ def main():
         if t_flop >= t_byte:
             a = wk['flops'] / t_s / 1e12
             return {'kernel': k, 'bound': 'tensor', 'achieved': a, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': a / pk['bf16_tflops_sustained'], 'traffic': None,
+                    'frac': a / pk['bf16_tflops_sustained'], 'traffic': traffic.get(k),
                     'peak_source': pk['source'] + ' (cuBLAS bf16, sustained)'}
         a = wk['bytes'] / t_s / 1e9
         return {'kernel': k, 'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                'frac': a / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'] + ' (copy)'}
+                'frac': a / pk['hbm_gbs'], 'traffic': traffic.get(k), 'algorithmic_bytes': wk['bytes'],
+                'peak_source': pk['source'] + ' (copy)'}
 
     roofline = roof(dom)
     roofline['ms_per_launch'] = per_kernel[dom]['ms_per_step'] / per_kernel[dom]['launches_per_step']
