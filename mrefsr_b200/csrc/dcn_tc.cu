@@ -54,6 +54,7 @@ struct DcnTcParams {
     int P, total_rows, tiles, n_slabs, taps, cdg, gs, stages, nbuf, stage_bytes;
     // fused DynAgg mode
     int fused, flow_scale, hp, wp;
+    unsigned wp_magic;   // ceil(2^32 / wp): idx / wp == umulhi(idx, wp_magic) for idx < hp * wp  (hp * wp * wp < 2^32)
 };
 
 __device__ __forceinline__ float to_tf32(float v) {
@@ -119,94 +120,41 @@ __global__ void dcn_weight_repack_kernel(const float* __restrict__ w, float* __r
 
 constexpr int TAB_STRIDE = TBM + 4;   // per-group row stride of the sample table (+4: no bank conflicts)
 
-// One table entry = one (row, deform-group-in-slab).  Raw inputs are loaded one K step before they are decoded.
-struct RowCoord {
-    int b, p, oy, ox;   // b < 0: row outside the problem
-};
-struct RawParam {
-    float dy, dx, mk;
-    int b, yx, tij;   // yx = oy << 16 | ox, tij = ti << 8 | tj
-    int mi, fyx;      // fused mode: matched index and flow-grid cell (fy << 16 | fx), fyx < 0: no pre-offset
-};
-
-template <bool FUSED>
-__device__ __forceinline__ RawParam load_raw_param(const DcnTcParams& prm, const float* __restrict__ offset,
-                                                   const float* __restrict__ mask,
-                                                   const long long* __restrict__ max_idx, const RowCoord& rc, int dgi,
-                                                   int tap, int ti, int tj) {
-    const DcnShape& s = prm.s;
-    RawParam r;
-    r.dy = r.dx = r.mk = 0.f;
-    r.mi = 0;
-    r.fyx = -1;
-    r.b = rc.b;
-    r.yx = (rc.oy << 16) | rc.ox;
-    r.tij = (ti << 8) | tj;
-    if (rc.b < 0) return r;
-    const int K = prm.taps, P = prm.P;
-    if (!FUSED) {
-        const size_t ob = ((size_t)(rc.b * s.DG + dgi) * 2 * K + 2 * tap) * P + rc.p;
-        r.dy = ldg_early(offset + ob);
-        r.dx = ldg_early(offset + ob + P);
-        r.mk = mask ? ldg_early(mask + ((size_t)(rc.b * s.DG + dgi) * K + tap) * P + rc.p) : 1.f;
-    } else {
-        const size_t cb = (size_t)rc.b * 3 * s.DG * K * P + rc.p;
-        r.dy = ldg_early(offset + cb + (size_t)(2 * (dgi * K + tap)) * P);
-        r.dx = ldg_early(offset + cb + (size_t)(2 * (dgi * K + tap) + 1) * P);
-        r.mk = ldg_early(offset + cb + (size_t)(2 * s.DG * K + dgi * K + tap) * P);   // raw; sigmoid at decode
-        // pre-offset: s * flow[Y/s - i, X/s - j], zero outside the (h-2) x (w-2) flow grid; the arg-max value
-        // is kept raw (r.mi) and turned into a flow at decode time so that this load is not waited on here
-        const int fy = rc.oy / prm.flow_scale - ti, fx = rc.ox / prm.flow_scale - tj;
-        r.fyx = -1;
-        if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
-            r.mi = (int)ldg_early_s64(max_idx + ((size_t)rc.b * prm.hp + fy) * prm.wp + fx);
-            r.fyx = (fy << 16) | fx;
-        }
-    }
-    return r;
+__device__ __forceinline__ int ldg_early_s32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
-// Decode into the shared-memory sample table: element offset of the (clamped) top-left corner into the NHWC
-// input with two flag bits (bit0: +1 pixel in x is addressable, bit1: +1 row is addressable) and the four
-// bilinear weights with the modulation mask and corner validity folded in
-// (deform_conv_cuda_kernel.cu:468-497, :618-627).
-template <bool FUSED>
-__device__ __forceinline__ void store_param(const DcnTcParams& prm, const RawParam& r, int* __restrict__ tbase,
-                                            float* __restrict__ tw, int e, int wstride) {
-    const DcnShape& s = prm.s;
-    int base = 0;
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-    if (r.b >= 0) {
-        const int ti = r.tij >> 8, tj = r.tij & 255;
-        float dy = r.dy, dx = r.dx;
-        if (FUSED && r.fyx >= 0) {
-            const int my = r.mi / prm.wp, mx = r.mi - my * prm.wp;
-            dy += (float)((my - (r.fyx >> 16)) * prm.flow_scale);
-            dx += (float)((mx - (r.fyx & 0xffff)) * prm.flow_scale);
-        }
-        const float y = (float)((r.yx >> 16) * s.sh - s.ph + ti * s.dh) + dy;
-        const float x = (float)((r.yx & 0xffff) * s.sw - s.pw + tj * s.dw) + dx;
-        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
-            const float mk = FUSED ? 1.f / (1.f + __expf(-r.mk)) : r.mk;
-            const int y0 = (int)floorf(y), x0 = (int)floorf(x);
-            const float ly = y - (float)y0, lx = x - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
-            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
-            base = ((r.b * s.H + yc) * s.W + xc) * s.C;
-            if (tx0 && tx1) base |= 1;
-            if (ty0 && ty1) base |= 2;
-            // when the low corner is clamped away (y0 = -1 or x0 = -1) the "high" corner sits at the base itself
-            w0 = (ty0 && tx0) ? hy * hx * mk : 0.f;
-            w1 = (ty0 && tx1) ? hy * lx * mk : 0.f;
-            w2 = (ty1 && tx0) ? ly * hx * mk : 0.f;
-            w3 = (ty1 && tx1) ? ly * lx * mk : 0.f;
+// Drain one finished accumulator tile: tcgen05.ld 32x32b, bias add, position-major coalesced NCHW stores.
+// (Inlined at the four poll sites of the producer loop: an out-of-line call forces spills at the 96-register cap.)
+__device__ __forceinline__ void dcn_epilogue_tile(float* __restrict__ out, const float* __restrict__ bias,
+                                               uint32_t tmem_base, uint64_t* tempty_bar, int tile, int buf, int warp,
+                                               int lane, int Co, int P, int total_rows) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int m = tile * TBM + half * 128 + warp * 32 + lane;
+        const bool ok = m < total_rows;
+        const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
+        float* o = out + (size_t)b * Co * P + p;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * Co + half * Co;
+#pragma unroll 1
+        for (int c0 = 0; c0 < Co; c0 += 8) {
+            uint32_t v[8];
+            tmem_ld_32x8(taddr + c0, v);
+            tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float bv = bias ? __ldg(bias + c0 + e) : 0.f;
+                    o[(size_t)(c0 + e) * P] = __uint_as_float(v[e]) + bv;
+                }
+            }
         }
     }
-    tbase[e] = base;
-    tw[e] = w0;
-    tw[e + wstride] = w1;
-    tw[e + 2 * wstride] = w2;
-    tw[e + 3 * wstride] = w3;
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar);
 }
 
 template <bool FUSED>
@@ -270,6 +218,9 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         // Everything is mbarrier dataflow with one elected arrive per warp, so warps drift by up to two K steps
         // and hide each other's latency.  Warps 0..3 additionally drain finished accumulators (epilogue): they
         // poll the TMEM-full barrier while they wait and at every K step.
+        // The loop is instruction-issue sensitive (ncu: >50 % issue-slot use), so everything that is constant per
+        // tile (row coordinates, flow-grid cell, tensor base pointers) or per thread (shared-memory offsets) is
+        // hoisted, and the two table entries of a thread -- same row, different deform group -- share it.
         const int tid = threadIdx.x;
         const int ch = tid & 7;                    // 16-byte chunk (4 channels) within the 32-channel slab
         const int r0 = tid >> 3;                   // rows r0 + T_RSTEP*i, i < T_ITEMS
@@ -277,42 +228,23 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         const int gslab = TBK / prm.cdg;           // deform groups per slab when cdg < 32 (else 0)
         // table entries owned by this thread: e = tid + 512 j -> row = tid % 256, group-in-slab = tid / 256 + 2 j
         const int erow = tid & (TBM - 1), eg0 = tid >> 8;
+        const bool has_entries = eg0 < prm.gs;
+        // swizzled A-tile byte offset of item i is a_off + i * (T_RSTEP * 128): rows r0 + 64 i keep (row & 7)
+        const uint32_t a_off = (uint32_t)r0 * 128u + (uint32_t)((ch ^ (r0 & 7)) << 4);
 
         // ---- epilogue duty (warps 0..3): tiles fully produced but not yet drained
         const bool is_epi = warp < 4;
         int ep_done = 0, prod_done = 0;            // tiles drained / tiles whose K steps this warp has all produced
+        const int nbuf_mask = prm.nbuf - 1;        // nbuf is 1 or 2: buffer = it & mask, phase = (it >> mask) & 1
         auto epilogue_tile = [&](int it) {
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const int buf = it % prm.nbuf;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int m = tile * TBM + half * 128 + warp * 32 + lane;
-                const bool ok = m < prm.total_rows;
-                const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
-                float* o = out + (size_t)b * Co * P + p;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * Co + half * Co;
-#pragma unroll 1
-                for (int c0 = 0; c0 < Co; c0 += 8) {
-                    uint32_t v[8];
-                    tmem_ld_32x8(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (ok) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float bv = bias ? __ldg(bias + c0 + e) : 0.f;
-                            o[(size_t)(c0 + e) * P] = __uint_as_float(v[e]) + bv;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
+            const int buf = it & nbuf_mask;
+            dcn_epilogue_tile(out, bias, tmem_base, &tempty[buf], (int)blockIdx.x + it * (int)gridDim.x, buf, warp, lane,
+                              Co, P, prm.total_rows);
         };
         auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
             if (is_epi && ep_done < prod_done) {
-                const int buf = ep_done % prm.nbuf;
-                if (mbar_try_wait(&tfull[buf], (ep_done / prm.nbuf) & 1)) {
+                const int buf = ep_done & nbuf_mask;
+                if (mbar_try_wait(&tfull[buf], (ep_done >> nbuf_mask) & 1)) {
                     tc_fence_after();
                     epilogue_tile(ep_done);
                     ++ep_done;
@@ -323,28 +255,63 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             while (!mbar_try_wait(bar, parity)) poll_epilogue();
         };
 
-        // ---- table pipeline
-        int l_kb = 0, l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0;   // load cursor
-        RowCoord rc;
+        // ---- table pipeline: per-tile row state of this thread's table row
+        int l_kb = 0, l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0, l_dg0 = 0;   // load cursor
+        int row_yx = -1, row_bH = 0, row_qyx = 0, row_idx0 = 0;   // oy<<16|ox (-1: outside), b*H, flow-grid cell, b*hp*wp
+        const float* row_off = offset;                            // offset / conv_out of (b, plane 0, p)
+        const float* row_msk = mask;                              // mask of (b, plane 0, p)
         auto decode_rows = [&](int tile) {
             const int m = tile * TBM + erow;
-            rc.b = -1;
-            rc.p = rc.oy = rc.ox = 0;
-            if (m < prm.total_rows) {
-                rc.b = m / P;
-                rc.p = m - rc.b * P;
-                rc.oy = rc.p / s.Wo;
-                rc.ox = rc.p - rc.oy * s.Wo;
+            row_yx = -1;
+            if (m < prm.total_rows && has_entries) {
+                const int b = m / P, p = m - b * P, oy = p / s.Wo, ox = p - oy * s.Wo;
+                row_yx = (oy << 16) | ox;
+                row_bH = b * s.H;
+                if (FUSED) {
+                    row_off = offset + (size_t)b * 3 * s.DG * K * P + p;
+                    row_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
+                    row_idx0 = b * prm.hp * prm.wp;
+                } else {
+                    row_off = offset + (size_t)b * 2 * s.DG * K * P + p;
+                    if (mask) row_msk = mask + (size_t)b * s.DG * K * P + p;
+                }
             }
         };
-        RawParam raw[2];
+        // raw inputs of the table being loaded (decoded one K step later)
+        float raw_dy[2], raw_dx[2], raw_mk[2];
+        int raw_yx = -1, raw_bH = 0, raw_tij = 0, raw_mi = 0, raw_fyx = -1;
         auto load_next = [&]() {      // raw <- inputs of table l_kb, then advance the load cursor
+            raw_yx = row_yx;
+            raw_bH = row_bH;
+            raw_tij = (l_ti << 8) | l_tj;
+            raw_fyx = -1;
+            if (row_yx >= 0) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int g = eg0 + 2 * j;
-                if (g < prm.gs) {
-                    const int dgi = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * gslab + g;
-                    raw[j] = load_raw_param<FUSED>(prm, offset, mask, max_idx, rc, dgi, l_tap, l_ti, l_tj);
+                for (int j = 0; j < 2; ++j) {
+                    const int g = eg0 + 2 * j;
+                    if (g < prm.gs) {
+                        const int dgi = l_dg0 + g;
+                        if (!FUSED) {
+                            const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
+                            raw_dy[j] = ldg_early(row_off + o);
+                            raw_dx[j] = ldg_early(row_off + o + (unsigned)P);
+                            raw_mk[j] = mask ? ldg_early(row_msk + (unsigned)((dgi * K + l_tap) * P)) : 1.f;
+                        } else {
+                            const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
+                            raw_dy[j] = ldg_early(row_off + o);
+                            raw_dx[j] = ldg_early(row_off + o + (unsigned)P);
+                            raw_mk[j] = ldg_early(row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));   // raw; sigmoid at decode
+                        }
+                    }
+                }
+                if (FUSED) {
+                    // pre-offset: s * flow[Y/s - i, X/s - j], zero outside the (h-2) x (w-2) flow grid; the arg-max
+                    // value is kept raw and turned into a flow at decode time so that this load is not waited on here
+                    const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
+                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
+                        raw_mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + (row_idx0 + fy * prm.wp + fx)));   // low word
+                        raw_fyx = (fy << 16) | fx;
+                    }
                 }
             }
             ++l_kb;
@@ -359,18 +326,66 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
                     l_tile += gridDim.x;
                     if (l_kb < total_kb) decode_rows(l_tile);
                 }
+                l_dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * gslab;
             }
         };
         int d_slot = 0;
         uint32_t d_phase = 0;
+        // Decode into the shared-memory sample table: element offset of the (clamped) top-left corner into the
+        // NHWC input with two flag bits (bit0: +1 pixel in x is addressable, bit1: +1 row is addressable) and the
+        // four bilinear weights with the modulation mask and corner validity folded in
+        // (deform_conv_cuda_kernel.cu:468-497, :618-627).
         auto decode_store = [&]() {   // raw -> ring slot d_slot
             wait_poll(&tab_empty[d_slot], d_phase ^ 1);
-            int* tb = tab_base + d_slot * tab_n;
-            float* tw = tab_w + d_slot * 4 * tab_n;
+            if (has_entries) {
+                int* tb = tab_base + d_slot * tab_n + erow;
+                float* tw = tab_w + d_slot * 4 * tab_n + erow;
+                float ybase = 0.f, xbase = 0.f, fly = 0.f, flx = 0.f;
+                if (raw_yx >= 0) {
+                    ybase = (float)((raw_yx >> 16) * s.sh - s.ph + (raw_tij >> 8) * s.dh);
+                    xbase = (float)((raw_yx & 0xffff) * s.sw - s.pw + (raw_tij & 255) * s.dw);
+                    if (FUSED && raw_fyx >= 0) {
+                        const int my = (int)__umulhi((unsigned)raw_mi, prm.wp_magic), mx = raw_mi - my * prm.wp;
+                        fly = (float)((my - (raw_fyx >> 16)) * prm.flow_scale);
+                        flx = (float)((mx - (raw_fyx & 0xffff)) * prm.flow_scale);
+                    }
+                }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int g = eg0 + 2 * j;
-                if (g < prm.gs) store_param<FUSED>(prm, raw[j], tb, tw, g * TAB_STRIDE + erow, tab_n);
+                for (int j = 0; j < 2; ++j) {
+                    const int g = eg0 + 2 * j;
+                    if (g < prm.gs) {
+                        int base = 0;
+                        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                        if (raw_yx >= 0) {
+                            const float y = ybase + (FUSED ? raw_dy[j] + fly : raw_dy[j]);
+                            const float x = xbase + (FUSED ? raw_dx[j] + flx : raw_dx[j]);
+                            if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+                                const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-raw_mk[j])) : raw_mk[j];
+                                const float fy0 = floorf(y), fx0 = floorf(x);
+                                const int y0 = (int)fy0, x0 = (int)fx0;
+                                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                                const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+                                const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+                                base = ((raw_bH + yc) * s.W + xc) * C;
+                                if (tx0 && tx1) base |= 1;
+                                if (ty0 && ty1) base |= 2;
+                                // when the low corner is clamped away (y0 = -1 or x0 = -1) the "high" corner sits at
+                                // the base itself
+                                const float hym = hy * mk, lym = ly * mk;
+                                w0 = (ty0 && tx0) ? hym * hx : 0.f;
+                                w1 = (ty0 && tx1) ? hym * lx : 0.f;
+                                w2 = (ty1 && tx0) ? lym * hx : 0.f;
+                                w3 = (ty1 && tx1) ? lym * lx : 0.f;
+                            }
+                        }
+                        const int e = g * TAB_STRIDE;
+                        tb[e] = base;
+                        tw[e] = w0;
+                        tw[e + tab_n] = w1;
+                        tw[e + 2 * tab_n] = w2;
+                        tw[e + 3 * tab_n] = w3;
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&tab_full[d_slot]);
@@ -389,13 +404,14 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
 
         int stage = 0, c_slab = 0, c_tap = 0, g_slot = 0;
         uint32_t phase = 0, g_phase = 0;
+        const int dx_elems = C, dy_elems = s.W * C;
         for (int kb = 0; kb < total_kb; ++kb) {
             if (kb + T_AHEAD < total_kb) decode_store();
             if (kb + T_AHEAD + 1 < total_kb) load_next();
             poll_epilogue();
-            const int c0 = c_slab * TBK + ch * 4;
-            const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE;
-            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE;
+            const float* xs = xt + (c_slab * TBK + ch * 4);
+            const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE + r0;
+            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE + r0;
             wait_poll(&tab_full[g_slot], g_phase);
             wait_poll(&empty[stage], phase ^ 1);
             uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
@@ -403,36 +419,36 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
                 mbar_expect_tx(&full[stage], Co * 128);
                 tma_load_3d(A + T_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
             }
+            uint8_t* Ad = A + a_off;
 #pragma unroll
             for (int bt = 0; bt < T_ITEMS / T_BATCH; ++bt) {
                 float4 v[T_BATCH][4];
                 float w[T_BATCH][4];
 #pragma unroll
                 for (int ii = 0; ii < T_BATCH; ++ii) {
-                    const int r = r0 + T_RSTEP * (bt * T_BATCH + ii);
+                    const int r = T_RSTEP * (bt * T_BATCH + ii);
                     const int bf = tb[r];
                     w[ii][0] = tw[r];
                     w[ii][1] = tw[r + tab_n];
                     w[ii][2] = tw[r + 2 * tab_n];
                     w[ii][3] = tw[r + 3 * tab_n];
-                    const float* base = xt + (size_t)(bf & ~3) + c0;
-                    const int dxo = (bf & 1) ? C : 0, dyo = (bf & 2) ? s.W * C : 0;
-                    v[ii][0] = ldg4(base);
-                    v[ii][1] = ldg4(base + dxo);
-                    v[ii][2] = ldg4(base + dyo);
-                    v[ii][3] = ldg4(base + dyo + dxo);
+                    const unsigned i0 = (unsigned)(bf & ~3);
+                    const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
+                    const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
+                    const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+                    v[ii][0] = ldg4(xs + i0);
+                    v[ii][1] = ldg4(xs + i1);
+                    v[ii][2] = ldg4(xs + i2);
+                    v[ii][3] = ldg4(xs + i3);
                 }
 #pragma unroll
                 for (int ii = 0; ii < T_BATCH; ++ii) {
-                    const int r = r0 + T_RSTEP * (bt * T_BATCH + ii);
                     float4 o;
                     o.x = tf32_round_bits(w[ii][0] * v[ii][0].x + w[ii][1] * v[ii][1].x + w[ii][2] * v[ii][2].x + w[ii][3] * v[ii][3].x);
                     o.y = tf32_round_bits(w[ii][0] * v[ii][0].y + w[ii][1] * v[ii][1].y + w[ii][2] * v[ii][2].y + w[ii][3] * v[ii][3].y);
                     o.z = tf32_round_bits(w[ii][0] * v[ii][0].z + w[ii][1] * v[ii][1].z + w[ii][2] * v[ii][2].z + w[ii][3] * v[ii][3].z);
                     o.w = tf32_round_bits(w[ii][0] * v[ii][0].w + w[ii][1] * v[ii][1].w + w[ii][2] * v[ii][2].w + w[ii][3] * v[ii][3].w);
-                    const int rr = r & 127;
-                    uint8_t* dst = A + (r >> 7) * (128 * 128) + rr * 128 + ((ch ^ (rr & 7)) << 4);
-                    *reinterpret_cast<float4*>(dst) = o;
+                    *reinterpret_cast<float4*>(Ad + (bt * T_BATCH + ii) * (T_RSTEP * 128)) = o;
                 }
             }
             fence_proxy_async();
@@ -459,8 +475,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         }
         // drain the remaining accumulators
         while (is_epi && ep_done < prod_done) {
-            const int buf = ep_done % prm.nbuf;
-            mbar_wait_backoff(&tfull[buf], (ep_done / prm.nbuf) & 1, 64);
+            const int buf = ep_done & nbuf_mask;
+            mbar_wait_backoff(&tfull[buf], (ep_done >> nbuf_mask) & 1, 64);
             tc_fence_after();
             epilogue_tile(ep_done);
             ++ep_done;
@@ -472,8 +488,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
-                const int buf = it % prm.nbuf;
-                const uint32_t bphase = (it / prm.nbuf) & 1;
+                const int buf = it & (prm.nbuf - 1);
+                const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
                 mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + buf * 2 * Co;
@@ -570,12 +586,16 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
 
     prm.flow_scale = flow_scale;
     prm.hp = prm.wp = 0;
+    prm.wp_magic = 0;
     if (prm.fused) {
         MREFSR_CHECK(flow_scale >= 1 && s.Ho % flow_scale == 0 && s.Wo % flow_scale == 0, ERR_BAD_ARG,
                      "fused DynAgg: output %dx%d not a multiple of the flow scale %d", s.Ho, s.Wo, flow_scale);
         prm.hp = s.Ho / flow_scale - 2;
         prm.wp = s.Wo / flow_scale - 2;
-        MREFSR_CHECK(prm.hp > 0 && prm.wp > 0, ERR_BAD_ARG, "fused DynAgg: feature grid too small");
+        MREFSR_CHECK(prm.hp > 0 && prm.wp > 1, ERR_BAD_ARG, "fused DynAgg: feature grid too small");
+        MREFSR_CHECK((unsigned long long)prm.hp * prm.wp * prm.wp < (1ull << 32), ERR_BAD_ARG,
+                     "fused DynAgg: feature grid %dx%d too large", prm.hp, prm.wp);
+        prm.wp_magic = 0xFFFFFFFFu / (unsigned)prm.wp + 1u;
     }
     const size_t smem = (size_t)prm.stages * prm.stage_bytes + 256 + table_bytes + 1024;
     int grid = sm_count();
