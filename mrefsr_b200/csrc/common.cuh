@@ -145,6 +145,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// contiguous global range -> L2 (no destination, no completion to wait on); addr and bytes multiples of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- tcgen05 / TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {

@@ -39,9 +39,8 @@ constexpr int TBM = 256;            // rows (output positions) per CTA tile
 constexpr int TBK = 32;             // fp32 channels per K step (128-byte rows)
 constexpr int T_A_BYTES = TBM * 128;
 constexpr int T_PW = 16;             // producer warps: sample table (2 K steps ahead) + gather; warps 0..3 also drain TMEM
-constexpr int T_RSTEP = T_PW * 4;    // row stride between a thread's gather items
-constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items per thread per K step (4)
-constexpr int T_BATCH = 2;                         // items whose loads are issued together
+constexpr int T_RSTEP = T_PW * 8;    // row stride between a thread's gather items (a warp covers 8 rows x 4 chunks)
+constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items (row, 8-channel chunk) per thread per K step (2)
 constexpr int T_PRODUCERS = T_PW * 32;
 constexpr int T_MMA_WARP = T_PW;
 constexpr int T_THREADS = T_PRODUCERS + 32;        // + the MMA warp (17 warps: register budget 100/thread)
@@ -79,7 +78,18 @@ __device__ __forceinline__ long long ldg_early_s64(const long long* p) {
 // round-to-nearest (ties away) to tf32 in one integer add: the tensor core ignores the low 13 mantissa bits
 __device__ __forceinline__ float tf32_round_bits(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 256-bit read-only load: 8 consecutive channels of one corner (one full 32-byte sector per lane)
+struct F8 {
+    float2 v[4];
+};
+__device__ __forceinline__ F8 ldg8(const float* p) {
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0].x), "=f"(r.v[0].y), "=f"(r.v[1].x), "=f"(r.v[1].y), "=f"(r.v[2].x), "=f"(r.v[2].y),
+          "=f"(r.v[3].x), "=f"(r.v[3].y)
+        : "l"(p));
+    return r;
+}
 
 // NCHW -> NHWC (fp32): tile = 32 pixels x up to 128 channels per CTA (256 threads).  Loads: lane = pixel (128-byte
 // coalesced, 16 independent loads per thread in flight); stores: one float4 (4 channels) per lane, 512 bytes
@@ -87,7 +97,9 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
     __shared__ float tile[128][33];
-    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    // samples are converted last-to-first: what is still in L2 when the DCN kernel starts is then the data its
+    // first tiles gather from
+    const int b = gridDim.z - 1 - blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* s = src + (size_t)b * C * HW;
     float* d = dst + (size_t)b * C * HW;
@@ -222,15 +234,17 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         // tile (row coordinates, flow-grid cell, tensor base pointers) or per thread (shared-memory offsets) is
         // hoisted, and the two table entries of a thread -- same row, different deform group -- share it.
         const int tid = threadIdx.x;
-        const int ch = tid & 7;                    // 16-byte chunk (4 channels) within the 32-channel slab
-        const int r0 = tid >> 3;                   // rows r0 + T_RSTEP*i, i < T_ITEMS
-        const int gsub = (ch * 4) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
+        const int ch = tid & 3;                    // 8-channel chunk (two 16-byte pieces) within the 32-channel slab
+        const int r0 = tid >> 2;                   // rows r0 + T_RSTEP*i, i < T_ITEMS
+        const int gsub = (ch * 8) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
         const int gslab = TBK / prm.cdg;           // deform groups per slab when cdg < 32 (else 0)
         // table entries owned by this thread: e = tid + 512 j -> row = tid % 256, group-in-slab = tid / 256 + 2 j
         const int erow = tid & (TBM - 1), eg0 = tid >> 8;
         const bool has_entries = eg0 < prm.gs;
-        // swizzled A-tile byte offset of item i is a_off + i * (T_RSTEP * 128): rows r0 + 64 i keep (row & 7)
-        const uint32_t a_off = (uint32_t)r0 * 128u + (uint32_t)((ch ^ (r0 & 7)) << 4);
+        // swizzled A-tile byte offsets of the two 16-byte pieces of item i are a_off{0,1} + i * (T_RSTEP * 128):
+        // rows r0 + 128 i keep (row & 7), and 128 rows are one 16 KB M-half of the tile
+        const uint32_t a_off0 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch) ^ (r0 & 7)) << 4);
+        const uint32_t a_off1 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch + 1) ^ (r0 & 7)) << 4);
 
         // ---- epilogue duty (warps 0..3): tiles fully produced but not yet drained
         const bool is_epi = warp < 4;
@@ -409,7 +423,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             if (kb + T_AHEAD < total_kb) decode_store();
             if (kb + T_AHEAD + 1 < total_kb) load_next();
             poll_epilogue();
-            const float* xs = xt + (c_slab * TBK + ch * 4);
+            const float* xs = xt + (c_slab * TBK + ch * 8);
             const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE + r0;
             const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE + r0;
             wait_poll(&tab_full[g_slot], g_phase);
@@ -419,37 +433,29 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
                 mbar_expect_tx(&full[stage], Co * 128);
                 tma_load_3d(A + T_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
             }
-            uint8_t* Ad = A + a_off;
 #pragma unroll
-            for (int bt = 0; bt < T_ITEMS / T_BATCH; ++bt) {
-                float4 v[T_BATCH][4];
-                float w[T_BATCH][4];
+            for (int i = 0; i < T_ITEMS; ++i) {
+                const int r = T_RSTEP * i;
+                const int bf = tb[r];
+                const float w0 = tw[r], w1 = tw[r + tab_n], w2 = tw[r + 2 * tab_n], w3 = tw[r + 3 * tab_n];
+                const unsigned i0 = (unsigned)(bf & ~3);
+                const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
+                const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
+                const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+                const F8 v0 = ldg8(xs + i0), v1 = ldg8(xs + i1), v2 = ldg8(xs + i2), v3 = ldg8(xs + i3);
+                const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
+                             p3 = make_float2(w3, w3);
+                float2 o[4];
 #pragma unroll
-                for (int ii = 0; ii < T_BATCH; ++ii) {
-                    const int r = T_RSTEP * (bt * T_BATCH + ii);
-                    const int bf = tb[r];
-                    w[ii][0] = tw[r];
-                    w[ii][1] = tw[r + tab_n];
-                    w[ii][2] = tw[r + 2 * tab_n];
-                    w[ii][3] = tw[r + 3 * tab_n];
-                    const unsigned i0 = (unsigned)(bf & ~3);
-                    const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
-                    const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
-                    const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
-                    v[ii][0] = ldg4(xs + i0);
-                    v[ii][1] = ldg4(xs + i1);
-                    v[ii][2] = ldg4(xs + i2);
-                    v[ii][3] = ldg4(xs + i3);
+                for (int e = 0; e < 4; ++e) {      // packed fp32x2 FMAs: two channels per instruction
+                    float2 a = __fmul2_rn(p0, v0.v[e]);
+                    a = __ffma2_rn(p1, v1.v[e], a);
+                    a = __ffma2_rn(p2, v2.v[e], a);
+                    a = __ffma2_rn(p3, v3.v[e], a);
+                    o[e] = make_float2(tf32_round_bits(a.x), tf32_round_bits(a.y));
                 }
-#pragma unroll
-                for (int ii = 0; ii < T_BATCH; ++ii) {
-                    float4 o;
-                    o.x = tf32_round_bits(w[ii][0] * v[ii][0].x + w[ii][1] * v[ii][1].x + w[ii][2] * v[ii][2].x + w[ii][3] * v[ii][3].x);
-                    o.y = tf32_round_bits(w[ii][0] * v[ii][0].y + w[ii][1] * v[ii][1].y + w[ii][2] * v[ii][2].y + w[ii][3] * v[ii][3].y);
-                    o.z = tf32_round_bits(w[ii][0] * v[ii][0].z + w[ii][1] * v[ii][1].z + w[ii][2] * v[ii][2].z + w[ii][3] * v[ii][3].z);
-                    o.w = tf32_round_bits(w[ii][0] * v[ii][0].w + w[ii][1] * v[ii][1].w + w[ii][2] * v[ii][2].w + w[ii][3] * v[ii][3].w);
-                    *reinterpret_cast<float4*>(Ad + (bt * T_BATCH + ii) * (T_RSTEP * 128)) = o;
-                }
+                *reinterpret_cast<float4*>(A + a_off0 + i * (T_RSTEP * 128)) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                *reinterpret_cast<float4*>(A + a_off1 + i * (T_RSTEP * 128)) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
             }
             fence_proxy_async();
             __syncwarp();
@@ -487,7 +493,25 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             const uint32_t idesc = umma_idesc(2, 128, Co);
             int stage = 0, it = 0;
             uint32_t phase = 0;
+            // L2 prefetch of the NHWC input, paced by the MMA progress: the gather of a tile may touch any pixel
+            // of its sample, so the input slice that belongs to tile t is requested one sample plus one wave of
+            // tiles before tile t is gathered (otherwise nearly every warp-wide gather waits on a DRAM miss).
+            const unsigned long long in_bytes = (unsigned long long)s.B * s.H * s.W * C * 4;
+            const int pf_ahead = (int)gridDim.x + (P + TBM - 1) / TBM + 1;
+            auto prefetch_tile = [&](int t) {
+                if (t >= prm.tiles) return;
+                unsigned long long a = (unsigned long long)t * TBM * (s.H * s.W) / P * C * 4;
+                unsigned long long e = (unsigned long long)(t + 1) * TBM * (s.H * s.W) / P * C * 4;
+                if (e > in_bytes) e = in_bytes;
+                a &= ~15ull;
+                for (; a < e; a += 32768) {
+                    const unsigned long long n = e - a < 32768 ? e - a : 32768;
+                    bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(xt) + a, (uint32_t)((n + 15) & ~15ull));
+                }
+            };
+            for (int t = blockIdx.x; t < pf_ahead; t += gridDim.x) prefetch_tile(t);
             for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
+                prefetch_tile(tile + pf_ahead);
                 const int buf = it & (prm.nbuf - 1);
                 const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
                 mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
@@ -529,7 +553,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
 bool dcn_tc_eligible(const DcnShape& s) {
     const int cdg = s.C / s.DG;
     // a 32-channel slab must cover whole deform groups (cdg | 32) or lie inside one (32 | cdg)
-    const bool slab_ok = (cdg >= TBK) ? (cdg % TBK == 0) : (TBK % cdg == 0 && cdg % 4 == 0 && TBK / cdg <= 4);
+    const bool slab_ok = (cdg >= TBK) ? (cdg % TBK == 0) : (TBK % cdg == 0 && cdg % 8 == 0);
     return s.G == 1 && s.C % TBK == 0 && slab_ok && s.Co % 32 == 0 && s.Co >= 32 && s.Co <= 256 &&
            (size_t)s.B * s.C * s.H * s.W < ((size_t)1 << 31) && s.Ho < 32768 && s.Wo < 65536;
 }
