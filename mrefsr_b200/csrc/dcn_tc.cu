@@ -19,11 +19,17 @@
 //   epilogue   : producer warps 0..3 also drain finished accumulators (tcgen05.ld 32x32b, bias add,
 //                position-major coalesced NCHW stores); they poll the TMEM-full barrier while they wait.
 //
-// Measured limits (profiles/r01_dcn_gather_microbench.txt): the bilinear gather alone needs 0.35 / 0.79 / 2.07 ms
-// per 80-sample call at 32+ warps/SM and 0.60 / 1.31 / 2.75 ms at the 16 gather warps this kernel can afford
-// (register-bound); this kernel takes 0.82 / 1.57 / 4.2 ms.  Variants tried and rejected on B200 this round:
-// separate table warps, register-resident decode with 256-bit loads, a group-major zero-bordered layout, two
-// 128-row CTAs per SM (spills at 56 registers) -- none beat this version.
+// Measured limits (profiles/r01_dcn_gather_microbench.txt, profiles/r01_dcn_tc_ncu.md): the bilinear gather alone
+// needs 0.35 / 0.79 / 2.07 ms per 80-sample call with 32+ warps/SM -- about one 32-byte sector per clock per SM
+// through L1, whatever the layout -- and this kernel takes 0.74 / 1.33 / 2.84 ms (0.7 sectors/clk/SM at the
+// large scale).  ncu shows ~50 % issue-slot use with 4.25 warps per scheduler, so the K loop is kept lean: no
+// integer division, per-tile row state, 8-channel gather items (one 256-bit load per corner, packed fp32x2 FMAs).
+// Tried and rejected on B200 this round: separate table warps, register-resident decode, a group-major
+// zero-bordered layout, two 128-row CTAs per SM, a 16-warp CTA whose last-arriving warp issues the MMAs (128
+// registers, two items in flight: slower, more L1 queueing), corner fetch by TMA tile::gather4 (10 clk per
+// gather4 per SM: 5 ms at the large scale), an fp16 2x2-packed corner layout (-24 % in the microbenchmark, not
+// worth the precision and the packing pass), cp.async.bulk.prefetch.L2 of the input ahead of the gather (no
+// effect: the wait is L1 queueing, not DRAM).
 //
 // Offsets / masks come either as materialised tensors (the reference operator API) or -- fused DynAgg mode --
 // straight from the raw conv_offset_mask output plus the matcher's arg-max map: offset = conv + s*flow shifted
@@ -97,9 +103,7 @@ __device__ __forceinline__ F8 ldg8(const float* p) {
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
     __shared__ float tile[128][33];
-    // samples are converted last-to-first: what is still in L2 when the DCN kernel starts is then the data its
-    // first tiles gather from
-    const int b = gridDim.z - 1 - blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* s = src + (size_t)b * C * HW;
     float* d = dst + (size_t)b * C * HW;
@@ -493,25 +497,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
             const uint32_t idesc = umma_idesc(2, 128, Co);
             int stage = 0, it = 0;
             uint32_t phase = 0;
-            // L2 prefetch of the NHWC input, paced by the MMA progress: the gather of a tile may touch any pixel
-            // of its sample, so the input slice that belongs to tile t is requested one sample plus one wave of
-            // tiles before tile t is gathered (otherwise nearly every warp-wide gather waits on a DRAM miss).
-            const unsigned long long in_bytes = (unsigned long long)s.B * s.H * s.W * C * 4;
-            const int pf_ahead = (int)gridDim.x + (P + TBM - 1) / TBM + 1;
-            auto prefetch_tile = [&](int t) {
-                if (t >= prm.tiles) return;
-                unsigned long long a = (unsigned long long)t * TBM * (s.H * s.W) / P * C * 4;
-                unsigned long long e = (unsigned long long)(t + 1) * TBM * (s.H * s.W) / P * C * 4;
-                if (e > in_bytes) e = in_bytes;
-                a &= ~15ull;
-                for (; a < e; a += 32768) {
-                    const unsigned long long n = e - a < 32768 ? e - a : 32768;
-                    bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(xt) + a, (uint32_t)((n + 15) & ~15ull));
-                }
-            };
-            for (int t = blockIdx.x; t < pf_ahead; t += gridDim.x) prefetch_tile(t);
             for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
-                prefetch_tile(tile + pf_ahead);
                 const int buf = it & (prm.nbuf - 1);
                 const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
                 mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
