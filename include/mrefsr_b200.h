@@ -150,6 +150,49 @@ MREFSR_API int mrefsr_dynagg_dcn_forward(const float* input, const float* weight
                               const int64_t* max_idx, int flow_scale, float* output, int B, int C, int H, int W,
                               int Co, int deformable_group, int with_bias, void* workspace, size_t workspace_bytes,
                               void* stream);
+/* Same, for a channels-last caller (feature hand-off layout): layout_flags says that `input` already
+ * is [B, H, W, C] (the layout the gather wants: no transpose pass) and / or that `output` is to be written as
+ * [B, H, W, Co]; conv_out stays [B, 3*dg*9, H, W] planes.  out_slope: leaky-ReLU slope applied to the output in the
+ * epilogue (the lrelu that follows DynAgg at ref_mrapa_restoration_arch.py:228-229; 1.0f = none). */
+enum {
+    MREFSR_DCN_IN_NHWC = 1,
+    MREFSR_DCN_OUT_NHWC = 2,
+};
+MREFSR_API int mrefsr_dynagg_dcn_forward_ex(const float* input, const float* weight, const float* bias,
+                                 const float* conv_out, const int64_t* max_idx, int flow_scale, float* output, int B,
+                                 int C, int H, int W, int Co, int deformable_group, int with_bias, int layout_flags,
+                                 float out_slope, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Trunk glue (the plain-convolution network either side of the path; convolutions
+ * themselves stay cuDNN).  One streaming pass instead of torch's bias-add / activation /
+ * residual-add kernels:
+ *   mrefsr_bias_act:      x[b,c,:] = act(x[b,c,:] + bias[c]) * scale + residual[b,c,:]   (in place)
+ *       ResidualBlockNoBN (basicsr/archs/arch_util.py:88-117), offset convs + tails
+ *       (ref_mrapa_restoration_arch.py:140-259), VGG conv+ReLU (vgg_arch.py:141-161),
+ *       MRAPAFusion embeddings conv+PReLU (* C^-0.5) (ref_mrapa_restoration_arch.py:293-302, 321-323).
+ *       bias / residual may be NULL; slope_dev (device, 1 or C entries: nn.PReLU weight) overrides
+ *       `slope` when non-NULL.  x, residual: dense fp32, NCHW planes (channels_last = 0) or NHWC
+ *       (channels_last = 1, torch.channels_last), HW = H*W.
+ *       res_div: sample b of x takes residual sample b / res_div (a per-image term shared by its res_div
+ *       references; 1 = same batch).  res_pre = 1 adds the residual before the activation instead:
+ *       x = act(x + bias + residual) * scale  -- the per-image half of a convolution over cat([x, feat]) that
+ *       was split by input channels (small/medium/large_offset_conv1, ref_mrapa_restoration_arch.py:222-227).
+ *   mrefsr_layout_convert: dense [B,C,HW] <-> [B,HW,C] (torch.channels_last), C % 4 == 0, out of place.
+ *   mrefsr_attn_modulate: refs = refs * sigmoid(attn_mul + bias_mul[c]) * 2 + (attn_add + bias_add[c])
+ *       (ref_mrapa_restoration_arch.py:341-344), in place on refs.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    MREFSR_ACT_NONE = 0,
+    MREFSR_ACT_LEAKY = 1,   /* v > 0 ? v : slope * v   (ReLU: slope 0; PReLU: slope_dev) */
+    MREFSR_ACT_SIGMOID = 2,
+};
+MREFSR_API int mrefsr_bias_act(float* x, const float* bias, const float* slope_dev, int slope_n, const float* residual,
+                    int res_div, int res_pre, int B, int C, int HW, int channels_last, int act, float slope,
+                    float scale, void* stream);
+MREFSR_API int mrefsr_layout_convert(const float* src, float* dst, int B, int C, int HW, int to_channels_last, void* stream);
+MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,
+                         const float* bias_add, int B, int C, int HW, int channels_last, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Multi-reference attention fusion core

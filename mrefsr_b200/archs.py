@@ -11,6 +11,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
+from . import trunk as T
 from .matcher import correspondence
 
 _VGG19_NAMES = [
@@ -59,6 +60,9 @@ class VGGFeatureExtractor(nn.Module):
         if self.use_input_norm:
             x = (x - self.mean) / self.std
         output = {}
+        if T.fast_ok(x):    # inference: conv + [bias + ReLU] pairs fused (csrc/trunk.cu)
+            T.run_sequential(self.vgg_net, x, taps=self.layer_name_list, out=output)
+            return output
         for key, layer in self.vgg_net._modules.items():
             x = layer(x)
             if key in self.layer_name_list:

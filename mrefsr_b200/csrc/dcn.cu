@@ -513,10 +513,28 @@ int mrefsr_dynagg_dcn_forward(const float* input, const float* weight, const flo
     int rc = dcn_make_shape(&s, B, C, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, deformable_group);
     if (rc) return rc;
     MREFSR_CHECK(dcn_tc_eligible(s), ERR_UNSUPPORTED,
-                 "dynagg forward: needs C %% 32 == 0, (C/deformable_group) %% 4 == 0, Co %% 32 == 0, Co <= 256");
+                 "dynagg forward: needs C %% 32 == 0, (C/deformable_group) %% 8 == 0, Co %% 32 == 0, Co <= 256");
     return dcn_forward_tc_impl(input, weight, with_bias ? bias : nullptr, conv_out, nullptr,
                                reinterpret_cast<const long long*>(max_idx), flow_scale, output, s, workspace,
-                               workspace_bytes, static_cast<cudaStream_t>(stream));
+                               workspace_bytes, static_cast<cudaStream_t>(stream), 0, 1.f);
+}
+
+int mrefsr_dynagg_dcn_forward_ex(const float* input, const float* weight, const float* bias, const float* conv_out,
+                                 const int64_t* max_idx, int flow_scale, float* output, int B, int C, int H, int W,
+                                 int Co, int deformable_group, int with_bias, int layout_flags, float out_slope,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    MREFSR_CHECK(input && weight && conv_out && max_idx && output, ERR_BAD_ARG, "dynagg forward: null pointer argument");
+    MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dynagg forward: with_bias set but bias is NULL");
+    MREFSR_CHECK((layout_flags & ~(MREFSR_DCN_IN_NHWC | MREFSR_DCN_OUT_NHWC)) == 0, ERR_BAD_ARG,
+                 "dynagg forward: unknown layout flags 0x%x", layout_flags);
+    DcnShape s;
+    int rc = dcn_make_shape(&s, B, C, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, deformable_group);
+    if (rc) return rc;
+    MREFSR_CHECK(dcn_tc_eligible(s), ERR_UNSUPPORTED,
+                 "dynagg forward: needs C %% 32 == 0, (C/deformable_group) %% 8 == 0, Co %% 32 == 0, Co <= 256");
+    return dcn_forward_tc_impl(input, weight, with_bias ? bias : nullptr, conv_out, nullptr,
+                               reinterpret_cast<const long long*>(max_idx), flow_scale, output, s, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream), layout_flags, out_slope);
 }
 
 int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float* offset, float* mask, float* abs_sum,

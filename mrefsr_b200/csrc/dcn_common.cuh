@@ -37,7 +37,7 @@ bool dcn_tc_eligible(const DcnShape& s);
 size_t dcn_tc_workspace_bytes(const DcnShape& s, int mode);
 int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const float* off, const float* mask,
                         const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
-                        size_t workspace_bytes, cudaStream_t st);
+                        size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope);
 int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                    const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

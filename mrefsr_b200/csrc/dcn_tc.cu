@@ -59,6 +59,8 @@ struct DcnTcParams {
     int P, total_rows, tiles, n_slabs, taps, cdg, gs, stages, nbuf, stage_bytes;
     // fused DynAgg mode
     int fused, flow_scale, hp, wp;
+    int out_nhwc;        // epilogue writes [B, Ho, Wo, Co] instead of [B, Co, Ho, Wo]
+    float out_slope;     // leaky-ReLU slope applied to the output (1: none)
     unsigned wp_magic;   // ceil(2^32 / wp): idx / wp == umulhi(idx, wp_magic) for idx < hp * wp  (hp * wp * wp < 2^32)
 };
 
@@ -145,14 +147,14 @@ __device__ __forceinline__ int ldg_early_s32(const int* p) {
 // Drain one finished accumulator tile: tcgen05.ld 32x32b, bias add, position-major coalesced NCHW stores.
 // (Inlined at the four poll sites of the producer loop: an out-of-line call forces spills at the 96-register cap.)
 __device__ __forceinline__ void dcn_epilogue_tile(float* __restrict__ out, const float* __restrict__ bias,
-                                               uint32_t tmem_base, uint64_t* tempty_bar, int tile, int buf, int warp,
-                                               int lane, int Co, int P, int total_rows) {
+                                                  uint32_t tmem_base, uint64_t* tempty_bar, int tile, int buf, int warp,
+                                                  int lane, int Co, int P, int total_rows, int out_nhwc, float out_slope) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         const int m = tile * TBM + half * 128 + warp * 32 + lane;
         const bool ok = m < total_rows;
         const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
-        float* o = out + (size_t)b * Co * P + p;
+        float* o = out_nhwc ? out + (size_t)(ok ? m : 0) * Co : out + (size_t)b * Co * P + p;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * Co + half * Co;
 #pragma unroll 1
         for (int c0 = 0; c0 < Co; c0 += 8) {
@@ -160,10 +162,18 @@ __device__ __forceinline__ void dcn_epilogue_tile(float* __restrict__ out, const
             tmem_ld_32x8(taddr + c0, v);
             tmem_ld_wait();
             if (ok) {
+                float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float bv = bias ? __ldg(bias + c0 + e) : 0.f;
-                    o[(size_t)(c0 + e) * P] = __uint_as_float(v[e]) + bv;
+                    f[e] = __uint_as_float(v[e]) + (bias ? __ldg(bias + c0 + e) : 0.f);
+                    f[e] = f[e] > 0.f ? f[e] : f[e] * out_slope;
+                }
+                if (out_nhwc) {        // 32 contiguous bytes per thread: one full sector
+                    *reinterpret_cast<float4*>(o + c0) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {               // position-major: 32 lanes = 32 consecutive positions of one channel plane
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * P] = f[e];
                 }
             }
         }
@@ -257,7 +267,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         auto epilogue_tile = [&](int it) {
             const int buf = it & nbuf_mask;
             dcn_epilogue_tile(out, bias, tmem_base, &tempty[buf], (int)blockIdx.x + it * (int)gridDim.x, buf, warp, lane,
-                              Co, P, prm.total_rows);
+                              Co, P, prm.total_rows, prm.out_nhwc, prm.out_slope);
         };
         auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
             if (is_epi && ep_done < prod_done) {
@@ -557,7 +567,7 @@ static int make_weight_map(CUtensorMap* map, const float* wt, int Co, int Ktot) 
 
 int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const float* off, const float* mask,
                         const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
-                        size_t workspace_bytes, cudaStream_t st) {
+                        size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope) {
     const size_t need = dcn_tc_workspace_bytes(s, MREFSR_DCN_TF32);
     MREFSR_CHECK(workspace && workspace_bytes >= need, ERR_WORKSPACE, "dcn forward: workspace too small (%zu < %zu)",
                  workspace_bytes, need);
@@ -568,11 +578,17 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     const int K = s.kh * s.kw, HW = s.H * s.W;
     {
         ScopedTiming tm(MREFSR_K_DCN_AUX, st);
-        nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(s.C, 128), s.B), 256, 0, st>>>(x, xt, s.C, HW);
-        MREFSR_LAUNCH_CHECK();
+        if (layout_flags & MREFSR_DCN_IN_NHWC) {      // the caller's tensor already is the gather layout
+            MREFSR_CHECK((reinterpret_cast<uintptr_t>(x) & 31) == 0, ERR_BAD_ARG, "dcn forward: NHWC input must be 32-byte aligned");
+            xt = const_cast<float*>(x);
+        } else {
+            nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(s.C, 128), s.B), 256, 0, st>>>(x, xt, s.C, HW);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
+        }
         dcn_weight_repack_kernel<<<cdiv(s.Co * s.C * K, 256), 256, 0, st>>>(w, wt, s.Co, s.C, K);
         MREFSR_LAUNCH_CHECK();
-        count_launches(2);
+        count_launches(1);
     }
     CUtensorMap mapW;
     int rc = make_weight_map(&mapW, wt, s.Co, K * s.C);
@@ -593,6 +609,8 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     if (prm.stages < 2) prm.stages = 2;
     prm.nbuf = (2 * s.Co * 2 <= 512) ? 2 : 1;
     prm.fused = max_idx != nullptr;
+    prm.out_nhwc = (layout_flags & MREFSR_DCN_OUT_NHWC) ? 1 : 0;
+    prm.out_slope = out_slope;
 
     prm.flow_scale = flow_scale;
     prm.hp = prm.wp = 0;
@@ -627,7 +645,7 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
 
 int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                    const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    return dcn_forward_tc_impl(x, w, bias, off, mask, nullptr, 1, out, s, workspace, workspace_bytes, st);
+    return dcn_forward_tc_impl(x, w, bias, off, mask, nullptr, 1, out, s, workspace, workspace_bytes, st, 0, 1.f);
 }
 
 }  // namespace mrefsr

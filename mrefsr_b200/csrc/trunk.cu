@@ -1,0 +1,318 @@
+// mrefsr_b200/csrc/trunk.cu -- elementwise glue of the plain-convolution trunk around the hot path, one pass each.
+//
+// torch runs a convolution's bias add as a separate broadcast kernel (not vectorised: 12.8 ms of a 58.8 ms batch-16
+// forward, profiles/r01_full_model.md), then the activation and the residual add as further passes.  Here
+//     x[b,c,:] = act(x[b,c,:] + bias[c]) * scale + residual[b,c,:]                      (in place, NCHW planes)
+// covers ResidualBlockNoBN (basicsr/archs/arch_util.py:88-117), the offset convolutions and tails of
+// DynamicAggregationRestoration (ref_mrapa_restoration_arch.py:140-259), the VGG / extractor conv+ReLU pairs and the
+// MRAPAFusion embeddings (conv + PReLU, * C^-0.5; :293-302, :321-323), and
+//     refs = refs * sigmoid(attn_mul + b_mul) * 2 + (attn_add + b_add)                   (:341-344)
+// is the spatial-attention modulation.  Both are HBM-bound streaming kernels (float4 per lane).
+#include "common.cuh"
+#include "../../include/mrefsr_b200.h"
+
+namespace mrefsr {
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+    if (act == MREFSR_ACT_LEAKY) return v > 0.f ? v : v * slope;
+    if (act == MREFSR_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+// grid (ceil(HW4 / (256 * 2)), planes-chunk): plane = b * C + c
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ slope_dev, int slope_n,
+                const float* __restrict__ residual, int planes, int C, int HW, int act, float slope, float scale,
+                int res_div, int res_pre) {
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const int c = plane % C;
+        const float b = bias ? __ldg(bias + c) : 0.f;
+        const float sl = slope_dev ? __ldg(slope_dev + (slope_n == 1 ? 0 : c)) : slope;
+        float* xp = x + (size_t)plane * HW;
+        const float* rp = residual ? residual + ((size_t)(plane / C / res_div) * C + c) * HW : nullptr;
+        if (VEC) {
+            const int n4 = HW >> 2;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+                float4 v = reinterpret_cast<float4*>(xp)[i];
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rp) r = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                const float4 pre = res_pre ? r : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 post = res_pre ? make_float4(0.f, 0.f, 0.f, 0.f) : r;
+                v.x = act_apply(v.x + b + pre.x, act, sl) * scale + post.x;
+                v.y = act_apply(v.y + b + pre.y, act, sl) * scale + post.y;
+                v.z = act_apply(v.z + b + pre.z, act, sl) * scale + post.z;
+                v.w = act_apply(v.w + b + pre.w, act, sl) * scale + post.w;
+                reinterpret_cast<float4*>(xp)[i] = v;
+            }
+        } else {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+                const float r = rp ? __ldg(rp + i) : 0.f;
+                xp[i] = act_apply(xp[i] + b + (res_pre ? r : 0.f), act, sl) * scale + (res_pre ? 0.f : r);
+            }
+        }
+    }
+}
+
+// refs = refs * sigmoid(mul + bias_mul[c]) * 2 + (add + bias_add[c]), in place on refs
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+attn_modulate_kernel(float* __restrict__ refs, const float* __restrict__ mul, const float* __restrict__ add,
+                     const float* __restrict__ bias_mul, const float* __restrict__ bias_add, int planes, int C, int HW) {
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const int c = plane % C;
+        const float bm = bias_mul ? __ldg(bias_mul + c) : 0.f, ba = bias_add ? __ldg(bias_add + c) : 0.f;
+        const size_t o = (size_t)plane * HW;
+        if (VEC) {
+            const int n4 = HW >> 2;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+                float4 r = reinterpret_cast<float4*>(refs + o)[i];
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mul + o) + i);
+                const float4 a = __ldg(reinterpret_cast<const float4*>(add + o) + i);
+                r.x = r.x * (2.f / (1.f + __expf(-(m.x + bm)))) + (a.x + ba);
+                r.y = r.y * (2.f / (1.f + __expf(-(m.y + bm)))) + (a.y + ba);
+                r.z = r.z * (2.f / (1.f + __expf(-(m.z + bm)))) + (a.z + ba);
+                r.w = r.w * (2.f / (1.f + __expf(-(m.w + bm)))) + (a.w + ba);
+                reinterpret_cast<float4*>(refs + o)[i] = r;
+            }
+        } else {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+                refs[o + i] = refs[o + i] * (2.f / (1.f + __expf(-(mul[o + i] + bm)))) + (add[o + i] + ba);
+        }
+    }
+}
+
+// channels-last variants: x[b, p, c], c fastest; C % 4 == 0 on the float4 path
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+bias_act_nhwc_kernel(float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ slope_dev,
+                     int slope_n, const float* __restrict__ residual, long long total, int C, int act, float slope,
+                     float scale, long long per_sample, int res_div, int res_pre) {
+    // residual of sample b lives at sample b / res_div: element i -> i - (b - b / res_div) * per_sample
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (VEC) {
+        const int c4n = C >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (total >> 2); i += stride) {
+            const int c = (int)(i % c4n) * 4;
+            float4 v = reinterpret_cast<float4*>(x)[i];
+            const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 sl = make_float4(slope, slope, slope, slope);
+            if (slope_dev) {
+                if (slope_n == 1) sl.x = sl.y = sl.z = sl.w = __ldg(slope_dev);
+                else sl = __ldg(reinterpret_cast<const float4*>(slope_dev + c));
+            }
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (residual) {
+                long long ri = i;
+                if (res_div > 1) {
+                    const long long bb = (i * 4) / per_sample;
+                    ri = i - (bb - bb / res_div) * (per_sample >> 2);
+                }
+                r = __ldg(reinterpret_cast<const float4*>(residual) + ri);
+            }
+            const float4 pre = res_pre ? r : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 post = res_pre ? make_float4(0.f, 0.f, 0.f, 0.f) : r;
+            v.x = act_apply(v.x + b.x + pre.x, act, sl.x) * scale + post.x;
+            v.y = act_apply(v.y + b.y + pre.y, act, sl.y) * scale + post.y;
+            v.z = act_apply(v.z + b.z + pre.z, act, sl.z) * scale + post.z;
+            v.w = act_apply(v.w + b.w + pre.w, act, sl.w) * scale + post.w;
+            reinterpret_cast<float4*>(x)[i] = v;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c = (int)(i % C);
+            const float sl = slope_dev ? __ldg(slope_dev + (slope_n == 1 ? 0 : c)) : slope;
+            float r = 0.f;
+            if (residual) {
+                const long long bb = i / per_sample;
+                r = __ldg(residual + (i - (bb - bb / res_div) * per_sample));
+            }
+            x[i] = act_apply(x[i] + (bias ? __ldg(bias + c) : 0.f) + (res_pre ? r : 0.f), act, sl) * scale + (res_pre ? 0.f : r);
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+attn_modulate_nhwc_kernel(float* __restrict__ refs, const float* __restrict__ mul, const float* __restrict__ add,
+                          const float* __restrict__ bias_mul, const float* __restrict__ bias_add, long long total, int C) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (VEC) {
+        const int c4n = C >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (total >> 2); i += stride) {
+            const int c = (int)(i % c4n) * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bm = bias_mul ? __ldg(reinterpret_cast<const float4*>(bias_mul + c)) : z;
+            const float4 ba = bias_add ? __ldg(reinterpret_cast<const float4*>(bias_add + c)) : z;
+            float4 r = reinterpret_cast<float4*>(refs)[i];
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mul) + i);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(add) + i);
+            r.x = r.x * (2.f / (1.f + __expf(-(m.x + bm.x)))) + (a.x + ba.x);
+            r.y = r.y * (2.f / (1.f + __expf(-(m.y + bm.y)))) + (a.y + ba.y);
+            r.z = r.z * (2.f / (1.f + __expf(-(m.z + bm.z)))) + (a.z + ba.z);
+            r.w = r.w * (2.f / (1.f + __expf(-(m.w + bm.w)))) + (a.w + ba.w);
+            reinterpret_cast<float4*>(refs)[i] = r;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c = (int)(i % C);
+            refs[i] = refs[i] * (2.f / (1.f + __expf(-(mul[i] + (bias_mul ? bias_mul[c] : 0.f))))) +
+                      (add[i] + (bias_add ? bias_add[c] : 0.f));
+        }
+    }
+}
+
+// Dense layout conversion, 32 positions x 128 channels per CTA through shared memory, both directions at streaming
+// rate (torch's strided copy_ runs these at ~1/4 of it).  grid (ceil(HW/32), ceil(C/128), B); C % 4 == 0.
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[128][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* s = src + (size_t)b * C * HW;
+    float* d = dst + (size_t)b * C * HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {        // loads: one float4 (4 channels) per lane, 512 contiguous bytes per warp
+        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+        if (pp < HW && c < C) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(s + (size_t)pp * C + c));
+            tile[lane * 4][pl] = v.x;
+            tile[lane * 4 + 1][pl] = v.y;
+            tile[lane * 4 + 2][pl] = v.z;
+            tile[lane * 4 + 3][pl] = v.w;
+        }
+    }
+    __syncthreads();
+    const int p = p0 + lane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {       // stores: lane = position, 128-byte coalesced rows of one channel plane
+        const int cl = warp + 8 * i, c = c0 + cl;
+        if (c < C && p < HW) d[(size_t)c * HW + p] = tile[cl][lane];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[128][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* s = src + (size_t)b * C * HW;
+    float* d = dst + (size_t)b * C * HW;
+    const int p = p0 + lane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int cl = warp + 8 * i, c = c0 + cl;
+        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+        if (pp < HW && c < C)
+            *reinterpret_cast<float4*>(d + (size_t)pp * C + c) =
+                make_float4(tile[lane * 4][pl], tile[lane * 4 + 1][pl], tile[lane * 4 + 2][pl], tile[lane * 4 + 3][pl]);
+    }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace mrefsr
+
+using namespace mrefsr;
+
+extern "C" {
+
+int mrefsr_bias_act(float* x, const float* bias, const float* slope_dev, int slope_n, const float* residual,
+                    int res_div, int res_pre, int B, int C, int HW, int channels_last, int act, float slope,
+                    float scale, void* stream) {
+    MREFSR_CHECK(res_div >= 1 && (!residual || B % res_div == 0), ERR_BAD_ARG, "bias_act: batch %d not a multiple of res_div %d", B, res_div);
+    MREFSR_CHECK(x, ERR_BAD_ARG, "bias_act: null tensor");
+    MREFSR_CHECK(B > 0 && C > 0 && HW > 0, ERR_BAD_ARG, "bias_act: bad shape B=%d C=%d HW=%d", B, C, HW);
+    MREFSR_CHECK(act == MREFSR_ACT_NONE || act == MREFSR_ACT_LEAKY || act == MREFSR_ACT_SIGMOID, ERR_BAD_ARG,
+                 "bias_act: unknown activation %d", act);
+    MREFSR_CHECK(!slope_dev || slope_n == 1 || slope_n == C, ERR_BAD_ARG, "bias_act: slope tensor has %d entries, C=%d",
+                 slope_n, C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long planes_ll = (long long)B * C;
+    MREFSR_CHECK(planes_ll < (1ll << 31), ERR_BAD_ARG, "bias_act: too many planes");
+    const int planes = (int)planes_ll;
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    if (channels_last) {
+        const long long total = planes_ll * HW;
+        const bool v4 = C % 4 == 0 && al16(x) && (!residual || al16(residual)) && (!bias || al16(bias)) &&
+                        (!slope_dev || slope_n == 1 || al16(slope_dev));
+        const long long work = v4 ? total / 4 : total;
+        const int blocks = (int)((work + 256 * 4 - 1) / (256 * 4) < 1 ? 1 : (work + 256 * 4 - 1) / (256 * 4) > 148 * 32 ? 148 * 32 : (work + 256 * 4 - 1) / (256 * 4));
+        if (v4)
+            bias_act_nhwc_kernel<true><<<blocks, 256, 0, st>>>(x, bias, slope_dev, slope_n, residual, total, C, act, slope, scale, (long long)C * HW, res_div, res_pre);
+        else
+            bias_act_nhwc_kernel<false><<<blocks, 256, 0, st>>>(x, bias, slope_dev, slope_n, residual, total, C, act, slope, scale, (long long)C * HW, res_div, res_pre);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+        return 0;
+    }
+    const bool vec = HW % 4 == 0 && al16(x) && (!residual || al16(residual));
+    const int per = vec ? HW / 4 : HW;
+    dim3 grid(cdiv(per, 256 * 2) < 1 ? 1 : cdiv(per, 256 * 2), planes < 32768 ? planes : 32768);
+    if (vec)
+        bias_act_kernel<true><<<grid, 256, 0, st>>>(x, bias, slope_dev, slope_n, residual, planes, C, HW, act, slope, scale, res_div, res_pre);
+    else
+        bias_act_kernel<false><<<grid, 256, 0, st>>>(x, bias, slope_dev, slope_n, residual, planes, C, HW, act, slope, scale, res_div, res_pre);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,
+                         const float* bias_add, int B, int C, int HW, int channels_last, void* stream) {
+    MREFSR_CHECK(refs && attn_mul && attn_add, ERR_BAD_ARG, "attn_modulate: null tensor");
+    MREFSR_CHECK(B > 0 && C > 0 && HW > 0, ERR_BAD_ARG, "attn_modulate: bad shape B=%d C=%d HW=%d", B, C, HW);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long planes_ll = (long long)B * C;
+    MREFSR_CHECK(planes_ll < (1ll << 31), ERR_BAD_ARG, "attn_modulate: too many planes");
+    const int planes = (int)planes_ll;
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    if (channels_last) {
+        const long long total = planes_ll * HW;
+        const bool v4 = C % 4 == 0 && al16(refs) && al16(attn_mul) && al16(attn_add) && (!bias_mul || al16(bias_mul)) &&
+                        (!bias_add || al16(bias_add));
+        const long long work = v4 ? total / 4 : total;
+        const int blocks = (int)((work + 256 * 4 - 1) / (256 * 4) < 1 ? 1 : (work + 256 * 4 - 1) / (256 * 4) > 148 * 32 ? 148 * 32 : (work + 256 * 4 - 1) / (256 * 4));
+        if (v4)
+            attn_modulate_nhwc_kernel<true><<<blocks, 256, 0, st>>>(refs, attn_mul, attn_add, bias_mul, bias_add, total, C);
+        else
+            attn_modulate_nhwc_kernel<false><<<blocks, 256, 0, st>>>(refs, attn_mul, attn_add, bias_mul, bias_add, total, C);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+        return 0;
+    }
+    const bool vec = HW % 4 == 0 && al16(refs) && al16(attn_mul) && al16(attn_add);
+    const int per = vec ? HW / 4 : HW;
+    dim3 grid(cdiv(per, 256 * 2) < 1 ? 1 : cdiv(per, 256 * 2), planes < 32768 ? planes : 32768);
+    if (vec)
+        attn_modulate_kernel<true><<<grid, 256, 0, st>>>(refs, attn_mul, attn_add, bias_mul, bias_add, planes, C, HW);
+    else
+        attn_modulate_kernel<false><<<grid, 256, 0, st>>>(refs, attn_mul, attn_add, bias_mul, bias_add, planes, C, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_layout_convert(const float* src, float* dst, int B, int C, int HW, int to_channels_last, void* stream) {
+    MREFSR_CHECK(src && dst && src != dst, ERR_BAD_ARG, "layout_convert: bad pointers");
+    MREFSR_CHECK(B > 0 && C > 0 && HW > 0 && C % 4 == 0, ERR_BAD_ARG, "layout_convert: needs C %% 4 == 0 (B=%d C=%d HW=%d)", B, C, HW);
+    MREFSR_CHECK(al16(src) && al16(dst), ERR_BAD_ARG, "layout_convert: tensors must be 16-byte aligned");
+    MREFSR_CHECK(B <= 65535 && cdiv(C, 128) <= 65535, ERR_BAD_ARG, "layout_convert: batch too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    const dim3 grid(cdiv(HW, 32), cdiv(C, 128), B);
+    if (to_channels_last)
+        nchw_to_nhwc_conv_kernel<<<grid, 256, 0, st>>>(src, dst, C, HW);
+    else
+        nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(src, dst, C, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+}  // extern "C"

@@ -69,14 +69,25 @@ def dcn_forward_raw(input, offset, mask, weight, bias, stride, padding, dilation
     return out
 
 
-def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups):
+def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups, out_slope=1.0,
+                       out_channels_last=None):
     """Fused DynAgg forward for inference (no autograd): DCNv2 (3x3, stride 1, pad 1) whose offsets and masks are
     assembled inside the gather from the raw conv_offset_mask output and the matcher's arg-max map
     (ref_mrapa_restoration_arch.py:45-76 + corres_generation_arch.py:30-47, :70-105 for one scale).
-    input [B,C,H,W], conv_out [B,3*dg*9,H,W], max_idx int64 [B,H/s-2,W/s-2] -> [B,Co,H,W]."""
+    input [B,C,H,W], conv_out [B,3*dg*9,H,W], max_idx int64 [B,H/s-2,W/s-2] -> [B,Co,H,W].
+    A torch.channels_last `input` is consumed as it is (it already is the gather layout); the result is
+    channels_last when `out_channels_last` (default: follows the input).  out_slope: leaky-ReLU slope applied to the
+    result in the epilogue (1.0 = none)."""
     _lib.require_cuda(input, conv_out, max_idx, weight, bias)
     lib = _lib.lib()
-    x, co_, wgt = (t.contiguous().float() for t in (input, conv_out, weight))
+    x = input.float()
+    in_cl = x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+    if not in_cl:
+        x = x.contiguous()
+    if out_channels_last is None:
+        out_channels_last = in_cl
+    from .trunk import to_nchw
+    co_, wgt = to_nchw(conv_out.float()), weight.contiguous().float()
     bs = bias.contiguous().float() if bias is not None else None
     mi = max_idx.contiguous()
     b, c, h, w = x.shape
@@ -86,14 +97,16 @@ def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, defor
         raise RuntimeError('conv_out shape %s, expected %s' % (tuple(co_.shape), (b, 3 * dg * 9, h, w)))
     if mi.dtype != torch.int64 or tuple(mi.shape) != (b, h // flow_scale - 2, w // flow_scale - 2):
         raise RuntimeError('max_idx must be int64 [%d,%d,%d]' % (b, h // flow_scale - 2, w // flow_scale - 2))
-    out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device)
+    out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last if out_channels_last else torch.contiguous_format)
+    flags = (1 if in_cl else 0) | (2 if out_channels_last else 0)
     with torch.cuda.device(x.device):
         nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, DCN_TF32, 0)
         ws, ws_bytes = _lib.workspace(nbytes, x.device)
-        rc = lib.mrefsr_dynagg_dcn_forward(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
-                                           int(flow_scale), _lib.ptr(out), b, c, h, w, co, dg, int(bs is not None), ws,
-                                           ws_bytes, _lib.stream_ptr(x.device))
-    _lib.check(rc, 'mrefsr_dynagg_dcn_forward')
+        rc = lib.mrefsr_dynagg_dcn_forward_ex(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
+                                              int(flow_scale), _lib.ptr(out), b, c, h, w, co, dg, int(bs is not None),
+                                              flags, float(out_slope), ws, ws_bytes, _lib.stream_ptr(x.device))
+    _lib.check(rc, 'mrefsr_dynagg_dcn_forward_ex')
     return out
 
 

@@ -69,16 +69,20 @@ class DynAgg(ModulatedDeformConv2d):
             return None
         return float(self._stats.item()) / self._stats_count
 
-    def forward_fused(self, x, max_idx, flow_scale):
+    def forward_fused(self, x, max_idx, flow_scale, out_slope=1.0):
         """Inference fast path (no autograd): same result as forward(x, pre_offset) where pre_offset is the
         matcher's shifted flow at this scale, but offsets / masks / pre-offsets never touch HBM."""
         from .dcn import dynagg_dcn_forward
+        from . import trunk as T
+        feat = x[1] if self.extra_offset_mask else x
         if self.extra_offset_mask:
-            out = self.conv_offset_mask(x[1])
             x = x[0]
+        if T.fast_ok(feat):    # bias of the 216-plane tensor in one vectorised pass (torch's broadcast add is slow)
+            out = T.conv_bias_act(feat, self.conv_offset_mask)
         else:
-            out = self.conv_offset_mask(x)
-        return dynagg_dcn_forward(x, out, max_idx, flow_scale, self.weight, self.bias, self.deform_groups)
+            out = self.conv_offset_mask(feat)
+        return dynagg_dcn_forward(x, out, max_idx, flow_scale, self.weight, self.bias, self.deform_groups,
+                                  out_slope=out_slope)
 
     def forward(self, x, pre_offset):
         if self.extra_offset_mask:

@@ -12,6 +12,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
+from . import trunk as T
 
 
 class MRAPAAttentionFunction(Function):
@@ -21,7 +22,7 @@ class MRAPAAttentionFunction(Function):
     def forward(ctx, emb_t, emb, ass, t):
         _lib.require_cuda(emb_t, emb, ass)
         ctx.in_dtype = emb_t.dtype
-        q, k, v = (x.contiguous().float() for x in (emb_t, emb, ass))
+        q, k, v = (T.to_nchw(x.float()) for x in (emb_t, emb, ass))
         n, c, h, w = q.shape
         if k.shape[0] != n * t or k.shape[1] != c or v.shape[0] != n * t or k.shape[2:] != q.shape[2:] \
                 or v.shape[2:] != q.shape[2:]:
@@ -86,13 +87,20 @@ class MRAPAFusion(nn.Module):
         _, _, h, w = feats.size()
         pad_h = (4 - h % 4) % 4
         pad_w = (4 - w % 4) % 4
+        if pad_h == 0 and pad_w == 0:      # F.pad would still copy the tensor
+            return feats
         return F.pad(feats, [0, pad_w, 0, pad_h], mode='reflect')
 
     def forward(self, target, refs):
+        return self.forward_stacked(target, torch.stack(refs, dim=1).flatten(0, 1), len(refs))
+
+    def forward_stacked(self, target, refs, t):
+        """Same as forward() with the t references already stacked: refs [n*t, ref_nf, h, w] (pairs laid out [n, t])."""
         n, _, h_input, w_input = target.size()
-        t = len(refs)
         target = self.spatial_padding(target)
-        refs = self.spatial_padding(torch.stack(refs, dim=1).flatten(0, 1))
+        refs = self.spatial_padding(refs)
+        if T.fast_ok(target, refs):
+            return self._forward_fused_glue(target, refs, t, h_input, w_input)
         # multi-ref attention: one fused kernel instead of 3 permute copies + 2 batched matmuls (:321-335)
         emb_t = self.conv_emb1(target) * self.scale
         emb = self.conv_emb2(refs)
@@ -105,4 +113,21 @@ class MRAPAFusion(nn.Module):
         attn_mul = torch.sigmoid(attn_mul)
         refs = refs * attn_mul * 2 + attn_add
         feat = self.lrelu(self.feat_fusion(torch.cat([target, refs], dim=1)))
+        return feat[:, :, :h_input, :w_input]
+
+    def _forward_fused_glue(self, target, refs, t, h_input, w_input):
+        """Inference path: same arithmetic, every conv's bias / activation / scale epilogue in one pass and the
+        spatial-attention modulation (sigmoid, * 2, + add, both conv biases) in one kernel."""
+        emb_t = T.conv_bias_act(target, self.conv_emb1[0], prelu=self.conv_emb1[1], scale=self.scale)
+        emb = T.conv_bias_act(refs, self.conv_emb2[0], prelu=self.conv_emb2[1])
+        ass = T.conv_bias_act(refs, self.conv_ass)
+        refs = mrapa_attention(emb_t, emb, ass, t)
+        if T.layout_of(target) == 1:      # keep the channels-last trunk channels-last
+            refs = T.to_nhwc(refs)
+        attn = T.conv_bias_act(torch.cat([target, refs], dim=1), self.spatial_attn, T.ACT_LEAKY, 0.1)
+        attn_mul = T.conv_raw(T.conv_bias_act(attn, self.spatial_attn_mul1, T.ACT_LEAKY, 0.1), self.spatial_attn_mul2)
+        attn_add = T.conv_raw(T.conv_bias_act(attn, self.spatial_attn_add1, T.ACT_LEAKY, 0.1), self.spatial_attn_add2)
+        refs = T.attn_modulate_(refs, T.dense(attn_mul), T.dense(attn_add), self.spatial_attn_mul2.bias,
+                                self.spatial_attn_add2.bias)
+        feat = T.conv_bias_act(torch.cat([target, refs], dim=1), self.feat_fusion, T.ACT_LEAKY, 0.1)
         return feat[:, :, :h_input, :w_input]

@@ -38,8 +38,9 @@ def feature_match_index_batched(feat_input, feat_ref, patch_size=3, input_stride
     _lib.require_cuda(feat_input, feat_ref)
     if feat_input.dim() != 4 or feat_ref.dim() != 4 or feat_input.shape[1] != feat_ref.shape[1]:
         raise ValueError('expected [n,C,h,w] features with equal channel counts')
-    fi = feat_input.contiguous().float()
-    fr = feat_ref.contiguous().float()
+    from .trunk import to_nchw
+    fi = to_nchw(feat_input.float())
+    fr = to_nchw(feat_ref.float())
     n_in, c, h, w = fi.shape
     n_pairs, _, h2, w2 = fr.shape
     if in_div is None:

@@ -19,6 +19,7 @@ from torch.nn import init
 
 from .archs import CorrespondenceGenerationArch
 from .dynagg import DynAgg
+from . import trunk as T
 from .fusion import MRAPAFusion
 from .matcher import feature_match_index_batched, pre_offsets
 
@@ -69,6 +70,9 @@ class ResidualBlockNoBN(nn.Module):
             default_init_weights([self.conv1, self.conv2], 0.1)
 
     def forward(self, x):
+        if T.fast_ok(x):    # inference: conv -> [bias + ReLU] -> conv -> [bias, * res_scale, + x], two epilogue passes
+            t = T.conv_bias_act(x, self.conv1, T.ACT_LEAKY, 0.0)
+            return T.conv_bias_act(t, self.conv2, T.ACT_NONE, residual=x, scale=self.res_scale)
         return x + self.conv2(self.relu(self.conv1(x))) * self.res_scale
 
 
@@ -90,7 +94,10 @@ class ContrasExtractorLayer(nn.Module):
         self.register_buffer('std', torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
 
     def forward(self, batch):
-        return self.model((batch - self.mean) / self.std)
+        x = (batch - self.mean) / self.std
+        if T.fast_ok(x):
+            return T.run_sequential(self.model, x)
+        return self.model(x)
 
 
 class ContrasMultiExtractorSep(nn.Module):
@@ -120,6 +127,8 @@ class ContentExtractor(nn.Module):
         default_init_weights([self.conv_first], 0.1)
 
     def forward(self, x):
+        if T.fast_ok(x):
+            return self.body(T.conv_bias_act(x, self.conv_first, T.ACT_LEAKY, 0.1))
         return self.body(self.lrelu(self.conv_first(x)))
 
 
@@ -142,6 +151,17 @@ class DynamicAggregationRestoration(nn.Module):
         self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
 
     _SCALES = (('small', 'relu3_1'), ('medium', 'relu2_1'), ('large', 'relu1_1'))
+
+    def _split_conv1(self, conv, n_x, channels_last):
+        """(weight[:, :n_x], weight[:, n_x:]) of an offset_conv1 as dense tensors, cached until the weight changes."""
+        cache = self.__dict__.setdefault('_conv1_split', {})
+        key = id(conv)
+        ver = (conv.weight._version, conv.weight.data_ptr(), channels_last)
+        if key not in cache or cache[key][0] != ver:
+            fmt = torch.channels_last if channels_last else torch.contiguous_format
+            w = conv.weight.detach()
+            cache[key] = (ver, w[:, :n_x].contiguous(memory_format=fmt), w[:, n_x:].contiguous(memory_format=fmt))
+        return cache[key][1], cache[key][2]
 
     def forward(self, x, pre_offset_list, img_ref_feat_list):
         """Reference contract: lists over references of pre_offset / VGG feature dicts."""
@@ -166,15 +186,32 @@ class DynamicAggregationRestoration(nn.Module):
             conv1, conv2 = getattr(self, f'{name}_offset_conv1'), getattr(self, f'{name}_offset_conv2')
             agg = getattr(self, f'{name}_dyn_agg')
             feat = ref_feats[key]                                           # [B*R, C, H, W]
-            xr = x.repeat_interleave(r, dim=0)                              # [B*R, ngf, H, W]
-            o = self.lrelu(conv1(torch.cat([xr, feat], 1)))
-            o = self.lrelu(conv2(o))
-            y = self.lrelu(agg.forward_fused([feat, o], max_idx, s))        # [B*R, C, H, W]
-            b = x.shape[0]
-            swapped = list(y.view(b, r, *y.shape[1:]).unbind(1))
-            h = getattr(self, f'head_{name}')(x, swapped)
+            fast = T.fast_ok(x, feat)
+            if fast:
+                # conv1 over cat([x repeated per reference, feat]) split by input channels: the x half is computed
+                # once per image and enters the feat half's epilogue as a per-image, pre-activation term -- no
+                # repeat_interleave, no cat, (R-1)/R of the x-half FLOPs gone
+                wx, wf = self._split_conv1(conv1, x.shape[1], T.layout_of(x) == 1)
+                ox = F.conv2d(x, wx, None, conv1.stride, conv1.padding)
+                o = T.dense(F.conv2d(feat, wf, None, conv1.stride, conv1.padding))
+                o = T.bias_act_(o, conv1.bias, T.ACT_LEAKY, 0.1, residual=T.dense(ox), res_div=r, res_pre=True)
+                o = T.conv_bias_act(o, conv2, T.ACT_LEAKY, 0.1)
+                y = agg.forward_fused([feat, o], max_idx, s, out_slope=0.1)   # lrelu folded into the DCN epilogue
+            else:
+                xr = x.repeat_interleave(r, dim=0)                          # [B*R, ngf, H, W]
+                o = self.lrelu(conv1(torch.cat([xr, feat], 1)))
+                o = self.lrelu(conv2(o))
+                y = self.lrelu(agg.forward_fused([feat, o], max_idx, s))    # [B*R, C, H, W]
+            h = getattr(self, f'head_{name}').forward_stacked(x, y, r)     # y is already [B*R, C, H, W]
             h = getattr(self, f'body_{name}')(h) + x
-            x = getattr(self, f'tail_{name}')(h)
+            tail = getattr(self, f'tail_{name}')
+            if fast and T.fast_ok(h):
+                if name == 'large':     # conv -> lrelu -> conv
+                    x = T.conv_bias_act(T.conv_bias_act(h, tail[0], T.ACT_LEAKY, 0.1), tail[2])
+                else:                   # conv -> pixel shuffle -> lrelu == conv -> lrelu -> pixel shuffle
+                    x = F.pixel_shuffle(T.conv_bias_act(h, tail[0], T.ACT_LEAKY, 0.1), 2)
+            else:
+                x = tail(h)
         return x
 
 
@@ -210,11 +247,24 @@ class MRefSRPipeline(nn.Module):
                                                     match_mode=match_mode)
         self.net_g = MRAPARestorationNet(ngf=ngf, n_blocks=n_blocks, groups=groups)
         self.match_mode = match_mode
+        self._channels_last = False
+
+    def channels_last_(self):
+        """Run the plain-convolution trunk in torch.channels_last (cuDNN's native layout for its tensor-core kernels:
+        no NCHW<->NHWC conversion around every convolution).  The alignment kernels take it from there: the DCN
+        gathers from the NHWC features as they are and writes NHWC, the glue kernels follow the tensor's layout."""
+        self.to(memory_format=torch.channels_last)
+        self._channels_last = True
+        return self
 
     @torch.no_grad()
     def forward(self, img_in_lq, img_in_up, img_refs):
         """img_in_lq [B,3,H/4,W/4], img_in_up [B,3,H,W] (the LR input upsampled x4), img_refs [B,R,3,H,W] -> SR [B,3,H,W]."""
         b, r = img_refs.shape[:2]
+        if self._channels_last:
+            img_in_lq = img_in_lq.contiguous(memory_format=torch.channels_last)
+            img_in_up = img_in_up.contiguous(memory_format=torch.channels_last)
+            img_refs = img_refs.flatten(0, 1).contiguous(memory_format=torch.channels_last).unflatten(0, (b, r))
         f1, f2 = self.net_extractor.forward_batched(img_in_up, img_refs)
         max_idx, _ = feature_match_index_batched(f1, f2, 3, 1, 1, True, True, normalize_pixels=True, in_div=r,
                                                  mode=self.match_mode)

@@ -1,0 +1,149 @@
+"""Inference fast path for the plain-convolution trunk around the hot path.
+
+The convolutions stay cuDNN library calls (``F.conv2d`` without bias); what torch runs after each of them as
+separate kernels -- a non-vectorised broadcast bias add, the activation, the residual add -- is one streaming
+pass of csrc/trunk.cu.  Used only when autograd is off and the tensors are contiguous fp32 CUDA tensors;
+otherwise the caller keeps the ordinary ``nn.Module`` path (training, CPU construction, other dtypes).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+ACT_NONE, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2
+
+
+def layout_of(t):
+    """0: dense NCHW, 1: dense channels-last (NHWC), None: neither."""
+    if t.is_contiguous():
+        return 0
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return 1
+    return None
+
+
+def fast_ok(*tensors):
+    """True when the fused inference path applies to these tensors (no autograd, no autocast, dense fp32 CUDA)."""
+    return (not torch.is_grad_enabled()) and (not torch.is_autocast_enabled()) and all(
+        t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and layout_of(t) is not None for t in tensors)
+
+
+def dense(t):
+    """t if it is dense NCHW or channels-last, else a contiguous copy."""
+    return t if layout_of(t) is not None else t.contiguous()
+
+
+def bias_act_(x, bias=None, act=ACT_NONE, slope=0.0, residual=None, slope_dev=None, scale=1.0, res_div=1,
+              res_pre=False):
+    """x[b,c] = act(x[b,c] + bias[c]) * scale + residual[b // res_div, c], in place; returns x.
+    res_pre: x[b,c] = act(x[b,c] + bias[c] + residual[b // res_div, c]) * scale instead."""
+    b, c, h, w = x.shape
+    cl = layout_of(x)
+    if cl is None:
+        raise ValueError('x must be dense (NCHW or channels_last)')
+    if residual is not None:
+        if b % res_div or tuple(residual.shape) != (b // res_div, c, h, w):
+            raise ValueError('residual must have shape [B / res_div, C, H, W] of x')
+        if layout_of(residual) != cl:
+            residual = to_nhwc(residual) if cl else to_nchw(residual)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().mrefsr_bias_act(_lib.ptr(x), _lib.ptr(bias), _lib.ptr(slope_dev),
+                                        0 if slope_dev is None else slope_dev.numel(), _lib.ptr(residual),
+                                        int(res_div), int(res_pre), b, c, h * w, cl, act, float(slope), float(scale),
+                                        _lib.stream_ptr(x.device))
+    _lib.check(rc, 'mrefsr_bias_act')
+    return x
+
+
+def _convert(t, to_cl):
+    b, c, h, w = t.shape
+    out = torch.empty(b, c, h, w, dtype=t.dtype, device=t.device,
+                      memory_format=torch.channels_last if to_cl else torch.contiguous_format)
+    with torch.cuda.device(t.device):
+        rc = _lib.lib().mrefsr_layout_convert(_lib.ptr(t), _lib.ptr(out), b, c, h * w, int(to_cl),
+                                              _lib.stream_ptr(t.device))
+    _lib.check(rc, 'mrefsr_layout_convert')
+    return out
+
+
+def _convertible(t):
+    return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] % 4 == 0 and t.shape[0] <= 65535
+            and t.numel() > 0 and not t.requires_grad)
+
+
+def to_nchw(t):
+    """Dense NCHW tensor with the values of t; a channels-last fp32 CUDA tensor goes through csrc/trunk.cu's tiled
+    transpose (torch's strided copy runs at a fraction of HBM speed)."""
+    if t.is_contiguous():
+        return t
+    if _convertible(t) and layout_of(t) == 1:
+        return _convert(t, False)
+    return t.contiguous()
+
+
+def to_nhwc(t):
+    """torch.channels_last tensor with the values of t."""
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    if _convertible(t) and layout_of(t) == 0:
+        return _convert(t, True)
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def attn_modulate_(refs, attn_mul, attn_add, bias_mul=None, bias_add=None):
+    """refs = refs * sigmoid(attn_mul + bias_mul[c]) * 2 + (attn_add + bias_add[c]), in place; returns refs."""
+    b, c, h, w = refs.shape
+    cl = layout_of(refs)
+    if cl is None:
+        raise ValueError('refs must be dense (NCHW or channels_last)')
+    attn_mul, attn_add = ((to_nhwc(t) if cl else to_nchw(t)) for t in (attn_mul, attn_add))
+    with torch.cuda.device(refs.device):
+        rc = _lib.lib().mrefsr_attn_modulate(_lib.ptr(refs), _lib.ptr(attn_mul), _lib.ptr(attn_add), _lib.ptr(bias_mul),
+                                             _lib.ptr(bias_add), b, c, h * w, cl, _lib.stream_ptr(refs.device))
+    _lib.check(rc, 'mrefsr_attn_modulate')
+    return refs
+
+
+def conv_raw(x, conv):
+    """The convolution alone (no bias): cuDNN."""
+    return F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def conv_bias_act(x, conv, act=ACT_NONE, slope=0.0, residual=None, prelu=None, scale=1.0):
+    """act(conv(x) + bias) * scale + residual with the epilogue in one pass.  `prelu`: an nn.PReLU module."""
+    y = dense(conv_raw(x, conv))
+    if prelu is not None:
+        return bias_act_(y, conv.bias, ACT_LEAKY, 0.0, residual, prelu.weight, scale)
+    return bias_act_(y, conv.bias, act, slope, residual, None, scale)
+
+
+def run_sequential(seq, x, taps=None, out=None):
+    """nn.Sequential of Conv2d / ReLU / LeakyReLU / MaxPool2d (VGG-style): every Conv2d that is followed by an
+    activation runs fused.  `taps`: names whose outputs are collected into `out` (a dict), as the reference's
+    VGGFeatureExtractor.forward does (vgg_arch.py:141-161)."""
+    items = list(seq._modules.items())
+    i = 0
+    while i < len(items):
+        name, m = items[i]
+        nxt = items[i + 1] if i + 1 < len(items) else (None, None)
+        if isinstance(m, nn.Conv2d) and isinstance(nxt[1], (nn.ReLU, nn.LeakyReLU)):
+            slope = nxt[1].negative_slope if isinstance(nxt[1], nn.LeakyReLU) else 0.0
+            if taps is not None and name in taps:          # a tap on the pre-activation output: keep it separate
+                x = conv_bias_act(x, m)
+                out[name] = x.clone()
+                x = bias_act_(x, None, ACT_LEAKY, slope)
+            else:
+                x = conv_bias_act(x, m, ACT_LEAKY, slope)
+            if taps is not None and nxt[0] in taps:
+                out[nxt[0]] = x                            # later layers never write into x (convs / pools allocate)
+            i += 2
+            continue
+        if isinstance(m, nn.Conv2d):
+            x = conv_bias_act(x, m)
+        else:
+            x = m(x)
+        if taps is not None and name in taps:
+            out[name] = x
+        i += 1
+    return x

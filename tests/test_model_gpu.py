@@ -55,3 +55,26 @@ def test_fast_path_equals_reference_order(pipeline):
     base = torch.nn.functional.interpolate(lq, None, 4, 'bilinear', False)
     rel_l2, _ = _err(a, c, base)
     assert rel_l2 <= 2e-3
+
+
+def test_channels_last_trunk_matches_reference(golden):
+    """The channels-last trunk (cuDNN NHWC kernels, DCN reading / writing NHWC, layout-following glue kernels)
+    against the same golden output of the reference."""
+    import copy
+    m = MRefSRPipeline().eval()
+    refill_parameters(m.net_extractor, 1)
+    refill_parameters(m.net_map, 2)
+    refill_parameters(m.net_g, 3)
+    m = copy.deepcopy(m).to(DEV).channels_last_()
+    g = golden('full_model')
+    lq, up, refs, sr_ref = (g(k).to(DEV) for k in ('lq', 'up', 'refs', 'sr'))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sr = m(lq, up, refs)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    base = torch.nn.functional.interpolate(lq, None, 4, 'bilinear', False)
+    rel_l2, rel_max = _err(sr, sr_ref, base)
+    assert rel_l2 <= 1e-3, (rel_l2, rel_max)
+    assert float((sr.cpu() - sr_ref.cpu()).abs().max()) <= 1e-3

@@ -1,4 +1,5 @@
-"""Full-model throughput variants (cudnn.benchmark, channels_last) -- exploratory."""
+"""Full-model throughput variants of the plain-convolution trunk (memory format, cuDNN autotune, bf16 autocast)
+with the SR-output deviation of each variant from the fp32/NCHW default -- exploratory, feeds models.py."""
 import os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mrefsr_b200.models import MRefSRPipeline
@@ -10,16 +11,45 @@ g = torch.Generator().manual_seed(99)
 lq = torch.rand(b, 3, 40, 40, generator=g).to(dev)
 up = torch.nn.functional.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
 refs = torch.rand(b, r, 3, 160, 160, generator=g).to(dev)
-def run(tag):
-    for _ in range(3): net(lq, up, refs)
+ref_out = [None]
+
+
+def run(tag, fn=None, prof=False):
+    fn = fn or (lambda: net(lq, up, refs))
+    for _ in range(3):
+        out = fn()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(5): net(lq, up, refs)
+    for _ in range(5):
+        out = fn()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
-    print(f'{tag}: {dt*1e3:.1f} ms/step  {b/dt:.0f} img/s', flush=True)
-run('default')
-torch.backends.cudnn.benchmark = True
-run('cudnn.benchmark')
-from torch.profiler import profile, ProfilerActivity
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    net(lq, up, refs); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=14, max_name_column_width=70))
+    out = out.float()
+    if ref_out[0] is None:
+        ref_out[0] = out
+    err = float((out - ref_out[0]).abs().max() / ref_out[0].abs().max())
+    print(f'{tag}: {dt*1e3:.1f} ms/step  {b/dt:.0f} img/s   rel dev from default {err:.2e}', flush=True)
+    if prof:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as p:
+            fn(); torch.cuda.synchronize()
+        print(p.key_averages().table(sort_by='cuda_time_total', row_limit=22, max_name_column_width=80))
+
+
+which = sys.argv[1:] or ['default', 'notf32', 'bench', 'cl', 'bf16']
+if 'default' in which:
+    run('default (NCHW, cuDNN TF32)', prof='prof' in which)
+if 'notf32' in which:
+    torch.backends.cudnn.allow_tf32 = False
+    run('NCHW, cuDNN fp32 (allow_tf32 off)')
+    torch.backends.cudnn.allow_tf32 = True
+if 'bench' in which:
+    torch.backends.cudnn.benchmark = True
+    run('NCHW + cudnn.benchmark')
+if 'cl' in which:
+    torch.backends.cudnn.benchmark = True
+    net.channels_last_()
+    run('channels_last + cudnn.benchmark', prof='prof' in which)
+if 'bf16' in which:
+    def f():
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            return net(lq, up, refs)
+    run('bf16 autocast (plain convs), current layout', f)
