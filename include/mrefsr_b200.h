@@ -203,6 +203,15 @@ MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const fl
  * ------------------------------------------------------------------------------------------ */
 MREFSR_API int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const float* ass, float* out, float* prob,
                                    int n, int t, int C, int Cv, int h, int w, void* stream);
+/* Channels-last inference variant with the producing convolutions' epilogues folded in: the inputs are the RAW
+ * cuDNN outputs of conv_emb1 / conv_emb2 / conv_ass in NHWC ([n,h,w,C], [n*t,h,w,C], [n*t,h,w,Cv]);
+ * q = prelu(q_raw + bias_q, slope_q) * q_scale, k = prelu(k_raw + bias_k, slope_k), v = v_raw + bias_v are applied
+ * on the fly (ref_mrapa_restoration_arch.py:293-302, 321-323), out [n,h,w,Cv].  Any bias / slope pointer may be
+ * NULL (no bias / no activation); slope_*_n is 1 or C (nn.PReLU).  C in {64,128,256}, Cv = 2C, t <= 8. */
+MREFSR_API int mrefsr_mrapa_attention_nhwc(const float* q_raw, const float* k_raw, const float* v_raw, const float* bias_q,
+                                const float* bias_k, const float* bias_v, const float* slope_q, int slope_q_n,
+                                const float* slope_k, int slope_k_n, float q_scale, float* out, int n, int t, int C,
+                                int Cv, int h, int w, void* stream);
 MREFSR_API int mrefsr_mrapa_attention_backward(const float* emb_t, const float* emb, const float* ass, const float* prob,
                                     const float* grad_out, float* grad_emb_t, float* grad_emb, float* grad_ass,
                                     int n, int t, int C, int Cv, int h, int w, void* stream);

@@ -243,6 +243,126 @@ static int check_args(int n, int t, int C, int Cv, int h, int w) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Channels-last forward with the three producing convolutions' epilogues folded in (inference):
+//   q = prelu(q_raw + bias_q) * q_scale,  k = prelu(k_raw + bias_k),  v = v_raw + bias_v     (conv_emb1 / conv_emb2 /
+//   conv_ass of MRAPAFusion, ref_mrapa_restoration_arch.py:293-302, 321-323) are applied on the fly, so the raw cuDNN
+//   outputs are read exactly once and never rewritten.  One warp per pixel, lane = V consecutive channels of every
+//   32*V-channel group: every access is a contiguous 128*V-byte row segment.  sum_t p_t = 1, so bias_v is added once.
+template <int V>
+struct VecT;
+template <>
+struct VecT<2> { using type = float2; };
+template <>
+struct VecT<4> { using type = float4; };
+
+template <int V>
+__device__ __forceinline__ void vload(float (&d)[V], const float* p) {
+    const typename VecT<V>::type v = __ldcs(reinterpret_cast<const typename VecT<V>::type*>(p));
+    const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+    for (int e = 0; e < V; ++e) d[e] = f[e];
+}
+template <int V>
+__device__ __forceinline__ void vload_param(float (&d)[V], const float* p, int n, int c, float dflt) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) d[e] = p ? __ldg(p + (n == 1 ? 0 : c + e)) : dflt;
+}
+
+template <int V, int J>   // C = 32 * V * J, Cv = 2 * C
+__global__ void __launch_bounds__(256)
+mrapa_fwd_nhwc_kernel(const float* __restrict__ q_raw, const float* __restrict__ k_raw, const float* __restrict__ v_raw,
+                      const float* __restrict__ bias_q, const float* __restrict__ bias_k,
+                      const float* __restrict__ bias_v, const float* __restrict__ slope_q, int slope_q_n,
+                      const float* __restrict__ slope_k, int slope_k_n, float q_scale, float* __restrict__ out, int n,
+                      int t, long long HW) {
+    constexpr int C = 32 * V * J, Cv = 2 * C, JV = 2 * J;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float bq[J][V], bk[J][V], sq[J][V], sk[J][V];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int c = j * 32 * V + lane * V;
+        vload_param<V>(bq[j], bias_q, 0, c, 0.f);
+        vload_param<V>(bk[j], bias_k, 0, c, 0.f);
+        vload_param<V>(sq[j], slope_q, slope_q_n, c, 1.f);     // no activation = slope 1
+        vload_param<V>(sk[j], slope_k, slope_k_n, c, 1.f);
+    }
+    for (long long px = warp0; px < (long long)n * HW; px += nwarps) {
+        const long long img = px / HW, p = px - img * HW;
+        float q[J][V];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            vload<V>(q[j], q_raw + px * C + j * 32 * V + lane * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float a = q[j][e] + bq[j][e];
+                q[j][e] = (a > 0.f ? a : a * sq[j][e]) * q_scale;
+            }
+        }
+        float l[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            l[i] = 0.f;
+            if (i < t) {
+                const float* kp = k_raw + ((img * t + i) * HW + p) * C + lane * V;
+                float part = 0.f;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    float k[V];
+                    vload<V>(k, kp + j * 32 * V);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const float a = k[e] + bk[j][e];
+                        part = fmaf(q[j][e], a > 0.f ? a : a * sk[j][e], part);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                l[i] = part;
+                mx = fmaxf(mx, part);
+            }
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            l[i] = (i < t) ? expf(l[i] - mx) : 0.f;
+            den += l[i];
+        }
+        const float inv = 1.f / den;
+        float acc[JV][V];
+#pragma unroll
+        for (int j = 0; j < JV; ++j)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[j][e] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < t) {
+                const float pi = l[i] * inv;
+                const float* vp = v_raw + ((img * t + i) * HW + p) * Cv + lane * V;
+#pragma unroll
+                for (int j = 0; j < JV; ++j) {
+                    float v[V];
+                    vload<V>(v, vp + j * 32 * V);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[j][e] = fmaf(pi, v[e], acc[j][e]);
+                }
+            }
+        }
+        float* op = out + px * Cv + lane * V;
+#pragma unroll
+        for (int j = 0; j < JV; ++j) {
+            typename VecT<V>::type o;
+            float* f = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = acc[j][e] + (bias_v ? __ldg(bias_v + j * 32 * V + lane * V + e) : 0.f);
+            *reinterpret_cast<typename VecT<V>::type*>(op + j * 32 * V) = o;
+        }
+    }
+}
+
 }  // namespace mrefsr
 
 using namespace mrefsr;
@@ -302,6 +422,38 @@ int mrefsr_mrapa_attention_backward(const float* emb_t, const float* emb, const 
     else
         mrapa_bwd_kernel<16><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, prob, grad_out, grad_emb_t, grad_emb, grad_ass,
                                                        t, C, Cv, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_mrapa_attention_nhwc(const float* q_raw, const float* k_raw, const float* v_raw, const float* bias_q,
+                                const float* bias_k, const float* bias_v, const float* slope_q, int slope_q_n,
+                                const float* slope_k, int slope_k_n, float q_scale, float* out, int n, int t, int C,
+                                int Cv, int h, int w, void* stream) {
+    MREFSR_CHECK(q_raw && k_raw && v_raw && out, ERR_BAD_ARG, "mrapa attention nhwc: null pointer argument");
+    int rc = check_args(n, t, C, Cv, h, w);
+    if (rc) return rc;
+    MREFSR_CHECK(t <= 8, ERR_UNSUPPORTED, "mrapa attention nhwc: at most 8 references per call (t=%d)", t);
+    MREFSR_CHECK(Cv == 2 * C && (C == 64 || C == 128 || C == 256), ERR_UNSUPPORTED,
+                 "mrapa attention nhwc: needs C in {64,128,256} and Cv = 2C (C=%d Cv=%d)", C, Cv);
+    MREFSR_CHECK((!slope_q || slope_q_n == 1 || slope_q_n == C) && (!slope_k || slope_k_n == 1 || slope_k_n == C),
+                 ERR_BAD_ARG, "mrapa attention nhwc: PReLU weights must have 1 or C entries");
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    MREFSR_CHECK(al16(q_raw) && al16(k_raw) && al16(v_raw) && al16(out), ERR_BAD_ARG,
+                 "mrapa attention nhwc: tensors must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long HW = (long long)h * w, warps = (long long)n * HW;
+    long long blocks = (warps + 7) / 8;
+    if (blocks > 148 * 8 * 4) blocks = 148 * 8 * 4;
+    ScopedTiming tm(MREFSR_K_FUSION_FWD, st);
+#define MREFSR_NHWC(V, J)                                                                                             \
+    mrapa_fwd_nhwc_kernel<V, J><<<(int)blocks, 256, 0, st>>>(q_raw, k_raw, v_raw, bias_q, bias_k, bias_v, slope_q,    \
+                                                             slope_q_n, slope_k, slope_k_n, q_scale, out, n, t, HW)
+    if (C == 64) MREFSR_NHWC(2, 1);
+    else if (C == 128) MREFSR_NHWC(4, 1);
+    else MREFSR_NHWC(4, 2);
+#undef MREFSR_NHWC
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

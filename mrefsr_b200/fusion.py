@@ -63,6 +63,30 @@ def mrapa_attention(emb_t, emb, ass, t):
     return MRAPAAttentionFunction.apply(emb_t, emb, ass, t)
 
 
+def mrapa_attention_nhwc(q_raw, k_raw, v_raw, t, bias_q=None, bias_k=None, bias_v=None, slope_q=None, slope_k=None,
+                         q_scale=1.0):
+    """Channels-last inference variant: inputs are the raw (bias-free) outputs of conv_emb1 / conv_emb2 / conv_ass as
+    torch.channels_last tensors; bias, PReLU and the C^-0.5 scale are applied inside the kernel.
+    q_raw [n,C,h,w], k_raw [n*t,C,h,w], v_raw [n*t,2C,h,w] -> channels_last [n,2C,h,w]."""
+    _lib.require_cuda(q_raw, k_raw, v_raw)
+    n, c, h, w = q_raw.shape
+    cv = v_raw.shape[1]
+    cl = torch.channels_last
+    if not all(x.dtype == torch.float32 and x.is_contiguous(memory_format=cl) for x in (q_raw, k_raw, v_raw)):
+        raise ValueError('expected fp32 torch.channels_last tensors')
+    if tuple(k_raw.shape) != (n * t, c, h, w) or tuple(v_raw.shape) != (n * t, cv, h, w):
+        raise ValueError('expected q_raw [n,C,h,w], k_raw [n*t,C,h,w], v_raw [n*t,Cv,h,w]')
+    out = torch.empty(n, cv, h, w, dtype=torch.float32, device=q_raw.device, memory_format=cl)
+    with torch.cuda.device(q_raw.device):
+        rc = _lib.lib().mrefsr_mrapa_attention_nhwc(
+            _lib.ptr(q_raw), _lib.ptr(k_raw), _lib.ptr(v_raw), _lib.ptr(bias_q), _lib.ptr(bias_k), _lib.ptr(bias_v),
+            _lib.ptr(slope_q), 0 if slope_q is None else slope_q.numel(), _lib.ptr(slope_k),
+            0 if slope_k is None else slope_k.numel(), float(q_scale), _lib.ptr(out), n, t, c, cv, h, w,
+            _lib.stream_ptr(q_raw.device))
+    _lib.check(rc, 'mrefsr_mrapa_attention_nhwc')
+    return out
+
+
 class MRAPAFusion(nn.Module):
     """Drop-in for basicsr.archs.ref_mrapa_restoration_arch.MRAPAFusion (same parameters and forward)."""
 
@@ -118,12 +142,24 @@ class MRAPAFusion(nn.Module):
     def _forward_fused_glue(self, target, refs, t, h_input, w_input):
         """Inference path: same arithmetic, every conv's bias / activation / scale epilogue in one pass and the
         spatial-attention modulation (sigmoid, * 2, + add, both conv biases) in one kernel."""
-        emb_t = T.conv_bias_act(target, self.conv_emb1[0], prelu=self.conv_emb1[1], scale=self.scale)
-        emb = T.conv_bias_act(refs, self.conv_emb2[0], prelu=self.conv_emb2[1])
-        ass = T.conv_bias_act(refs, self.conv_ass)
-        refs = mrapa_attention(emb_t, emb, ass, t)
-        if T.layout_of(target) == 1:      # keep the channels-last trunk channels-last
-            refs = T.to_nhwc(refs)
+        c = self.conv_emb2[0].out_channels
+        if T.layout_of(target) == 1 and T.layout_of(refs) == 1 and c in (64, 128, 256) and t <= 8:
+            # channels-last: the attention kernel reads the raw convolution outputs and applies their bias / PReLU /
+            # scale itself -- no epilogue pass over emb_t / emb / ass and no layout conversion
+            cl = torch.channels_last
+            q, k, v = (T.conv_raw(target, self.conv_emb1[0]).contiguous(memory_format=cl),
+                       T.conv_raw(refs, self.conv_emb2[0]).contiguous(memory_format=cl),
+                       T.conv_raw(refs, self.conv_ass).contiguous(memory_format=cl))
+            refs = mrapa_attention_nhwc(q, k, v, t, self.conv_emb1[0].bias, self.conv_emb2[0].bias,
+                                        self.conv_ass.bias, self.conv_emb1[1].weight, self.conv_emb2[1].weight,
+                                        self.scale)
+        else:
+            emb_t = T.conv_bias_act(target, self.conv_emb1[0], prelu=self.conv_emb1[1], scale=self.scale)
+            emb = T.conv_bias_act(refs, self.conv_emb2[0], prelu=self.conv_emb2[1])
+            ass = T.conv_bias_act(refs, self.conv_ass)
+            refs = mrapa_attention(emb_t, emb, ass, t)
+            if T.layout_of(target) == 1:      # keep the channels-last trunk channels-last
+                refs = T.to_nhwc(refs)
         attn = T.conv_bias_act(torch.cat([target, refs], dim=1), self.spatial_attn, T.ACT_LEAKY, 0.1)
         attn_mul = T.conv_raw(T.conv_bias_act(attn, self.spatial_attn_mul1, T.ACT_LEAKY, 0.1), self.spatial_attn_mul2)
         attn_add = T.conv_raw(T.conv_bias_act(attn, self.spatial_attn_add1, T.ACT_LEAKY, 0.1), self.spatial_attn_add2)

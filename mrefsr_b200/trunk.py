@@ -111,7 +111,14 @@ def conv_raw(x, conv):
 
 
 def conv_bias_act(x, conv, act=ACT_NONE, slope=0.0, residual=None, prelu=None, scale=1.0):
-    """act(conv(x) + bias) * scale + residual with the epilogue in one pass.  `prelu`: an nn.PReLU module."""
+    """act(conv(x) + bias) * scale + residual with the epilogue in one pass.  `prelu`: an nn.PReLU module.
+    conv + bias + ReLU on a channels-last tensor goes to cuDNN's own fused epilogue (cudnnConvolutionBiasActivation:
+    measured 63 vs 103 us for 16x64x160x160 on B200; in NCHW it is no faster than conv + one glue pass)."""
+    if (act == ACT_LEAKY and slope == 0.0 and prelu is None and residual is None and scale == 1.0
+            and conv.bias is not None and layout_of(x) == 1 and conv.padding_mode == 'zeros'
+            and not isinstance(conv.padding, str)):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation,
+                                            conv.groups)
     y = dense(conv_raw(x, conv))
     if prelu is not None:
         return bias_act_(y, conv.bias, ACT_LEAKY, 0.0, residual, prelu.weight, scale)

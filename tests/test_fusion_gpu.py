@@ -72,3 +72,34 @@ def test_too_many_refs_errors():
     q = torch.randn(1, 8, 4, 4, device=DEV)
     with pytest.raises(RuntimeError):
         M.mrapa_attention(q, torch.randn(17, 8, 4, 4, device=DEV), torch.randn(17, 8, 4, 4, device=DEV), 17)
+
+
+@pytest.mark.parametrize('c,t', [(64, 5), (128, 3), (256, 8), (64, 1)])
+def test_nhwc_variant_with_folded_epilogues(c, t):
+    """channels-last kernel (bias / PReLU / scale applied inside) against the NCHW core fed the finished tensors."""
+    from mrefsr_b200.fusion import mrapa_attention_nhwc
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(c + t)
+    n, h, w = 2, 12, 20
+    cl = torch.channels_last
+    q_raw = torch.randn(n, c, h, w, generator=g).to(DEV)
+    k_raw = torch.randn(n * t, c, h, w, generator=g).to(DEV)
+    v_raw = torch.randn(n * t, 2 * c, h, w, generator=g).to(DEV)
+    bq, bk = (torch.randn(c, generator=g).to(DEV) for _ in range(2))
+    bv = torch.randn(2 * c, generator=g).to(DEV)
+    sq, sk = torch.rand(1, generator=g).to(DEV), torch.rand(c, generator=g).to(DEV)       # nn.PReLU(1) and nn.PReLU(C)
+    scale = c ** -0.5
+    q = F.prelu(q_raw + bq.view(1, -1, 1, 1), sq) * scale
+    k = F.prelu(k_raw + bk.view(1, -1, 1, 1), sk)
+    v = v_raw + bv.view(1, -1, 1, 1)
+    want = M.mrapa_attention(q, k, v, t)
+    assert rel_err(want, oracle.mrapa_attention_oracle(q.cpu(), k.cpu(), v.cpu(), t)) <= 1e-5
+    got = mrapa_attention_nhwc(q_raw.contiguous(memory_format=cl), k_raw.contiguous(memory_format=cl),
+                               v_raw.contiguous(memory_format=cl), t, bq, bk, bv, sq, sk, scale)
+    assert got.is_contiguous(memory_format=cl)
+    assert rel_err(got, want) <= 1e-5
+    # no bias / no activation
+    want2 = M.mrapa_attention(q_raw, k_raw, v_raw, t)
+    got2 = mrapa_attention_nhwc(q_raw.contiguous(memory_format=cl), k_raw.contiguous(memory_format=cl),
+                                v_raw.contiguous(memory_format=cl), t)
+    assert rel_err(got2, want2) <= 1e-5

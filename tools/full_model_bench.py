@@ -53,3 +53,42 @@ if 'bf16' in which:
         with torch.autocast('cuda', dtype=torch.bfloat16):
             return net(lq, up, refs)
     run('bf16 autocast (plain convs), current layout', f)
+if 'graph' in which:
+    # CUDA-graph replay of the whole forward (static input buffers)
+    static = [t.clone() for t in (lq, up, refs)]
+    s_ = torch.cuda.Stream()
+    s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        for _ in range(3):
+            net(*static)
+    torch.cuda.current_stream().wait_stream(s_)
+    g_ = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_):
+        out_static = net(*static)
+
+    def replay():
+        g_.replay()
+        return out_static
+    run('CUDA graph replay of the current configuration', replay)
+if 'fusedconv' in which:
+    # micro: conv + bias + ReLU as F.conv2d + bias_act_ vs torch.cudnn_convolution_relu (cuDNN fused epilogue)
+    from mrefsr_b200 import trunk as T
+    for cl in (False, True):
+        for (n, c, hw) in ((16, 64, 160), (96, 64, 160), (16, 64, 40)):
+            x = torch.randn(n, c, hw, hw, device=dev)
+            conv = torch.nn.Conv2d(c, c, 3, 1, 1).to(dev)
+            if cl:
+                x = x.contiguous(memory_format=torch.channels_last); conv = conv.to(memory_format=torch.channels_last)
+            def a():
+                with torch.no_grad():
+                    return T.conv_bias_act(x, conv, T.ACT_LEAKY, 0.0)
+            def b_():
+                with torch.no_grad():
+                    return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, (1, 1), (1, 1), (1, 1), 1)
+            for tag, f in (('conv2d + bias_act_', a), ('cudnn_convolution_relu', b_)):
+                for _ in range(5): y = f()
+                torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20): y = f()
+                e1.record(); torch.cuda.synchronize()
+                print(f'cl={cl} [{n},{c},{hw},{hw}] {tag}: {e0.elapsed_time(e1)/20*1e3:.0f} us', flush=True)
