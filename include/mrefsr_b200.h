@@ -178,7 +178,8 @@ MREFSR_API int mrefsr_dynagg_dcn_forward_ex(const float* input, const float* wei
  *       references; 1 = same batch).  res_pre = 1 adds the residual before the activation instead:
  *       x = act(x + bias + residual) * scale  -- the per-image half of a convolution over cat([x, feat]) that
  *       was split by input channels (small/medium/large_offset_conv1, ref_mrapa_restoration_arch.py:222-227).
- *   mrefsr_layout_convert: dense [B,C,HW] <-> [B,HW,C] (torch.channels_last), C % 4 == 0, out of place.
+ *   mrefsr_layout_convert: dense [B,C,HW] <-> [B,HW,C] (torch.channels_last), C % 4 == 0, out of place;
+ *       bias (C entries, may be NULL) is added on the way: a convolution's bias folded into the conversion.
  *   mrefsr_attn_modulate: refs = refs * sigmoid(attn_mul + bias_mul[c]) * 2 + (attn_add + bias_add[c])
  *       (ref_mrapa_restoration_arch.py:341-344), in place on refs.
  * ------------------------------------------------------------------------------------------ */
@@ -190,7 +191,8 @@ enum {
 MREFSR_API int mrefsr_bias_act(float* x, const float* bias, const float* slope_dev, int slope_n, const float* residual,
                     int res_div, int res_pre, int B, int C, int HW, int channels_last, int act, float slope,
                     float scale, void* stream);
-MREFSR_API int mrefsr_layout_convert(const float* src, float* dst, int B, int C, int HW, int to_channels_last, void* stream);
+MREFSR_API int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B, int C, int HW,
+                          int to_channels_last, void* stream);
 MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,
                          const float* bias_add, int B, int C, int HW, int channels_last, void* stream);
 

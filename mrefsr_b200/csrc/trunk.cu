@@ -165,7 +165,7 @@ attn_modulate_nhwc_kernel(float* __restrict__ refs, const float* __restrict__ mu
 // Dense layout conversion, 32 positions x 128 channels per CTA through shared memory, both directions at streaming
 // rate (torch's strided copy_ runs these at ~1/4 of it).  grid (ceil(HW/32), ceil(C/128), B); C % 4 == 0.
 __global__ void __launch_bounds__(256)
-nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ bias, int C, int HW) {
     __shared__ float tile[128][33];
     const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,12 +187,12 @@ nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
 #pragma unroll
     for (int i = 0; i < 16; ++i) {       // stores: lane = position, 128-byte coalesced rows of one channel plane
         const int cl = warp + 8 * i, c = c0 + cl;
-        if (c < C && p < HW) d[(size_t)c * HW + p] = tile[cl][lane];
+        if (c < C && p < HW) d[(size_t)c * HW + p] = tile[cl][lane] + (bias ? __ldg(bias + c) : 0.f);
     }
 }
 
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ bias, int C, int HW) {
     __shared__ float tile[128][33];
     const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,7 +202,7 @@ nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst,
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int cl = warp + 8 * i, c = c0 + cl;
-        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) + (bias ? __ldg(bias + c) : 0.f) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -298,7 +298,8 @@ int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_a
     return 0;
 }
 
-int mrefsr_layout_convert(const float* src, float* dst, int B, int C, int HW, int to_channels_last, void* stream) {
+int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B, int C, int HW, int to_channels_last,
+                          void* stream) {
     MREFSR_CHECK(src && dst && src != dst, ERR_BAD_ARG, "layout_convert: bad pointers");
     MREFSR_CHECK(B > 0 && C > 0 && HW > 0 && C % 4 == 0, ERR_BAD_ARG, "layout_convert: needs C %% 4 == 0 (B=%d C=%d HW=%d)", B, C, HW);
     MREFSR_CHECK(al16(src) && al16(dst), ERR_BAD_ARG, "layout_convert: tensors must be 16-byte aligned");
@@ -307,9 +308,9 @@ int mrefsr_layout_convert(const float* src, float* dst, int B, int C, int HW, in
     ScopedTiming tm(MREFSR_K_GLUE, st);
     const dim3 grid(cdiv(HW, 32), cdiv(C, 128), B);
     if (to_channels_last)
-        nchw_to_nhwc_conv_kernel<<<grid, 256, 0, st>>>(src, dst, C, HW);
+        nchw_to_nhwc_conv_kernel<<<grid, 256, 0, st>>>(src, dst, bias, C, HW);
     else
-        nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(src, dst, C, HW);
+        nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(src, dst, bias, C, HW);
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

@@ -77,8 +77,8 @@ class DynAgg(ModulatedDeformConv2d):
         feat = x[1] if self.extra_offset_mask else x
         if self.extra_offset_mask:
             x = x[0]
-        if T.fast_ok(feat):    # bias of the 216-plane tensor in one vectorised pass (torch's broadcast add is slow)
-            out = T.conv_bias_act(feat, self.conv_offset_mask)
+        if T.fast_ok(feat):    # the DCN reads planes: bias (+ the NHWC -> NCHW conversion of a channels-last conv) in one pass
+            out = T.conv_bias_to_nchw(feat, self.conv_offset_mask)
         else:
             out = self.conv_offset_mask(feat)
         return dynagg_dcn_forward(x, out, max_idx, flow_scale, self.weight, self.bias, self.deform_groups,

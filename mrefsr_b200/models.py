@@ -210,6 +210,8 @@ class DynamicAggregationRestoration(nn.Module):
                     x = T.conv_bias_act(T.conv_bias_act(h, tail[0], T.ACT_LEAKY, 0.1), tail[2])
                 else:                   # conv -> pixel shuffle -> lrelu == conv -> lrelu -> pixel shuffle
                     x = F.pixel_shuffle(T.conv_bias_act(h, tail[0], T.ACT_LEAKY, 0.1), 2)
+                    if T.layout_of(h) == 1:     # pixel_shuffle hands back NCHW: keep the channels-last trunk intact
+                        x = T.to_nhwc(x)
             else:
                 x = tail(h)
         return x

@@ -56,12 +56,12 @@ def bias_act_(x, bias=None, act=ACT_NONE, slope=0.0, residual=None, slope_dev=No
     return x
 
 
-def _convert(t, to_cl):
+def _convert(t, to_cl, bias=None):
     b, c, h, w = t.shape
     out = torch.empty(b, c, h, w, dtype=t.dtype, device=t.device,
                       memory_format=torch.channels_last if to_cl else torch.contiguous_format)
     with torch.cuda.device(t.device):
-        rc = _lib.lib().mrefsr_layout_convert(_lib.ptr(t), _lib.ptr(out), b, c, h * w, int(to_cl),
+        rc = _lib.lib().mrefsr_layout_convert(_lib.ptr(t), _lib.ptr(out), _lib.ptr(bias), b, c, h * w, int(to_cl),
                                               _lib.stream_ptr(t.device))
     _lib.check(rc, 'mrefsr_layout_convert')
     return out
@@ -80,6 +80,15 @@ def to_nchw(t):
     if _convertible(t) and layout_of(t) == 1:
         return _convert(t, False)
     return t.contiguous()
+
+
+def conv_bias_to_nchw(x, conv):
+    """conv(x) + bias as a dense NCHW tensor.  From a channels-last convolution the bias rides on the layout
+    conversion (one pass instead of two); otherwise it is the ordinary conv + bias epilogue."""
+    y = conv_raw(x, conv)
+    if layout_of(y) == 1 and not y.is_contiguous() and _convertible(y):
+        return _convert(y, False, conv.bias)
+    return bias_act_(to_nchw(dense(y)), conv.bias)
 
 
 def to_nhwc(t):

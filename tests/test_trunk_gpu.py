@@ -176,3 +176,15 @@ def test_layout_convert(shape):
     assert T.to_nchw(x) is x and T.to_nhwc(cl) is cl
     odd = torch.randn(2, 6, 5, 5, device=DEV)                 # C % 4 != 0: torch's copy
     assert torch.equal(T.to_nchw(T.to_nhwc(odd)), odd)
+
+
+def test_conv_bias_to_nchw():
+    conv = torch.nn.Conv2d(8, 216, 3, 1, 1).to(DEV)
+    x = torch.randn(2, 8, 12, 12, device=DEV)
+    with torch.no_grad():
+        want = conv(x)
+        a = T.conv_bias_to_nchw(x, conv)                                             # NCHW convolution
+        conv_cl = conv.to(memory_format=torch.channels_last)
+        b = T.conv_bias_to_nchw(x.contiguous(memory_format=torch.channels_last), conv_cl)   # bias on the conversion
+    assert a.is_contiguous() and b.is_contiguous()
+    assert rel_err(a, want) <= 1e-3 and rel_err(b, want) <= 1e-3
