@@ -193,6 +193,8 @@ MREFSR_API int mrefsr_bias_act(float* x, const float* bias, const float* slope_d
                     float scale, void* stream);
 MREFSR_API int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B, int C, int HW,
                           int to_channels_last, void* stream);
+/* 2x2 / stride-2 max pooling, channels-last [B,H,W,C] -> [B,H/2,W/2,C] (VGG pool1 / pool2), C % 4 == 0, H, W even. */
+MREFSR_API int mrefsr_maxpool2x2_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,
                          const float* bias_add, int B, int C, int HW, int channels_last, void* stream);
 

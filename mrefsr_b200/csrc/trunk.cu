@@ -214,6 +214,29 @@ nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst,
     }
 }
 
+// 2x2 / stride 2 max pooling on channels-last data (VGG pool1 / pool2, vgg_arch.py:141-161): float4 over channels,
+// every access a contiguous row segment.  torch's max_pool_forward_nhwc takes 1.7 ms for the six calls of a batch-16
+// forward; this is the streaming rate.
+__global__ void __launch_bounds__(256)
+maxpool2_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, long long total4, int C4, int Wo, int Ho, int W) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const long long b = r / Ho;
+        const float4* s = reinterpret_cast<const float4*>(src) + ((b * (2 * Ho) + 2 * oy) * (long long)W + 2 * ox) * C4 + c4;
+        const float4 a = __ldcs(s), bb = __ldcs(s + C4), c = __ldcs(s + (long long)W * C4), d = __ldcs(s + (long long)W * C4 + C4);
+        float4 o;
+        o.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, d.x));
+        o.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, d.y));
+        o.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, d.z));
+        o.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, d.w));
+        reinterpret_cast<float4*>(dst)[i] = o;
+    }
+}
+
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace mrefsr
@@ -311,6 +334,22 @@ int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B
         nchw_to_nhwc_conv_kernel<<<grid, 256, 0, st>>>(src, dst, bias, C, HW);
     else
         nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(src, dst, bias, C, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_maxpool2x2_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream) {
+    MREFSR_CHECK(src && dst, ERR_BAD_ARG, "maxpool2x2_nhwc: null tensor");
+    MREFSR_CHECK(B > 0 && C > 0 && C % 4 == 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, ERR_BAD_ARG,
+                 "maxpool2x2_nhwc: needs C %% 4 == 0 and even H, W (B=%d C=%d H=%d W=%d)", B, C, H, W);
+    MREFSR_CHECK(al16(src) && al16(dst), ERR_BAD_ARG, "maxpool2x2_nhwc: tensors must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total4 = (long long)B * (H / 2) * (W / 2) * (C / 4);
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    maxpool2_nhwc_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, total4, C / 4, W / 2, H / 2, W);
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

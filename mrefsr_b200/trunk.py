@@ -134,6 +134,21 @@ def conv_bias_act(x, conv, act=ACT_NONE, slope=0.0, residual=None, prelu=None, s
     return bias_act_(y, conv.bias, act, slope, residual, None, scale)
 
 
+def maxpool2x2(x, m=None):
+    """nn.MaxPool2d(2, 2) on a channels-last fp32 CUDA tensor through csrc/trunk.cu; anything else through torch."""
+    b, c, h, w = x.shape
+    plain = m is None or (m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2)) and m.padding in (0, (0, 0))
+                          and m.dilation in (1, (1, 1)) and not m.ceil_mode and not m.return_indices)
+    if not (plain and layout_of(x) == 1 and x.is_cuda and x.dtype == torch.float32 and c % 4 == 0 and h % 2 == 0
+            and w % 2 == 0 and not x.requires_grad):
+        return m(x) if m is not None else F.max_pool2d(x, 2, 2)
+    out = torch.empty(b, c, h // 2, w // 2, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().mrefsr_maxpool2x2_nhwc(_lib.ptr(x), _lib.ptr(out), b, c, h, w, _lib.stream_ptr(x.device))
+    _lib.check(rc, 'mrefsr_maxpool2x2_nhwc')
+    return out
+
+
 def run_sequential(seq, x, taps=None, out=None):
     """nn.Sequential of Conv2d / ReLU / LeakyReLU / MaxPool2d (VGG-style): every Conv2d that is followed by an
     activation runs fused.  `taps`: names whose outputs are collected into `out` (a dict), as the reference's
@@ -157,6 +172,8 @@ def run_sequential(seq, x, taps=None, out=None):
             continue
         if isinstance(m, nn.Conv2d):
             x = conv_bias_act(x, m)
+        elif isinstance(m, nn.MaxPool2d):
+            x = maxpool2x2(x, m)
         else:
             x = m(x)
         if taps is not None and name in taps:

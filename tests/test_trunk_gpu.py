@@ -188,3 +188,12 @@ def test_conv_bias_to_nchw():
         b = T.conv_bias_to_nchw(x.contiguous(memory_format=torch.channels_last), conv_cl)   # bias on the conversion
     assert a.is_contiguous() and b.is_contiguous()
     assert rel_err(a, want) <= 1e-3 and rel_err(b, want) <= 1e-3
+
+
+def test_maxpool2x2_nhwc():
+    x = torch.randn(3, 64, 10, 14, device=DEV)
+    want = F.max_pool2d(x, 2, 2)
+    got = T.maxpool2x2(x.contiguous(memory_format=torch.channels_last), torch.nn.MaxPool2d(2, 2))
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
+    odd = torch.randn(1, 6, 9, 9, device=DEV).contiguous(memory_format=torch.channels_last)     # torch path
+    assert torch.equal(T.maxpool2x2(odd, torch.nn.MaxPool2d(2, 2)), F.max_pool2d(odd, 2, 2))
