@@ -384,16 +384,29 @@ def main():
     # ---- e2e: same step through the operator API with HOST (pinned) buffers, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        hd = make_inputs(b, r, 1234 + rank, 'cpu', pin=True)
-        h2d = input_bytes(hd)
+        # allocation may fail on a crowded host (pinned memory: 6.3 GB per rank) -- decide collectively, so that no
+        # rank is left waiting in a barrier
+        alloc_err = None
+        try:
+            hd = make_inputs(b, r, 1234 + rank, 'cpu', pin=True)
+            h2d = input_bytes(hd)
+            del d
+            torch.cuda.empty_cache()
+            dev_in = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in hd.items()} for _ in range(2)]
+        except Exception as e:  # noqa: BLE001
+            alloc_err = repr(e)[:200]
+        ok = torch.tensor([0 if alloc_err else 1], dtype=torch.int32, device=dev)
+        if dist is not None:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not args.no_e2e and int(ok.item()) == 0:
+        e2e = {'error': alloc_err or 'allocation failed on another rank'}
+    elif not args.no_e2e:
         d2h = [0]
-
         copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
         # Double-buffered pipeline over steps: while step i computes and its results stream back to the host
         # (PCIe is full duplex), the inputs of step i+1 are already crossing the bus into the second buffer set.
         # Every step still pays its own H2D of all inputs and its own D2H of all results inside the timed region.
-        dev_in = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in hd.items()} for _ in range(2)]
         host_out = [None, None]
         in_ready = [torch.cuda.Event(), torch.cuda.Event()]
         in_free = [torch.cuda.Event(), torch.cuda.Event()]
@@ -433,8 +446,6 @@ def main():
                 d2h[0] = sum(o.numel() * o.element_size() for o in outs)
             copy_out.synchronize()
             torch.cuda.synchronize()
-        del d
-        torch.cuda.empty_cache()
         e2e_run(2)
         barrier()
         n_e2e = max(4, min(args.steps, 8))
