@@ -10,6 +10,7 @@
 //     (deform_conv_cuda.cpp:612-672) is batched over chunks of samples sized to a bounded workspace.
 #include "common.cuh"
 #include "dcn_common.cuh"
+#include <cublas_v2.h>
 #include "../../include/mrefsr_b200.h"
 
 namespace mrefsr {
@@ -254,6 +255,65 @@ __global__ void dcn_im2col_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
+// (4a') position-major columns for the library-GEMM path: colP[bl][p][tap*C + c] from the NHWC copy of the input.
+// One thread = (position, tap, 8-channel chunk): one sample decode, four 256-bit corner loads, one 32-byte store;
+// lanes = consecutive positions (coalesced offset / mask reads).  The planar kernel above issues 8x the L1 sectors.
+struct __align__(32) Col8 {
+    float v[8];
+};
+__device__ __forceinline__ Col8 ldg_col8(const float* p) {
+    Col8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p));
+    return r;
+}
+__global__ void __launch_bounds__(256)
+dcn_im2col_nhwc_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
+                       float* __restrict__ colP, const DcnShape s, int b0, int nb) {
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG, C8 = s.C >> 3;
+    const size_t total = (size_t)nb * K * C8 * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int j = (idx / P) % C8;
+        const int tap = (idx / ((size_t)P * C8)) % K;
+        const int bl = idx / ((size_t)P * C8 * K);
+        const int b = b0 + bl, c0 = j * 8, dgi = c0 / cdg;
+        const int oy = p / s.Wo, ox = p - oy * s.Wo, ti = tap / s.kw, tj = tap - ti * s.kw;
+        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldg(offset + ob);
+        const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldg(offset + ob + P);
+        const float m = mask ? __ldg(mask + ((size_t)(b * s.DG + dgi) * K + tap) * P + p) : 1.f;
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+            const float fy0 = floorf(y), fx0 = floorf(x);
+            const int y0 = (int)fy0, x0 = (int)fx0;
+            const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+            const float* base = xt + ((size_t)(b * s.H + yc) * s.W + xc) * s.C + c0;
+            const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
+            const float w0 = (ty0 && tx0) ? hy * hx * m : 0.f, w1 = (ty0 && tx1) ? hy * lx * m : 0.f;
+            const float w2 = (ty1 && tx0) ? ly * hx * m : 0.f, w3 = (ty1 && tx1) ? ly * lx * m : 0.f;
+            const Col8 v0 = ldg_col8(base), v1 = ldg_col8(base + dxo), v2 = ldg_col8(base + dyo), v3 = ldg_col8(base + dyo + dxo);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = w0 * v0.v[e] + w1 * v1.v[e] + w2 * v2.v[e] + w3 * v3.v[e];
+        }
+        float* dst = colP + ((size_t)bl * P + p) * ((size_t)K * s.C) + (size_t)tap * s.C + c0;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// grad_weight[oc][c][tap] += gwT[oc][tap*C + c]   (the library GEMM above works in the tap-major column order)
+__global__ void dcn_gw_permute_add_kernel(const float* __restrict__ gwT, float* __restrict__ gw, int Co, int C, int K) {
+    const int total = Co * C * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % K, c = (i / K) % C, oc = i / (K * C);
+        gw[i] += gwT[((size_t)oc * K + tap) * C + c];
+    }
+}
+
 // (4b) grad_weight[oc][m] += sum_{bl, p} gout[b][oc][p] * col[bl][m][p]   (deform_conv_cuda.cpp:659-664)
 // grid (G * ceil(MK/64), ceil(opg/64), nb * pchunks), block 256; split-K partial sums merged with atomicAdd.
 constexpr int WCHUNK = 2048;
@@ -308,12 +368,13 @@ dcn_bwd_weight_kernel(const float* __restrict__ gout, const float* __restrict__ 
     }
 }
 
-// (5) grad_bias[oc] += sum_{b, p} gout[b][oc][p]   (deform_conv_cuda.cpp:665-671); one block per channel
+// (5) grad_bias[oc] += sum_{b, p} gout[b][oc][p]   (deform_conv_cuda.cpp:665-671); grid (Co, batch split), the
+// partial sums of a channel are merged with one atomicAdd per block
 __global__ void dcn_bwd_bias_kernel(const float* __restrict__ gout, float* __restrict__ gb, int B, int Co, int P) {
     __shared__ float red[32];
     const int oc = blockIdx.x;
     float sum = 0.f;
-    for (int b = 0; b < B; ++b) {
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const float* g = gout + ((size_t)b * Co + oc) * P;
         for (int p = threadIdx.x; p < P; p += blockDim.x) sum += g[p];
     }
@@ -325,7 +386,7 @@ __global__ void dcn_bwd_bias_kernel(const float* __restrict__ gout, float* __res
         float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) gb[oc] += v;
+        if (threadIdx.x == 0) atomicAdd(gb + oc, v);
     }
 }
 
@@ -378,6 +439,29 @@ int dcn_make_shape(DcnShape* s, int B, int C, int H, int W, int Co, int kh, int 
     return 0;
 }
 
+// ---- plain GEMMs of the backward pass: cuBLAS (TF32 tensor cores unless the caller asks for exact fp32).
+// One handle per host thread and device, created on first use; the stream is set per call.
+static cublasHandle_t cublas_handle(cudaStream_t st, bool tf32) {
+    static thread_local cublasHandle_t handles[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!handles[dev] && cublasCreate(&handles[dev]) != CUBLAS_STATUS_SUCCESS) {
+        handles[dev] = nullptr;
+        return nullptr;
+    }
+    cublasSetStream(handles[dev], st);
+    cublasSetMathMode(handles[dev], tf32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH);
+    return handles[dev];
+}
+#define MREFSR_CUBLAS(call)                                                                             \
+    do {                                                                                                \
+        cublasStatus_t cs_ = (call);                                                                    \
+        if (cs_ != CUBLAS_STATUS_SUCCESS) {                                                             \
+            ::mrefsr::set_error("cuBLAS call failed with status %d (%s:%d)", (int)cs_, __FILE__, __LINE__); \
+            return -102;                                                                                \
+        }                                                                                               \
+    } while (0)
+
 static int bwd_chunk(const DcnShape& s) {
     const size_t per = (size_t)s.C * s.kh * s.kw * s.Ho * s.Wo * 4;
     size_t nb = ((size_t)256 << 20) / per;
@@ -416,7 +500,9 @@ size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, in
     if (dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
                        deformable_group))
         return 0;
-    if (backward) return 2 * (size_t)bwd_chunk(s) * C * kh * kw * s.Ho * s.Wo * 4 + 1024;
+    if (backward)   // gcol + col chunks, NHWC copy of the input, tap-major grad_weight scratch
+        return 2 * align_up((size_t)bwd_chunk(s) * C * kh * kw * s.Ho * s.Wo * 4, 1024) +
+               align_up((size_t)B * C * H * W * 4, 1024) + align_up((size_t)Co * C * kh * kw * 4, 1024) + 1024;
     return dcn_tc_workspace_bytes(s, mode) + 1024;
 }
 
@@ -450,8 +536,9 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
                                           int pad_h, int pad_w, int dil_h, int dil_w, int group, int deformable_group,
                                           int with_bias, int mode, void* workspace, size_t workspace_bytes,
                                           void* stream) {
-    (void)mode;
     MREFSR_CHECK(input && weight && offset && grad_output, ERR_BAD_ARG, "dcn backward: null pointer argument");
+    // MREFSR_DCN_FP32: exact-fp32 CUDA-core GEMMs of this file; otherwise the two plain GEMMs go to cuBLAS (TF32)
+    const bool lib_gemm = mode != MREFSR_DCN_FP32;
     MREFSR_CHECK(grad_offset || !grad_mask, ERR_BAD_ARG, "dcn backward: grad_mask requires grad_offset");
     MREFSR_CHECK(!with_bias || grad_bias, ERR_BAD_ARG, "dcn backward: with_bias set but grad_bias is NULL");
     DcnShape s;
@@ -461,15 +548,40 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int K = kh * kw, P = s.Ho * s.Wo, cpg = C / group, opg = Co / group, MK = cpg * K;
     const int nbmax = bwd_chunk(s);
-    const size_t buf = (size_t)nbmax * C * K * P * 4;
-    MREFSR_CHECK(workspace && workspace_bytes >= 2 * buf, ERR_WORKSPACE, "dcn backward: workspace too small (%zu < %zu)",
-                 workspace_bytes, 2 * buf);
+    const size_t buf = align_up((size_t)nbmax * C * K * P * 4, 1024);
+    const size_t xt_bytes = align_up((size_t)B * C * H * W * 4, 1024), gwt_bytes = align_up((size_t)Co * C * K * 4, 1024);
+    // position-major im2col + one library GEMM per sample for grad_weight (needs whole 8-channel chunks per group)
+    const bool nhwc_cols = lib_gemm && grad_weight && group == 1 && C % 8 == 0 && (C / deformable_group) % 8 == 0 &&
+                           (size_t)B * C * H * W < ((size_t)1 << 31);
+    const size_t need = 2 * buf + (nhwc_cols ? xt_bytes + gwt_bytes : 0);
+    MREFSR_CHECK(workspace && workspace_bytes >= need, ERR_WORKSPACE, "dcn backward: workspace too small (%zu < %zu)",
+                 workspace_bytes, need);
+    MREFSR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 31) == 0, ERR_WORKSPACE, "dcn backward: workspace must be 32-byte aligned");
     float* gcol = static_cast<float*>(workspace);
     float* col = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + buf);
+    float* xt = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * buf);
+    float* gwT = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * buf + xt_bytes);
+    if (nhwc_cols) {
+        rc = dcn_nchw_to_nhwc(input, xt, B, C, H * W, st);
+        if (rc) return rc;
+        MREFSR_CUDA(cudaMemsetAsync(gwT, 0, (size_t)Co * C * K * 4, st));
+    }
     if (grad_input) MREFSR_CUDA(cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * 4, st));
     for (int b0 = 0; b0 < B; b0 += nbmax) {
         const int nb = (B - b0 < nbmax) ? B - b0 : nbmax;
-        if (grad_input || grad_offset) {
+        if ((grad_input || grad_offset) && lib_gemm) {
+            // gcol[bl] (MK x P) = W_g^T (MK x opg) . gout[b, g] (opg x P)   (deform_conv_cuda.cpp:623-626), row-major
+            // operands handed to column-major cuBLAS as their transposes
+            cublasHandle_t h = cublas_handle(st, true);
+            MREFSR_CHECK(h, -102, "dcn backward: cuBLAS handle creation failed");
+            const float one = 1.f, zero = 0.f;
+            for (int gi = 0; gi < group; ++gi)
+                MREFSR_CUBLAS(cublasSgemmStridedBatched(
+                    h, CUBLAS_OP_N, CUBLAS_OP_T, P, MK, opg, &one, grad_output + ((size_t)b0 * Co + (size_t)gi * opg) * P, P,
+                    (long long)Co * P, weight + (size_t)gi * opg * MK, MK, 0, &zero, gcol + (size_t)gi * MK * P, P,
+                    (long long)C * K * P, nb));
+            count_launches(group);
+        } else if (grad_input || grad_offset) {
             dcn_bwd_gcol_kernel<<<dim3(cdiv(P, DT), group * cdiv(MK, DT), nb), 256, 0, st>>>(weight, grad_output, gcol, s, b0);
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
@@ -485,18 +597,49 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }
-        if (grad_weight) {
+        if (grad_weight && nhwc_cols) {
+            dcn_im2col_nhwc_kernel<<<grid_for((size_t)nb * K * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
+            MREFSR_LAUNCH_CHECK();
+            // gwT (Co x K*C, tap-major) += gout[b] (Co x P) . colP[bl] (P x K*C)
+            cublasHandle_t h = cublas_handle(st, true);
+            MREFSR_CHECK(h, -102, "dcn backward: cuBLAS handle creation failed");
+            const float one = 1.f;
+            for (int bl = 0; bl < nb; ++bl)
+                MREFSR_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, K * C, Co, P, &one, col + (size_t)bl * P * K * C, K * C,
+                                          grad_output + (size_t)(b0 + bl) * Co * P, P, &one, gwT, K * C));
+            count_launches(1 + nb);
+        } else if (grad_weight) {
             dcn_im2col_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(input, offset, mask, col, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
-            const int pchunks = cdiv(P, WCHUNK);
-            dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
-                grad_output, col, grad_weight, s, b0, pchunks);
-            MREFSR_LAUNCH_CHECK();
-            count_launches(2);
+            count_launches(1);
+            if (lib_gemm) {
+                // gW_g (opg x MK) += gout[b, g] (opg x P) . col[bl]^T (P x MK)   (deform_conv_cuda.cpp:659-666)
+                cublasHandle_t h = cublas_handle(st, true);
+                MREFSR_CHECK(h, -102, "dcn backward: cuBLAS handle creation failed");
+                const float one = 1.f;
+                for (int bl = 0; bl < nb; ++bl)
+                    for (int gi = 0; gi < group; ++gi)
+                        MREFSR_CUBLAS(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, MK, opg, P, &one,
+                                                  col + ((size_t)bl * C * K + (size_t)gi * MK) * P, P,
+                                                  grad_output + ((size_t)(b0 + bl) * Co + (size_t)gi * opg) * P, P, &one,
+                                                  grad_weight + (size_t)gi * opg * MK, MK));
+                count_launches(nb * group);
+            } else {
+                const int pchunks = cdiv(P, WCHUNK);
+                dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
+                    grad_output, col, grad_weight, s, b0, pchunks);
+                MREFSR_LAUNCH_CHECK();
+                count_launches(1);
+            }
         }
     }
+    if (nhwc_cols) {
+        dcn_gw_permute_add_kernel<<<cdiv(Co * C * K, 256), 256, 0, st>>>(gwT, grad_weight, Co, C, K);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+    }
     if (with_bias) {
-        dcn_bwd_bias_kernel<<<Co, 256, 0, st>>>(grad_output, grad_bias, B, Co, P);
+        dcn_bwd_bias_kernel<<<dim3(Co, B < 32 ? B : 32), 256, 0, st>>>(grad_output, grad_bias, B, Co, P);
         MREFSR_LAUNCH_CHECK();
         count_launches(1);
     }

@@ -32,6 +32,9 @@ int dcn_make_shape(DcnShape* s, int B, int C, int H, int W, int Co, int kh, int 
 int dcn_forward_fp32(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                      const DcnShape& s, cudaStream_t st);
 
+// NCHW -> NHWC copy (dcn_tc.cu), also used by the backward's position-major im2col
+int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st);
+
 // tcgen05 (TF32) forward, dcn_tc.cu
 bool dcn_tc_eligible(const DcnShape& s);
 size_t dcn_tc_workspace_bytes(const DcnShape& s, int mode);

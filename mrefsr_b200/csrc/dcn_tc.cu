@@ -545,6 +545,13 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
     }
 }
 
+int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st) {
+    nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 128), B), 256, 0, st>>>(x, xt, C, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 bool dcn_tc_eligible(const DcnShape& s) {
     const int cdg = s.C / s.DG;

@@ -110,6 +110,12 @@ def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, defor
     return out
 
 
+def _nchw(t):
+    """dense NCHW fp32 view / copy of an activation (channels-last tensors go through the tiled transpose kernel)."""
+    from .trunk import to_nchw
+    return to_nchw(t.float())
+
+
 class ModulatedDeformConvFunction(Function):
 
     @staticmethod
@@ -123,7 +129,8 @@ class ModulatedDeformConvFunction(Function):
             raise NotImplementedError  # same as deform_conv.py:143-144
         _lib.require_cuda(offset, mask, weight, bias)
         ctx.in_dtype = input.dtype
-        x, off, msk, wgt = (t.contiguous().float() for t in (input, offset, mask, weight))
+        x, off, msk = (_nchw(t) for t in (input, offset, mask))
+        wgt = weight.contiguous().float()
         bs = bias.contiguous().float() if bias is not None else None
         if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
             ctx.save_for_backward(x, off, msk, wgt)
@@ -137,7 +144,7 @@ class ModulatedDeformConvFunction(Function):
             raise NotImplementedError
         x, off, msk, wgt = ctx.saved_tensors
         grad_input, grad_offset, grad_mask, grad_weight, grad_bias = dcn_backward_raw(
-            x, off, msk, wgt, grad_output.contiguous().float(), ctx.stride, ctx.padding, ctx.dilation, ctx.groups,
+            x, off, msk, wgt, _nchw(grad_output), ctx.stride, ctx.padding, ctx.dilation, ctx.groups,
             ctx.deformable_groups, ctx.with_bias, need_input=ctx.needs_input_grad[0])
         dt = ctx.in_dtype
         cast = (lambda t: None if t is None else t.to(dt))

@@ -22,7 +22,8 @@ class DynAggOffsetsFunction(Function):
     def forward(ctx, conv_out, pre_offset, dg, stats):
         _lib.require_cuda(conv_out, pre_offset)
         ctx.in_dtype = conv_out.dtype
-        co = conv_out.contiguous().float()
+        from .trunk import to_nchw
+        co = to_nchw(conv_out.float())
         pre = pre_offset.contiguous().float()
         b, ch, h, w = co.shape
         k = pre.shape[1]

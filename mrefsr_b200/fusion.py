@@ -45,7 +45,7 @@ class MRAPAAttentionFunction(Function):
     @once_differentiable
     def backward(ctx, grad_out):
         q, k, v, prob = ctx.saved_tensors
-        go = grad_out.contiguous().float()
+        go = T.to_nchw(grad_out.float())
         n, c, h, w = q.shape
         cv = v.shape[1]
         gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)

@@ -68,8 +68,9 @@ def _convert(t, to_cl, bias=None):
 
 
 def _convertible(t):
+    # (inside an autograd.Function's forward / backward grad mode is off and the raw kernel is safe on any tensor)
     return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] % 4 == 0 and t.shape[0] <= 65535
-            and t.numel() > 0 and not t.requires_grad)
+            and t.numel() > 0 and (not t.requires_grad or not torch.is_grad_enabled()))
 
 
 def to_nchw(t):

@@ -23,6 +23,7 @@ ap.add_argument('--batch', type=int, default=4)
 ap.add_argument('--refs', type=int, default=5)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--hr', type=int, default=160)
+ap.add_argument('--channels-last', action='store_true', help='run net_g in torch.channels_last (cuDNN native layout)')
 ap.add_argument('--bf16', action='store_true', help='bf16 autocast for the plain convolutions (hot-path ops stay fp32)')
 args = ap.parse_args()
 
@@ -40,6 +41,8 @@ pipe.net_map.eval()
 for p in list(pipe.net_extractor.parameters()) + list(pipe.net_map.parameters()):
     p.requires_grad_(False)
 net_g = pipe.net_g.train()
+if args.channels_last:
+    net_g.to(memory_format=torch.channels_last)
 # learned offsets start at zero in the reference; give them a little signal so every backward path is exercised
 for name in ('small', 'medium', 'large'):
     getattr(net_g.dyn_agg_restore, f'{name}_dyn_agg').conv_offset_mask.weight.data.normal_(0, 1e-3)
@@ -63,8 +66,9 @@ def step():
             pres.append(pre)
             rfs.append(rf)
     opt.zero_grad(set_to_none=True)
+    x_in = lq.contiguous(memory_format=torch.channels_last) if args.channels_last else lq
     with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.bf16):
-        out = model(lq, pres, rfs)
+        out = model(x_in, pres, rfs)
     loss = torch.nn.functional.l1_loss(out.float(), gt)
     loss.backward()
     opt.step()
