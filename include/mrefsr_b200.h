@@ -162,6 +162,19 @@ MREFSR_API int mrefsr_dynagg_dcn_forward_ex(const float* input, const float* wei
                                  const float* conv_out, const int64_t* max_idx, int flow_scale, float* output, int B,
                                  int C, int H, int W, int Co, int deformable_group, int with_bias, int layout_flags,
                                  float out_slope, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with the exchange step of the reference-sharded mode folded into the epilogue: every
+ * finished output tile is stored to each of `outputs[0..n_outputs)` -- this GPU's and the peers' copies of the
+ * gathered tensor [n, R, Co, H, W], peer copies being NVLink-mapped device pointers (CUDA IPC / symmetric memory) --
+ * at sample slot (b / dst_group) * dst_stride + dst_offset + b % dst_group (dst_group = references held by this rank,
+ * dst_stride = R, dst_offset = first global reference of this rank; dst_group = 0: slot b).  Replaces
+ * {DCN -> transpose copy -> ncclAllGather -> cat}; the caller still needs a cross-GPU barrier before the consumer
+ * reads the buffer and before the next forward overwrites it.  `outputs` is a HOST array of device pointers. */
+MREFSR_API int mrefsr_dynagg_dcn_forward_multi(const float* input, const float* weight, const float* bias,
+                                    const float* conv_out, const int64_t* max_idx, int flow_scale,
+                                    float* const* outputs, int n_outputs, int dst_group, int dst_stride,
+                                    int dst_offset, int B, int C, int H, int W, int Co, int deformable_group,
+                                    int with_bias, int layout_flags, float out_slope, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Trunk glue (the plain-convolution network either side of the path; convolutions

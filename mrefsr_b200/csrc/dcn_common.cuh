@@ -35,12 +35,19 @@ int dcn_forward_fp32(const float* x, const float* w, const float* bias, const fl
 // NCHW -> NHWC copy (dcn_tc.cu), also used by the backward's position-major im2col
 int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st);
 
+// several destination buffers for one forward (reference-sharded mode: local + peer copies of the gathered tensor)
+struct DcnOutputs {
+    float* ptr[8];
+    int n, group, stride, offset;   // sample b -> slot (b / group) * stride + offset + b % group  (group 0: slot b)
+};
+
 // tcgen05 (TF32) forward, dcn_tc.cu
 bool dcn_tc_eligible(const DcnShape& s);
 size_t dcn_tc_workspace_bytes(const DcnShape& s, int mode);
 int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const float* off, const float* mask,
                         const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
-                        size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope);
+                        size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope,
+                        const DcnOutputs* multi);
 int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                    const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

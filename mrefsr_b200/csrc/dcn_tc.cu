@@ -59,6 +59,11 @@ struct DcnTcParams {
     int P, total_rows, tiles, n_slabs, taps, cdg, gs, stages, nbuf, stage_bytes;
     // fused DynAgg mode
     int fused, flow_scale, hp, wp;
+    // Outputs: the epilogue stores every finished tile to each of n_outs buffers (this GPU's and, in the
+    // reference-sharded mode, the peers' copies of the gathered tensor, mapped over NVLink), at sample slot
+    // (b / dst_group) * dst_stride + dst_offset + b % dst_group  (dst_group == 0: slot b).
+    float* outs[8];
+    int n_outs, dst_group, dst_stride, dst_offset;
     int out_nhwc;        // epilogue writes [B, Ho, Wo, Co] instead of [B, Co, Ho, Wo]
     float out_slope;     // leaky-ReLU slope applied to the output (1: none)
     unsigned wp_magic;   // ceil(2^32 / wp): idx / wp == umulhi(idx, wp_magic) for idx < hp * wp  (hp * wp * wp < 2^32)
@@ -146,15 +151,17 @@ __device__ __forceinline__ int ldg_early_s32(const int* p) {
 
 // Drain one finished accumulator tile: tcgen05.ld 32x32b, bias add, position-major coalesced NCHW stores.
 // (Inlined at the four poll sites of the producer loop: an out-of-line call forces spills at the 96-register cap.)
-__device__ __forceinline__ void dcn_epilogue_tile(float* __restrict__ out, const float* __restrict__ bias,
+__device__ __forceinline__ void dcn_epilogue_tile(const DcnTcParams& prm, const float* __restrict__ bias,
                                                   uint32_t tmem_base, uint64_t* tempty_bar, int tile, int buf, int warp,
-                                                  int lane, int Co, int P, int total_rows, int out_nhwc, float out_slope) {
+                                                  int lane) {
+    const int Co = prm.s.Co, P = prm.P;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         const int m = tile * TBM + half * 128 + warp * 32 + lane;
-        const bool ok = m < total_rows;
+        const bool ok = m < prm.total_rows;
         const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
-        float* o = out_nhwc ? out + (size_t)(ok ? m : 0) * Co : out + (size_t)b * Co * P + p;
+        const int bd = prm.dst_group ? (b / prm.dst_group) * prm.dst_stride + prm.dst_offset + b % prm.dst_group : b;
+        const size_t o_off = prm.out_nhwc ? ((size_t)bd * P + p) * Co : (size_t)bd * Co * P + p;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * Co + half * Co;
 #pragma unroll 1
         for (int c0 = 0; c0 < Co; c0 += 8) {
@@ -166,14 +173,18 @@ __device__ __forceinline__ void dcn_epilogue_tile(float* __restrict__ out, const
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     f[e] = __uint_as_float(v[e]) + (bias ? __ldg(bias + c0 + e) : 0.f);
-                    f[e] = f[e] > 0.f ? f[e] : f[e] * out_slope;
+                    f[e] = f[e] > 0.f ? f[e] : f[e] * prm.out_slope;
                 }
-                if (out_nhwc) {        // 32 contiguous bytes per thread: one full sector
-                    *reinterpret_cast<float4*>(o + c0) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                } else {               // position-major: 32 lanes = 32 consecutive positions of one channel plane
+#pragma unroll 1
+                for (int k = 0; k < prm.n_outs; ++k) {
+                    float* o = prm.outs[k] + o_off;
+                    if (prm.out_nhwc) {        // 32 contiguous bytes per thread: one full sector
+                        *reinterpret_cast<float4*>(o + c0) = make_float4(f[0], f[1], f[2], f[3]);
+                        *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                    } else {               // position-major: 32 lanes = 32 consecutive positions of one channel plane
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * P] = f[e];
+                        for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * P] = f[e];
+                    }
                 }
             }
         }
@@ -189,7 +200,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
               const float* __restrict__ offset,   // !FUSED: offset [B,2*DG*K,P];  FUSED: conv_out [B,3*DG*K,P]
               const float* __restrict__ mask,     // !FUSED: mask [B,DG*K,P];      FUSED: unused
               const long long* __restrict__ max_idx,  // FUSED: [B, hp, wp]
-              const float* __restrict__ bias, float* __restrict__ out, const DcnTcParams prm) {
+              const float* __restrict__ bias, const __grid_constant__ DcnTcParams prm) {
     // 1024-byte aligned dynamic shared memory (SWIZZLE_128B atoms); no pointer<->integer round trip, so the
     // compiler keeps every access in the shared address space (LDS/STS, 32-bit addressing)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -266,8 +277,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         const int nbuf_mask = prm.nbuf - 1;        // nbuf is 1 or 2: buffer = it & mask, phase = (it >> mask) & 1
         auto epilogue_tile = [&](int it) {
             const int buf = it & nbuf_mask;
-            dcn_epilogue_tile(out, bias, tmem_base, &tempty[buf], (int)blockIdx.x + it * (int)gridDim.x, buf, warp, lane,
-                              Co, P, prm.total_rows, prm.out_nhwc, prm.out_slope);
+            dcn_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + it * (int)gridDim.x, buf, warp, lane);
         };
         auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
             if (is_epi && ep_done < prod_done) {
@@ -574,7 +584,8 @@ static int make_weight_map(CUtensorMap* map, const float* wt, int Co, int Ktot) 
 
 int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const float* off, const float* mask,
                         const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
-                        size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope) {
+                        size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope,
+                        const DcnOutputs* multi) {
     const size_t need = dcn_tc_workspace_bytes(s, MREFSR_DCN_TF32);
     MREFSR_CHECK(workspace && workspace_bytes >= need, ERR_WORKSPACE, "dcn forward: workspace too small (%zu < %zu)",
                  workspace_bytes, need);
@@ -616,6 +627,24 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     if (prm.stages < 2) prm.stages = 2;
     prm.nbuf = (2 * s.Co * 2 <= 512) ? 2 : 1;
     prm.fused = max_idx != nullptr;
+    for (int k = 0; k < 8; ++k) prm.outs[k] = nullptr;
+    if (multi) {
+        MREFSR_CHECK(multi->n >= 1 && multi->n <= 8, ERR_BAD_ARG, "dcn forward: 1..8 output buffers (got %d)", multi->n);
+        MREFSR_CHECK(multi->group >= 0 && (multi->group == 0 || s.B % multi->group == 0), ERR_BAD_ARG,
+                     "dcn forward: batch %d not a multiple of the destination group %d", s.B, multi->group);
+        for (int k = 0; k < multi->n; ++k) {
+            MREFSR_CHECK(multi->ptr[k], ERR_BAD_ARG, "dcn forward: output buffer %d is NULL", k);
+            prm.outs[k] = multi->ptr[k];
+        }
+        prm.n_outs = multi->n;
+        prm.dst_group = multi->group;
+        prm.dst_stride = multi->stride;
+        prm.dst_offset = multi->offset;
+    } else {
+        prm.outs[0] = out;
+        prm.n_outs = 1;
+        prm.dst_group = prm.dst_stride = prm.dst_offset = 0;
+    }
     prm.out_nhwc = (layout_flags & MREFSR_DCN_OUT_NHWC) ? 1 : 0;
     prm.out_slope = out_slope;
 
@@ -639,11 +668,11 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     if (prm.fused) {
         auto kern = dcn_tc_kernel<true>;
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, nullptr, max_idx, bias, out, prm);
+        kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, nullptr, max_idx, bias, prm);
     } else {
         auto kern = dcn_tc_kernel<false>;
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, mask, nullptr, bias, out, prm);
+        kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, mask, nullptr, bias, prm);
     }
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
@@ -652,7 +681,7 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
 
 int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                    const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    return dcn_forward_tc_impl(x, w, bias, off, mask, nullptr, 1, out, s, workspace, workspace_bytes, st, 0, 1.f);
+    return dcn_forward_tc_impl(x, w, bias, off, mask, nullptr, 1, out, s, workspace, workspace_bytes, st, 0, 1.f, nullptr);
 }
 
 }  // namespace mrefsr

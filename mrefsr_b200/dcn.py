@@ -69,6 +69,41 @@ def dcn_forward_raw(input, offset, mask, weight, bias, stride, padding, dilation
     return out
 
 
+def dynagg_dcn_forward_into(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups, out_ptrs,
+                            dst_group, dst_stride, dst_offset, out_slope=1.0):
+    """Fused DynAgg forward whose epilogue stores straight into several gathered buffers [n, R, Co, H, W] (NCHW
+    planes): `out_ptrs` are device addresses of this GPU's and the peers' copies (see parallel.PeerGatherBuffer);
+    sample b lands in slot (b // dst_group) * dst_stride + dst_offset + b % dst_group.  Returns nothing: the data is
+    in the buffers once the kernel and the caller's cross-GPU barrier have completed."""
+    import ctypes
+    from .trunk import to_nchw
+    _lib.require_cuda(input, conv_out, max_idx, weight, bias)
+    lib = _lib.lib()
+    x = input.float()
+    in_cl = x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+    if not in_cl:
+        x = x.contiguous()
+    co_, wgt = to_nchw(conv_out.float()), weight.contiguous().float()
+    bs = bias.contiguous().float() if bias is not None else None
+    mi = max_idx.contiguous()
+    b, c, h, w = x.shape
+    co, dg = wgt.shape[0], deformable_groups
+    if tuple(co_.shape) != (b, 3 * dg * 9, h, w):
+        raise RuntimeError('conv_out shape %s, expected %s' % (tuple(co_.shape), (b, 3 * dg * 9, h, w)))
+    if not 1 <= len(out_ptrs) <= 8:
+        raise ValueError('1..8 destination buffers')
+    arr = (ctypes.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+    with torch.cuda.device(x.device):
+        nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, DCN_TF32, 0)
+        ws, ws_bytes = _lib.workspace(nbytes, x.device)
+        rc = lib.mrefsr_dynagg_dcn_forward_multi(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
+                                                 int(flow_scale), ctypes.cast(arr, ctypes.c_void_p), len(out_ptrs),
+                                                 int(dst_group), int(dst_stride), int(dst_offset), b, c, h, w, co, dg,
+                                                 int(bs is not None), 1 if in_cl else 0, float(out_slope), ws, ws_bytes,
+                                                 _lib.stream_ptr(x.device))
+    _lib.check(rc, 'mrefsr_dynagg_dcn_forward_multi')
+
+
 def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups, out_slope=1.0,
                        out_channels_last=None):
     """Fused DynAgg forward for inference (no autograd): DCNv2 (3x3, stride 1, pad 1) whose offsets and masks are

@@ -91,3 +91,36 @@ def align_reference_sharded(align_fn, refs_global, n_refs_total, group=None):
         raise RuntimeError('align_reference_sharded: a rank without references needs a template shape; '
                            'use world_size <= n_refs')
     return all_gather_refs(local, n_refs_total, group)
+
+
+class PeerGatherBuffer:
+    """The gathered tensor [n, R, C, H, W] of the reference-sharded mode as symmetric memory: one copy per GPU, every
+    copy mapped into every process over NVLink (torch.distributed._symmetric_memory).  The DCN epilogue of each rank
+    stores its references' aligned features into ALL copies (dcn.dynagg_dcn_forward_into), so the exchange overlaps
+    the kernel tile by tile and there is no transpose copy, no ncclAllGather and no cat afterwards.
+
+        buf = PeerGatherBuffer((n, R, C, H, W), device)
+        buf.begin()                      # peers have finished reading the previous contents
+        dynagg_dcn_forward_into(..., out_ptrs=buf.ptrs, dst_group=r_local, dst_stride=R, dst_offset=lo)
+        full = buf.finish()              # all ranks' stores have landed -> [n, R, C, H, W] on this GPU
+    """
+
+    def __init__(self, shape, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized():
+            raise RuntimeError('PeerGatherBuffer needs an initialised process group')
+        self.group = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty(*shape, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        rank = dist.get_rank(self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptrs = [ptrs[rank]] + [p for i, p in enumerate(ptrs) if i != rank]     # local copy first
+        if len(self.ptrs) > 8:
+            raise RuntimeError('PeerGatherBuffer: at most 8 ranks per group')
+
+    def begin(self):
+        self.hdl.barrier(channel=0)
+
+    def finish(self):
+        self.hdl.barrier(channel=1)
+        return self.buf

@@ -252,3 +252,25 @@ def test_against_reference_cuda_extension():
     ext.deform_conv_forward(x, wgt, off, out1, x.new_empty(0), x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 8, 2)
     mine = M.deform_conv(x, off, wgt, 1, 1, 1, 1, 8)
     assert rel_err(mine, out1) <= TOL
+
+
+def test_dynagg_dcn_forward_into_several_buffers():
+    """Epilogue of the reference-sharded mode: every tile stored to each destination buffer, at the global reference
+    slot of the gathered [n, R, C, H, W] tensor (here two local buffers stand in for the peers' copies)."""
+    from mrefsr_b200.dcn import dynagg_dcn_forward, dynagg_dcn_forward_into
+    g = torch.Generator().manual_seed(21)
+    n, r_local, R, lo, c, hw, dg, s = 2, 3, 8, 4, 64, 16, 8, 1
+    b = n * r_local
+    x = torch.randn(b, c, hw, hw, generator=g).to(DEV)
+    conv_out = torch.randn(b, 3 * dg * 9, hw, hw, generator=g).to(DEV)
+    hp = hw // s - 2
+    max_idx = torch.randint(0, hp * hp, (b, hp, hp), generator=g).to(DEV)
+    wgt = (torch.randn(c, c, 3, 3, generator=g) * 0.05).to(DEV)
+    bias = torch.randn(c, generator=g).to(DEV)
+    want = dynagg_dcn_forward(x, conv_out, max_idx, s, wgt, bias, dg).view(n, r_local, c, hw, hw)
+    bufs = [torch.full((n, R, c, hw, hw), -7.0, device=DEV) for _ in range(2)]
+    dynagg_dcn_forward_into(x, conv_out, max_idx, s, wgt, bias, dg, [t.data_ptr() for t in bufs], r_local, R, lo)
+    torch.cuda.synchronize()
+    for t in bufs:
+        assert torch.equal(t[:, lo:lo + r_local], want)
+        assert bool((t[:, :lo] == -7.0).all()) and bool((t[:, lo + r_local:] == -7.0).all())   # other slots untouched

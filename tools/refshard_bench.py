@@ -13,12 +13,13 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mrefsr_b200 as M  # noqa: E402
 from mrefsr_b200 import parallel as P  # noqa: E402
-from mrefsr_b200.dcn import dynagg_dcn_forward  # noqa: E402
+from mrefsr_b200.dcn import dynagg_dcn_forward, dynagg_dcn_forward_into  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--hw', type=int, default=512)
 ap.add_argument('--refs', type=int, default=8)
 ap.add_argument('--steps', type=int, default=3)
+ap.add_argument('--fused-gather', action='store_true', help='DCN epilogue stores into every GPU\'s gathered buffer over NVLink (no NCCL all-gather)')
 ap.add_argument('--check', action='store_true', help='rank 0 recomputes everything alone and compares')
 args = ap.parse_args()
 
@@ -61,15 +62,25 @@ def run(ref_ids, gather):
     for c, s in SCALES:
         xs = torch.stack([on_dev(('x', c), x[c], r) for r in ref_ids], 0).flatten(0, 1)
         cs = torch.stack([on_dev(('conv', c), conv[c], r) for r in ref_ids], 0).flatten(0, 1)
-        y = dynagg_dcn_forward(xs, cs, idx, s, wgt[c], bias[c], 8)                    # [r_local*n, C, H, W]
-        y = y.view(len(ref_ids), n, c, h * s, h * s).transpose(0, 1).contiguous()     # [n, r_local, C, H, W]
-        full = P.all_gather_refs(y, R) if gather else y                               # [n, R, C, H, W]
+        if gather and args.fused_gather:
+            pg = peer_bufs[c]
+            pg.begin()
+            dynagg_dcn_forward_into(xs, cs, idx, s, wgt[c], bias[c], 8, pg.ptrs, len(ref_ids), R, ref_ids[0])
+            full = pg.finish()                                                        # [n, R, C, H, W]
+        else:
+            y = dynagg_dcn_forward(xs, cs, idx, s, wgt[c], bias[c], 8)                # [r_local*n, C, H, W]
+            y = y.view(len(ref_ids), n, c, h * s, h * s).transpose(0, 1).contiguous() # [n, r_local, C, H, W]
+            full = P.all_gather_refs(y, R) if gather else y                           # [n, R, C, H, W]
         ass = full.flatten(0, 1).repeat(1, 2, 1, 1)
         emb = full.flatten(0, 1)
         outs.append(M.mrapa_attention(emb_t[c], emb, ass, R))
     return outs
 
 
+peer_bufs = {}
+if world > 1 and args.fused_gather:
+    assert n == 1, 'the bench stacks references first; with n == 1 that is the [n, R] slot order'
+    peer_bufs = {c: P.PeerGatherBuffer((n, R, c, h * s, h * s), dev) for c, s in SCALES}
 lo, hi = P.shard_range(R, rank, world)
 mine = list(range(lo, hi))
 for _ in range(2):
@@ -93,7 +104,7 @@ if args.check and rank == 0:
     ref = run(list(range(R)), False)
     err = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(outs, ref))
 if rank == 0:
-    print(json.dumps({'test': 'reference_sharded', 'hw': args.hw, 'refs': R, 'n_gpus': world, 'ms_per_image': float(ms),
+    print(json.dumps({'test': 'reference_sharded', 'hw': args.hw, 'refs': R, 'n_gpus': world, 'fused_gather': bool(args.fused_gather and world > 1), 'ms_per_image': float(ms),
                       'images_per_s': 1e3 / float(ms), 'max_rel_diff_vs_single_gpu': err,
                       'all_gather_bytes_per_image': sum(4 * c * (h * s) ** 2 * R for c, s in SCALES)}), flush=True)
 if world > 1:
