@@ -260,9 +260,12 @@ def gen_dcnv1():
     print('dcnv1.npz', tuple(y.shape))
 
 
-def gen_full_model():
+def gen_full_model(name='full_model', b=2, r=2, H=48, W=56, seed=2024):
     """End-to-end reference forward (extractor -> net_map per reference -> net_g), exactly as
-    basicsr/models/multi_ref_restoration_model.py:284-293 wires it, with key-seeded weights (tests/util.py)."""
+    basicsr/models/multi_ref_restoration_model.py:284-293 wires it, with key-seeded weights (tests/util.py).
+    `full_model_lmr` is the LMR shape class of BASELINE config 3 in small: feature grids 15 / 30 / 60 are not
+    multiples of 4, so MRAPAFusion reflect-pads and crops (ref_mrapa_restoration_arch.py:306-311, :348), and the
+    reference count is 3."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
     from tests.util import refill_parameters
     from basicsr.archs.contras_multi_extractor_arch import ContrasMultiExtractorSep
@@ -273,8 +276,7 @@ def gen_full_model():
                                                           vgg_layer_list=['relu1_1', 'relu2_1', 'relu3_1'],
                                                           vgg_type='vgg19').eval(), 2)
     netg = refill_parameters(MRAPARestorationNet(ngf=64, n_blocks=16, groups=8).eval(), 3)
-    g = torch.Generator().manual_seed(2024)
-    b, r, H, W = 2, 2, 48, 56
+    g = torch.Generator().manual_seed(seed)
     gt = torch.rand(b, 3, H, W, generator=g)
     gt = F.avg_pool2d(F.pad(gt, (2, 2, 2, 2), mode='reflect'), 5, 1)            # band-limited image
     lq = F.interpolate(gt, scale_factor=0.25, mode='bicubic', align_corners=False).clamp(0, 1)
@@ -295,17 +297,18 @@ def gen_full_model():
                keys_ext=np.array(sorted(ext.state_dict().keys())), keys_map=np.array(sorted(nmap.state_dict().keys())),
                keys_g=np.array(sorted(netg.state_dict().keys())),
                shapes_g=np.array([str(tuple(v.shape)) for k, v in sorted(netg.state_dict().items())]))
-    np.savez_compressed(os.path.join(OUT, 'full_model.npz'), **out)
-    print('full_model.npz sr', tuple(sr.shape), 'mean', float(sr.mean()), 'std', float(sr.std()), 'n_keys', len(out['keys_g']))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name + '.npz sr', tuple(sr.shape), 'mean', float(sr.mean()), 'std', float(sr.std()), 'n_keys', len(out['keys_g']))
 
 
 if __name__ == '__main__':
     torch.set_num_threads(8)
     install_shims()
-    gen_matcher()
-    gen_correspondence()
-    gen_dynagg()
-    gen_fusion()
-    gen_dcnv1()
-    gen_full_model()
+    only = set(sys.argv[1:])      # e.g. `make_golden.py full_model_lmr` regenerates one fixture
+    gens = dict(matcher=gen_matcher, correspondence=gen_correspondence, dynagg=gen_dynagg, fusion=gen_fusion,
+                dcnv1=gen_dcnv1, full_model=gen_full_model,
+                full_model_lmr=lambda: gen_full_model('full_model_lmr', b=1, r=3, H=60, W=60, seed=2025))
+    for key, fn in gens.items():
+        if not only or key in only:
+            fn()
     print('sizes:', {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT)) if f.endswith('.npz')})

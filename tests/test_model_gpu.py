@@ -78,3 +78,25 @@ def test_channels_last_trunk_matches_reference(golden):
     rel_l2, rel_max = _err(sr, sr_ref, base)
     assert rel_l2 <= 1e-3, (rel_l2, rel_max)
     assert float((sr.cpu() - sr_ref.cpu()).abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize('path', ['fast', 'reference_order', 'channels_last'])
+def test_lmr_shape_class_matches_reference(golden, pipeline, path):
+    """BASELINE config 3's shape class in small (tests/golden/make_golden.py::gen_full_model('full_model_lmr')):
+    60x60 HR -> feature grids 15 / 30 / 60, so MRAPAFusion reflect-pads to 16 / 32 and crops
+    (ref_mrapa_restoration_arch.py:306-311, :348), the matcher sees a 13x13 origin grid, and there are 3 references."""
+    import copy
+    g = golden('full_model_lmr')
+    lq, up, refs, sr_ref = (g(k).to(DEV) for k in ('lq', 'up', 'refs', 'sr'))
+    m = copy.deepcopy(pipeline).channels_last_() if path == 'channels_last' else pipeline
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sr = m.forward_reference_order(lq, up, refs) if path == 'reference_order' else m(lq, up, refs)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert sr.shape == sr_ref.shape == (1, 3, 60, 60)
+    base = torch.nn.functional.interpolate(lq, None, 4, 'bilinear', False)
+    rel_l2, rel_max = _err(sr, sr_ref, base)
+    assert rel_l2 <= 1e-3, (rel_l2, rel_max)
+    assert float((sr.cpu() - sr_ref.cpu()).abs().max()) <= 1e-3
