@@ -36,6 +36,7 @@
 // by the tap, mask = sigmoid(conv) (basicsr/archs/ref_mrapa_restoration_arch.py:55-68 and
 // corres_generation_arch.py:70-105 folded into the gather), which removes two full passes over the
 // 216-plane tensor.
+#include <stdlib.h>
 #include "dcn_common.cuh"
 #include "../../include/mrefsr_b200.h"
 
@@ -50,8 +51,8 @@ constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items (row, 8-chann
 constexpr int T_PRODUCERS = T_PW * 32;
 constexpr int T_MMA_WARP = T_PW;
 constexpr int T_THREADS = T_PRODUCERS + 32;        // + the MMA warp (17 warps: register budget 100/thread)
-constexpr int T_NTAB = 4;                          // sample-table ring depth
-constexpr int T_AHEAD = 2;                         // tables are decoded this many K steps before their gather
+constexpr int T_NTAB = 3;                          // sample-table ring depth
+constexpr int T_AHEAD = 1;                         // tables are decoded this many K steps before their gather
 constexpr int T_SMEM_BUDGET = 150 * 1024;          // stage ring; the rest of the 228 KB stays L1 for the gather
 
 struct DcnTcParams {
@@ -67,7 +68,32 @@ struct DcnTcParams {
     int out_nhwc;        // epilogue writes [B, Ho, Wo, Co] instead of [B, Co, Ho, Wo]
     float out_slope;     // leaky-ReLU slope applied to the output (1: none)
     unsigned wp_magic;   // ceil(2^32 / wp): idx / wp == umulhi(idx, wp_magic) for idx < hp * wp  (hp * wp * wp < 2^32)
+    // Row -> output position mapping of a CTA tile.  tile2d == 0: rows are 256 consecutive positions of the
+    // B*Ho*Wo concatenation.  tile2d == 1: the tile is 2^subs_log square-ish patches of 2^tx_log x 2^ty_log
+    // positions (nsx patches per output row, nsub per sample), so that the bilinear corners of x- AND y-neighbours
+    // fall into the same K step and hit in L1.
+    int tile2d, tx_log, ty_log, sub_log, subs_log, nsx, nsub;
 };
+
+// (tile, row within the tile) -> (sample, oy, ox); false for padding rows
+__device__ __forceinline__ bool dcn_row_coords(const DcnTcParams& prm, int tile, int r, int& b, int& oy, int& ox) {
+    if (!prm.tile2d) {
+        const int m = tile * TBM + r;
+        if (m >= prm.total_rows) return false;
+        b = m / prm.P;
+        const int p = m - b * prm.P;
+        oy = p / prm.s.Wo;
+        ox = p - oy * prm.s.Wo;
+        return true;
+    }
+    const int st = (tile << prm.subs_log) + (r >> prm.sub_log);   // patch index over the whole batch
+    const int within = r & ((1 << prm.sub_log) - 1);
+    b = st / prm.nsub;
+    const int rem = st - b * prm.nsub, ty = rem / prm.nsx, tx = rem - ty * prm.nsx;
+    oy = (ty << prm.ty_log) + (within >> prm.tx_log);
+    ox = (tx << prm.tx_log) + (within & ((1 << prm.tx_log) - 1));
+    return b < prm.s.B && oy < prm.s.Ho && ox < prm.s.Wo;
+}
 
 __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
@@ -79,7 +105,8 @@ __device__ __forceinline__ float to_tf32(float v) {
 // mbarrier waits, so the compiler cannot sink them down to their first use one K step later.
 __device__ __forceinline__ float ldg_early(const float* p) {
     float v;
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    // offsets / masks are read exactly once: keep them out of L1, which the gather needs
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ long long ldg_early_s64(const long long* p) {
@@ -157,9 +184,10 @@ __device__ __forceinline__ void dcn_epilogue_tile(const DcnTcParams& prm, const 
     const int Co = prm.s.Co, P = prm.P;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-        const int m = tile * TBM + half * 128 + warp * 32 + lane;
-        const bool ok = m < prm.total_rows;
-        const int b = ok ? m / P : 0, p = ok ? m - (m / P) * P : 0;
+        int b = 0, oy = 0, ox = 0;
+        const bool ok = dcn_row_coords(prm, tile, half * 128 + warp * 32 + lane, b, oy, ox);
+        const int p = ok ? oy * prm.s.Wo + ox : 0;
+        if (!ok) b = 0;
         const int bd = prm.dst_group ? (b / prm.dst_group) * prm.dst_stride + prm.dst_offset + b % prm.dst_group : b;
         const size_t o_off = prm.out_nhwc ? ((size_t)bd * P + p) * Co : (size_t)bd * Co * P + p;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 2 * Co + half * Co;
@@ -299,10 +327,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         const float* row_off = offset;                            // offset / conv_out of (b, plane 0, p)
         const float* row_msk = mask;                              // mask of (b, plane 0, p)
         auto decode_rows = [&](int tile) {
-            const int m = tile * TBM + erow;
+            int b = 0, oy = 0, ox = 0;
             row_yx = -1;
-            if (m < prm.total_rows && has_entries) {
-                const int b = m / P, p = m - b * P, oy = p / s.Wo, ox = p - oy * s.Wo;
+            if (has_entries && dcn_row_coords(prm, tile, erow, b, oy, ox)) {
+                const int p = oy * s.Wo + ox;
                 row_yx = (oy << 16) | ox;
                 row_bH = b * s.H;
                 if (FUSED) {
@@ -576,6 +604,16 @@ size_t dcn_tc_workspace_bytes(const DcnShape& s, int mode) {
     return align_up((size_t)s.B * s.C * s.H * s.W * 4, 1024) + align_up((size_t)s.Co * s.C * s.kh * s.kw * 4, 1024);
 }
 
+// MREFSR_DCN_TILE=linear|2d (tuning knob; default 2d): how a CTA tile's 256 rows map to output positions
+static int dcn_tile_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("MREFSR_DCN_TILE");
+        mode = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return mode;
+}
+
 static int make_weight_map(CUtensorMap* map, const float* wt, int Co, int Ktot) {
     // 2-D tensor [Co rows][Ktot cols] fp32, box = 32 cols x Co rows, 128-byte swizzle; encoded as 3-D with d2 = 1
     return make_tensor_map_3d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wt, (uint64_t)Ktot, (uint64_t)Co, 1, TBK,
@@ -616,6 +654,29 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     prm.P = s.Ho * s.Wo;
     prm.total_rows = s.B * prm.P;
     prm.tiles = cdiv(prm.total_rows, TBM);
+    prm.tile2d = prm.tx_log = prm.ty_log = prm.sub_log = prm.subs_log = prm.nsx = prm.nsub = 0;
+    if (dcn_tile_mode() != 0) {
+        // patch shape with the fewest padding rows; near-ties go to the larger patch (more neighbours share corners)
+        static const int cand[5][2] = {{4, 4}, {4, 3}, {3, 4}, {3, 3}, {5, 3}};   // log2 (x, y): 16x16, 16x8, 8x16, 8x8, 32x8
+        long long best = -1;
+        for (int k = 0; k < 5; ++k) {
+            const int tx = cand[k][0], ty = cand[k][1];
+            const long long nsx = cdiv(s.Wo, 1 << tx), nsy = cdiv(s.Ho, 1 << ty);
+            const long long rows = (long long)s.B * nsx * nsy << (tx + ty);
+            const long long tiles = (rows + TBM - 1) / TBM;
+            if (best < 0 || tiles * 100 < best * 97) {
+                best = tiles;
+                prm.tx_log = tx;
+                prm.ty_log = ty;
+                prm.nsx = (int)nsx;
+                prm.nsub = (int)(nsx * nsy);
+            }
+        }
+        prm.tile2d = 1;
+        prm.sub_log = prm.tx_log + prm.ty_log;
+        prm.subs_log = 8 - prm.sub_log;        // TBM = 256 rows = 2^subs_log patches
+        prm.tiles = (int)best;
+    }
     prm.n_slabs = s.C / TBK;
     prm.taps = K;
     prm.cdg = s.C / s.DG;

@@ -274,3 +274,43 @@ def test_dynagg_dcn_forward_into_several_buffers():
     for t in bufs:
         assert torch.equal(t[:, lo:lo + r_local], want)
         assert bool((t[:, :lo] == -7.0).all()) and bool((t[:, lo + r_local:] == -7.0).all())   # other slots untouched
+
+
+@pytest.mark.parametrize('scale', [1.0, 3e5, 1e-6, float('inf')])
+@pytest.mark.parametrize('nhwc', [False, True])
+def test_input_dynamic_range(scale, nhwc):
+    """The tcgen05 path keeps fp32's exponent range end to end (fp32 staging copy, TF32 operands): inputs scaled far
+    outside fp16's range must come out as accurate as O(1) inputs, and Inf must propagate to exactly the outputs the
+    reference formula makes non-finite.  (Guards the rejected fp16-staging experiment of profiles/r01s_dcn_ab.md
+    against coming back without a range check.)"""
+    b, c, h, w, co, dg = 2, 64, 12, 16, 64, 8
+    x, off, mask, wgt, bias = _rand_problem(b, c, h, w, co, dg, 11)
+    bias = torch.zeros_like(bias)
+    if scale == float('inf'):
+        x = x.clone()
+        x[0, 3, 5, 7] = float('inf')
+        xs = x
+    else:
+        xs = x * scale
+    ref = oracle.modulated_deform_conv_oracle(xs, off, mask, wgt, bias, 1, 1, 1, 1, dg, dtype=torch.float64)
+    xd = xs.to(DEV)
+    if nhwc:
+        # the channels-last entry point: raw conv_offset_mask output + arg-max map; zero flow, so that
+        # offset = conv_out[:, :144], mask = sigmoid(conv_out[:, 144:])
+        conv_out = torch.cat([off, torch.logit(mask.clamp(1e-4, 1 - 1e-4))], 1)
+        ref = oracle.modulated_deform_conv_oracle(xs, off, mask.clamp(1e-4, 1 - 1e-4), wgt, bias, 1, 1, 1, 1, dg,
+                                                  dtype=torch.float64)
+        ys, xg = torch.meshgrid(torch.arange(h - 2), torch.arange(w - 2), indexing='ij')
+        idx = (ys * (w - 2) + xg).expand(b, -1, -1).contiguous().to(DEV)
+        out = D.dynagg_dcn_forward(xd.contiguous(memory_format=torch.channels_last), conv_out.to(DEV), idx, 1,
+                                   wgt.to(DEV), bias.to(DEV), dg)
+    else:
+        out = D.dcn_forward_raw(xd, off.to(DEV), mask.to(DEV), wgt.to(DEV), bias.to(DEV), (1, 1), (1, 1), (1, 1), 1, dg,
+                                mode='tf32')
+    if scale == float('inf'):
+        bad_ref, bad = ~torch.isfinite(ref), ~torch.isfinite(out.cpu())
+        assert bad_ref.any() and torch.equal(bad, bad_ref)
+        ok = ~bad_ref
+        assert float((out.cpu().double() - ref)[ok].abs().max() / ref[ok].abs().max()) <= TOL
+    else:
+        assert rel_err(out, ref) <= TOL
