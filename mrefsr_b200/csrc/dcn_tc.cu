@@ -4,32 +4,39 @@
 // (basicsr/ops/dcn/src/deform_conv_cuda.cpp:539-555, deform_conv_cuda_kernel.cu:571-633) with ONE launch over
 // the whole batch in which the deformable im2col tile never leaves the SM:
 //
-//   CTA tile   : 256 consecutive output positions (of the B*Ho*Wo concatenation) x all Co output channels
+//   CTA tile   : 256 output positions x all Co output channels.  The 256 rows are square-ish patches of positions
+//                (16x16, or four 8x8 for small grids) so that the bilinear corners of x- and y-neighbours meet
+//                in L1 within one K step; grids that would need > 3 % padding rows use 256 consecutive positions
+//                of the B*Ho*Wo concatenation instead.
 //   K loop     : (32-channel slab) x (tap).  Per step the A tile [256 x 32] fp32 is produced on the SM by 16
 //                producer warps and stored straight into 128B-swizzled shared memory; the B tile [Co x 32] of the
 //                repacked (tf32-rounded) weights arrives by TMA; one elected thread of a 17th warp issues
 //                2 (M halves) x 4 (K = 8 steps) tcgen05.mma.kind::tf32 into TMEM.
-//   producers  : (a) two K steps ahead, decode a shared-memory sample table -- per (row, deform group): corner
+//   producers  : (a) one K step ahead, decode a shared-memory sample table -- per (row, deform group): corner
 //                offset into an NHWC copy of the input + the four bilinear weights with mask and corner validity
 //                folded in -- from position-major (coalesced) offset / mask reads issued one step earlier;
-//                (b) gather: per (row, 4-channel chunk) four float4 corner loads, blend, round to tf32, one
-//                16-byte swizzled store.  All hand-offs are mbarriers with ONE elected arrive per warp (table
+//                (b) gather: per (row, 8-channel chunk) four 256-bit corner loads, blend, round to tf32, two
+//                16-byte swizzled stores.  All hand-offs are mbarriers with ONE elected arrive per warp (table
 //                ring full/empty, stage ring full/empty); there is no CTA-wide barrier in the loop, so warps
-//                drift by up to two K steps and hide each other's latency.
+//                drift by a K step and hide each other's latency.
 //   epilogue   : producer warps 0..3 also drain finished accumulators (tcgen05.ld 32x32b, bias add,
 //                position-major coalesced NCHW stores); they poll the TMEM-full barrier while they wait.
 //
-// Measured limits (profiles/r01_dcn_gather_microbench.txt, profiles/r01_dcn_tc_ncu.md): the bilinear gather alone
-// needs 0.35 / 0.79 / 2.07 ms per 80-sample call with 32+ warps/SM -- about one 32-byte sector per clock per SM
-// through L1, whatever the layout -- and this kernel takes 0.74 / 1.33 / 2.84 ms (0.7 sectors/clk/SM at the
-// large scale).  ncu shows ~50 % issue-slot use with 4.25 warps per scheduler, so the K loop is kept lean: no
-// integer division, per-tile row state, 8-channel gather items (one 256-bit load per corner, packed fp32x2 FMAs).
-// Tried and rejected on B200 this round: separate table warps, register-resident decode, a group-major
+// Measured limits (profiles/r01_dcn_gather_microbench.txt, r01_dcn_tc_ncu.md, r01s_dcn_ab.md): the bilinear gather
+// alone needs 0.35 / 0.79 / 2.07 ms per 80-sample call with 64 warps/SM -- about one 32-byte sector per clock per
+// SM through L1 -- and this kernel takes 0.73 / 1.26 / 2.74 ms (0.8 sectors/clk/SM).  It is latency bound inside
+// the producer loop, not bandwidth bound: 17 warps (96 registers each: one SM sub-partition hosts 5 of them) walk
+// a serial chain of ~440 instructions and two dependent memory round trips per K step; raising the L1 hit rate
+// from 45 % to 65 % (2-D patches), halving the gathered bytes (fp16 staging) or keeping the offset stream out of
+// L1 each bought 2-4 %, and more loads in flight per warp cost 15-20 %.  The K loop is kept lean: no integer
+// division, per-tile row state, 8-channel gather items (one 256-bit load per corner, packed fp32x2 FMAs).
+// Tried and rejected on B200: separate table warps (still 17 warps), register-resident decode, a group-major
 // zero-bordered layout, two 128-row CTAs per SM, a 16-warp CTA whose last-arriving warp issues the MMAs (128
-// registers, two items in flight: slower, more L1 queueing), corner fetch by TMA tile::gather4 (10 clk per
-// gather4 per SM: 5 ms at the large scale), an fp16 2x2-packed corner layout (-24 % in the microbenchmark, not
-// worth the precision and the packing pass), cp.async.bulk.prefetch.L2 of the input ahead of the gather (no
-// effect: the wait is L1 queueing, not DRAM).
+// registers, two items in flight), corner fetch by TMA tile::gather4 (10 clk per gather4 per SM: 5 ms at the large
+// scale), an fp16 2x2-packed corner layout, an fp16 NHWC staging copy with a device-side range gate (-2 %),
+// cp.async.bulk.prefetch.L2 of the input, deeper stage rings at the expense of L1 (+8 %), the table decode moved
+// under the corner loads' latency (spills at the register cap: +16 %).  Next: role-split producers (gather-only /
+// decode-only warps with half the state each) at 25-32 warps per SM.
 //
 // Offsets / masks come either as materialised tensors (the reference operator API) or -- fused DynAgg mode --
 // straight from the raw conv_offset_mask output plus the matcher's arg-max map: offset = conv + s*flow shifted
@@ -45,7 +52,7 @@ namespace mrefsr {
 constexpr int TBM = 256;            // rows (output positions) per CTA tile
 constexpr int TBK = 32;             // fp32 channels per K step (128-byte rows)
 constexpr int T_A_BYTES = TBM * 128;
-constexpr int T_PW = 16;             // producer warps: sample table (2 K steps ahead) + gather; warps 0..3 also drain TMEM
+constexpr int T_PW = 16;             // producer warps: sample table (T_AHEAD K steps ahead) + gather; warps 0..3 also drain TMEM
 constexpr int T_RSTEP = T_PW * 8;    // row stride between a thread's gather items (a warp covers 8 rows x 4 chunks)
 constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items (row, 8-channel chunk) per thread per K step (2)
 constexpr int T_PRODUCERS = T_PW * 32;
@@ -278,9 +285,9 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
 
     if (warp < T_PW) {
         // ------------------------------------------------------------------ producer warps
-        // Iteration kb:  (D) decode table kb+2 into the ring,  (L) issue the raw offset/mask loads of table kb+3,
+        // Iteration kb:  (D) decode table kb+T_AHEAD into the ring,  (L) issue the raw offset/mask loads of the next one,
         // (G) gather K step kb from table kb into a free A stage (warp 0 also starts the weight-tile TMA).
-        // Everything is mbarrier dataflow with one elected arrive per warp, so warps drift by up to two K steps
+        // Everything is mbarrier dataflow with one elected arrive per warp, so warps drift by a K step
         // and hide each other's latency.  Warps 0..3 additionally drain finished accumulators (epilogue): they
         // poll the TMEM-full barrier while they wait and at every K step.
         // The loop is instruction-issue sensitive (ncu: >50 % issue-slot use), so everything that is constant per
@@ -672,10 +679,14 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
                 prm.nsub = (int)(nsx * nsy);
             }
         }
-        prm.tile2d = 1;
-        prm.sub_log = prm.tx_log + prm.ty_log;
-        prm.subs_log = 8 - prm.sub_log;        // TBM = 256 rows = 2^subs_log patches
-        prm.tiles = (int)best;
+        // patches pay ~3-10 % (measured, profiles/r01s_dcn_ab.md); feature grids that tile badly (75 x 75: +14 % rows)
+        // stay on the linear mapping
+        if (best * 100 <= (long long)prm.tiles * 103) {
+            prm.tile2d = 1;
+            prm.sub_log = prm.tx_log + prm.ty_log;
+            prm.subs_log = 8 - prm.sub_log;        // TBM = 256 rows = 2^subs_log patches
+            prm.tiles = (int)best;
+        }
     }
     prm.n_slabs = s.C / TBK;
     prm.taps = K;

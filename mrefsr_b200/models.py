@@ -273,6 +273,12 @@ class MRefSRPipeline(nn.Module):
         ref_feats = self.net_map.vgg(img_refs.flatten(0, 1))
         return self.net_g.forward_batched(img_in_lq, max_idx, ref_feats, r)
 
+    def graphed(self, img_in_lq, img_in_up, img_refs, warmup=3):
+        """Capture `forward` for these shapes into a CUDA graph and return a GraphedForward runner.  The forward is
+        ~700 kernel launches for 25 ms of GPU work, so launched eagerly it is one slow host core away from being
+        launch-bound; replaying the graph removes the host from the loop."""
+        return GraphedForward(self, img_in_lq, img_in_up, img_refs, warmup)
+
     @torch.no_grad()
     def forward_reference_order(self, img_in_lq, img_in_up, img_refs):
         """The reference's own operator order (one net_map call per reference, materialised pre-offsets, DynAgg through
@@ -285,3 +291,34 @@ class MRefSRPipeline(nn.Module):
             pres.append(pre)
             rfs.append(rf)
         return self.net_g(img_in_lq, pres, rfs)
+
+
+class GraphedForward:
+    """CUDA-graph replay of MRefSRPipeline.forward for fixed shapes.  Inputs are copied into static device buffers
+    (from host or device tensors, asynchronously on the current stream), the graph is replayed, and the static
+    output tensor is returned (valid until the next call; `out=` copies it into a caller tensor, e.g. pinned host
+    memory, on the same stream)."""
+
+    def __init__(self, net, img_in_lq, img_in_up, img_refs, warmup=3):
+        dev = next(net.parameters()).device
+        self.static_in = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in (img_in_lq, img_in_up, img_refs)]
+        for s_, t in zip(self.static_in, (img_in_lq, img_in_up, img_refs)):
+            s_.copy_(t)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):           # warm-up off the capture: cuDNN plans, workspaces, lazy module init
+            for _ in range(max(1, warmup)):
+                net(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = net(*self.static_in)
+
+    def __call__(self, img_in_lq, img_in_up, img_refs, out=None):
+        for s_, t in zip(self.static_in, (img_in_lq, img_in_up, img_refs)):
+            s_.copy_(t, non_blocking=True)
+        self.graph.replay()
+        if out is not None:
+            out.copy_(self.static_out, non_blocking=True)
+            return out
+        return self.static_out

@@ -100,3 +100,24 @@ def test_lmr_shape_class_matches_reference(golden, pipeline, path):
     rel_l2, rel_max = _err(sr, sr_ref, base)
     assert rel_l2 <= 1e-3, (rel_l2, rel_max)
     assert float((sr.cpu() - sr_ref.cpu()).abs().max()) <= 1e-3
+
+
+def test_graphed_forward_equals_eager(golden, pipeline):
+    """CUDA-graph replay (MRefSRPipeline.graphed) against the eager forward: same kernels, same order, so the SR
+    images must be bit-identical -- also for new inputs copied into the static buffers after the capture."""
+    import copy
+    g = golden('full_model')
+    lq, up, refs = (g(k).to(DEV) for k in ('lq', 'up', 'refs'))
+    m = copy.deepcopy(pipeline).channels_last_()
+    eager = m(lq, up, refs).clone()
+    runner = m.graphed(lq, up, refs)
+    assert torch.equal(runner(lq, up, refs), eager)
+    gen = torch.Generator().manual_seed(77)
+    lq2 = torch.rand(lq.shape, generator=gen)
+    up2 = torch.nn.functional.interpolate(lq2, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    refs2 = torch.rand(refs.shape, generator=gen)
+    host_out = torch.empty(eager.shape).pin_memory()
+    runner(lq2.pin_memory(), up2.pin_memory(), refs2.pin_memory(), out=host_out)      # host tensors in, host tensor out
+    torch.cuda.synchronize()
+    eager2 = m(lq2.to(DEV), up2.to(DEV), refs2.to(DEV))
+    assert torch.equal(host_out, eager2.cpu())
