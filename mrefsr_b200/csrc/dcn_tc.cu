@@ -590,6 +590,366 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Role-split variant (MREFSR_DCN_SPLIT=1): the producer work of dcn_tc_kernel divided between 16 gather warps
+// (table read, corner loads, blend, swizzled store; warps 0..3 also drain TMEM while they wait) and 8 decode warps
+// (thread = tile row: raw offset / mask loads two tables ahead, sample-table decode: nothing else), plus the MMA warp:
+// 25 warps under a 72-register cap instead of 17 under 96.  Each warp carries half the state and a chain half as
+// long per K step.  Same shared-memory layout, barriers and outputs as dcn_tc_kernel.
+constexpr int S_GW = 16;                            // gather warps (threads 0..511)
+constexpr int S_DW = 8;                             // decode warps (threads 512..767), one thread per tile row
+constexpr int S_MMA_WARP = S_GW + S_DW;
+constexpr int S_THREADS = (S_GW + S_DW + 1) * 32;   // 800
+#ifndef MREFSR_S_NTAB
+#define MREFSR_S_NTAB 4
+#endif
+constexpr int S_NTAB = MREFSR_S_NTAB;               // sample-table ring depth (decode warps run up to this far ahead)
+static_assert((S_NTAB & (S_NTAB - 1)) == 0, "ring slot and phase are derived from the K-step index");
+constexpr int S_MAXG = TBK / 8;                     // deform groups per 32-channel slab, at most (cdg >= 8)
+
+struct DcnRaw {                                     // inputs of one table row (one tap, up to 4 deform groups)
+    float dy[S_MAXG], dx[S_MAXG], mk[S_MAXG];
+    int tij, mi, fyx;
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(S_THREADS, 1)
+dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ xt,
+                    const float* __restrict__ offset, const float* __restrict__ mask,
+                    const long long* __restrict__ max_idx, const float* __restrict__ bias,
+                    const __grid_constant__ DcnTcParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    const DcnShape& s = prm.s;
+    const int S = prm.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * prm.stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* tab_full = tempty + 2;          // [S_NTAB]
+    uint64_t* tab_empty = tab_full + S_NTAB;  // [S_NTAB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_empty + S_NTAB);
+    const int tab_n = prm.gs * TAB_STRIDE;
+    int* tab_base = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* tab_w = reinterpret_cast<float*>(tab_base + S_NTAB * tab_n);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Co = s.Co, C = s.C, K = prm.taps, P = prm.P;
+    const int nkb_tile = prm.n_slabs * K;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapW);
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], S_GW + 1);   // one elected arrive per gather warp + the TMA expect_tx arrive
+            mbar_init(&empty[i], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        for (int a = 0; a < S_NTAB; ++a) {
+            mbar_init(&tab_full[a], S_DW);
+            mbar_init(&tab_empty[a], S_GW);
+        }
+        fence_mbar_init();
+    }
+    if (warp == S_MMA_WARP) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = (prm.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_kb = my_tiles * nkb_tile;   // K steps of this CTA, flattened over its tiles: (tile, slab, tap)
+
+    if (warp < S_GW) {
+        // ------------------------------------------------------------------ gather warps
+        const int tid = threadIdx.x;
+        const int ch = tid & 3;                    // 8-channel chunk within the 32-channel slab
+        const int r0 = tid >> 2;                   // rows r0 and r0 + 128
+        const int gsub = (ch * 8) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
+        const uint32_t a_off0 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch) ^ (r0 & 7)) << 4);
+        const uint32_t a_off1 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch + 1) ^ (r0 & 7)) << 4);
+        // ---- epilogue duty (warps 0..3): tiles whose K steps this warp has all produced, not yet drained
+        const bool is_epi = warp < 4;
+        int ep_done = 0, prod_done = 0;
+        const int nbuf_mask = prm.nbuf - 1;
+        auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
+            if (is_epi && ep_done < prod_done) {
+                const int buf = ep_done & nbuf_mask;
+                if (mbar_try_wait(&tfull[buf], (ep_done >> nbuf_mask) & 1)) {
+                    tc_fence_after();
+                    dcn_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf,
+                                      warp, lane);
+                    ++ep_done;
+                }
+            }
+        };
+        auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
+            while (!mbar_try_wait(bar, parity)) poll_epilogue();
+        };
+        int stage = 0, c_slab = 0, c_tap = 0;
+        uint32_t phase = 0;
+        const int dx_elems = C, dy_elems = s.W * C;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            const int g_slot = kb & (S_NTAB - 1);
+            const uint32_t g_phase = (uint32_t)(kb / S_NTAB) & 1u;
+            poll_epilogue();
+            const float* xs = xt + (c_slab * TBK + ch * 8);
+            const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE + r0;
+            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE + r0;
+            wait_poll(&tab_full[g_slot], g_phase);
+            wait_poll(&empty[stage], phase ^ 1);
+            uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
+            if (tid == 0) {       // weight tile of this K step (TMA, lands on the same full barrier)
+                mbar_expect_tx(&full[stage], Co * 128);
+                tma_load_3d(A + T_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = 128 * i;
+                const int bf = tb[r];
+                const float w0 = tw[r], w1 = tw[r + tab_n], w2 = tw[r + 2 * tab_n], w3 = tw[r + 3 * tab_n];
+                const unsigned i0 = (unsigned)(bf & ~3);
+                const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
+                const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
+                const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+                const F8 v0 = ldg8(xs + i0), v1 = ldg8(xs + i1), v2 = ldg8(xs + i2), v3 = ldg8(xs + i3);
+                const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
+                             p3 = make_float2(w3, w3);
+                float2 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 a = __fmul2_rn(p0, v0.v[e]);
+                    a = __ffma2_rn(p1, v1.v[e], a);
+                    a = __ffma2_rn(p2, v2.v[e], a);
+                    a = __ffma2_rn(p3, v3.v[e], a);
+                    o[e] = make_float2(tf32_round_bits(a.x), tf32_round_bits(a.y));
+                }
+                *reinterpret_cast<float4*>(A + a_off0 + i * (128 * 128)) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                *reinterpret_cast<float4*>(A + a_off1 + i * (128 * 128)) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[stage]);
+                mbar_arrive(&tab_empty[g_slot]);
+            }
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+            if (++c_tap == K) {
+                c_tap = 0;
+                if (++c_slab == prm.n_slabs) {
+                    c_slab = 0;
+                    ++prod_done;      // every K step of this tile has been produced by this warp
+                }
+            }
+        }
+        while (is_epi && ep_done < prod_done) {    // drain the remaining accumulators
+            const int buf = ep_done & nbuf_mask;
+            mbar_wait_backoff(&tfull[buf], (ep_done >> nbuf_mask) & 1, 64);
+            tc_fence_after();
+            dcn_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf, warp,
+                              lane);
+            ++ep_done;
+        }
+    } else if (warp < S_MMA_WARP) {
+        // ------------------------------------------------------------------ decode warps
+        const int erow = threadIdx.x - S_GW * 32;  // tile row owned by this thread
+        // ---- per-tile state of this thread's row, load cursor
+        int l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0, l_dg0 = 0;
+        int row_yx = -1, row_bH = 0, row_qyx = 0, row_idx0 = 0;
+        const float* row_off = offset;
+        const float* row_msk = mask;
+        auto decode_rows = [&](int tile) {
+            int b = 0, oy = 0, ox = 0;
+            row_yx = -1;
+            if (dcn_row_coords(prm, tile, erow, b, oy, ox)) {
+                const int p = oy * s.Wo + ox;
+                row_yx = (oy << 16) | ox;
+                row_bH = b * s.H;
+                if (FUSED) {
+                    row_off = offset + (size_t)b * 3 * s.DG * K * P + p;
+                    row_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
+                    row_idx0 = b * prm.hp * prm.wp;
+                } else {
+                    row_off = offset + (size_t)b * 2 * s.DG * K * P + p;
+                    if (mask) row_msk = mask + (size_t)b * s.DG * K * P + p;
+                }
+            }
+        };
+        // the row coordinates travel with the raw inputs: a table loaded for the next tile is decoded after
+        // decode_rows has already moved this thread to that tile, but one loaded for the LAST step of a tile must be
+        // decoded with that tile's coordinates -> keep (yx, bH) per raw set
+        struct RawRow {
+            DcnRaw r;
+            int yx, bH;
+        };
+        auto load_next = [&](RawRow& rr, int l_kb) {      // rr <- inputs of table l_kb, then advance the load cursor
+            rr.yx = row_yx;
+            rr.bH = row_bH;
+            rr.r.tij = (l_ti << 8) | l_tj;
+            rr.r.fyx = -1;
+            if (row_yx >= 0) {
+#pragma unroll
+                for (int g = 0; g < S_MAXG; ++g) {
+                    if (g < prm.gs) {
+                        const int dgi = l_dg0 + g;
+                        if (!FUSED) {
+                            const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
+                            rr.r.dy[g] = ldg_early(row_off + o);
+                            rr.r.dx[g] = ldg_early(row_off + o + (unsigned)P);
+                            rr.r.mk[g] = mask ? ldg_early(row_msk + (unsigned)((dgi * K + l_tap) * P)) : 1.f;
+                        } else {
+                            const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
+                            rr.r.dy[g] = ldg_early(row_off + o);
+                            rr.r.dx[g] = ldg_early(row_off + o + (unsigned)P);
+                            rr.r.mk[g] = ldg_early(row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));
+                        }
+                    }
+                }
+                if (FUSED) {
+                    const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
+                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
+                        rr.r.mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + (row_idx0 + fy * prm.wp + fx)));
+                        rr.r.fyx = (fy << 16) | fx;
+                    }
+                }
+            }
+            if (++l_tj == s.kw) {
+                l_tj = 0;
+                ++l_ti;
+            }
+            if (++l_tap == K) {
+                l_tap = l_ti = l_tj = 0;
+                if (++l_slab == prm.n_slabs) {
+                    l_slab = 0;
+                    l_tile += gridDim.x;
+                    if (l_kb + 1 < total_kb) decode_rows(l_tile);
+                }
+                l_dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
+            }
+        };
+        auto decode_store = [&](const RawRow& rr, int d_kb) {   // rr = inputs of table d_kb -> its ring slot
+            const int d_slot = d_kb & (S_NTAB - 1);
+            const uint32_t d_phase = (uint32_t)(d_kb / S_NTAB) & 1u;
+            mbar_wait(&tab_empty[d_slot], d_phase ^ 1);
+            int* tb = tab_base + d_slot * tab_n + erow;
+            float* tw = tab_w + d_slot * 4 * tab_n + erow;
+            float ybase = 0.f, xbase = 0.f, fly = 0.f, flx = 0.f;
+            if (rr.yx >= 0) {
+                ybase = (float)((rr.yx >> 16) * s.sh - s.ph + (rr.r.tij >> 8) * s.dh);
+                xbase = (float)((rr.yx & 0xffff) * s.sw - s.pw + (rr.r.tij & 255) * s.dw);
+                if (FUSED && rr.r.fyx >= 0) {
+                    const int my = (int)__umulhi((unsigned)rr.r.mi, prm.wp_magic), mx = rr.r.mi - my * prm.wp;
+                    fly = (float)((my - (rr.r.fyx >> 16)) * prm.flow_scale);
+                    flx = (float)((mx - (rr.r.fyx & 0xffff)) * prm.flow_scale);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < S_MAXG; ++g) {
+                if (g < prm.gs) {
+                    int base = 0;
+                    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                    if (rr.yx >= 0) {
+                        const float y = ybase + (FUSED ? rr.r.dy[g] + fly : rr.r.dy[g]);
+                        const float x = xbase + (FUSED ? rr.r.dx[g] + flx : rr.r.dx[g]);
+                        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+                            const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-rr.r.mk[g])) : rr.r.mk[g];
+                            const float fy0 = floorf(y), fx0 = floorf(x);
+                            const int y0 = (int)fy0, x0 = (int)fx0;
+                            const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+                            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+                            base = ((rr.bH + yc) * s.W + xc) * C;
+                            if (tx0 && tx1) base |= 1;
+                            if (ty0 && ty1) base |= 2;
+                            const float hym = hy * mk, lym = ly * mk;
+                            w0 = (ty0 && tx0) ? hym * hx : 0.f;
+                            w1 = (ty0 && tx1) ? hym * lx : 0.f;
+                            w2 = (ty1 && tx0) ? lym * hx : 0.f;
+                            w3 = (ty1 && tx1) ? lym * lx : 0.f;
+                        }
+                    }
+                    const int e = g * TAB_STRIDE;
+                    tb[e] = base;
+                    tw[e] = w0;
+                    tw[e + tab_n] = w1;
+                    tw[e + 2 * tab_n] = w2;
+                    tw[e + 3 * tab_n] = w3;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tab_full[d_slot]);
+        };
+        // two raw sets in flight: the loads of table kb+2 are issued before table kb+1 is decoded
+        RawRow ra, rb;
+        ra.yx = rb.yx = -1;
+        ra.bH = rb.bH = 0;
+        ra.r.tij = rb.r.tij = 0;
+        ra.r.mi = rb.r.mi = 0;
+        ra.r.fyx = rb.r.fyx = -1;
+#pragma unroll
+        for (int g = 0; g < S_MAXG; ++g) ra.r.dy[g] = ra.r.dx[g] = ra.r.mk[g] = rb.r.dy[g] = rb.r.dx[g] = rb.r.mk[g] = 0.f;
+        if (total_kb > 0) {
+            decode_rows(l_tile);
+            load_next(ra, 0);
+        }
+        if (total_kb > 1) load_next(rb, 1);
+        for (int kb = 0; kb < total_kb; kb += 2) {
+            decode_store(ra, kb);
+            if (kb + 2 < total_kb) load_next(ra, kb + 2);
+            if (kb + 1 < total_kb) {
+                decode_store(rb, kb + 1);
+                if (kb + 3 < total_kb) load_next(rb, kb + 3);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(2, 128, Co);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
+                const int buf = it & (prm.nbuf - 1);
+                const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
+                mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * 2 * Co;
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < nkb_tile; ++kb) {
+                    mbar_wait_backoff(&full[stage], phase, 20);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
+                    const uint32_t sb = sa + T_A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t db = umma_desc_sw128(sb + kk * 32, 0);
+                        umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), db, idesc, accumulate);
+                        umma_tf32(tacc + Co, umma_desc_sw128(sa + 128 * 128 + kk * 32, 0), db, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[buf]);
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == S_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st) {
     nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 128), B), 256, 0, st>>>(x, xt, C, HW);
     MREFSR_LAUNCH_CHECK();
@@ -617,6 +977,16 @@ static int dcn_tile_mode() {
     if (mode < 0) {
         const char* e = getenv("MREFSR_DCN_TILE");
         mode = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return mode;
+}
+
+// MREFSR_DCN_SPLIT=0|1 (tuning knob): role-split producer warps (dcn_tc_split_kernel)
+static int dcn_split_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("MREFSR_DCN_SPLIT");
+        mode = (e && e[0] == '1') ? 1 : 0;
     }
     return mode;
 }
@@ -693,7 +1063,8 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     prm.cdg = s.C / s.DG;
     prm.gs = prm.cdg >= TBK ? 1 : TBK / prm.cdg;
     prm.stage_bytes = T_A_BYTES + s.Co * 128;
-    const size_t table_bytes = (size_t)T_NTAB * 5 * prm.gs * (TBM + 4) * 4;
+    const bool split = dcn_split_mode() != 0;
+    const size_t table_bytes = (size_t)(split ? S_NTAB : T_NTAB) * 5 * prm.gs * (TBM + 4) * 4;
     prm.stages = (int)((T_SMEM_BUDGET - (int)table_bytes) / prm.stage_bytes);
     if (prm.stages > 4) prm.stages = 4;
     if (prm.stages < 2) prm.stages = 2;
@@ -737,7 +1108,17 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     int grid = sm_count();
     if (grid > prm.tiles) grid = prm.tiles;
     ScopedTiming tm(MREFSR_K_DCN_FWD, st);
-    if (prm.fused) {
+    if (split) {
+        if (prm.fused) {
+            auto kern = dcn_tc_split_kernel<true>;
+            MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, S_THREADS, smem, st>>>(mapW, xt, off, nullptr, max_idx, bias, prm);
+        } else {
+            auto kern = dcn_tc_split_kernel<false>;
+            MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, S_THREADS, smem, st>>>(mapW, xt, off, mask, nullptr, bias, prm);
+        }
+    } else if (prm.fused) {
         auto kern = dcn_tc_kernel<true>;
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, T_THREADS, smem, st>>>(mapW, xt, off, nullptr, max_idx, bias, prm);
