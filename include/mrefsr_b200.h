@@ -109,6 +109,11 @@ enum {
 MREFSR_API size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
                                   int pad_h, int pad_w, int dil_h, int dil_w, int group, int deformable_group,
                                   int mode, int backward);
+/* Host-only introspection of the tcgen05 DCN kernel's work decomposition (no device work; used by the CPU tests):
+ * how the B*Ho*Wo output positions of a call are laid out over 256-row CTA tiles.  meta[4] = {patches (1) or
+ * consecutive positions (0), patch width, patch height, number of tiles}; coords (optional, 3 ints per row, room for
+ * max_rows rows) receives (sample, oy, ox) of every row of every tile, (-1, -1, -1) for padding rows. */
+MREFSR_API int mrefsr_dcn_tile_plan(int B, int Ho, int Wo, int* meta, int* coords, size_t max_rows);
 MREFSR_API int mrefsr_modulated_deform_conv_forward(const float* input, const float* weight, const float* bias,
                                          const float* offset, const float* mask, float* output, int B, int C, int H,
                                          int W, int Co, int kh, int kw, int stride_h, int stride_w, int pad_h,

@@ -493,6 +493,12 @@ using namespace mrefsr;
 
 extern "C" {
 
+int mrefsr_dcn_tile_plan(int B, int Ho, int Wo, int* meta, int* coords, size_t max_rows) {
+    MREFSR_CHECK(B > 0 && Ho > 0 && Wo > 0 && meta, ERR_BAD_ARG, "tile plan: bad arguments");
+    MREFSR_CHECK((long long)B * Ho * Wo < (1ll << 31) - 256, ERR_BAD_ARG, "tile plan: too many positions");
+    return dcn_tc_tile_plan(B, Ho, Wo, meta, coords, max_rows);
+}
+
 size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
                                   int pad_h, int pad_w, int dil_h, int dil_w, int group, int deformable_group, int mode,
                                   int backward) {

@@ -48,6 +48,7 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
                         const long long* max_idx, int flow_scale, float* out, const DcnShape& s, void* workspace,
                         size_t workspace_bytes, cudaStream_t st, int layout_flags, float out_slope,
                         const DcnOutputs* multi);
+int dcn_tc_tile_plan(int B, int Ho, int Wo, int* meta, int* coords, size_t max_rows);
 int dcn_forward_tc(const float* x, const float* w, const float* bias, const float* off, const float* mask, float* out,
                    const DcnShape& s, void* workspace, size_t workspace_bytes, cudaStream_t st);
 

@@ -83,7 +83,7 @@ struct DcnTcParams {
 };
 
 // (tile, row within the tile) -> (sample, oy, ox); false for padding rows
-__device__ __forceinline__ bool dcn_row_coords(const DcnTcParams& prm, int tile, int r, int& b, int& oy, int& ox) {
+__host__ __device__ __forceinline__ bool dcn_row_coords(const DcnTcParams& prm, int tile, int r, int& b, int& oy, int& ox) {
     if (!prm.tile2d) {
         const int m = tile * TBM + r;
         if (m >= prm.total_rows) return false;
@@ -991,6 +991,70 @@ static int dcn_split_mode() {
     return mode;
 }
 
+// Row -> position mapping of the CTA tiles for prm.s (fills tiles, tile2d and the patch geometry)
+static void dcn_plan_tiles(DcnTcParams& prm) {
+    const DcnShape& s = prm.s;
+    prm.tiles = cdiv(prm.total_rows, TBM);
+    prm.tile2d = prm.tx_log = prm.ty_log = prm.sub_log = prm.subs_log = prm.nsx = prm.nsub = 0;
+    if (dcn_tile_mode() != 0) {
+        // patch shape with the fewest padding rows; near-ties go to the larger patch (more neighbours share corners)
+        static const int cand[5][2] = {{4, 4}, {4, 3}, {3, 4}, {3, 3}, {5, 3}};   // log2 (x, y): 16x16, 16x8, 8x16, 8x8, 32x8
+        long long best = -1;
+        for (int k = 0; k < 5; ++k) {
+            const int tx = cand[k][0], ty = cand[k][1];
+            const long long nsx = cdiv(s.Wo, 1 << tx), nsy = cdiv(s.Ho, 1 << ty);
+            const long long rows = (long long)s.B * nsx * nsy << (tx + ty);
+            const long long tiles = (rows + TBM - 1) / TBM;
+            if (best < 0 || tiles * 100 < best * 97) {
+                best = tiles;
+                prm.tx_log = tx;
+                prm.ty_log = ty;
+                prm.nsx = (int)nsx;
+                prm.nsub = (int)(nsx * nsy);
+            }
+        }
+        // patches pay ~3-10 % (measured, profiles/r01s_dcn_ab.md); feature grids that tile badly (75 x 75: +14 % rows)
+        // stay on the linear mapping
+        if (best * 100 <= (long long)prm.tiles * 103) {
+            prm.tile2d = 1;
+            prm.sub_log = prm.tx_log + prm.ty_log;
+            prm.subs_log = 8 - prm.sub_log;        // TBM = 256 rows = 2^subs_log patches
+            prm.tiles = (int)best;
+        }
+    }
+}
+
+// Test hook (host only, no device work): the tile plan of a [B, *, Ho, Wo] output and, when `coords` is given, the
+// (sample, oy, ox) of every row of every tile (-1, -1, -1 for padding rows).  meta = {tile2d, patch_w, patch_h, tiles}.
+int dcn_tc_tile_plan(int B, int Ho, int Wo, int* meta, int* coords, size_t max_rows) {
+    DcnTcParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.s.B = B;
+    prm.s.Ho = Ho;
+    prm.s.Wo = Wo;
+    prm.P = Ho * Wo;
+    prm.total_rows = B * prm.P;
+    dcn_plan_tiles(prm);
+    meta[0] = prm.tile2d;
+    meta[1] = prm.tile2d ? 1 << prm.tx_log : TBM;
+    meta[2] = prm.tile2d ? 1 << prm.ty_log : 1;
+    meta[3] = prm.tiles;
+    if (coords) {
+        MREFSR_CHECK((size_t)prm.tiles * TBM <= max_rows, ERR_BAD_ARG, "tile plan: %d rows, room for %zu", prm.tiles * TBM,
+                     max_rows);
+        for (int t = 0; t < prm.tiles; ++t)
+            for (int r = 0; r < TBM; ++r) {
+                int b = -1, oy = -1, ox = -1;
+                if (!dcn_row_coords(prm, t, r, b, oy, ox)) b = oy = ox = -1;
+                int* c = coords + ((size_t)t * TBM + r) * 3;
+                c[0] = b;
+                c[1] = oy;
+                c[2] = ox;
+            }
+    }
+    return 0;
+}
+
 static int make_weight_map(CUtensorMap* map, const float* wt, int Co, int Ktot) {
     // 2-D tensor [Co rows][Ktot cols] fp32, box = 32 cols x Co rows, 128-byte swizzle; encoded as 3-D with d2 = 1
     return make_tensor_map_3d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wt, (uint64_t)Ktot, (uint64_t)Co, 1, TBK,
@@ -1030,34 +1094,7 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     prm.s = s;
     prm.P = s.Ho * s.Wo;
     prm.total_rows = s.B * prm.P;
-    prm.tiles = cdiv(prm.total_rows, TBM);
-    prm.tile2d = prm.tx_log = prm.ty_log = prm.sub_log = prm.subs_log = prm.nsx = prm.nsub = 0;
-    if (dcn_tile_mode() != 0) {
-        // patch shape with the fewest padding rows; near-ties go to the larger patch (more neighbours share corners)
-        static const int cand[5][2] = {{4, 4}, {4, 3}, {3, 4}, {3, 3}, {5, 3}};   // log2 (x, y): 16x16, 16x8, 8x16, 8x8, 32x8
-        long long best = -1;
-        for (int k = 0; k < 5; ++k) {
-            const int tx = cand[k][0], ty = cand[k][1];
-            const long long nsx = cdiv(s.Wo, 1 << tx), nsy = cdiv(s.Ho, 1 << ty);
-            const long long rows = (long long)s.B * nsx * nsy << (tx + ty);
-            const long long tiles = (rows + TBM - 1) / TBM;
-            if (best < 0 || tiles * 100 < best * 97) {
-                best = tiles;
-                prm.tx_log = tx;
-                prm.ty_log = ty;
-                prm.nsx = (int)nsx;
-                prm.nsub = (int)(nsx * nsy);
-            }
-        }
-        // patches pay ~3-10 % (measured, profiles/r01s_dcn_ab.md); feature grids that tile badly (75 x 75: +14 % rows)
-        // stay on the linear mapping
-        if (best * 100 <= (long long)prm.tiles * 103) {
-            prm.tile2d = 1;
-            prm.sub_log = prm.tx_log + prm.ty_log;
-            prm.subs_log = 8 - prm.sub_log;        // TBM = 256 rows = 2^subs_log patches
-            prm.tiles = (int)best;
-        }
-    }
+    dcn_plan_tiles(prm);
     prm.n_slabs = s.C / TBK;
     prm.taps = K;
     prm.cdg = s.C / s.DG;

@@ -114,3 +114,41 @@ def test_full_model_state_dict_keys_match_reference(golden):
     sd = m.net_g.state_dict()
     assert sorted(sd.keys()) == list(g('keys_g')) and len(sd) == 350
     assert [str(tuple(v.shape)) for k, v in sorted(sd.items())] == list(g('shapes_g'))
+
+
+@pytest.mark.parametrize('shape', [(80, 160, 160), (80, 80, 80), (80, 40, 40), (5, 75, 75), (3, 150, 150), (2, 300, 300),
+                                   (2, 12, 12), (3, 7, 5), (1, 1, 1), (2, 33, 17)])
+def test_dcn_tile_plan_covers_every_position_once(shape):
+    """Host logic of the tcgen05 DCN kernel (no GPU): the row -> (sample, oy, ox) mapping of its 256-row CTA tiles,
+    2-D patches or consecutive positions, must hit every output position exactly once, in range, and patches must
+    not cost more than 3 % extra tiles over the linear mapping."""
+    import ctypes
+    import numpy as np
+    from mrefsr_b200 import _lib
+    b, ho, wo = shape
+    lib = _lib.lib()
+    meta = (ctypes.c_int * 4)()
+    assert lib.mrefsr_dcn_tile_plan(b, ho, wo, ctypes.cast(meta, ctypes.c_void_p), None, 0) == 0
+    tile2d, pw, ph, tiles = list(meta)
+    lin_tiles = -(-b * ho * wo // 256)
+    assert tiles >= lin_tiles and tiles * 100 <= lin_tiles * 103
+    if not tile2d:
+        assert tiles == lin_tiles and (pw, ph) == (256, 1)
+    else:
+        assert pw * ph in (64, 128, 256)
+    coords = np.full((tiles * 256, 3), -7, dtype=np.int32)
+    assert lib.mrefsr_dcn_tile_plan(b, ho, wo, ctypes.cast(meta, ctypes.c_void_p),
+                                    coords.ctypes.data_as(ctypes.c_void_p), tiles * 256) == 0
+    valid = coords[:, 0] >= 0
+    assert (coords[~valid] == -1).all()
+    c = coords[valid]
+    assert (c[:, 0] < b).all() and (c[:, 1] >= 0).all() and (c[:, 1] < ho).all() and (c[:, 2] >= 0).all() and (c[:, 2] < wo).all()
+    lin = (c[:, 0].astype(np.int64) * ho + c[:, 1]) * wo + c[:, 2]
+    assert len(lin) == b * ho * wo and len(np.unique(lin)) == b * ho * wo
+    if tile2d:       # rows of one patch are x-fastest and stay inside one sample
+        first = coords[:pw * ph]
+        ok = first[first[:, 0] >= 0]
+        assert (ok[:, 0] == ok[0, 0]).all() and ok[:, 1].max() - ok[:, 1].min() < ph and ok[:, 2].max() - ok[:, 2].min() < pw
+    # too small a buffer is an error, not an overrun
+    assert lib.mrefsr_dcn_tile_plan(b, ho, wo, ctypes.cast(meta, ctypes.c_void_p),
+                                    coords.ctypes.data_as(ctypes.c_void_p), tiles * 256 - 1) != 0

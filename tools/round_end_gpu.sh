@@ -5,6 +5,7 @@ TAG=${1:-r01s}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/${TAG}_pytest.log
 tail -3 gpurun_out/${TAG}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python tests/perf_reference_gpu.py > gpurun_out/${TAG}_gpu_reference.jsonl 2> gpurun_out/${TAG}_gpu_reference.err
 tail -1 gpurun_out/${TAG}_gpu_reference.jsonl
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
