@@ -605,14 +605,14 @@ constexpr int S_THREADS = (S_GW + S_DW + 1) * 32;   // 800
 #endif
 constexpr int S_NTAB = MREFSR_S_NTAB;               // sample-table ring depth (decode warps run up to this far ahead)
 static_assert((S_NTAB & (S_NTAB - 1)) == 0, "ring slot and phase are derived from the K-step index");
-constexpr int S_MAXG = TBK / 8;                     // deform groups per 32-channel slab, at most (cdg >= 8)
 
-struct DcnRaw {                                     // inputs of one table row (one tap, up to 4 deform groups)
-    float dy[S_MAXG], dx[S_MAXG], mk[S_MAXG];
-    int tij, mi, fyx;
+template <int GS>
+struct DcnRaw {                                     // inputs of one table row (one tap, GS deform groups)
+    float dy[GS], dx[GS], mk[GS];
+    int mi, fyx;
 };
 
-template <bool FUSED>
+template <bool FUSED, int GS>       // GS = deform groups per 32-channel slab (prm.gs: 1, 2 or 4)
 __global__ void __launch_bounds__(S_THREADS, 1)
 dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ xt,
                     const float* __restrict__ offset, const float* __restrict__ mask,
@@ -759,7 +759,8 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
         // ------------------------------------------------------------------ decode warps
         const int erow = threadIdx.x - S_GW * 32;  // tile row owned by this thread
         // ---- per-tile state of this thread's row, load cursor
-        int l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_ti = 0, l_tj = 0, l_dg0 = 0;
+        int l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_dg0 = 0;
+        const unsigned kw_magic = 65536u / (unsigned)s.kw + 1u;      // tap / kw == (tap * kw_magic) >> 16 for tap < 256
         int row_yx = -1, row_bH = 0, row_qyx = 0, row_idx0 = 0;
         const float* row_off = offset;
         const float* row_msk = mask;
@@ -784,18 +785,17 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
         // decode_rows has already moved this thread to that tile, but one loaded for the LAST step of a tile must be
         // decoded with that tile's coordinates -> keep (yx, bH) per raw set
         struct RawRow {
-            DcnRaw r;
+            DcnRaw<GS> r;
             int yx, bH;
         };
         auto load_next = [&](RawRow& rr, int l_kb) {      // rr <- inputs of table l_kb, then advance the load cursor
             rr.yx = row_yx;
             rr.bH = row_bH;
-            rr.r.tij = (l_ti << 8) | l_tj;
             rr.r.fyx = -1;
             if (row_yx >= 0) {
 #pragma unroll
-                for (int g = 0; g < S_MAXG; ++g) {
-                    if (g < prm.gs) {
+                for (int g = 0; g < GS; ++g) {
+                    {
                         const int dgi = l_dg0 + g;
                         if (!FUSED) {
                             const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
@@ -811,6 +811,7 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
                     }
                 }
                 if (FUSED) {
+                    const int l_ti = (int)(((unsigned)l_tap * kw_magic) >> 16), l_tj = l_tap - l_ti * s.kw;
                     const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
                     if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
                         rr.r.mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + (row_idx0 + fy * prm.wp + fx)));
@@ -818,12 +819,8 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
                     }
                 }
             }
-            if (++l_tj == s.kw) {
-                l_tj = 0;
-                ++l_ti;
-            }
             if (++l_tap == K) {
-                l_tap = l_ti = l_tj = 0;
+                l_tap = 0;
                 if (++l_slab == prm.n_slabs) {
                     l_slab = 0;
                     l_tile += gridDim.x;
@@ -832,6 +829,7 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
                 l_dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
             }
         };
+        int d_tap = 0;                                           // tap of the table being decoded
         auto decode_store = [&](const RawRow& rr, int d_kb) {   // rr = inputs of table d_kb -> its ring slot
             const int d_slot = d_kb & (S_NTAB - 1);
             const uint32_t d_phase = (uint32_t)(d_kb / S_NTAB) & 1u;
@@ -840,59 +838,55 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
             float* tw = tab_w + d_slot * 4 * tab_n + erow;
             float ybase = 0.f, xbase = 0.f, fly = 0.f, flx = 0.f;
             if (rr.yx >= 0) {
-                ybase = (float)((rr.yx >> 16) * s.sh - s.ph + (rr.r.tij >> 8) * s.dh);
-                xbase = (float)((rr.yx & 0xffff) * s.sw - s.pw + (rr.r.tij & 255) * s.dw);
+                const int d_ti = (int)(((unsigned)d_tap * kw_magic) >> 16), d_tj = d_tap - d_ti * s.kw;
+                ybase = (float)((rr.yx >> 16) * s.sh - s.ph + d_ti * s.dh);
+                xbase = (float)((rr.yx & 0xffff) * s.sw - s.pw + d_tj * s.dw);
                 if (FUSED && rr.r.fyx >= 0) {
                     const int my = (int)__umulhi((unsigned)rr.r.mi, prm.wp_magic), mx = rr.r.mi - my * prm.wp;
                     fly = (float)((my - (rr.r.fyx >> 16)) * prm.flow_scale);
                     flx = (float)((mx - (rr.r.fyx & 0xffff)) * prm.flow_scale);
                 }
             }
+            // Branch-free per entry (everything is computed and then selected), so that the up-to-four entries of a
+            // row are independent straight-line chains the scheduler can interleave; same arithmetic as
+            // dcn_tc_kernel's decode, bit for bit.
+            const bool row_ok = rr.yx >= 0;
 #pragma unroll
-            for (int g = 0; g < S_MAXG; ++g) {
-                if (g < prm.gs) {
-                    int base = 0;
-                    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                    if (rr.yx >= 0) {
-                        const float y = ybase + (FUSED ? rr.r.dy[g] + fly : rr.r.dy[g]);
-                        const float x = xbase + (FUSED ? rr.r.dx[g] + flx : rr.r.dx[g]);
-                        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
-                            const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-rr.r.mk[g])) : rr.r.mk[g];
-                            const float fy0 = floorf(y), fx0 = floorf(x);
-                            const int y0 = (int)fy0, x0 = (int)fx0;
-                            const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
-                            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
-                            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
-                            base = ((rr.bH + yc) * s.W + xc) * C;
-                            if (tx0 && tx1) base |= 1;
-                            if (ty0 && ty1) base |= 2;
-                            const float hym = hy * mk, lym = ly * mk;
-                            w0 = (ty0 && tx0) ? hym * hx : 0.f;
-                            w1 = (ty0 && tx1) ? hym * lx : 0.f;
-                            w2 = (ty1 && tx0) ? lym * hx : 0.f;
-                            w3 = (ty1 && tx1) ? lym * lx : 0.f;
-                        }
-                    }
+            for (int g = 0; g < GS; ++g) {
+                {
+                    const float y = ybase + (FUSED ? rr.r.dy[g] + fly : rr.r.dy[g]);
+                    const float x = xbase + (FUSED ? rr.r.dx[g] + flx : rr.r.dx[g]);
+                    const bool in = row_ok && y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W;
+                    const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-rr.r.mk[g])) : rr.r.mk[g];
+                    const float fy0 = floorf(y), fx0 = floorf(x);
+                    const int y0 = (int)fy0, x0 = (int)fx0;       // saturating conversions: garbage in, garbage selected away
+                    const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                    const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
+                    const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
+                    int base = ((rr.bH + yc) * s.W + xc) * C;
+                    base |= (tx0 && tx1) ? 1 : 0;
+                    base |= (ty0 && ty1) ? 2 : 0;
+                    const float hym = hy * mk, lym = ly * mk;
                     const int e = g * TAB_STRIDE;
-                    tb[e] = base;
-                    tw[e] = w0;
-                    tw[e + tab_n] = w1;
-                    tw[e + 2 * tab_n] = w2;
-                    tw[e + 3 * tab_n] = w3;
+                    tb[e] = in ? base : 0;
+                    tw[e] = (in && ty0 && tx0) ? hym * hx : 0.f;
+                    tw[e + tab_n] = (in && ty0 && tx1) ? hym * lx : 0.f;
+                    tw[e + 2 * tab_n] = (in && ty1 && tx0) ? lym * hx : 0.f;
+                    tw[e + 3 * tab_n] = (in && ty1 && tx1) ? lym * lx : 0.f;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&tab_full[d_slot]);
+            if (++d_tap == K) d_tap = 0;
         };
         // two raw sets in flight: the loads of table kb+2 are issued before table kb+1 is decoded
         RawRow ra, rb;
         ra.yx = rb.yx = -1;
         ra.bH = rb.bH = 0;
-        ra.r.tij = rb.r.tij = 0;
         ra.r.mi = rb.r.mi = 0;
         ra.r.fyx = rb.r.fyx = -1;
 #pragma unroll
-        for (int g = 0; g < S_MAXG; ++g) ra.r.dy[g] = ra.r.dx[g] = ra.r.mk[g] = rb.r.dy[g] = rb.r.dx[g] = rb.r.mk[g] = 0.f;
+        for (int g = 0; g < GS; ++g) ra.r.dy[g] = ra.r.dx[g] = ra.r.mk[g] = rb.r.dy[g] = rb.r.dx[g] = rb.r.mk[g] = 0.f;
         if (total_kb > 0) {
             decode_rows(l_tile);
             load_next(ra, 0);
@@ -981,12 +975,13 @@ static int dcn_tile_mode() {
     return mode;
 }
 
-// MREFSR_DCN_SPLIT=0|1 (tuning knob): role-split producer warps (dcn_tc_split_kernel)
+// MREFSR_DCN_SPLIT=0|1 (tuning knob; default 1): role-split producer warps (dcn_tc_split_kernel) or the
+// 17-warp kernel in which every producer warp decodes and gathers (dcn_tc_kernel)
 static int dcn_split_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("MREFSR_DCN_SPLIT");
-        mode = (e && e[0] == '1') ? 1 : 0;
+        mode = (e && e[0] == '0') ? 0 : 1;
     }
     return mode;
 }
@@ -1146,15 +1141,22 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     if (grid > prm.tiles) grid = prm.tiles;
     ScopedTiming tm(MREFSR_K_DCN_FWD, st);
     if (split) {
+#define MREFSR_LAUNCH_SPLIT(F, G)                                                                                  \
+    do {                                                                                                            \
+        auto kern = dcn_tc_split_kernel<F, G>;                                                                      \
+        MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, S_THREADS, smem, st>>>(mapW, xt, off, F ? nullptr : mask, F ? max_idx : nullptr, bias, prm);   \
+    } while (0)
         if (prm.fused) {
-            auto kern = dcn_tc_split_kernel<true>;
-            MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, S_THREADS, smem, st>>>(mapW, xt, off, nullptr, max_idx, bias, prm);
+            if (prm.gs == 1) MREFSR_LAUNCH_SPLIT(true, 1);
+            else if (prm.gs == 2) MREFSR_LAUNCH_SPLIT(true, 2);
+            else MREFSR_LAUNCH_SPLIT(true, 4);
         } else {
-            auto kern = dcn_tc_split_kernel<false>;
-            MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, S_THREADS, smem, st>>>(mapW, xt, off, mask, nullptr, bias, prm);
+            if (prm.gs == 1) MREFSR_LAUNCH_SPLIT(false, 1);
+            else if (prm.gs == 2) MREFSR_LAUNCH_SPLIT(false, 2);
+            else MREFSR_LAUNCH_SPLIT(false, 4);
         }
+#undef MREFSR_LAUNCH_SPLIT
     } else if (prm.fused) {
         auto kern = dcn_tc_kernel<true>;
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
