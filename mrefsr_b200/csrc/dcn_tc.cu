@@ -591,11 +591,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Role-split variant (MREFSR_DCN_SPLIT=1): the producer work of dcn_tc_kernel divided between 16 gather warps
-// (table read, corner loads, blend, swizzled store; warps 0..3 also drain TMEM while they wait) and 8 decode warps
-// (thread = tile row: raw offset / mask loads two tables ahead, sample-table decode: nothing else), plus the MMA warp:
-// 25 warps under a 72-register cap instead of 17 under 96.  Each warp carries half the state and a chain half as
-// long per K step.  Same shared-memory layout, barriers and outputs as dcn_tc_kernel.
+// ---------------------------------------------------------------------------------------------------------
+// dcn_tc_split_kernel: the default.  The producer work of dcn_tc_kernel divided between 16 gather warps (table
+// read, corner loads, blend, swizzled store; warps 0..3 also drain TMEM while they wait) and 8 decode warps (thread
+// = tile row: raw offset / mask loads two tables ahead in two register sets, branch-free sample-table decode whose
+// GS entries per row are independent chains), plus the MMA warp: 25 warps under a 72-register cap instead of 17
+// under 96.  Each warp carries half the state and walks a chain half as long per K step; ring slot and phase are
+// derived from the K-step index.  Same shared-memory layout, barriers, arithmetic and outputs (bit for bit) as
+// dcn_tc_kernel.  Measured on B200 (profiles/r01s_dcn_ab.md): 4.81 -> 3.77 ms per step (0.56 / 0.99 / 2.21 ms per
+// launch).  Staging the raw words in shared memory with cp.async instead of registers (2-4 tables ahead, no spills)
+// was 3-6 % slower and is not kept.
 constexpr int S_GW = 16;                            // gather warps (threads 0..511)
 constexpr int S_DW = 8;                             // decode warps (threads 512..767), one thread per tile row
 constexpr int S_MMA_WARP = S_GW + S_DW;
