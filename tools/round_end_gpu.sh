@@ -14,6 +14,6 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_
 head -c 300 gpurun_out/${TAG}_bench_reference.json; echo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-full-model > gpurun_out/${TAG}_ncu_bench.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:dcn_tc_kernel -s 3 -c 3 -o gpurun_out/${TAG}_dcn_full -f \
+ncu --set full --import-source on --clock-control none -k regex:dcn_tc_ -s 3 -c 3 -o gpurun_out/${TAG}_dcn_full -f \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-full-model > gpurun_out/${TAG}_ncu_dcn.log 2>&1
 ls -la gpurun_out/${TAG}_* | head -20
