@@ -296,11 +296,20 @@ def full_model_leg(dev, b, r, rank, world, dist, barrier, steps=5):
     up = torch.nn.functional.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1).pin_memory()
     refs = torch.rand(b, r, 3, 160, 160, generator=g).pin_memory()
 
-    runner = net.graphed(lq, up, refs)          # CUDA-graph replay: the host launches one graph per batch
     sr_host = torch.empty(b, 3, 160, 160).pin_memory()
+    try:
+        runner = net.graphed(lq, up, refs)      # CUDA-graph replay: the host launches one graph per batch
+        graphed = True
 
-    def step():                                  # pinned host images in -> pinned host SR out, every step
-        return runner(lq, up, refs, out=sr_host)
+        def step():                              # pinned host images in -> pinned host SR out, every step
+            return runner(lq, up, refs, out=sr_host)
+    except Exception:  # noqa: BLE001  (a failed capture must not desynchronise the ranks: same steps, launched eagerly)
+        torch.cuda.synchronize()
+        graphed = False
+
+        def step():
+            sr = net(lq.to(dev, non_blocking=True), up.to(dev, non_blocking=True), refs.to(dev, non_blocking=True))
+            return sr_host.copy_(sr, non_blocking=True)
     for _ in range(4):
         step()
     barrier()
@@ -316,7 +325,8 @@ def full_model_leg(dev, b, r, rank, world, dist, barrier, steps=5):
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': out.numel() * 4, 'steps': steps,
             'note': 'whole x4 MRefSR network, random-init weights, host images in -> SR images out; '
                     'convolutions = cuDNN (TF32 allowed, channels_last), bias / activation / residual epilogues, '
-                    'layout hand-offs and the alignment path = this library; the forward is replayed as one CUDA graph'}
+                    'layout hand-offs and the alignment path = this library; ' +
+                    ('the forward is replayed as one CUDA graph' if graphed else 'launched eagerly (graph capture failed)')}
 
 
 # ----------------------------------------------------------------------------------------------------------

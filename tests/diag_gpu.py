@@ -1,5 +1,5 @@
 """First-contact diagnostics on the GPU box: matcher descriptor variants, parity stats, rough kernel timings.
-Usage: python tools/diag_gpu.py  (prints JSON lines; also written to gpurun_out/diag.jsonl)"""
+Usage: python tests/diag_gpu.py  (lives under tests/: it checks against the oracle)  (prints JSON lines; also written to gpurun_out/diag.jsonl)"""
 import json
 import os
 import sys
