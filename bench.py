@@ -520,6 +520,19 @@ def main():
     roofline['ms_per_launch'] = per_kernel[dom]['ms_per_step'] / per_kernel[dom]['launches_per_step']
     roof_all = {k: roof(k) for k in per_kernel if k in work}
 
+    # The DCN's HBM fraction is low by construction in fp32: every sampling point is four scattered 32-byte
+    # sectors, 6.7x the algorithmic bytes through L1.  Its practical ceiling is the bilinear gather alone, measured
+    # on B200 by tools/micro/gather_bench.cu (64 warps/SM, no MMA; profiles/r01_dcn_gather_microbench.txt):
+    # 0.353 / 0.794 / 2.066 ms per 80 samples at the three scales.  Reported next to the HBM roofline, not instead.
+    if 'dcn_fwd' in per_kernel:
+        floor_ms = (0.353 + 0.794 + 2.066) * (b * r) / 80.0
+        roof_all['dcn_fwd']['l1_gather'] = {
+            'bound': 'l1-sector gather (microbenchmark of the gather alone, same shapes)', 'floor_ms': floor_ms,
+            'achieved_ms': per_kernel['dcn_fwd']['ms_per_step'], 'frac': floor_ms / per_kernel['dcn_fwd']['ms_per_step'],
+            'sectors_per_step': 4.0 * 9 * (b * r) * sum(hw * hw * c / 8 for c, hw in SCALES)}
+        if dom == 'dcn_fwd':
+            roofline['l1_gather'] = roof_all['dcn_fwd']['l1_gather']
+
     cpu = None if args.no_cpu_baseline else cpu_baseline(args.cpu_images, r)
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
