@@ -273,6 +273,14 @@ class MRefSRPipeline(nn.Module):
         ref_feats = self.net_map.vgg(img_refs.flatten(0, 1))
         return self.net_g.forward_batched(img_in_lq, max_idx, ref_feats, r)
 
+    def forward_ragged(self, samples, max_batch=16):
+        """Images with different reference counts / sizes (LMR-shaped groups, BASELINE config 3): samples[i] =
+        (lq [3,h,w], up [3,H,W], refs [R_i,3,H,W]); images sharing (R, H, W) go through one batched `forward`.
+        Returns the SR images in input order (parallel.run_ragged; shard a ragged batch over ranks with
+        parallel.shard_ragged first)."""
+        from .parallel import run_ragged
+        return run_ragged(self, samples, max_batch)
+
     def graphed(self, img_in_lq, img_in_up, img_refs, warmup=3):
         """Capture `forward` for these shapes into a CUDA graph and return a GraphedForward runner.  The forward is
         ~700 kernel launches for 25 ms of GPU work, so launched eagerly it is one slow host core away from being

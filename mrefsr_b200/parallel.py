@@ -11,6 +11,11 @@ Two modes, as SURVEY.md section 8e derives from the reference's data flow:
   Each rank aligns its own references and `all_gather_refs` exchanges the aligned features (one NCCL all-gather
   per scale); every rank then runs the fusion on the full set.
 
+* **ragged reference groups** (BASELINE config 3: LMR-shaped groups with 2-6 references per image) -- still batch
+  sharding, but images cost differently and cannot all share one launch: `shard_ragged` balances images over the
+  ranks by a cost model (no communication: every rank computes the same assignment), `batches_by_shape` /
+  `run_ragged` bucket a rank's images by (reference count, size) so that each bucket is one batched forward.
+
 Only the exchange lives here; the kernels are the single-GPU ones.  Uneven splits (R not divisible by the world
 size) are padded to the largest shard for the collective and trimmed afterwards.
 """
@@ -39,6 +44,77 @@ def shard_batch(tensors, rank, world, dim=0):
     if isinstance(tensors, (list, tuple)):
         return type(tensors)(cut(v) for v in tensors)
     return cut(tensors)
+
+
+def image_cost(n_refs, pixels=1.0):
+    """Relative cost of one image of the x4 network: a part that does not depend on the references (content
+    extractor, residual trunk, upsampling: ~1/3 of a 5-reference image in profiles/r01_full_model.md) plus a part per
+    reference (VGG / extractor features, matcher, offset convolutions, DCN, fusion inputs); both scale with the
+    pixel count, the matcher with its square (N_lr x N_ref correlations)."""
+    return pixels * (1.0 + 0.4 * n_refs) + 0.05 * n_refs * pixels * pixels
+
+
+def shard_ragged(ref_counts, world, rank=None, pixels=None):
+    """Balanced assignment of images with different reference counts (and optionally sizes) to ranks.
+
+    Longest-processing-time-first on `image_cost`: images sorted by cost (ties by index), each given to the least
+    loaded rank (ties to the lowest rank).  Deterministic, so every rank derives the same assignment locally.
+    Returns the sorted image indices of `rank`, or the list for all ranks when rank is None."""
+    n = len(ref_counts)
+    px = [1.0] * n if pixels is None else [float(p) for p in pixels]
+    if pixels is not None and len(px) != n:
+        raise ValueError('shard_ragged: %d pixel counts for %d images' % (len(px), n))
+    if world < 1:
+        raise ValueError('shard_ragged: world size must be positive')
+    base = min(px) if px else 1.0
+    cost = [image_cost(int(r), p / base) for r, p in zip(ref_counts, px)]
+    order = sorted(range(n), key=lambda i: (-cost[i], i))
+    load = [0.0] * world
+    owned = [[] for _ in range(world)]
+    for i in order:
+        k = min(range(world), key=lambda q: (load[q], q))
+        owned[k].append(i)
+        load[k] += cost[i]
+    owned = [sorted(o) for o in owned]
+    return owned if rank is None else owned[rank]
+
+
+def batches_by_shape(keys, max_batch):
+    """Bucket item indices by key (e.g. (n_refs, H, W)), order-preserving, at most max_batch per bucket.
+    Returns a list of (key, [indices])."""
+    if max_batch < 1:
+        raise ValueError('batches_by_shape: max_batch must be positive')
+    open_buckets, out = {}, []
+    for i, k in enumerate(keys):
+        b = open_buckets.get(k)
+        if b is None or len(b) == max_batch:
+            b = []
+            open_buckets[k] = b
+            out.append((k, b))
+        b.append(i)
+    return out
+
+
+def run_ragged(forward, samples, max_batch=16):
+    """Run `forward(lq [B,3,h,w], up [B,3,H,W], refs [B,R,3,H,W]) -> [B,3,H,W]` (e.g. MRefSRPipeline) over samples
+    with different reference counts / sizes: sample i = (lq [3,h,w], up [3,H,W], refs [R_i,3,H,W]).  Samples that
+    share (R, H, W) go through one batched call; results come back in input order."""
+    keys = []
+    for lq, up, refs in samples:
+        if refs.dim() != 4 or tuple(refs.shape[-2:]) != tuple(up.shape[-2:]):
+            raise ValueError('run_ragged: refs must be [R,3,H,W] with the size of the upsampled input')
+        keys.append((int(refs.shape[0]),) + tuple(up.shape[-2:]) + tuple(lq.shape[-2:]))
+    out = [None] * len(samples)
+    for _, idxs in batches_by_shape(keys, max_batch):
+        lq = torch.stack([samples[i][0] for i in idxs])
+        up = torch.stack([samples[i][1] for i in idxs])
+        refs = torch.stack([samples[i][2] for i in idxs])
+        sr = forward(lq, up, refs)
+        if sr.shape[0] != len(idxs):
+            raise RuntimeError('run_ragged: forward returned %d images for a batch of %d' % (sr.shape[0], len(idxs)))
+        for j, i in enumerate(idxs):
+            out[i] = sr[j]
+    return out
 
 
 def all_gather_refs(local, n_refs_total, group=None):
