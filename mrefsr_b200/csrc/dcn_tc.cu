@@ -229,6 +229,44 @@ __device__ __forceinline__ void dcn_epilogue_tile(const DcnTcParams& prm, const 
     if (lane == 0) mbar_arrive(tempty_bar);
 }
 
+// MMA issuer (one elected thread of the MMA warp; shared by both DCN kernels): per tile wait for a free TMEM
+// accumulator, per K step wait for the A / B stage, issue 2 (M halves) x 4 (K = 8) tcgen05.mma.kind::tf32, release
+// the stage with a commit; a last commit hands the accumulator to the epilogue warps.
+__device__ __forceinline__ void dcn_mma_issuer(const DcnTcParams& prm, uint8_t* smem, uint64_t* full, uint64_t* empty,
+                                               uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int nkb_tile) {
+    const int Co = prm.s.Co, S = prm.stages;
+    const uint32_t idesc = umma_idesc(2, 128, Co);
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & (prm.nbuf - 1);
+        const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
+        mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * 2 * Co;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nkb_tile; ++kb) {
+            mbar_wait_backoff(&full[stage], phase, 20);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
+            const uint32_t sb = sa + T_A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t db = umma_desc_sw128(sb + kk * 32, 0);
+                umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), db, idesc, accumulate);
+                umma_tf32(tacc + Co, umma_desc_sw128(sa + 128 * 128 + kk * 32, 0), db, idesc, accumulate);
+                accumulate = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        umma_commit(&tfull[buf]);
+    }
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(T_THREADS, 1)
 dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ xt,
@@ -548,38 +586,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict_
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(2, 128, Co);
-            int stage = 0, it = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
-                const int buf = it & (prm.nbuf - 1);
-                const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
-                mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + buf * 2 * Co;
-                uint32_t accumulate = 0;
-                for (int kb = 0; kb < nkb_tile; ++kb) {
-                    mbar_wait_backoff(&full[stage], phase, 20);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
-                    const uint32_t sb = sa + T_A_BYTES;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t db = umma_desc_sw128(sb + kk * 32, 0);
-                        umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), db, idesc, accumulate);
-                        umma_tf32(tacc + Co, umma_desc_sw128(sa + 128 * 128 + kk * 32, 0), db, idesc, accumulate);
-                        accumulate = 1;
-                    }
-                    umma_commit(&empty[stage]);
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                umma_commit(&tfull[buf]);
-            }
-        }
+        if (lane == 0) dcn_mma_issuer(prm, smem, full, empty, tfull, tempty, tmem_base, nkb_tile);
         __syncwarp();
     }
     tc_fence_before();
@@ -907,38 +914,7 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
         }
     } else {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(2, 128, Co);
-            int stage = 0, it = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
-                const int buf = it & (prm.nbuf - 1);
-                const uint32_t bphase = (it >> (prm.nbuf - 1)) & 1;
-                mbar_wait_backoff(&tempty[buf], bphase ^ 1, 32);
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + buf * 2 * Co;
-                uint32_t accumulate = 0;
-                for (int kb = 0; kb < nkb_tile; ++kb) {
-                    mbar_wait_backoff(&full[stage], phase, 20);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
-                    const uint32_t sb = sa + T_A_BYTES;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t db = umma_desc_sw128(sb + kk * 32, 0);
-                        umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), db, idesc, accumulate);
-                        umma_tf32(tacc + Co, umma_desc_sw128(sa + 128 * 128 + kk * 32, 0), db, idesc, accumulate);
-                        accumulate = 1;
-                    }
-                    umma_commit(&empty[stage]);
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                umma_commit(&tfull[buf]);
-            }
-        }
+        if (lane == 0) dcn_mma_issuer(prm, smem, full, empty, tfull, tempty, tmem_base, nkb_tile);
         __syncwarp();
     }
     tc_fence_before();
