@@ -2,41 +2,42 @@
 //
 // Replaces the reference's per-sample {im2col kernel -> columns buffer in HBM -> cuBLAS addmm_}
 // (basicsr/ops/dcn/src/deform_conv_cuda.cpp:539-555, deform_conv_cuda_kernel.cu:571-633) with ONE launch over
-// the whole batch in which the deformable im2col tile never leaves the SM:
+// the whole batch in which the deformable im2col tile never leaves the SM.  Two kernels share this design:
+// dcn_tc_split_kernel (the default: gather and decode on different warps, 25 warps per SM; see its header below)
+// and dcn_tc_kernel (every producer warp does both, 17 warps; MREFSR_DCN_SPLIT=0, kept as the cross-check).
 //
 //   CTA tile   : 256 output positions x all Co output channels.  The 256 rows are square-ish patches of positions
 //                (16x16, or four 8x8 for small grids) so that the bilinear corners of x- and y-neighbours meet
 //                in L1 within one K step; grids that would need > 3 % padding rows use 256 consecutive positions
 //                of the B*Ho*Wo concatenation instead.
-//   K loop     : (32-channel slab) x (tap).  Per step the A tile [256 x 32] fp32 is produced on the SM by 16
+//   K loop     : (32-channel slab) x (tap).  Per step the A tile [256 x 32] fp32 is produced on the SM by the
 //                producer warps and stored straight into 128B-swizzled shared memory; the B tile [Co x 32] of the
-//                repacked (tf32-rounded) weights arrives by TMA; one elected thread of a 17th warp issues
+//                repacked (tf32-rounded) weights arrives by TMA; one elected thread of the MMA warp issues
 //                2 (M halves) x 4 (K = 8 steps) tcgen05.mma.kind::tf32 into TMEM.
-//   producers  : (a) one K step ahead, decode a shared-memory sample table -- per (row, deform group): corner
+//   producers  : (a) ahead of the gather, decode a shared-memory sample table -- per (row, deform group): corner
 //                offset into an NHWC copy of the input + the four bilinear weights with mask and corner validity
-//                folded in -- from position-major (coalesced) offset / mask reads issued one step earlier;
+//                folded in -- from position-major (coalesced) offset / mask reads issued earlier;
 //                (b) gather: per (row, 8-channel chunk) four 256-bit corner loads, blend, round to tf32, two
 //                16-byte swizzled stores.  All hand-offs are mbarriers with ONE elected arrive per warp (table
-//                ring full/empty, stage ring full/empty); there is no CTA-wide barrier in the loop, so warps
-//                drift by a K step and hide each other's latency.
-//   epilogue   : producer warps 0..3 also drain finished accumulators (tcgen05.ld 32x32b, bias add,
+//                ring full/empty, stage ring full/empty); there is no CTA-wide barrier in the loop.
+//   epilogue   : gather warps 0..3 also drain finished accumulators (tcgen05.ld 32x32b, bias add,
 //                position-major coalesced NCHW stores); they poll the TMEM-full barrier while they wait.
 //
-// Measured limits (profiles/r01_dcn_gather_microbench.txt, r01_dcn_tc_ncu.md, r01s_dcn_ab.md): the bilinear gather
-// alone needs 0.35 / 0.79 / 2.07 ms per 80-sample call with 64 warps/SM -- about one 32-byte sector per clock per
-// SM through L1 -- and this kernel takes 0.73 / 1.26 / 2.74 ms (0.8 sectors/clk/SM).  It is latency bound inside
-// the producer loop, not bandwidth bound: 17 warps (96 registers each: one SM sub-partition hosts 5 of them) walk
-// a serial chain of ~440 instructions and two dependent memory round trips per K step; raising the L1 hit rate
-// from 45 % to 65 % (2-D patches), halving the gathered bytes (fp16 staging) or keeping the offset stream out of
-// L1 each bought 2-4 %, and more loads in flight per warp cost 15-20 %.  The K loop is kept lean: no integer
+// Measured (profiles/r01_dcn_gather_microbench.txt, r01s_dcn_ab.md, r01u_dcn_tc_split_ncu_full.txt): the bilinear
+// gather alone needs 0.35 / 0.79 / 2.07 ms per 80-sample call with 64 warps/SM -- about one 32-byte sector per
+// clock per SM through L1.  dcn_tc_kernel takes 0.73 / 1.26 / 2.74 ms: latency bound inside the producer loop, not
+// bandwidth bound -- 17 warps (96 registers each: one SM sub-partition hosts 5 of them) walk a serial chain of
+// ~440 instructions and two dependent memory round trips per K step; raising the L1 hit rate from 45 % to 65 %
+// (2-D patches), halving the gathered bytes (fp16 staging) or keeping the offset stream out of L1 each bought
+// 2-4 %, and more loads in flight per warp cost 15-20 %.  dcn_tc_split_kernel takes 0.56 / 0.99 / 2.22 ms: 0.93
+// sectors/clk/SM at the large scale, i.e. at the gather's own ceiling.  Both K loops are kept lean: no integer
 // division, per-tile row state, 8-channel gather items (one 256-bit load per corner, packed fp32x2 FMAs).
-// Tried and rejected on B200: separate table warps (still 17 warps), register-resident decode, a group-major
+// Tried and rejected on B200: separate table warps at 17 warps, register-resident decode, a group-major
 // zero-bordered layout, two 128-row CTAs per SM, a 16-warp CTA whose last-arriving warp issues the MMAs (128
 // registers, two items in flight), corner fetch by TMA tile::gather4 (10 clk per gather4 per SM: 5 ms at the large
 // scale), an fp16 2x2-packed corner layout, an fp16 NHWC staging copy with a device-side range gate (-2 %),
 // cp.async.bulk.prefetch.L2 of the input, deeper stage rings at the expense of L1 (+8 %), the table decode moved
-// under the corner loads' latency (spills at the register cap: +16 %).  Next: role-split producers (gather-only /
-// decode-only warps with half the state each) at 25-32 warps per SM.
+// under the corner loads' latency (spills at the register cap: +16 %), cp.async staging of the raw offsets (+5 %).
 //
 // Offsets / masks come either as materialised tensors (the reference operator API) or -- fused DynAgg mode --
 // straight from the raw conv_offset_mask output plus the matcher's arg-max map: offset = conv + s*flow shifted
@@ -57,7 +58,7 @@ constexpr int T_RSTEP = T_PW * 8;    // row stride between a thread's gather ite
 constexpr int T_ITEMS = TBM / T_RSTEP;             // gather items (row, 8-channel chunk) per thread per K step (2)
 constexpr int T_PRODUCERS = T_PW * 32;
 constexpr int T_MMA_WARP = T_PW;
-constexpr int T_THREADS = T_PRODUCERS + 32;        // + the MMA warp (17 warps: register budget 100/thread)
+constexpr int T_THREADS = T_PRODUCERS + 32;        // + the MMA warp (17 warps: one sub-partition hosts 5 -> 96 registers/thread)
 constexpr int T_NTAB = 3;                          // sample-table ring depth
 constexpr int T_AHEAD = 1;                         // tables are decoded this many K steps before their gather
 constexpr int T_SMEM_BUDGET = 150 * 1024;          // stage ring; the rest of the 228 KB stays L1 for the gather
