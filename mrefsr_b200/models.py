@@ -319,7 +319,8 @@ class GraphedForward:
                 net(*self.static_in)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: CUDA calls of other threads (the NCCL watchdog under torchrun) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.static_out = net(*self.static_in)
 
     def __call__(self, img_in_lq, img_in_up, img_refs, out=None):
