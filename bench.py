@@ -533,7 +533,8 @@ def main():
         if dom == 'dcn_fwd':
             roofline['l1_gather'] = roof_all['dcn_fwd']['l1_gather']
 
-    cpu = None if args.no_cpu_baseline else cpu_baseline(args.cpu_images, r)
+    # contract: the CPU baseline is timed on rank 0 at N = 1 only (at N > 1 the host cores are shared by the ranks)
+    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.cpu_images, r)
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
