@@ -301,12 +301,113 @@ def gen_full_model(name='full_model', b=2, r=2, H=48, W=56, seed=2024):
     print(name + '.npz sr', tuple(sr.shape), 'mean', float(sr.mean()), 'std', float(sr.std()), 'n_keys', len(out['keys_g']))
 
 
+def gen_data():
+    """Data preparation and validation metrics produced by the reference's own code:
+    MultiRefCUFEDSet / MultiRefMegaDepthDataset.__getitem__ (basicsr/data/multi_ref_dataset.py) on synthetic PNGs
+    written to a temporary directory, tensor2img (basicsr/utils/img_util.py), calculate_psnr / calculate_ssim
+    (basicsr/metrics/psnr_ssim.py) and bgr2ycbcr (basicsr/utils/color_util.py).
+    Harness-side additions: ``mmcv.impad`` (mmcv is un-vendored; its documented behaviour -- constant padding at the
+    bottom / right up to `shape` -- via cv2.copyMakeBorder, as mmcv implements it) and a bare ``basicsr.data``
+    package object so that basicsr/data/__init__.py (which imports every dataset) is skipped; the random shuffle and
+    flips of the MegaDepth dataset are recorded by seeding `random` and replaying the same draws."""
+    import random
+    import tempfile
+    import cv2
+    mmcv = sys.modules['mmcv']
+
+    def impad(img, shape, pad_val=0):
+        return cv2.copyMakeBorder(img, 0, shape[0] - img.shape[0], 0, shape[1] - img.shape[1], cv2.BORDER_CONSTANT,
+                                  value=pad_val)
+    mmcv.impad = impad
+    dpkg = types.ModuleType('basicsr.data')
+    dpkg.__path__ = [os.path.join(REF, 'basicsr', 'data')]
+    sys.modules['basicsr.data'] = dpkg
+    from basicsr.data.multi_ref_dataset import MultiRefCUFEDSet, MultiRefMegaDepthDataset
+    from basicsr.utils.img_util import tensor2img
+    from basicsr.utils.color_util import bgr2ycbcr
+    from basicsr.metrics.psnr_ssim import calculate_psnr, calculate_ssim
+
+    rng = np.random.RandomState(7)
+
+    def smooth_image(h, w):       # band-limited colour noise, uint8 BGR
+        x = rng.rand(h // 4 + 2, w // 4 + 2, 3).astype(np.float32)
+        x = cv2.resize(x, (w, h), interpolation=cv2.INTER_CUBIC)
+        x = x + 0.05 * rng.randn(h, w, 3).astype(np.float32)
+        return (np.clip(x, 0, 1) * 255).round().astype(np.uint8)
+
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        # ---- CUFED5-style validation sample: 131 x 158 input (not a multiple of 4), five references of other sizes
+        imgs = [smooth_image(131, 158)] + [smooth_image(h, w) for h, w in ((120, 160), (97, 143), (160, 101), (64, 64), (200, 90))]
+        for k, im in enumerate(imgs):
+            cv2.imwrite(os.path.join(tmp, '000_%d.png' % k), im)
+        ds = MultiRefCUFEDSet({'dataroot_in': tmp, 'dataroot_ref': tmp, 'scale': 4, 'name': 'golden'})
+        # the reference pads to 500 x 500; keep the fixture small by patching nothing: 500 x 500 x 6 uint8 is fine
+        item = ds[0]
+        out['cufed.in_bgr'] = imgs[0]
+        for k in range(5):
+            out['cufed.ref%d_bgr' % k] = imgs[k + 1]
+        for key in ('img_in', 'img_in_lq', 'img_in_up', 'img_ref_list', 'img_ref_lq_list', 'img_ref_up_list'):
+            out['cufed.' + key] = (item[key].numpy() * 255).round().astype(np.uint8)      # exact: all are u8 / 255
+        out['cufed.original_size'] = np.array(item['original_size'])
+
+        # ---- MegaDepth / LMR-style training sample: crops of 48 around points, 5 references, seeded shuffle + flips
+        big = [smooth_image(140, 150) for _ in range(6)]
+        rgb = [cv2.cvtColor(b, cv2.COLOR_BGR2RGB) for b in big]
+        names = ['t.png', 'h.png', 'm1.png', 'm2.png', 'l1.png', 'l2.png']
+        os.makedirs(os.path.join(tmp, 'scene'))
+        for n, b in zip(names, big):
+            cv2.imwrite(os.path.join(tmp, 'scene', n), b)
+        pts = [(70, 60), (64, 80), (50, 50), (100, 90), (75, 75), (40, 100)]
+        import pandas as pd
+        df = pd.DataFrame([dict(target=names[0], H=names[1], M1=names[2], M2=names[3], L1=names[4], L2=names[5],
+                                p0=str(list(pts[0])), p1=str(list(pts[1])), p2=str(list(pts[2])), p3=str(list(pts[3])),
+                                p4=str(list(pts[4])), p5=str(list(pts[5])), scene='scene')])
+        ann = os.path.join(tmp, 'ann.csv')
+        df.to_csv(ann, index=False)
+        md = MultiRefMegaDepthDataset({'dataroot_in': tmp, 'dataroot_ref': tmp, 'ann_file': ann, 'scale': 4,
+                                       'gt_size': 48, 'use_flip': True, 'use_rot': True})
+        for seed in (1, 2, 5):
+            random.seed(seed)
+            item = md[0]
+            random.seed(seed)                       # replay the draws: shuffle, then hflip / vflip / rot90
+            order = list(range(5))
+            random.shuffle(order)
+            hflip, vflip, rot90 = random.random() < 0.5, random.random() < 0.5, random.random() < 0.5
+            out['md%d.order' % seed] = np.array(order)
+            out['md%d.flags' % seed] = np.array([hflip, vflip, rot90])
+            for key in ('img_in', 'img_in_lq', 'img_in_up', 'img_ref_list', 'img_ref_lq_list', 'img_ref_up_list'):
+                out['md%d.%s' % (seed, key)] = (item[key].numpy() * 255).round().astype(np.uint8)
+        for k in range(6):
+            out['md.img%d_rgb' % k] = rgb[k]
+        out['md.points'] = np.array(pts)
+
+    # ---- tensor2img and the metrics
+    g = torch.Generator().manual_seed(11)
+    sr = torch.rand(1, 3, 45, 52, generator=g) * 1.2 - 0.1          # values outside [0, 1] are clamped
+    gt = (sr + 0.05 * torch.randn(1, 3, 45, 52, generator=g)).clamp(0, 1)
+    sr_img, gt_img = tensor2img([sr, gt])
+    out['metric.sr'], out['metric.gt'] = sr.numpy(), gt.numpy()
+    out['metric.sr_img'], out['metric.gt_img'] = sr_img, gt_img
+    vals = []
+    for cb in (0, 4):
+        vals += [calculate_psnr(sr_img, gt_img, crop_border=cb, test_y_channel=False),
+                 calculate_psnr(sr_img, gt_img, crop_border=cb, test_y_channel=True),
+                 calculate_ssim(sr_img, gt_img, crop_border=cb, test_y_channel=True),
+                 calculate_ssim(sr_img, gt_img, crop_border=cb, test_y_channel=False)]
+    out['metric.values'] = np.array(vals, dtype=np.float64)      # [cb0: psnr, psnr_y, ssim_y, ssim] + [cb4: ...]
+    out['metric.y_u8'] = bgr2ycbcr(sr_img, y_only=True)
+    out['metric.y_f32'] = bgr2ycbcr(sr_img.astype(np.float32) / 255., y_only=True)
+    np.savez_compressed(os.path.join(OUT, 'data.npz'), **out)
+    print('data.npz', len(out), 'arrays; metric values', vals[:4])
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
     install_shims()
     only = set(sys.argv[1:])      # e.g. `make_golden.py full_model_lmr` regenerates one fixture
     gens = dict(matcher=gen_matcher, correspondence=gen_correspondence, dynagg=gen_dynagg, fusion=gen_fusion,
-                dcnv1=gen_dcnv1, full_model=gen_full_model,
+                dcnv1=gen_dcnv1, full_model=gen_full_model, data=gen_data,
                 full_model_lmr=lambda: gen_full_model('full_model_lmr', b=1, r=3, H=60, W=60, seed=2025))
     for key, fn in gens.items():
         if not only or key in only:
