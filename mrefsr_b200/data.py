@@ -262,3 +262,73 @@ def validate(forward, samples, crop_border=0, device=None):
     n = max(1, len(per_image))
     avg = {k: sum(p[k] for p in per_image) / n for k in ('psnr', 'psnr_y', 'ssim_y')}
     return avg, per_image
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the file-system side: the two dataset classes, same `opt` keys and returned dicts as the reference
+def _read_rgb(path):
+    """Decoded 8-bit RGB image (PNG / JPEG) as uint8 HWC."""
+    with Image.open(path) as im:
+        return np.array(im.convert('RGB'))
+
+
+class MultiRefCUFEDSet(torch.utils.data.Dataset):
+    """CUFED5 validation set (multi_ref_dataset.py:143-238): `<name>_0.png` inputs under opt['dataroot_in'],
+    `<name>_1.png` .. `<name>_5.png` references under opt['dataroot_ref'], opt['scale'].  Every item is padded to
+    500x500 and carries 'lq_path', 'padding' and 'original_size' for the validation loop."""
+
+    def __init__(self, opt):
+        import glob
+        import os.path as osp
+        self.opt = opt
+        self.input_list = sorted(glob.glob(osp.join(opt['dataroot_in'], '*_0.png')))
+        self.ref_lists = [sorted(glob.glob(osp.join(opt['dataroot_ref'], '*_%d.png' % k))) for k in range(1, 6)]
+
+    def __len__(self):
+        return len(self.input_list)
+
+    def __getitem__(self, idx):
+        img_in = _read_rgb(self.input_list[idx])[:, :, ::-1]                       # BGR, as cv2.imread decodes
+        refs = [_read_rgb(lst[idx])[:, :, ::-1] for lst in self.ref_lists]
+        item = prepare_cufed5_sample(img_in, refs, self.opt['scale'], (500, 500))
+        item['lq_path'] = self.ref_lists[0][idx].replace('_1.png', '_multi.png')
+        return item
+
+
+class MultiRefMegaDepthDataset(torch.utils.data.Dataset):
+    """MegaDepth / LMR training set (multi_ref_dataset.py:19-140): opt['ann_file'] is a CSV with the columns target,
+    H, M1, M2, L1, L2 (file names under opt['dataroot_in']/<scene>/), p0 .. p5 (the (x, y) crop centres as Python
+    literals) and scene; opt['gt_size'], opt['scale'], opt['use_flip'], opt['use_rot'].  The random draws come from
+    the `random` module in the reference's order (shuffle of the five references, then one draw per enabled flip),
+    so `random.seed` reproduces the reference's sample."""
+
+    def __init__(self, opt):
+        import csv
+        import os.path as osp
+        from ast import literal_eval
+        self.opt = opt
+        self.samples = []
+        with open(opt['ann_file'], newline='') as f:
+            for row in csv.DictReader(f):
+                scene = row['scene']
+                target = osp.join(opt['dataroot_in'], scene, row['target'])
+                refs = [osp.join(opt['dataroot_in'], scene, row[k]) for k in ('H', 'M1', 'M2', 'L1', 'L2')]
+                pts = [tuple(literal_eval(row['p%d' % k])) for k in range(6)]
+                self.samples.append((target, refs, pts[0], pts[1:]))
+
+    def __len__(self):
+        return len(self.samples)
+
+    def __getitem__(self, index):
+        import random
+        in_path, ref_paths, p0, p_refs = self.samples[index]
+        img_in = _read_rgb(in_path)
+        refs = [_read_rgb(p) for p in ref_paths]
+        order = list(range(len(refs)))
+        random.shuffle(order)                                      # multi_ref_dataset.py:86
+        use_flip, use_rot = self.opt['use_flip'], self.opt['use_rot']
+        hflip = bool(use_flip and random.random() < 0.5)           # transforms.py:116-118 (short-circuit: no draw when off)
+        vflip = bool(use_rot and random.random() < 0.5)
+        rot90 = bool(use_rot and random.random() < 0.5)
+        return prepare_megadepth_sample(img_in, refs, p0, p_refs, self.opt['gt_size'], self.opt['scale'], order, hflip,
+                                        vflip, rot90)

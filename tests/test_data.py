@@ -108,3 +108,51 @@ def test_evaluate_and_validate_loop(golden):
     assert 15 < avg['psnr'] < 60 and 0 < avg['ssim_y'] <= 1 and math.isfinite(avg['psnr_y'])
     m = D.evaluate_sr(s['img_in'], s['img_in'])
     assert m['psnr'] == float('inf') and m['sr_img'].shape == (128, 156, 3)
+
+
+def _write_png(path, rgb):
+    from PIL import Image
+    Image.fromarray(rgb).save(path)
+
+
+def test_dataset_classes_match_reference(golden, tmp_path):
+    """The file-system side: the two Dataset classes on PNGs written from the fixture images must return exactly
+    what the reference's classes returned for the same files and the same `random` seed."""
+    import csv
+    import random
+    g = golden('data')
+    # ---- CUFED5
+    root = tmp_path / 'cufed'
+    root.mkdir()
+    _write_png(str(root / '000_0.png'), g('cufed.in_bgr').numpy()[:, :, ::-1])
+    for k in range(5):
+        _write_png(str(root / ('000_%d.png' % (k + 1))), g('cufed.ref%d_bgr' % k).numpy()[:, :, ::-1])
+    ds = D.MultiRefCUFEDSet({'dataroot_in': str(root), 'dataroot_ref': str(root), 'scale': 4, 'name': 'golden'})
+    assert len(ds) == 1
+    item = ds[0]
+    for key in KEYS:
+        assert np.array_equal(_u8(item[key]), g('cufed.' + key).numpy()), key
+    assert item['lq_path'].endswith('000_multi.png') and item['padding'] and tuple(item['original_size']) == (128, 156)
+    # ---- MegaDepth / LMR
+    mroot = tmp_path / 'md'
+    (mroot / 'scene').mkdir(parents=True)
+    names = ['t.png', 'h.png', 'm1.png', 'm2.png', 'l1.png', 'l2.png']
+    for k, n in enumerate(names):
+        _write_png(str(mroot / 'scene' / n), g('md.img%d_rgb' % k).numpy())
+    pts = g('md.points').tolist()
+    ann = mroot / 'ann.csv'
+    with open(ann, 'w', newline='') as f:
+        w = csv.writer(f)
+        w.writerow(['target', 'H', 'M1', 'M2', 'L1', 'L2', 'p0', 'p1', 'p2', 'p3', 'p4', 'p5', 'scene'])
+        w.writerow(names + [str(list(p)) for p in pts] + ['scene'])
+    md = D.MultiRefMegaDepthDataset({'dataroot_in': str(mroot), 'dataroot_ref': str(mroot), 'ann_file': str(ann), 'scale': 4,
+                                     'gt_size': 48, 'use_flip': True, 'use_rot': True})
+    assert len(md) == 1
+    for seed in (1, 2, 5):
+        random.seed(seed)
+        item = md[0]
+        for key in KEYS:
+            assert np.array_equal(_u8(item[key]), g('md%d.%s' % (seed, key)).numpy()), (seed, key)
+    # a DataLoader with the reference's validation batch size (1) collates the items
+    batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=1)))
+    assert tuple(batch['img_ref_list'].shape) == (1, 5, 3, 500, 500) and tuple(batch['img_in_lq'].shape) == (1, 3, 125, 125)
