@@ -161,3 +161,18 @@ def test_dcn_tile_plan_covers_every_position_once(shape):
     # too small a buffer is an error, not an overrun
     assert lib.mrefsr_dcn_tile_plan(b, ho, wo, ctypes.cast(meta, ctypes.c_void_p),
                                     coords.ctypes.data_as(ctypes.c_void_p), tiles * 256 - 1) != 0
+
+
+def test_missing_library_fails_loudly_with_the_build_command():
+    """No fallback of any kind: with the shared library absent, the first use of an op raises and names the fix."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['MREFSR_LIB'] = '/nonexistent/libmrefsr_b200.so'\n"
+            "import torch, mrefsr_b200 as M\n"
+            "try:\n"
+            "    M._lib.lib()\n"
+            "except RuntimeError as e:\n"
+            "    print('RAISED', e)\n" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert 'RAISED' in r.stdout and 'python -m mrefsr_b200.build' in r.stdout and 'no CPU / PyTorch fallback' in r.stdout
