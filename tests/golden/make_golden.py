@@ -260,12 +260,13 @@ def gen_dcnv1():
     print('dcnv1.npz', tuple(y.shape))
 
 
-def gen_full_model(name='full_model', b=2, r=2, H=48, W=56, seed=2024):
+def gen_full_model(name='full_model', b=2, r=2, H=48, W=56, seed=2024, quantize=False):
     """End-to-end reference forward (extractor -> net_map per reference -> net_g), exactly as
     basicsr/models/multi_ref_restoration_model.py:284-293 wires it, with key-seeded weights (tests/util.py).
     `full_model_lmr` is the LMR shape class of BASELINE config 3 in small: feature grids 15 / 30 / 60 are not
     multiples of 4, so MRAPAFusion reflect-pads and crops (ref_mrapa_restoration_arch.py:306-311, :348), and the
-    reference count is 3."""
+    reference count is 3.  `full_model_cfg1` is BASELINE config 1 literally (one 160x160 sample, 5 references); its
+    inputs are 8-bit images (k / 255) and stored as uint8 to keep the fixture small."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
     from tests.util import refill_parameters
     from basicsr.archs.contras_multi_extractor_arch import ContrasMultiExtractorSep
@@ -285,6 +286,9 @@ def gen_full_model(name='full_model', b=2, r=2, H=48, W=56, seed=2024):
     for k in range(r):
         img = torch.roll(gt, shifts=(4 * (k + 1), -8 * (k + 1)), dims=(2, 3)) if k == 0 else torch.rand(b, 3, H, W, generator=g)
         refs.append(img)
+    if quantize:
+        q = lambda t: (t * 255).round() / 255            # noqa: E731
+        lq, up, refs = q(lq), q(up), [q(t) for t in refs]
     with torch.no_grad():
         feats = ext(up, refs)
         pres, rfs = [], []
@@ -293,7 +297,8 @@ def gen_full_model(name='full_model', b=2, r=2, H=48, W=56, seed=2024):
             pres.append(pre)
             rfs.append(rf)
         sr = netg(lq, pres, rfs)
-    out = dict(lq=lq.numpy(), up=up.numpy(), refs=torch.stack(refs, 1).numpy(), sr=sr.numpy(),
+    u8 = (lambda t: (t * 255).round().to(torch.uint8).numpy()) if quantize else (lambda t: t.numpy())
+    out = dict(lq=u8(lq), up=u8(up), refs=u8(torch.stack(refs, 1)), sr=sr.numpy(),
                keys_ext=np.array(sorted(ext.state_dict().keys())), keys_map=np.array(sorted(nmap.state_dict().keys())),
                keys_g=np.array(sorted(netg.state_dict().keys())),
                shapes_g=np.array([str(tuple(v.shape)) for k, v in sorted(netg.state_dict().items())]))
@@ -408,7 +413,8 @@ if __name__ == '__main__':
     only = set(sys.argv[1:])      # e.g. `make_golden.py full_model_lmr` regenerates one fixture
     gens = dict(matcher=gen_matcher, correspondence=gen_correspondence, dynagg=gen_dynagg, fusion=gen_fusion,
                 dcnv1=gen_dcnv1, full_model=gen_full_model, data=gen_data,
-                full_model_lmr=lambda: gen_full_model('full_model_lmr', b=1, r=3, H=60, W=60, seed=2025))
+                full_model_lmr=lambda: gen_full_model('full_model_lmr', b=1, r=3, H=60, W=60, seed=2025),
+                full_model_cfg1=lambda: gen_full_model('full_model_cfg1', b=1, r=5, H=160, W=160, seed=2026, quantize=True))
     for key, fn in gens.items():
         if not only or key in only:
             fn()
