@@ -1,7 +1,7 @@
 """Where a kernel's warps wait, from an `ncu --set full --import-source on` capture: per launch, the stall-reason
 totals of the warp-state samples and the instructions that collect the most samples (with their dominant reason).
 
-    python tools/ncu_stalls.py gpurun_out/r01u_dcn_full.ncu-rep [--top 40] [--launch -1]
+    python tools/ncu_stalls.py gpurun_out/r01u_dcn_full.ncu-rep [--top 40] [--launch -1]   (some ncu versions list every launch twice on this page: use --launch 0, 2, 4, ...)
 
 Reads the SASS source page (`ncu -i REP --page source --csv --print-source sass`).  This is the reading that showed
 the 17-warp DCN kernel to be latency bound (41 % long scoreboard, first FMA after the corner loads) rather than
