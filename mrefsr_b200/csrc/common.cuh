@@ -135,6 +135,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -260,5 +268,10 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 // with cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda.
 int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
                        uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle);
+// 4-D tiled tensor map [d3][d2][d1][d0] (d0 contiguous, densely packed), box = box0 x box1 x box2 x 1; out-of-bounds
+// elements of a box (negative or too large coordinates) are filled with zeros.
+int make_tensor_map_4d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
+                       uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box0, uint32_t box1, uint32_t box2,
+                       CUtensorMapSwizzle swizzle);
 
 }  // namespace mrefsr

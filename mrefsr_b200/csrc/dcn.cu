@@ -9,7 +9,7 @@
 //   * backward: the reference's per-sample {addmm_, col2im_coord, col2im, im2col, addmm_ x2} sequence
 //     (deform_conv_cuda.cpp:612-672) is batched over chunks of samples sized to a bounded workspace.
 #include "common.cuh"
-#include "dcn_common.cuh"
+#include "dcn_tc.cuh"
 #include <cublas_v2.h>
 #include "../../include/mrefsr_b200.h"
 
@@ -497,6 +497,14 @@ int mrefsr_dcn_tile_plan(int B, int Ho, int Wo, int* meta, int* coords, size_t m
     MREFSR_CHECK(B > 0 && Ho > 0 && Wo > 0 && meta, ERR_BAD_ARG, "tile plan: bad arguments");
     MREFSR_CHECK((long long)B * Ho * Wo < (1ll << 31) - 256, ERR_BAD_ARG, "tile plan: too many positions");
     return dcn_tc_tile_plan(B, Ho, Wo, meta, coords, max_rows);
+}
+
+int mrefsr_dcn_win_plan(int B, int C, int H, int W, int Co, int deformable_group, int* meta, int* coords,
+                        size_t max_rows) {
+    MREFSR_CHECK(B > 0 && C > 0 && H > 0 && W > 0 && Co > 0 && deformable_group > 0 && meta, ERR_BAD_ARG,
+                 "window plan: bad arguments");
+    MREFSR_CHECK((long long)B * H * W < (1ll << 31) - 256, ERR_BAD_ARG, "window plan: too many positions");
+    return dcn_win_plan_query(B, C, H, W, Co, deformable_group, meta, coords, max_rows);
 }
 
 size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,

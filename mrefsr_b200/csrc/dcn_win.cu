@@ -1,0 +1,668 @@
+// mrefsr_b200/csrc/dcn_win.cu -- DCNv2 forward on tcgen05 with the bilinear corners gathered from SHARED MEMORY.
+//
+// Same operator as dcn_tc.cu (basicsr/ops/dcn/src/deform_conv_cuda.cpp:490-569 + deform_conv_cuda_kernel.cu:571-633,
+// optionally with the DynAgg glue of ref_mrapa_restoration_arch.py:55-68 folded in), same arithmetic bit for bit, but
+// a different corner-fetch mechanism.  dcn_tc_split_kernel gathers every corner through L1 with 256-bit loads and
+// sits at the LSU's ceiling of about one 32-byte sector per clock per SM (profiles/r01u_dcn_tc_split_ncu_full.txt):
+// with C/dg = 8 channels per deform group a sampling point is four scattered sectors, 6.7x the algorithmic bytes.
+// In MRefSR the offsets are a large but spatially COHERENT flow (the matcher's arg-max map: a reference is mostly a
+// translated view) plus a small learned residual, so all nine taps of a patch of output positions sample one compact
+// window of the reference features.  This kernel stages that window in shared memory with ONE bulk tensor copy per
+// (patch, 32-channel slab) -- TMA box {32 channels, wx, wy} of the NHWC input, 128-byte swizzle, out-of-image pixels
+// zero-filled by the copy engine, which is exactly the reference's "corners outside the plane contribute 0" -- and
+// reads the corners with LDS.128 (128 B/clk/SM instead of ~32 B/clk/SM through L1).  Sampling points that fall
+// outside the window (incoherent flow, large learned offsets) take the global-memory path of dcn_tc.cu per item, so
+// the result never depends on the window guess.
+//
+//   CTA tile   : 128 output positions (one 16x8 / 8x16 patch or two 8x8 patches) x all Co.  M = 128 per MMA, two TMEM
+//                accumulators at every Co <= 256 (the 256-row kernel has one at Co = 256).
+//   window     : per patch (px + 2 + 2 mlo) x (py + 2 + 2 mlo) pixels around patch + predicted translation, where
+//                the prediction is the flow of the patch centre (fused mode: from the arg-max map; operator mode:
+//                the rounded offset of the centre tap of group 0) and mlo = 3 (2 when shared memory is short):
+//                residuals in [-mlo, mlo) hit.  Double buffered; reloaded per (tile, slab) by a dedicated warp.
+//   K loop     : (32-channel slab) x (tap), as in dcn_tc.cu; A tile [128 x 32] fp32 produced on the SM, B tile by TMA.
+//   warps      : 16 gather (thread = (row, 8-channel chunk): table read, 8 LDS.128 or 4 LDG.256, blend, round to
+//                tf32, two swizzled 16-byte stores; warps 0..3 also drain TMEM), 8 decode (thread = tile row; the two
+//                halves of the decode warps take even / odd K steps, raw offset / mask loads two of their own tables
+//                ahead), 1 MMA issuer, 1 window loader = 26 warps under a 72-register cap.
+//   table entry: base < 0: ~(128-byte row index of the top-left corner inside the window buffer); base >= 0: element
+//                offset into the NHWC input with the two addressability flags of dcn_tc.cu; + 4 bilinear weights with
+//                mask and corner validity folded in (identical in both paths, so both blend to the same bits).
+#include <stdlib.h>
+#include "dcn_tc.cuh"
+#include "../../include/mrefsr_b200.h"
+
+namespace mrefsr {
+
+constexpr int W_BM = 128;                         // rows (output positions) per CTA tile
+constexpr int W_A_BYTES = W_BM * 128;             // A stage: 128 rows x 32 fp32
+constexpr int W_GW = 16;                          // gather warps (threads 0..511): one (row, chunk) item each per K step
+constexpr int W_DW = 8;                           // decode warps: 0..3 take even K steps, 4..7 odd ones
+constexpr int W_MMA_WARP = W_GW + W_DW;
+constexpr int W_WIN_WARP = W_MMA_WARP + 1;
+constexpr int W_THREADS = (W_WIN_WARP + 1) * 32;  // 832
+constexpr int W_NTAB = 4;                         // sample-table ring depth
+constexpr int W_TAB_STRIDE = W_BM + 4;
+constexpr int W_SMEM_MAX = 227 * 1024;
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+// 8 consecutive channels (chunk ch of the slab) of window row `pix`: two 16-byte pieces at the 128-byte-swizzled
+// positions the bulk tensor copy wrote them to (window buffers are 1024-byte aligned, so the swizzle phase of a row
+// is its index modulo 8)
+__device__ __forceinline__ F8 lds_corner(uint32_t win, int pix, int ch) {
+    const uint32_t a = win + (uint32_t)pix * 128u + (uint32_t)((((2 * ch) ^ (pix & 7))) << 4);
+    const float4 lo = lds128(a), hi = lds128(a ^ 16u);
+    F8 r;
+    r.v[0] = make_float2(lo.x, lo.y);
+    r.v[1] = make_float2(lo.z, lo.w);
+    r.v[2] = make_float2(hi.x, hi.y);
+    r.v[3] = make_float2(hi.z, hi.w);
+    return r;
+}
+
+// Window of patch p of a tile: sample b and the image coordinates (wy0, wx0) of its first pixel.  Computed identically
+// by the window loader and by the decode threads.  false: the patch lies beyond the batch (no window).
+template <bool FUSED>
+__device__ __forceinline__ bool win_patch_geom(const DcnTcParams& prm, int tile, int p, const float* __restrict__ offset,
+                                               const long long* __restrict__ max_idx, int& b, int& wy0, int& wx0) {
+    const DcnShape& s = prm.s;
+    const int st = tile * prm.npatch + p;
+    b = st / prm.nsub;
+    if (b >= s.B) return false;
+    const int rem = st - b * prm.nsub, ty = rem / prm.nsx, tx = rem - ty * prm.nsx;
+    const int py0 = ty << prm.ty_log, px0 = tx << prm.tx_log;
+    const int cy = min(py0 + (1 << prm.ty_log >> 1), s.Ho - 1), cx = min(px0 + (1 << prm.tx_log >> 1), s.Wo - 1);
+    int fy = 0, fx = 0;                           // predicted translation of the patch
+    if (FUSED) {
+        // flow cell of the centre tap (tap (1,1) reads the cell one up / left, corres_generation_arch.py:74-79)
+        const int qy = min(max(cy / prm.flow_scale - 1, 0), prm.hp - 1), qx = min(max(cx / prm.flow_scale - 1, 0), prm.wp - 1);
+        const int mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + ((size_t)b * prm.hp * prm.wp + qy * prm.wp + qx)));
+        const int my = (int)__umulhi((unsigned)mi, prm.wp_magic), mx = mi - my * prm.wp;
+        fy = (my - qy) * prm.flow_scale;
+        fx = (mx - qx) * prm.flow_scale;
+    } else {
+        const int K = prm.taps, P = prm.P;
+        const float* o = offset + (size_t)b * 2 * s.DG * K * P + (size_t)(2 * (K >> 1)) * P + cy * s.Wo + cx;
+        fy = (int)rintf(fminf(fmaxf(__ldg(o), -30000.f), 30000.f));      // NaN -> 0
+        fx = (int)rintf(fminf(fmaxf(__ldg(o + P), -30000.f), 30000.f));
+    }
+    wy0 = min(max(py0 - s.ph + fy - prm.mlo, -30000), 30000);
+    wx0 = min(max(px0 - s.pw + fx - prm.mlo, -30000), 30000);
+    return true;
+}
+
+// Drain one finished accumulator tile (128 rows): tcgen05.ld 32x32b, bias add, leaky-ReLU, position-major stores.
+__device__ __forceinline__ void win_epilogue_tile(const DcnTcParams& prm, const float* __restrict__ bias,
+                                                  uint32_t tmem_base, uint64_t* tempty_bar, int tile, int buf, int warp,
+                                                  int lane) {
+    const int Co = prm.s.Co, P = prm.P;
+    int b = 0, oy = 0, ox = 0;
+    const bool ok = dcn_row_coords(prm, tile, warp * 32 + lane, b, oy, ox);
+    const int p = ok ? oy * prm.s.Wo + ox : 0;
+    if (!ok) b = 0;
+    const int bd = prm.dst_group ? (b / prm.dst_group) * prm.dst_stride + prm.dst_offset + b % prm.dst_group : b;
+    const size_t o_off = prm.out_nhwc ? ((size_t)bd * P + p) * Co : (size_t)bd * Co * P + p;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * Co;
+#pragma unroll 1
+    for (int c0 = 0; c0 < Co; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld_32x8(taddr + c0, v);
+        tmem_ld_wait();
+        if (ok) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                f[e] = __uint_as_float(v[e]) + (bias ? __ldg(bias + c0 + e) : 0.f);
+                f[e] = f[e] > 0.f ? f[e] : f[e] * prm.out_slope;
+            }
+#pragma unroll 1
+            for (int k = 0; k < prm.n_outs; ++k) {
+                float* o = prm.outs[k] + o_off;
+                if (prm.out_nhwc) {
+                    *reinterpret_cast<float4*>(o + c0) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * P] = f[e];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar);
+}
+
+template <int GS>
+struct WinRaw {                                   // inputs of one table row (one tap, GS deform groups) + its tile state
+    float dy[GS], dx[GS], mk[GS];
+    int mi, fyx, yx, bH, worg;
+};
+
+template <bool FUSED, int GS>
+__global__ void __launch_bounds__(W_THREADS, 1)
+dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
+               const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
+               const long long* __restrict__ max_idx, const float* __restrict__ bias,
+               const __grid_constant__ DcnTcParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    const DcnShape& s = prm.s;
+    const int S = prm.stages;
+    uint8_t* win = smem + (size_t)S * prm.stage_bytes;                 // two window buffers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(win + 2 * (size_t)prm.win_bytes);
+    uint64_t* full = bars;                    // [S]  A produced (16 gather warps) + B landed (expect_tx)
+    uint64_t* empty = bars + S;               // [S]  stage consumed by the MMAs
+    uint64_t* tfull = bars + 2 * S;           // [2]  accumulator complete
+    uint64_t* tempty = tfull + 2;             // [2]  accumulator drained (4 epilogue warps)
+    uint64_t* tab_full = tempty + 2;          // [W_NTAB]  (4 decode warps)
+    uint64_t* tab_empty = tab_full + W_NTAB;  // [W_NTAB]  (16 gather warps)
+    uint64_t* win_full = tab_empty + W_NTAB;  // [2]  window landed (expect_tx)
+    uint64_t* win_empty = win_full + 2;       // [2]  window released (16 gather warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(win_empty + 2);
+    const int tab_n = GS * W_TAB_STRIDE;
+    int* tab_base = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* tab_w = reinterpret_cast<float*>(tab_base + W_NTAB * tab_n);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Co = s.Co, C = s.C, K = prm.taps, P = prm.P;
+    const int nkb_tile = prm.n_slabs * K;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapX);
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], W_GW + 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+            mbar_init(&win_full[a], 1);
+            mbar_init(&win_empty[a], W_GW);
+        }
+        for (int a = 0; a < W_NTAB; ++a) {
+            mbar_init(&tab_full[a], GS == 4 ? W_DW : W_DW / 2);
+            mbar_init(&tab_empty[a], W_GW);
+        }
+        fence_mbar_init();
+    }
+    if (warp == W_MMA_WARP) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = (prm.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_kb = my_tiles * nkb_tile;   // K steps of this CTA, flattened over its tiles: (tile, slab, tap)
+
+    if (warp < W_GW) {
+        // ------------------------------------------------------------------ gather warps
+        const int tid = threadIdx.x;
+        const int ch = tid & 3;                    // 8-channel chunk within the 32-channel slab
+        const int r0 = tid >> 2;                   // tile row
+        const int gsub = (ch * 8) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
+        const uint32_t a_off0 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch) ^ (r0 & 7)) << 4);
+        const uint32_t win_u32 = smem_u32(win);
+        const bool is_epi = warp < 4;
+        int ep_done = 0, prod_done = 0;
+        auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
+            if (is_epi && ep_done < prod_done) {
+                const int buf = ep_done & 1;
+                if (mbar_try_wait(&tfull[buf], (ep_done >> 1) & 1)) {
+                    tc_fence_after();
+                    win_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf,
+                                      warp, lane);
+                    ++ep_done;
+                }
+            }
+        };
+        auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
+            while (!mbar_try_wait(bar, parity)) poll_epilogue();
+        };
+        int stage = 0, c_slab = 0, c_tap = 0, wq = 0;   // wq: index of the current (tile, slab) window
+        uint32_t phase = 0;
+        const int dx_elems = C, dy_elems = s.W * C;
+        const int wxr = prm.wx;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            const int g_slot = kb & (W_NTAB - 1);
+            const uint32_t g_phase = (uint32_t)(kb / W_NTAB) & 1u;
+            poll_epilogue();
+            const float* xs = xt + (c_slab * TBK + ch * 8);
+            const int* tb = tab_base + g_slot * tab_n + gsub * W_TAB_STRIDE + r0;
+            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * W_TAB_STRIDE + r0;
+            const uint32_t wcur = win_u32 + (uint32_t)(wq & 1) * (uint32_t)prm.win_bytes;
+            if (c_tap == 0) wait_poll(&win_full[wq & 1], (uint32_t)(wq >> 1) & 1u);
+            wait_poll(&tab_full[g_slot], g_phase);
+            wait_poll(&empty[stage], phase ^ 1);
+            uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
+            if (tid == 0) {       // weight tile of this K step (TMA, lands on the same full barrier)
+                mbar_expect_tx(&full[stage], Co * 128);
+                tma_load_3d(A + W_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
+            }
+            {
+                const int bf = tb[0];
+                const float w0 = tw[0], w1 = tw[tab_n], w2 = tw[2 * tab_n], w3 = tw[3 * tab_n];
+                F8 v0, v1, v2, v3;
+                if (bf < 0) {                      // all four corners inside the staged window
+                    const int pix = ~bf;
+                    v0 = lds_corner(wcur, pix, ch);
+                    v1 = lds_corner(wcur, pix + 1, ch);
+                    v2 = lds_corner(wcur, pix + wxr, ch);
+                    v3 = lds_corner(wcur, pix + wxr + 1, ch);
+                } else {                           // through L1, as dcn_tc_split_kernel
+                    const unsigned i0 = (unsigned)(bf & ~3);
+                    const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
+                    const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
+                    const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+                    v0 = ldg8(xs + i0);
+                    v1 = ldg8(xs + i1);
+                    v2 = ldg8(xs + i2);
+                    v3 = ldg8(xs + i3);
+                }
+                const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
+                             p3 = make_float2(w3, w3);
+                float2 o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 a = __fmul2_rn(p0, v0.v[e]);
+                    a = __ffma2_rn(p1, v1.v[e], a);
+                    a = __ffma2_rn(p2, v2.v[e], a);
+                    a = __ffma2_rn(p3, v3.v[e], a);
+                    o[e] = make_float2(tf32_round_bits(a.x), tf32_round_bits(a.y));
+                }
+                *reinterpret_cast<float4*>(A + a_off0) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                *reinterpret_cast<float4*>(A + (a_off0 ^ 16u)) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[stage]);
+                mbar_arrive(&tab_empty[g_slot]);
+                if (c_tap == K - 1) mbar_arrive(&win_empty[wq & 1]);   // last tap of the slab: window may be refilled
+            }
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+            if (++c_tap == K) {
+                c_tap = 0;
+                ++wq;
+                if (++c_slab == prm.n_slabs) {
+                    c_slab = 0;
+                    ++prod_done;      // every K step of this tile has been produced by this warp
+                }
+            }
+        }
+        while (is_epi && ep_done < prod_done) {    // drain the remaining accumulators
+            const int buf = ep_done & 1;
+            mbar_wait_backoff(&tfull[buf], (ep_done >> 1) & 1, 64);
+            tc_fence_after();
+            win_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf, warp, lane);
+            ++ep_done;
+        }
+    } else if (warp < W_MMA_WARP) {
+        // ------------------------------------------------------------------ decode warps
+        // Work split between the two halves of the decode warps (par = 0 / 1).  GS <= 2: by K step -- a thread decodes
+        // all GS entries of its row for the K steps kb = par (mod 2).  GS == 4: by deform group -- a thread decodes
+        // groups 2 par, 2 par + 1 of its row for every K step (four entries plus two raw sets do not fit 72 registers).
+        constexpr bool PARG = GS == 4;
+        constexpr int GSL = PARG ? GS / 2 : GS;                    // table entries per thread per decoded K step
+        constexpr int KSTEP = PARG ? 1 : 2;                        // K steps between two tables of a thread
+        const int dwi = warp - W_GW;
+        const int par = dwi >> 2;
+        const int kb0 = PARG ? 0 : par;                            // first K step of this thread
+        const int g0 = PARG ? par * GSL : 0;                       // first deform group (within the slab) of this thread
+        const int erow = (dwi & 3) * 32 + lane;                    // tile row owned by this thread
+        const int my_patch = erow >> prm.sub_log;
+        const int pixbase = my_patch * prm.win_rows;
+        const unsigned kw_magic = 65536u / (unsigned)s.kw + 1u;    // tap / kw == (tap * kw_magic) >> 16 for tap < 256
+        // ---- load cursor (tile, slab, tap) and the per-tile state of this thread's row
+        int l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_dg0 = 0;
+        bool tile_changed = false;
+        int row_yx = -1, row_bH = 0, row_qyx = 0, row_idx0 = 0, row_worg = 0;
+        const float* row_off = offset;
+        const float* row_msk = mask;
+        auto decode_rows = [&](int tile) {
+            int b = 0, oy = 0, ox = 0, pb = 0, wy0 = 0, wx0 = 0;
+            row_yx = -1;
+            row_worg = 0;
+            if (win_patch_geom<FUSED>(prm, tile, my_patch, offset, max_idx, pb, wy0, wx0))
+                row_worg = (int)(((unsigned)wy0 << 16) | ((unsigned)wx0 & 0xffffu));
+            if (dcn_row_coords(prm, tile, erow, b, oy, ox)) {
+                const int p = oy * s.Wo + ox;
+                row_yx = (oy << 16) | ox;
+                row_bH = b * s.H;
+                if (FUSED) {
+                    row_off = offset + (size_t)b * 3 * s.DG * K * P + p;
+                    row_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
+                    row_idx0 = b * prm.hp * prm.wp;
+                } else {
+                    row_off = offset + (size_t)b * 2 * s.DG * K * P + p;
+                    if (mask) row_msk = mask + (size_t)b * s.DG * K * P + p;
+                }
+            }
+        };
+        auto step = [&]() {                        // cursor one K step forward
+            if (++l_tap == K) {
+                l_tap = 0;
+                if (++l_slab == prm.n_slabs) {
+                    l_slab = 0;
+                    l_tile += gridDim.x;
+                    tile_changed = true;
+                }
+                l_dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
+            }
+        };
+        typedef WinRaw<GSL> Raw;
+        auto load_next = [&](Raw& rr, int l_kb) {   // rr <- inputs of table l_kb (the cursor), then cursor += KSTEP
+            rr.yx = row_yx;
+            rr.bH = row_bH;
+            rr.worg = row_worg;
+            rr.fyx = -1;
+            if (row_yx >= 0) {
+#pragma unroll
+                for (int g = 0; g < GSL; ++g) {
+                    const int dgi = l_dg0 + g0 + g;
+                    if (!FUSED) {
+                        const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
+                        rr.dy[g] = ldg_early(row_off + o);
+                        rr.dx[g] = ldg_early(row_off + o + (unsigned)P);
+                        rr.mk[g] = mask ? ldg_early(row_msk + (unsigned)((dgi * K + l_tap) * P)) : 1.f;
+                    } else {
+                        const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
+                        rr.dy[g] = ldg_early(row_off + o);
+                        rr.dx[g] = ldg_early(row_off + o + (unsigned)P);
+                        rr.mk[g] = ldg_early(row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));
+                    }
+                }
+                if (FUSED) {
+                    const int l_ti = (int)(((unsigned)l_tap * kw_magic) >> 16), l_tj = l_tap - l_ti * s.kw;
+                    const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
+                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
+                        rr.mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + (row_idx0 + fy * prm.wp + fx)));
+                        rr.fyx = (fy << 16) | fx;
+                    }
+                }
+            }
+            step();
+            if (KSTEP == 2) step();
+            if (tile_changed) {
+                tile_changed = false;
+                if (l_kb + KSTEP < total_kb) decode_rows(l_tile);
+            }
+        };
+        int d_tap = kb0 % K;                                    // tap of the table being decoded
+        auto decode_store = [&](const Raw& rr, int d_kb) {      // rr = inputs of table d_kb -> its ring slot
+            const int d_slot = d_kb & (W_NTAB - 1);
+            const uint32_t d_phase = (uint32_t)(d_kb / W_NTAB) & 1u;
+            mbar_wait(&tab_empty[d_slot], d_phase ^ 1);
+            int* tb = tab_base + d_slot * tab_n + erow;
+            float* tw = tab_w + d_slot * 4 * tab_n + erow;
+            float ybase = 0.f, xbase = 0.f, fly = 0.f, flx = 0.f;
+            if (rr.yx >= 0) {
+                const int d_ti = (int)(((unsigned)d_tap * kw_magic) >> 16), d_tj = d_tap - d_ti * s.kw;
+                ybase = (float)((rr.yx >> 16) * s.sh - s.ph + d_ti * s.dh);
+                xbase = (float)((rr.yx & 0xffff) * s.sw - s.pw + d_tj * s.dw);
+                if (FUSED && rr.fyx >= 0) {
+                    const int my = (int)__umulhi((unsigned)rr.mi, prm.wp_magic), mx = rr.mi - my * prm.wp;
+                    fly = (float)((my - (rr.fyx >> 16)) * prm.flow_scale);
+                    flx = (float)((mx - (rr.fyx & 0xffff)) * prm.flow_scale);
+                }
+            }
+            const bool row_ok = rr.yx >= 0;
+            const int wy0 = rr.worg >> 16, wx0 = (rr.worg << 16) >> 16;
+#pragma unroll
+            for (int g = 0; g < GSL; ++g) {
+                // same arithmetic as dcn_tc_split_kernel's decode (bit for bit); in addition the window test
+                const float y = ybase + (FUSED ? rr.dy[g] + fly : rr.dy[g]);
+                const float x = xbase + (FUSED ? rr.dx[g] + flx : rr.dx[g]);
+                const bool in = row_ok && y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W;
+                const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-rr.mk[g])) : rr.mk[g];
+                const float fy0 = floorf(y), fx0 = floorf(x);
+                const int y0 = (int)fy0, x0 = (int)fx0;
+                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
+                const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
+                int base = ((rr.bH + yc) * s.W + xc) * C;
+                base |= (tx0 && tx1) ? 1 : 0;
+                base |= (ty0 && ty1) ? 2 : 0;
+                const int ry = y0 - wy0, rx = x0 - wx0;
+                const bool hit = in && ry >= 0 && rx >= 0 && ry <= prm.wy - 2 && rx <= prm.wx - 2;
+                const int pix = pixbase + ry * prm.wx + rx;
+                const float hym = hy * mk, lym = ly * mk;
+                const int e = (g0 + g) * W_TAB_STRIDE;
+                tb[e] = hit ? ~pix : (in ? base : ~pixbase);
+                tw[e] = (in && ty0 && tx0) ? hym * hx : 0.f;
+                tw[e + tab_n] = (in && ty0 && tx1) ? hym * lx : 0.f;
+                tw[e + 2 * tab_n] = (in && ty1 && tx0) ? lym * hx : 0.f;
+                tw[e + 3 * tab_n] = (in && ty1 && tx1) ? lym * lx : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tab_full[d_slot]);
+            d_tap += KSTEP;
+            while (d_tap >= K) d_tap -= K;
+        };
+        // two raw sets in flight per thread: the loads of this thread's table after next are issued before its next
+        // table is decoded
+        Raw ra, rb;
+        ra.yx = rb.yx = -1;
+        ra.bH = rb.bH = ra.worg = rb.worg = 0;
+        ra.mi = rb.mi = 0;
+        ra.fyx = rb.fyx = -1;
+#pragma unroll
+        for (int g = 0; g < GSL; ++g) ra.dy[g] = ra.dx[g] = ra.mk[g] = rb.dy[g] = rb.dx[g] = rb.mk[g] = 0.f;
+        if (kb0 == 1) step();                   // (K = 9 taps per slab: no tile change here)
+        tile_changed = false;
+        if (kb0 < total_kb) {
+            decode_rows(l_tile);
+            load_next(ra, kb0);
+        }
+        if (kb0 + KSTEP < total_kb) load_next(rb, kb0 + KSTEP);
+        for (int kb = kb0; kb < total_kb; kb += 2 * KSTEP) {
+            decode_store(ra, kb);
+            if (kb + 2 * KSTEP < total_kb) load_next(ra, kb + 2 * KSTEP);
+            if (kb + KSTEP < total_kb) {
+                decode_store(rb, kb + KSTEP);
+                if (kb + 3 * KSTEP < total_kb) load_next(rb, kb + 3 * KSTEP);
+            }
+        }
+    } else if (warp == W_MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(2, 128, Co);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait_backoff(&tempty[buf], ((it >> 1) & 1) ^ 1, 32);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * Co;
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < nkb_tile; ++kb) {
+                    mbar_wait_backoff(&full[stage], phase, 20);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
+                    const uint32_t sb = sa + W_A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), umma_desc_sw128(sb + kk * 32, 0), idesc, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ window loader
+        if (lane == 0) {
+            int wq = 0;
+            const uint32_t patch_bytes = (uint32_t)prm.wx * prm.wy * 128u;
+            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x) {
+                int pb0 = 0, wy00 = 0, wx00 = 0, pb1 = 0, wy01 = 0, wx01 = 0;
+                const bool pv0 = win_patch_geom<FUSED>(prm, tile, 0, offset, max_idx, pb0, wy00, wx00);
+                const bool pv1 = prm.npatch > 1 && win_patch_geom<FUSED>(prm, tile, 1, offset, max_idx, pb1, wy01, wx01);
+                const uint32_t tx_bytes = ((pv0 ? 1u : 0u) + (pv1 ? 1u : 0u)) * patch_bytes;
+                for (int slab = 0; slab < prm.n_slabs; ++slab, ++wq) {
+                    const int buf = wq & 1;
+                    uint8_t* dst = win + (size_t)buf * prm.win_bytes;
+                    mbar_wait_backoff(&win_empty[buf], (((uint32_t)wq >> 1) & 1u) ^ 1u, 64);
+                    mbar_expect_tx(&win_full[buf], tx_bytes);
+                    if (pv0) tma_load_4d(dst, &mapX, &win_full[buf], slab * TBK, wx00, wy00, pb0);
+                    if (pv1) tma_load_4d(dst + (size_t)prm.win_rows * 128, &mapX, &win_full[buf], slab * TBK, wx01, wy01, pb1);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MREFSR_DCN_WIN=0|1 (tuning knob; default 1): shared-memory window gather (this file) for eligible shapes
+static int dcn_win_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("MREFSR_DCN_WIN");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode;
+}
+
+// 128-row tiles as patches; fills the tile / window geometry of prm.  false: shape not served by this kernel.
+static bool dcn_win_plan(DcnTcParams& prm) {
+    const DcnShape& s = prm.s;
+    if (!(s.kh == 3 && s.kw == 3 && s.sh == 1 && s.sw == 1 && s.dh == 1 && s.dw == 1)) return false;
+    if (s.H >= 30000 || s.W >= 30000) return false;
+    static const int cand[3][2] = {{4, 3}, {3, 4}, {3, 3}};   // log2 (x, y): 16x8, 8x16, two 8x8
+    long long best = -1;
+    for (int k = 0; k < 3; ++k) {
+        const int tx = cand[k][0], ty = cand[k][1];
+        const long long nsx = cdiv(s.Wo, 1 << tx), nsy = cdiv(s.Ho, 1 << ty);
+        const long long rows = ((long long)s.B * nsx * nsy) << (tx + ty);
+        const long long tiles = (rows + W_BM - 1) / W_BM;
+        if (best < 0 || tiles < best) {
+            best = tiles;
+            prm.tx_log = tx;
+            prm.ty_log = ty;
+            prm.nsx = (int)nsx;
+            prm.nsub = (int)(nsx * nsy);
+        }
+    }
+    if (best * W_BM > (long long)prm.total_rows * 140 / 100) return false;   // > 40 % padding rows: not worth it
+    prm.tile2d = 1;
+    prm.sub_log = prm.tx_log + prm.ty_log;
+    prm.subs_log = 7 - prm.sub_log;
+    prm.npatch = 1 << prm.subs_log;
+    prm.tiles = (int)best;
+    prm.stage_bytes = W_A_BYTES + s.Co * 128;
+    const size_t table_bytes = (size_t)W_NTAB * 5 * prm.gs * W_TAB_STRIDE * 4;
+    static const int cfg[3][2] = {{3, 3}, {3, 2}, {2, 2}};   // (margin, stages), most wanted first
+    for (int k = 0; k < 3; ++k) {
+        prm.mlo = cfg[k][0];
+        prm.stages = cfg[k][1];
+        prm.wx = (1 << prm.tx_log) + 2 + 2 * prm.mlo;
+        prm.wy = (1 << prm.ty_log) + 2 + 2 * prm.mlo;
+        prm.win_rows = (prm.wx * prm.wy + 7) / 8 * 8;
+        prm.win_bytes = prm.npatch * prm.win_rows * 128;
+        const size_t smem = (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + table_bytes + 1024;
+        if (smem <= (size_t)W_SMEM_MAX) return true;
+    }
+    return false;
+}
+
+// Test hook (host only, no device work): does the window kernel serve a [B, C, H, W] -> [B, Co, H, W] 3x3 / stride 1 /
+// pad 1 call with DG deform groups, and with which geometry.  meta[10] = {served, tiles, patch_w, patch_h, patches per
+// tile, window_w, window_h, margin, stages, dynamic shared memory bytes}; coords as dcn_tc_tile_plan (128 rows per tile).
+int dcn_win_plan_query(int B, int C, int H, int W, int Co, int DG, int* meta, int* coords, size_t max_rows) {
+    DcnTcParams prm;
+    memset(&prm, 0, sizeof(prm));
+    int rc = dcn_make_shape(&prm.s, B, C, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, DG);
+    if (rc) return rc;
+    prm.P = prm.s.Ho * prm.s.Wo;
+    prm.total_rows = B * prm.P;
+    prm.cdg = C / DG;
+    prm.gs = prm.cdg >= TBK ? 1 : TBK / prm.cdg;
+    const bool ok = dcn_tc_eligible(prm.s) && dcn_win_mode() != 0 && dcn_win_plan(prm);
+    for (int i = 0; i < 10; ++i) meta[i] = 0;
+    if (!ok) return 0;
+    const size_t table_bytes = (size_t)W_NTAB * 5 * prm.gs * W_TAB_STRIDE * 4;
+    meta[0] = 1;
+    meta[1] = prm.tiles;
+    meta[2] = 1 << prm.tx_log;
+    meta[3] = 1 << prm.ty_log;
+    meta[4] = prm.npatch;
+    meta[5] = prm.wx;
+    meta[6] = prm.wy;
+    meta[7] = prm.mlo;
+    meta[8] = prm.stages;
+    meta[9] = (int)((size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + table_bytes + 1024);
+    if (coords) {
+        MREFSR_CHECK((size_t)prm.tiles * W_BM <= max_rows, ERR_BAD_ARG, "window plan: %d rows, room for %zu",
+                     prm.tiles * W_BM, max_rows);
+        for (int t = 0; t < prm.tiles; ++t)
+            for (int r = 0; r < W_BM; ++r) {
+                int b = -1, oy = -1, ox = -1;
+                if (!dcn_row_coords(prm, t, r, b, oy, ox)) b = oy = ox = -1;
+                int* c = coords + ((size_t)t * W_BM + r) * 3;
+                c[0] = b;
+                c[1] = oy;
+                c[2] = ox;
+            }
+    }
+    return 0;
+}
+
+// Called by dcn_forward_tc_impl (dcn_tc.cu) with everything but the tile plan filled in.  Returns 1 when the shape is
+// not served here (the caller launches dcn_tc_split_kernel), 0 on success, < 0 on error.
+int dcn_win_launch(const CUtensorMap& mapW, const float* xt, const float* off, const float* mask,
+                   const long long* max_idx, const float* bias, DcnTcParams prm, cudaStream_t st) {
+    if (dcn_win_mode() == 0 || !dcn_win_plan(prm)) return 1;
+    const DcnShape& s = prm.s;
+    prm.nbuf = 2;
+    CUtensorMap mapX;
+    int rc = make_tensor_map_4d(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xt, (uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H,
+                                (uint64_t)s.B, TBK, (uint32_t)prm.wx, (uint32_t)prm.wy, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const size_t table_bytes = (size_t)W_NTAB * 5 * prm.gs * W_TAB_STRIDE * 4;
+    const size_t smem = (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + table_bytes + 1024;
+    int grid = sm_count();
+    if (grid > prm.tiles) grid = prm.tiles;
+    ScopedTiming tm(MREFSR_K_DCN_FWD, st);
+#define MREFSR_LAUNCH_WIN(F, G)                                                                                     \
+    do {                                                                                                            \
+        auto kern = dcn_win_kernel<F, G>;                                                                           \
+        MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, W_THREADS, smem, st>>>(mapW, mapX, xt, off, F ? nullptr : mask, F ? max_idx : nullptr, bias, prm); \
+    } while (0)
+    if (prm.fused) {
+        if (prm.gs == 1) MREFSR_LAUNCH_WIN(true, 1);
+        else if (prm.gs == 2) MREFSR_LAUNCH_WIN(true, 2);
+        else MREFSR_LAUNCH_WIN(true, 4);
+    } else {
+        if (prm.gs == 1) MREFSR_LAUNCH_WIN(false, 1);
+        else if (prm.gs == 2) MREFSR_LAUNCH_WIN(false, 2);
+        else MREFSR_LAUNCH_WIN(false, 4);
+    }
+#undef MREFSR_LAUNCH_WIN
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace mrefsr

@@ -66,6 +66,24 @@ int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_byt
     return 0;
 }
 
+int make_tensor_map_4d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
+                       uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box0, uint32_t box1, uint32_t box2,
+                       CUtensorMapSwizzle swizzle) {
+    PFN_encodeTiled fn = encode_fn();
+    MREFSR_CHECK(fn != nullptr, ERR_NOT_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {d0 * elem_bytes, d0 * d1 * elem_bytes, d0 * d1 * d2 * elem_bytes};
+    cuuint32_t box[4] = {box0, box1, box2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, dtype, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MREFSR_CHECK(r == CUDA_SUCCESS, ERR_BAD_ARG,
+                 "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu x %llu box %u x %u x %u", (int)r,
+                 (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3, box0,
+                 box1, box2);
+    return 0;
+}
+
 // ---------------------------------------------------------------- per-kernel timing
 static std::atomic<int> g_timing_on{0};
 struct EvPair {

@@ -322,33 +322,41 @@ sys.path.insert(0, %r)
 from mrefsr_b200.dcn import dynagg_dcn_forward, dcn_forward_raw
 g = torch.Generator().manual_seed(123)
 h = hashlib.sha256()
-for (b, c, hw, s) in ((3, 64, 24, 4), (2, 128, 20, 2), (2, 256, 12, 1)):          # 4 / 2 / 1 deform groups per slab
-    x = torch.randn(b, c, hw, hw + 8, generator=g).cuda()
-    conv_out = (torch.randn(b, 216, hw, hw + 8, generator=g) * 0.7).cuda()
-    hp, wp = hw // s - 2, (hw + 8) // s - 2
-    idx = torch.randint(0, hp * wp, (b, hp, wp), generator=g).cuda()
+for (b, c, hh, ww, s) in ((3, 64, 24, 32, 4), (2, 128, 20, 28, 2), (2, 256, 16, 24, 1)):   # 4 / 2 / 1 deform groups per slab
+    x = torch.randn(b, c, hh, ww, generator=g).cuda()
+    conv_out = (torch.randn(b, 216, hh, ww, generator=g) * 0.7).cuda()
+    hp, wp = hh // s - 2, ww // s - 2
+    ys, xs = torch.meshgrid(torch.arange(hp), torch.arange(wp), indexing='ij')
+    coherent = torch.stack([(ys + dy).clamp(0, hp - 1) * wp + (xs + dx).clamp(0, wp - 1)
+                            for dy, dx in ((1, -2), (-3, 2), (0, 0))][:b])
     w = (torch.randn(c, c, 3, 3, generator=g) * 0.05).cuda()
     bias = torch.randn(c, generator=g).cuda()
-    y = dynagg_dcn_forward(x, conv_out, idx, s, w, bias, 8)
+    for idx in (torch.randint(0, hp * wp, (b, hp, wp), generator=g), coherent):
+        y = dynagg_dcn_forward(x, conv_out, idx.cuda(), s, w, bias, 8)
+        h.update(y.cpu().numpy().tobytes())
     off, mask = conv_out[:, :144].contiguous(), torch.sigmoid(conv_out[:, 144:]).contiguous()
-    z = dcn_forward_raw(x, off, mask, w, bias, (1, 1), (1, 1), (1, 1), 1, 8, mode='tf32')
+    for shift in (0.0, 5.0):           # operator entry point: small offsets, and the same plus a common translation
+        z = dcn_forward_raw(x, off + shift, mask, w, bias, (1, 1), (1, 1), (1, 1), 1, 8, mode='tf32')
+        h.update(z.cpu().numpy().tobytes())
     torch.cuda.synchronize()
-    h.update(y.cpu().numpy().tobytes())
-    h.update(z.cpu().numpy().tobytes())
 print('HASH', h.hexdigest())
 '''
 
 
 def test_kernel_variants_agree_bit_for_bit():
-    """The role-split kernel (default), the 17-warp kernel (MREFSR_DCN_SPLIT=0) and the linear tile mapping
-    (MREFSR_DCN_TILE=linear) are the same arithmetic in a different schedule: identical bits, fused and operator
-    entry points, 1 / 2 / 4 deform groups per slab.  The knobs are read once per process, hence the subprocesses."""
+    """The shared-memory window kernel (default), the role-split 256-row kernel (MREFSR_DCN_WIN=0), the 17-warp kernel
+    (+ MREFSR_DCN_SPLIT=0) and the linear tile mapping (+ MREFSR_DCN_TILE=linear) are the same arithmetic in a
+    different schedule / through a different corner-fetch path: identical bits, fused and operator entry points,
+    1 / 2 / 4 deform groups per slab, random flows (window misses: global-memory corners) and coherent flows (window
+    hits, windows hanging over the image border).  The knobs are read once per process, hence the subprocesses."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hashes = {}
-    for name, env in (('split+2d', {}), ('17-warp', {'MREFSR_DCN_SPLIT': '0'}), ('linear', {'MREFSR_DCN_TILE': 'linear'})):
+    for name, env in (('window', {}), ('split+2d', {'MREFSR_DCN_WIN': '0'}),
+                      ('17-warp', {'MREFSR_DCN_WIN': '0', 'MREFSR_DCN_SPLIT': '0'}),
+                      ('linear', {'MREFSR_DCN_WIN': '0', 'MREFSR_DCN_TILE': 'linear'})):
         e = dict(os.environ)
         e.update(env)
         r = subprocess.run([sys.executable, '-c', _VARIANT_SCRIPT % root], env=e, capture_output=True, text=True,
@@ -358,3 +366,58 @@ def test_kernel_variants_agree_bit_for_bit():
         assert lines, (name, r.stdout[-500:], r.stderr[-500:])
         hashes[name] = lines[-1]
     assert len(set(hashes.values())) == 1, hashes
+
+
+def _win_served(b, c, h, w, co, dg):
+    import ctypes
+    from mrefsr_b200 import _lib
+    meta = (ctypes.c_int * 10)()
+    assert _lib.lib().mrefsr_dcn_win_plan(b, c, h, w, co, dg, ctypes.cast(meta, ctypes.c_void_p), None, 0) == 0
+    return list(meta)
+
+
+@pytest.mark.parametrize('cfg', [dict(b=3, c=64, h=48, w=64, s=4), dict(b=2, c=128, h=40, w=48, s=2),
+                                 dict(b=2, c=256, h=24, w=40, s=1), dict(b=2, c=64, h=75, w=75, s=1)])
+@pytest.mark.parametrize('flow', ['translate', 'piecewise', 'border'])
+def test_window_gather_vs_oracle(cfg, flow):
+    """Shared-memory window gather (csrc/dcn_win.cu) against the oracle on the flows it was built for: a common
+    translation + small learned residual ('translate': every corner from the window), two regions with different
+    translations ('piecewise': patches on the seam mix window and global-memory corners), and translations that push
+    the windows over the image border ('border': the copy engine's zero fill must equal the reference's "corners
+    outside the plane contribute 0", deform_conv_cuda_kernel.cu:468-497)."""
+    b, c, h, w, s = (cfg[k] for k in ('b', 'c', 'h', 'w', 's'))
+    dg = 8
+    assert _win_served(b, c, h, w, c, dg)[0] == 1, 'shape is not served by the window kernel: the test would not test it'
+    g = torch.Generator().manual_seed(31)
+    hc, wc = h // s, w // s
+    hp, wp = hc - 2, wc - 2
+    ys, xs = torch.meshgrid(torch.arange(hp), torch.arange(wp), indexing='ij')
+    idx = []
+    for i in range(b):
+        if flow == 'translate':
+            dy, dx = (2, -1) if i % 2 == 0 else (-1, 3)
+            m = (ys + dy).clamp(0, hp - 1) * wp + (xs + dx).clamp(0, wp - 1)
+        elif flow == 'piecewise':
+            left = (ys + 1).clamp(0, hp - 1) * wp + (xs + 2).clamp(0, wp - 1)
+            right = (ys - 2).clamp(0, hp - 1) * wp + (xs - 1).clamp(0, wp - 1)
+            m = torch.where(xs < wp // 2 + i, left, right)
+        else:
+            dy, dx = (hp - 2, wp - 2) if i % 2 == 0 else (-(hp - 2), -(wp - 2))
+            m = (ys + dy).clamp(0, hp - 1) * wp + (xs + dx).clamp(0, wp - 1)
+        idx.append(m)
+    max_idx = torch.stack(idx)
+    x = torch.randn(b, c, h, w, generator=g)
+    conv_out = torch.randn(b, 3 * dg * 9, h, w, generator=g) * 0.6
+    conv_out[:, :2 * dg * 9, ::7, ::5] *= 8          # a few large learned offsets: outside the window margin
+    wgt = torch.randn(c, c, 3, 3, generator=g) * (c * 9) ** -0.5
+    bias = torch.randn(c, generator=g) * 0.1
+    key = {1: 'relu3_1', 2: 'relu2_1', 4: 'relu1_1'}[s]
+    pre = torch.stack([oracle.pre_offsets_oracle(max_idx[i])[key] for i in range(b)], 0)
+    off, mask = oracle.dynagg_offsets_oracle(conv_out, pre, dg)
+    ref = oracle.modulated_deform_conv_oracle(x, off, mask, wgt, bias, 1, 1, 1, 1, dg, dtype=torch.float64)
+    out = D.dynagg_dcn_forward(x.to(DEV), conv_out.to(DEV), max_idx.to(DEV), s, wgt.to(DEV), bias.to(DEV), dg)
+    assert rel_err(out, ref) <= TOL
+    # the operator entry point with the same (materialised) offsets: window predicted from the offsets themselves
+    out2 = D.dcn_forward_raw(x.to(DEV), off.to(DEV), mask.to(DEV), wgt.to(DEV), bias.to(DEV), (1, 1), (1, 1), (1, 1), 1,
+                             dg, mode='tf32')
+    assert rel_err(out2, ref) <= TOL
