@@ -39,7 +39,7 @@ struct DcnTcParams {
     // dcn_win.cu only: per patch a (wx x wy)-pixel window of the NHWC input, mlo pixels of margin on the low side,
     // is staged in shared memory; win_rows = 128-byte rows reserved per patch window (multiple of 8),
     // win_bytes = bytes of one window buffer (all patches of a tile)
-    int wx, wy, mlo, win_rows, win_bytes, npatch;
+    int wx, wy, mlo, win_rows, win_bytes, npatch, rdepth, dbg;   // rdepth: raw offset / mask ring depth in K steps
 };
 
 // (tile, row within the tile) -> (sample, oy, ox); false for padding rows

@@ -2,17 +2,24 @@
 //
 // Same operator as dcn_tc.cu (basicsr/ops/dcn/src/deform_conv_cuda.cpp:490-569 + deform_conv_cuda_kernel.cu:571-633,
 // optionally with the DynAgg glue of ref_mrapa_restoration_arch.py:55-68 folded in), same arithmetic bit for bit, but
-// a different corner-fetch mechanism.  dcn_tc_split_kernel gathers every corner through L1 with 256-bit loads and
-// sits at the LSU's ceiling of about one 32-byte sector per clock per SM (profiles/r01u_dcn_tc_split_ncu_full.txt):
-// with C/dg = 8 channels per deform group a sampling point is four scattered sectors, 6.7x the algorithmic bytes.
-// In MRefSR the offsets are a large but spatially COHERENT flow (the matcher's arg-max map: a reference is mostly a
-// translated view) plus a small learned residual, so all nine taps of a patch of output positions sample one compact
-// window of the reference features.  This kernel stages that window in shared memory with ONE bulk tensor copy per
-// (patch, 32-channel slab) -- TMA box {32 channels, wx, wy} of the NHWC input, 128-byte swizzle, out-of-image pixels
-// zero-filled by the copy engine, which is exactly the reference's "corners outside the plane contribute 0" -- and
-// reads the corners with LDS.128 (128 B/clk/SM instead of ~32 B/clk/SM through L1).  Sampling points that fall
-// outside the window (incoherent flow, large learned offsets) take the global-memory path of dcn_tc.cu per item, so
-// the result never depends on the window guess.
+// different mechanisms for the two streams that bound dcn_tc_split_kernel:
+//
+//  * corners.  dcn_tc_split_kernel gathers every corner through L1 with 256-bit loads: with C/dg = 8 channels per
+//    deform group a sampling point is four scattered 32-byte sectors, 6.7x the algorithmic bytes, at about one sector
+//    per clock per SM.  In MRefSR the offsets are a large but spatially COHERENT flow (the matcher's arg-max map: a
+//    reference is mostly a translated view) plus a small learned residual, so all nine taps of a patch of output
+//    positions sample one compact window of the reference features.  This kernel stages that window in shared memory
+//    with ONE bulk tensor copy per (patch, 32-channel slab) -- TMA box {32 channels, wx, wy} of the NHWC input,
+//    128-byte swizzle, out-of-image pixels zero-filled by the copy engine, which is exactly the reference's "corners
+//    outside the plane contribute 0" -- and reads the corners with LDS.128 (128 B/clk/SM).  Sampling points outside
+//    the window (incoherent flow, large learned offsets) take the global-memory path of dcn_tc.cu per item, so the
+//    result never depends on the window guess.
+//  * offsets / masks.  27 dg planes per output position are the larger half of the algorithmic bytes.  Loaded into
+//    registers two tables ahead (dcn_tc_split_kernel, and the first version of this file) they are bound by memory
+//    latency x loads in flight: measured on B200, the first version ran at the SAME speed on coherent and random flows
+//    (2.87 ms at the large scale), i.e. the corner path was not what it waited for.  Here four loader warps stream
+//    them with cp.async (4-byte, position-major coalesced) into a shared-memory ring 6-8 K steps deep: no registers
+//    held across the latency, 36-45 KB in flight per SM.
 //
 //   CTA tile   : 128 output positions (one 16x8 / 8x16 patch or two 8x8 patches) x all Co.  M = 128 per MMA, two TMEM
 //                accumulators at every Co <= 256 (the 256-row kernel has one at Co = 256).
@@ -21,13 +28,10 @@
 //                the rounded offset of the centre tap of group 0) and mlo = 3 (2 when shared memory is short):
 //                residuals in [-mlo, mlo) hit.  Double buffered; reloaded per (tile, slab) by a dedicated warp.
 //   K loop     : (32-channel slab) x (tap), as in dcn_tc.cu; A tile [128 x 32] fp32 produced on the SM, B tile by TMA.
-//   warps      : 16 gather (thread = (row, 8-channel chunk): table read, 8 LDS.128 or 4 LDG.256, blend, round to
-//                tf32, two swizzled 16-byte stores; warps 0..3 also drain TMEM), 8 decode (thread = tile row; the two
-//                halves of the decode warps take even / odd K steps, raw offset / mask loads two of their own tables
-//                ahead), 1 MMA issuer, 1 window loader = 26 warps under a 72-register cap.
-//   table entry: base < 0: ~(128-byte row index of the top-left corner inside the window buffer); base >= 0: element
-//                offset into the NHWC input with the two addressability flags of dcn_tc.cu; + 4 bilinear weights with
-//                mask and corner validity folded in (identical in both paths, so both blend to the same bits).
+//   warps      : 16 gather (thread = (row, 8-channel chunk): raw offset / mask / arg-max words from the ring, sample
+//                decode in registers -- no sample table --, 8 LDS.128 or 4 LDG.256, blend, round to tf32, two swizzled
+//                16-byte stores; warps 0..3 also drain TMEM), 4 raw loaders (thread = tile row), 1 MMA issuer,
+//                1 window loader = 22 warps, 88 registers.
 #include <stdlib.h>
 #include "dcn_tc.cuh"
 #include "../../include/mrefsr_b200.h"
@@ -37,19 +41,52 @@ namespace mrefsr {
 constexpr int W_BM = 128;                         // rows (output positions) per CTA tile
 constexpr int W_A_BYTES = W_BM * 128;             // A stage: 128 rows x 32 fp32
 constexpr int W_GW = 16;                          // gather warps (threads 0..511): one (row, chunk) item each per K step
-constexpr int W_DW = 8;                           // decode warps: 0..3 take even K steps, 4..7 odd ones
-constexpr int W_MMA_WARP = W_GW + W_DW;
+constexpr int W_LW = 4;                           // raw-loader warps (thread = tile row)
+constexpr int W_MMA_WARP = W_GW + W_LW;
 constexpr int W_WIN_WARP = W_MMA_WARP + 1;
-constexpr int W_THREADS = (W_WIN_WARP + 1) * 32;  // 832
-constexpr int W_NTAB = 4;                         // sample-table ring depth
-constexpr int W_TAB_STRIDE = W_BM + 4;
+constexpr int W_THREADS = (W_WIN_WARP + 1) * 32;  // 704
+constexpr int W_RS = W_BM + 8;                    // words per plane of a raw-ring entry (+8: the 4 groups of a warp hit 32 banks)
+constexpr int W_TINFO_WORDS = 4 * W_BM;           // per-tile row state: yx, b*H, window origin, flow cell
 constexpr int W_SMEM_MAX = 227 * 1024;
+
+// Ablation switches for bottleneck hunting (variant builds only: -DMREFSR_DCN_DEBUG, env MREFSR_DCN_DBG = bit mask;
+// results are wrong by design): 1 gather warps skip corner loads / blend / stores, 2 no MMAs (commits only),
+// 4 raw loaders copy nothing, 8 no weight-tile TMA, 16 no window TMA, 32 no sample decode.
+#ifdef MREFSR_DCN_DEBUG
+#define DBG(bit) (prm.dbg & (bit))
+#else
+#define DBG(bit) (false)
+#endif
+
+// try_wait with a suspend-time hint: the warp is parked by the hardware for up to `ns` instead of spinning through
+// the issue slots the working warps need
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all cp.async of this thread issued so far have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // 8 consecutive channels (chunk ch of the slab) of window row `pix`: two 16-byte pieces at the 128-byte-swizzled
 // positions the bulk tensor copy wrote them to (window buffers are 1024-byte aligned, so the swizzle phase of a row
@@ -66,7 +103,7 @@ __device__ __forceinline__ F8 lds_corner(uint32_t win, int pix, int ch) {
 }
 
 // Window of patch p of a tile: sample b and the image coordinates (wy0, wx0) of its first pixel.  Computed identically
-// by the window loader and by the decode threads.  false: the patch lies beyond the batch (no window).
+// by the window loader and by the raw loaders.  false: the patch lies beyond the batch (no window).
 template <bool FUSED>
 __device__ __forceinline__ bool win_patch_geom(const DcnTcParams& prm, int tile, int p, const float* __restrict__ offset,
                                                const long long* __restrict__ max_idx, int& b, int& wy0, int& wx0) {
@@ -138,13 +175,9 @@ __device__ __forceinline__ void win_epilogue_tile(const DcnTcParams& prm, const 
     if (lane == 0) mbar_arrive(tempty_bar);
 }
 
-template <int GS>
-struct WinRaw {                                   // inputs of one table row (one tap, GS deform groups) + its tile state
-    float dy[GS], dx[GS], mk[GS];
-    int mi, fyx, yx, bH, worg;
-};
-
-template <bool FUSED, int GS>
+// Shared memory: [stages x (A 16 KB + B Co*128)] [2 window buffers] [barriers 256 B] [tile info 2 x 2 KB]
+//                [raw ring: rdepth x (3 gs + 1) planes x W_RS words]
+template <bool FUSED>
 __global__ void __launch_bounds__(W_THREADS, 1)
 dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
@@ -153,21 +186,22 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const DcnShape& s = prm.s;
-    const int S = prm.stages;
+    const int S = prm.stages, RD = prm.rdepth, GS = prm.gs;
     uint8_t* win = smem + (size_t)S * prm.stage_bytes;                 // two window buffers
     uint64_t* bars = reinterpret_cast<uint64_t*>(win + 2 * (size_t)prm.win_bytes);
-    uint64_t* full = bars;                    // [S]  A produced (16 gather warps) + B landed (expect_tx)
-    uint64_t* empty = bars + S;               // [S]  stage consumed by the MMAs
-    uint64_t* tfull = bars + 2 * S;           // [2]  accumulator complete
-    uint64_t* tempty = tfull + 2;             // [2]  accumulator drained (4 epilogue warps)
-    uint64_t* tab_full = tempty + 2;          // [W_NTAB]  (4 decode warps)
-    uint64_t* tab_empty = tab_full + W_NTAB;  // [W_NTAB]  (16 gather warps)
-    uint64_t* win_full = tab_empty + W_NTAB;  // [2]  window landed (expect_tx)
-    uint64_t* win_empty = win_full + 2;       // [2]  window released (16 gather warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(win_empty + 2);
-    const int tab_n = GS * W_TAB_STRIDE;
-    int* tab_base = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
-    float* tab_w = reinterpret_cast<float*>(tab_base + W_NTAB * tab_n);
+    uint64_t* full = bars;                    // [S]   A produced (16 gather warps) + B landed (expect_tx)
+    uint64_t* empty = full + 4;               // [S]   stage consumed by the MMAs
+    uint64_t* tfull = empty + 4;              // [2]   accumulator complete
+    uint64_t* tempty = tfull + 2;             // [2]   accumulator drained (4 epilogue warps)
+    uint64_t* win_full = tempty + 2;          // [2]   window landed (expect_tx)
+    uint64_t* win_empty = win_full + 2;       // [2]   window released (16 gather warps)
+    uint64_t* raw_full = win_empty + 2;       // [RD <= 8]  raw words landed (128 loader threads)
+    uint64_t* raw_empty = raw_full + 8;       // [RD <= 8]  raw words consumed (16 gather warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 8);
+    int* tinfo = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);       // [2][4][W_BM]
+    const int raw_planes = 3 * GS + 1;
+    const int raw_words = raw_planes * W_RS;                                            // words per ring entry
+    float* raw = reinterpret_cast<float*>(tinfo + 2 * W_TINFO_WORDS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Co = s.Co, C = s.C, K = prm.taps, P = prm.P;
@@ -186,9 +220,9 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             mbar_init(&win_full[a], 1);
             mbar_init(&win_empty[a], W_GW);
         }
-        for (int a = 0; a < W_NTAB; ++a) {
-            mbar_init(&tab_full[a], GS == 4 ? W_DW : W_DW / 2);
-            mbar_init(&tab_empty[a], W_GW);
+        for (int a = 0; a < RD; ++a) {
+            mbar_init(&raw_full[a], W_LW * 32);
+            mbar_init(&raw_empty[a], W_GW);
         }
         fence_mbar_init();
     }
@@ -206,6 +240,7 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const int ch = tid & 3;                    // 8-channel chunk within the 32-channel slab
         const int r0 = tid >> 2;                   // tile row
         const int gsub = (ch * 8) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
+        const int pixbase = (r0 >> prm.sub_log) * prm.win_rows;
         const uint32_t a_off0 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch) ^ (r0 & 7)) << 4);
         const uint32_t win_u32 = smem_u32(win);
         const bool is_epi = warp < 4;
@@ -222,31 +257,85 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             }
         };
         auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
-            while (!mbar_try_wait(bar, parity)) poll_epilogue();
+            while (!mbar_try_wait_hint(bar, parity, is_epi ? 200u : 2000u)) poll_epilogue();
         };
-        int stage = 0, c_slab = 0, c_tap = 0, wq = 0;   // wq: index of the current (tile, slab) window
-        uint32_t phase = 0;
+        int stage = 0, c_slab = 0, c_tap = 0, c_ti = 0, c_tj = 0, wq = 0, rslot = 0, tiq = 0;
+        uint32_t phase = 0, rphase = 0;
+        int row_yx = -1, row_bH = 0, row_worg = 0, row_qyx = 0;     // per-tile state of this thread's row (from tinfo)
         const int dx_elems = C, dy_elems = s.W * C;
         const int wxr = prm.wx;
         for (int kb = 0; kb < total_kb; ++kb) {
-            const int g_slot = kb & (W_NTAB - 1);
-            const uint32_t g_phase = (uint32_t)(kb / W_NTAB) & 1u;
             poll_epilogue();
             const float* xs = xt + (c_slab * TBK + ch * 8);
-            const int* tb = tab_base + g_slot * tab_n + gsub * W_TAB_STRIDE + r0;
-            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * W_TAB_STRIDE + r0;
             const uint32_t wcur = win_u32 + (uint32_t)(wq & 1) * (uint32_t)prm.win_bytes;
+            wait_poll(&raw_full[rslot], rphase);
+            if (c_tap == 0 && c_slab == 0) {       // first K step of a tile: this row's state, written by its raw loader
+                const int* ti = tinfo + (tiq & 1) * W_TINFO_WORDS + r0;
+                row_yx = ti[0];
+                row_bH = ti[W_BM];
+                row_worg = ti[2 * W_BM];
+                row_qyx = ti[3 * W_BM];
+                ++tiq;
+            }
+            // ---- raw words of (row, deform group, tap)
+            const float* rw = raw + rslot * raw_words + gsub * 3 * W_RS + r0;
+            const float raw_dy = rw[0], raw_dx = rw[W_RS], raw_mk = rw[2 * W_RS];
+            const int raw_mi = __float_as_int(raw[rslot * raw_words + 3 * GS * W_RS + r0]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rslot]);
+            // ---- sample decode: same arithmetic as dcn_tc_split_kernel's (bit for bit) + the window test
+            int bf = ~pixbase;
+            float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+            if (!DBG(32)) {
+                const bool row_ok = row_yx >= 0;
+                float y = (float)((row_yx >> 16) * s.sh - s.ph + c_ti * s.dh);
+                float x = (float)((row_yx & 0xffff) * s.sw - s.pw + c_tj * s.dw);
+                if (FUSED) {
+                    float fly = 0.f, flx = 0.f;
+                    const int fy = (row_qyx >> 16) - c_ti, fx = (row_qyx & 0xffff) - c_tj;
+                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
+                        const int my = (int)__umulhi((unsigned)raw_mi, prm.wp_magic), mx = raw_mi - my * prm.wp;
+                        fly = (float)((my - fy) * prm.flow_scale);
+                        flx = (float)((mx - fx) * prm.flow_scale);
+                    }
+                    y += raw_dy + fly;
+                    x += raw_dx + flx;
+                } else {
+                    y += raw_dy;
+                    x += raw_dx;
+                }
+                const bool in = row_ok && y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W;
+                const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-raw_mk)) : (mask ? raw_mk : 1.f);
+                const float fy0 = floorf(y), fx0 = floorf(x);
+                const int y0 = (int)fy0, x0 = (int)fx0;
+                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
+                const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
+                int base = ((row_bH + yc) * s.W + xc) * C;
+                base |= (tx0 && tx1) ? 1 : 0;
+                base |= (ty0 && ty1) ? 2 : 0;
+                const int ry = y0 - (row_worg >> 16), rx = x0 - ((row_worg << 16) >> 16);
+                const bool hit = in && ry >= 0 && rx >= 0 && ry <= prm.wy - 2 && rx <= prm.wx - 2;
+                const int pix = pixbase + ry * prm.wx + rx;
+                const float hym = hy * mk, lym = ly * mk;
+                bf = hit ? ~pix : (in ? base : ~pixbase);
+                w0 = (in && ty0 && tx0) ? hym * hx : 0.f;
+                w1 = (in && ty0 && tx1) ? hym * lx : 0.f;
+                w2 = (in && ty1 && tx0) ? lym * hx : 0.f;
+                w3 = (in && ty1 && tx1) ? lym * lx : 0.f;
+            }
             if (c_tap == 0) wait_poll(&win_full[wq & 1], (uint32_t)(wq >> 1) & 1u);
-            wait_poll(&tab_full[g_slot], g_phase);
             wait_poll(&empty[stage], phase ^ 1);
             uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
             if (tid == 0) {       // weight tile of this K step (TMA, lands on the same full barrier)
-                mbar_expect_tx(&full[stage], Co * 128);
-                tma_load_3d(A + W_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
+                if (DBG(8)) {
+                    mbar_arrive(&full[stage]);
+                } else {
+                    mbar_expect_tx(&full[stage], Co * 128);
+                    tma_load_3d(A + W_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
+                }
             }
-            {
-                const int bf = tb[0];
-                const float w0 = tw[0], w1 = tw[tab_n], w2 = tw[2 * tab_n], w3 = tw[3 * tab_n];
+            if (!DBG(1)) {
                 F8 v0, v1, v2, v3;
                 if (bf < 0) {                      // all four corners inside the staged window
                     const int pix = ~bf;
@@ -282,15 +371,22 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&full[stage]);
-                mbar_arrive(&tab_empty[g_slot]);
                 if (c_tap == K - 1) mbar_arrive(&win_empty[wq & 1]);   // last tap of the slab: window may be refilled
             }
             if (++stage == S) {
                 stage = 0;
                 phase ^= 1;
             }
+            if (++rslot == RD) {
+                rslot = 0;
+                rphase ^= 1;
+            }
+            if (++c_tj == s.kw) {
+                c_tj = 0;
+                ++c_ti;
+            }
             if (++c_tap == K) {
-                c_tap = 0;
+                c_tap = c_ti = c_tj = 0;
                 ++wq;
                 if (++c_slab == prm.n_slabs) {
                     c_slab = 0;
@@ -306,171 +402,97 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             ++ep_done;
         }
     } else if (warp < W_MMA_WARP) {
-        // ------------------------------------------------------------------ decode warps
-        // Work split between the two halves of the decode warps (par = 0 / 1).  GS <= 2: by K step -- a thread decodes
-        // all GS entries of its row for the K steps kb = par (mod 2).  GS == 4: by deform group -- a thread decodes
-        // groups 2 par, 2 par + 1 of its row for every K step (four entries plus two raw sets do not fit 72 registers).
-        constexpr bool PARG = GS == 4;
-        constexpr int GSL = PARG ? GS / 2 : GS;                    // table entries per thread per decoded K step
-        constexpr int KSTEP = PARG ? 1 : 2;                        // K steps between two tables of a thread
-        const int dwi = warp - W_GW;
-        const int par = dwi >> 2;
-        const int kb0 = PARG ? 0 : par;                            // first K step of this thread
-        const int g0 = PARG ? par * GSL : 0;                       // first deform group (within the slab) of this thread
-        const int erow = (dwi & 3) * 32 + lane;                    // tile row owned by this thread
+        // ------------------------------------------------------------------ raw loaders (thread = tile row)
+        // Per K step: cp.async of this row's offset / mask words (GS deform groups of the slab, one tap) and, in fused
+        // mode, of the arg-max word of the row's flow cell for this tap, into ring entry kb % RD.  Completion: one
+        // cp.async.mbarrier arrive per thread.  At the first K step of a tile the thread also publishes the row's tile
+        // state (coordinates, window origin) with ordinary stores, which an asynchronous arrive would not order, so
+        // that step waits for its copies and arrives normally.
+        const int erow = (warp - W_GW) * 32 + lane;
         const int my_patch = erow >> prm.sub_log;
-        const int pixbase = my_patch * prm.win_rows;
-        const unsigned kw_magic = 65536u / (unsigned)s.kw + 1u;    // tap / kw == (tap * kw_magic) >> 16 for tap < 256
-        // ---- load cursor (tile, slab, tap) and the per-tile state of this thread's row
-        int l_tile = blockIdx.x, l_slab = 0, l_tap = 0, l_dg0 = 0;
-        bool tile_changed = false;
-        int row_yx = -1, row_bH = 0, row_qyx = 0, row_idx0 = 0, row_worg = 0;
+        const uint32_t raw_u32 = smem_u32(raw);
+        int rslot = 0, l_tap = 0, l_ti = 0, l_tj = 0, l_slab = 0, l_tile = blockIdx.x, tiq = 0;
+        uint32_t rphase = 0;
+        int row_yx = -1, row_qyx = 0, row_idx0 = 0;
         const float* row_off = offset;
         const float* row_msk = mask;
-        auto decode_rows = [&](int tile) {
-            int b = 0, oy = 0, ox = 0, pb = 0, wy0 = 0, wx0 = 0;
-            row_yx = -1;
-            row_worg = 0;
-            if (win_patch_geom<FUSED>(prm, tile, my_patch, offset, max_idx, pb, wy0, wx0))
-                row_worg = (int)(((unsigned)wy0 << 16) | ((unsigned)wx0 & 0xffffu));
-            if (dcn_row_coords(prm, tile, erow, b, oy, ox)) {
-                const int p = oy * s.Wo + ox;
-                row_yx = (oy << 16) | ox;
-                row_bH = b * s.H;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            bool tile_start = false;
+            if (l_tap == 0 && l_slab == 0) {
+                tile_start = true;
+                int b = 0, oy = 0, ox = 0, pb = 0, wy0 = 0, wx0 = 0, worg = 0, bH = 0;
+                row_yx = -1;
+                row_qyx = 0;
+                if (win_patch_geom<FUSED>(prm, l_tile, my_patch, offset, max_idx, pb, wy0, wx0))
+                    worg = (int)(((unsigned)wy0 << 16) | ((unsigned)wx0 & 0xffffu));
+                if (dcn_row_coords(prm, l_tile, erow, b, oy, ox)) {
+                    const int p = oy * s.Wo + ox;
+                    row_yx = (oy << 16) | ox;
+                    bH = b * s.H;
+                    if (FUSED) {
+                        row_off = offset + (size_t)b * 3 * s.DG * K * P + p;
+                        row_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
+                        row_idx0 = b * prm.hp * prm.wp;
+                    } else {
+                        row_off = offset + (size_t)b * 2 * s.DG * K * P + p;
+                        if (mask) row_msk = mask + (size_t)b * s.DG * K * P + p;
+                    }
+                }
+                int* ti = tinfo + (tiq & 1) * W_TINFO_WORDS + erow;
+                ti[0] = row_yx;
+                ti[W_BM] = bH;
+                ti[2 * W_BM] = worg;
+                ti[3 * W_BM] = row_qyx;
+                ++tiq;
+            }
+            mbar_wait(&raw_empty[rslot], rphase ^ 1);
+            if (row_yx >= 0 && !DBG(4)) {
+                const uint32_t dst = raw_u32 + (uint32_t)(rslot * raw_words + erow) * 4u;
+                const int dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
+                for (int g = 0; g < GS; ++g) {
+                    const int dgi = dg0 + g;
+                    const uint32_t d = dst + (uint32_t)(g * 3 * W_RS) * 4u;
+                    if (!FUSED) {
+                        const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
+                        cp_async4(d, row_off + o);
+                        cp_async4(d + W_RS * 4u, row_off + o + (unsigned)P);
+                        if (mask) cp_async4(d + 2 * W_RS * 4u, row_msk + (unsigned)((dgi * K + l_tap) * P));
+                    } else {
+                        const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
+                        cp_async4(d, row_off + o);
+                        cp_async4(d + W_RS * 4u, row_off + o + (unsigned)P);
+                        cp_async4(d + 2 * W_RS * 4u, row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));
+                    }
+                }
                 if (FUSED) {
-                    row_off = offset + (size_t)b * 3 * s.DG * K * P + p;
-                    row_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
-                    row_idx0 = b * prm.hp * prm.wp;
-                } else {
-                    row_off = offset + (size_t)b * 2 * s.DG * K * P + p;
-                    if (mask) row_msk = mask + (size_t)b * s.DG * K * P + p;
+                    const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
+                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp)
+                        cp_async4(dst + (uint32_t)(3 * GS * W_RS) * 4u, max_idx + (row_idx0 + fy * prm.wp + fx));   // low word
                 }
             }
-        };
-        auto step = [&]() {                        // cursor one K step forward
+            if (tile_start) {
+                cp_async_wait_all();
+                mbar_arrive(&raw_full[rslot]);
+            } else {
+                cp_async_arrive_noinc(&raw_full[rslot]);
+            }
+            if (++rslot == RD) {
+                rslot = 0;
+                rphase ^= 1;
+            }
+            if (++l_tj == s.kw) {
+                l_tj = 0;
+                ++l_ti;
+            }
             if (++l_tap == K) {
-                l_tap = 0;
+                l_tap = l_ti = l_tj = 0;
                 if (++l_slab == prm.n_slabs) {
                     l_slab = 0;
                     l_tile += gridDim.x;
-                    tile_changed = true;
                 }
-                l_dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
-            }
-        };
-        typedef WinRaw<GSL> Raw;
-        auto load_next = [&](Raw& rr, int l_kb) {   // rr <- inputs of table l_kb (the cursor), then cursor += KSTEP
-            rr.yx = row_yx;
-            rr.bH = row_bH;
-            rr.worg = row_worg;
-            rr.fyx = -1;
-            if (row_yx >= 0) {
-#pragma unroll
-                for (int g = 0; g < GSL; ++g) {
-                    const int dgi = l_dg0 + g0 + g;
-                    if (!FUSED) {
-                        const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
-                        rr.dy[g] = ldg_early(row_off + o);
-                        rr.dx[g] = ldg_early(row_off + o + (unsigned)P);
-                        rr.mk[g] = mask ? ldg_early(row_msk + (unsigned)((dgi * K + l_tap) * P)) : 1.f;
-                    } else {
-                        const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
-                        rr.dy[g] = ldg_early(row_off + o);
-                        rr.dx[g] = ldg_early(row_off + o + (unsigned)P);
-                        rr.mk[g] = ldg_early(row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));
-                    }
-                }
-                if (FUSED) {
-                    const int l_ti = (int)(((unsigned)l_tap * kw_magic) >> 16), l_tj = l_tap - l_ti * s.kw;
-                    const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
-                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
-                        rr.mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + (row_idx0 + fy * prm.wp + fx)));
-                        rr.fyx = (fy << 16) | fx;
-                    }
-                }
-            }
-            step();
-            if (KSTEP == 2) step();
-            if (tile_changed) {
-                tile_changed = false;
-                if (l_kb + KSTEP < total_kb) decode_rows(l_tile);
-            }
-        };
-        int d_tap = kb0 % K;                                    // tap of the table being decoded
-        auto decode_store = [&](const Raw& rr, int d_kb) {      // rr = inputs of table d_kb -> its ring slot
-            const int d_slot = d_kb & (W_NTAB - 1);
-            const uint32_t d_phase = (uint32_t)(d_kb / W_NTAB) & 1u;
-            mbar_wait(&tab_empty[d_slot], d_phase ^ 1);
-            int* tb = tab_base + d_slot * tab_n + erow;
-            float* tw = tab_w + d_slot * 4 * tab_n + erow;
-            float ybase = 0.f, xbase = 0.f, fly = 0.f, flx = 0.f;
-            if (rr.yx >= 0) {
-                const int d_ti = (int)(((unsigned)d_tap * kw_magic) >> 16), d_tj = d_tap - d_ti * s.kw;
-                ybase = (float)((rr.yx >> 16) * s.sh - s.ph + d_ti * s.dh);
-                xbase = (float)((rr.yx & 0xffff) * s.sw - s.pw + d_tj * s.dw);
-                if (FUSED && rr.fyx >= 0) {
-                    const int my = (int)__umulhi((unsigned)rr.mi, prm.wp_magic), mx = rr.mi - my * prm.wp;
-                    fly = (float)((my - (rr.fyx >> 16)) * prm.flow_scale);
-                    flx = (float)((mx - (rr.fyx & 0xffff)) * prm.flow_scale);
-                }
-            }
-            const bool row_ok = rr.yx >= 0;
-            const int wy0 = rr.worg >> 16, wx0 = (rr.worg << 16) >> 16;
-#pragma unroll
-            for (int g = 0; g < GSL; ++g) {
-                // same arithmetic as dcn_tc_split_kernel's decode (bit for bit); in addition the window test
-                const float y = ybase + (FUSED ? rr.dy[g] + fly : rr.dy[g]);
-                const float x = xbase + (FUSED ? rr.dx[g] + flx : rr.dx[g]);
-                const bool in = row_ok && y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W;
-                const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-rr.mk[g])) : rr.mk[g];
-                const float fy0 = floorf(y), fx0 = floorf(x);
-                const int y0 = (int)fy0, x0 = (int)fx0;
-                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
-                const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
-                const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
-                int base = ((rr.bH + yc) * s.W + xc) * C;
-                base |= (tx0 && tx1) ? 1 : 0;
-                base |= (ty0 && ty1) ? 2 : 0;
-                const int ry = y0 - wy0, rx = x0 - wx0;
-                const bool hit = in && ry >= 0 && rx >= 0 && ry <= prm.wy - 2 && rx <= prm.wx - 2;
-                const int pix = pixbase + ry * prm.wx + rx;
-                const float hym = hy * mk, lym = ly * mk;
-                const int e = (g0 + g) * W_TAB_STRIDE;
-                tb[e] = hit ? ~pix : (in ? base : ~pixbase);
-                tw[e] = (in && ty0 && tx0) ? hym * hx : 0.f;
-                tw[e + tab_n] = (in && ty0 && tx1) ? hym * lx : 0.f;
-                tw[e + 2 * tab_n] = (in && ty1 && tx0) ? lym * hx : 0.f;
-                tw[e + 3 * tab_n] = (in && ty1 && tx1) ? lym * lx : 0.f;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tab_full[d_slot]);
-            d_tap += KSTEP;
-            while (d_tap >= K) d_tap -= K;
-        };
-        // two raw sets in flight per thread: the loads of this thread's table after next are issued before its next
-        // table is decoded
-        Raw ra, rb;
-        ra.yx = rb.yx = -1;
-        ra.bH = rb.bH = ra.worg = rb.worg = 0;
-        ra.mi = rb.mi = 0;
-        ra.fyx = rb.fyx = -1;
-#pragma unroll
-        for (int g = 0; g < GSL; ++g) ra.dy[g] = ra.dx[g] = ra.mk[g] = rb.dy[g] = rb.dx[g] = rb.mk[g] = 0.f;
-        if (kb0 == 1) step();                   // (K = 9 taps per slab: no tile change here)
-        tile_changed = false;
-        if (kb0 < total_kb) {
-            decode_rows(l_tile);
-            load_next(ra, kb0);
-        }
-        if (kb0 + KSTEP < total_kb) load_next(rb, kb0 + KSTEP);
-        for (int kb = kb0; kb < total_kb; kb += 2 * KSTEP) {
-            decode_store(ra, kb);
-            if (kb + 2 * KSTEP < total_kb) load_next(ra, kb + 2 * KSTEP);
-            if (kb + KSTEP < total_kb) {
-                decode_store(rb, kb + KSTEP);
-                if (kb + 3 * KSTEP < total_kb) load_next(rb, kb + 3 * KSTEP);
             }
         }
+        cp_async_wait_all();
     } else if (warp == W_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
@@ -490,7 +512,8 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                     const uint32_t sb = sa + W_A_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), umma_desc_sw128(sb + kk * 32, 0), idesc, accumulate);
+                        if (!DBG(2))
+                            umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), umma_desc_sw128(sb + kk * 32, 0), idesc, accumulate);
                         accumulate = 1;
                     }
                     umma_commit(&empty[stage]);
@@ -517,6 +540,10 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                     const int buf = wq & 1;
                     uint8_t* dst = win + (size_t)buf * prm.win_bytes;
                     mbar_wait_backoff(&win_empty[buf], (((uint32_t)wq >> 1) & 1u) ^ 1u, 64);
+                    if (DBG(16)) {
+                        mbar_arrive(&win_full[buf]);
+                        continue;
+                    }
                     mbar_expect_tx(&win_full[buf], tx_bytes);
                     if (pv0) tma_load_4d(dst, &mapX, &win_full[buf], slab * TBK, wx00, wy00, pb0);
                     if (pv1) tma_load_4d(dst + (size_t)prm.win_rows * 128, &mapX, &win_full[buf], slab * TBK, wx01, wy01, pb1);
@@ -542,6 +569,11 @@ static int dcn_win_mode() {
         mode = (e && e[0] == '0') ? 0 : 1;
     }
     return mode;
+}
+
+static size_t dcn_win_smem_bytes(const DcnTcParams& prm) {
+    return (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + 2 * W_TINFO_WORDS * 4 +
+           (size_t)prm.rdepth * (3 * prm.gs + 1) * W_RS * 4;
 }
 
 // 128-row tiles as patches; fills the tile / window geometry of prm.  false: shape not served by this kernel.
@@ -571,17 +603,16 @@ static bool dcn_win_plan(DcnTcParams& prm) {
     prm.npatch = 1 << prm.subs_log;
     prm.tiles = (int)best;
     prm.stage_bytes = W_A_BYTES + s.Co * 128;
-    const size_t table_bytes = (size_t)W_NTAB * 5 * prm.gs * W_TAB_STRIDE * 4;
-    static const int cfg[3][2] = {{3, 3}, {3, 2}, {2, 2}};   // (margin, stages), most wanted first
-    for (int k = 0; k < 3; ++k) {
+    static const int cfg[4][3] = {{3, 3, 8}, {3, 3, 6}, {3, 2, 8}, {2, 2, 8}};   // (margin, stages, ring depth), most wanted first
+    for (int k = 0; k < 4; ++k) {
         prm.mlo = cfg[k][0];
         prm.stages = cfg[k][1];
+        prm.rdepth = cfg[k][2];
         prm.wx = (1 << prm.tx_log) + 2 + 2 * prm.mlo;
         prm.wy = (1 << prm.ty_log) + 2 + 2 * prm.mlo;
         prm.win_rows = (prm.wx * prm.wy + 7) / 8 * 8;
         prm.win_bytes = prm.npatch * prm.win_rows * 128;
-        const size_t smem = (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + table_bytes + 1024;
-        if (smem <= (size_t)W_SMEM_MAX) return true;
+        if (dcn_win_smem_bytes(prm) <= (size_t)W_SMEM_MAX) return true;
     }
     return false;
 }
@@ -601,7 +632,6 @@ int dcn_win_plan_query(int B, int C, int H, int W, int Co, int DG, int* meta, in
     const bool ok = dcn_tc_eligible(prm.s) && dcn_win_mode() != 0 && dcn_win_plan(prm);
     for (int i = 0; i < 10; ++i) meta[i] = 0;
     if (!ok) return 0;
-    const size_t table_bytes = (size_t)W_NTAB * 5 * prm.gs * W_TAB_STRIDE * 4;
     meta[0] = 1;
     meta[1] = prm.tiles;
     meta[2] = 1 << prm.tx_log;
@@ -611,7 +641,7 @@ int dcn_win_plan_query(int B, int C, int H, int W, int Co, int DG, int* meta, in
     meta[6] = prm.wy;
     meta[7] = prm.mlo;
     meta[8] = prm.stages;
-    meta[9] = (int)((size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + table_bytes + 1024);
+    meta[9] = (int)dcn_win_smem_bytes(prm);
     if (coords) {
         MREFSR_CHECK((size_t)prm.tiles * W_BM <= max_rows, ERR_BAD_ARG, "window plan: %d rows, room for %zu",
                      prm.tiles * W_BM, max_rows);
@@ -635,30 +665,25 @@ int dcn_win_launch(const CUtensorMap& mapW, const float* xt, const float* off, c
     if (dcn_win_mode() == 0 || !dcn_win_plan(prm)) return 1;
     const DcnShape& s = prm.s;
     prm.nbuf = 2;
+#ifdef MREFSR_DCN_DEBUG
+    prm.dbg = getenv("MREFSR_DCN_DBG") ? atoi(getenv("MREFSR_DCN_DBG")) : 0;
+#endif
     CUtensorMap mapX;
     int rc = make_tensor_map_4d(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xt, (uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H,
                                 (uint64_t)s.B, TBK, (uint32_t)prm.wx, (uint32_t)prm.wy, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    const size_t table_bytes = (size_t)W_NTAB * 5 * prm.gs * W_TAB_STRIDE * 4;
-    const size_t smem = (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + table_bytes + 1024;
+    const size_t smem = dcn_win_smem_bytes(prm);
     int grid = sm_count();
     if (grid > prm.tiles) grid = prm.tiles;
     ScopedTiming tm(MREFSR_K_DCN_FWD, st);
-#define MREFSR_LAUNCH_WIN(F, G)                                                                                     \
+#define MREFSR_LAUNCH_WIN(F)                                                                                        \
     do {                                                                                                            \
-        auto kern = dcn_win_kernel<F, G>;                                                                           \
+        auto kern = dcn_win_kernel<F>;                                                                              \
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<grid, W_THREADS, smem, st>>>(mapW, mapX, xt, off, F ? nullptr : mask, F ? max_idx : nullptr, bias, prm); \
     } while (0)
-    if (prm.fused) {
-        if (prm.gs == 1) MREFSR_LAUNCH_WIN(true, 1);
-        else if (prm.gs == 2) MREFSR_LAUNCH_WIN(true, 2);
-        else MREFSR_LAUNCH_WIN(true, 4);
-    } else {
-        if (prm.gs == 1) MREFSR_LAUNCH_WIN(false, 1);
-        else if (prm.gs == 2) MREFSR_LAUNCH_WIN(false, 2);
-        else MREFSR_LAUNCH_WIN(false, 4);
-    }
+    if (prm.fused) MREFSR_LAUNCH_WIN(true);
+    else MREFSR_LAUNCH_WIN(false);
 #undef MREFSR_LAUNCH_WIN
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
