@@ -47,6 +47,8 @@ def parse():
     ap.add_argument('--match-mode', default='auto')
     ap.add_argument('--dcn-mode', default='auto')
     ap.add_argument('--no-full-model', action='store_true', help='skip the whole-network (images in -> SR out) leg')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the extra legs (sustained run, GPU reference route, configs 3 / 4 / 5)')
     ap.add_argument('--no-fused', action='store_true',
                     help='materialise pre-offsets / offset / mask (reference operator boundaries) instead of the '
                          'fused DynAgg gather')
@@ -330,10 +332,45 @@ def full_model_leg(dev, b, r, rank, world, dist, barrier, steps=5):
 
 
 # ----------------------------------------------------------------------------------------------------------
+def _guard_stdout():
+    """stdout carries exactly one JSON line.  Libraries write there too (NCCL_DEBUG=INFO prints its log on stdout), so
+    file descriptor 1 is pointed at stderr for the whole run and the line is written to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
+
+
+def gpu_reference_leg(b, r):
+    """SURVEY 8(d) GPU-side comparison set: the reference's own GPU route (per-pair unfold + cuDNN conv2d matcher, DynAgg
+    glue in torch, DCN through the reference's deform_conv_ext compiled unmodified for sm_100a and through torchvision,
+    fusion as written) on the same inputs in the same run.  It lives in tests/ (it loads the checker build oracle/_ref)
+    and runs as a subprocess; this function only relays its summary line."""
+    script = os.path.join(ROOT, 'tests', 'perf_reference_gpu.py')
+    try:
+        p = subprocess.run([sys.executable, script, '--batch', str(b), '--refs', str(r)], capture_output=True, text=True,
+                           timeout=600, cwd=ROOT)
+        lines = [json.loads(ln) for ln in p.stdout.splitlines() if ln.startswith('{')]
+        summ = [ln for ln in lines if ln.get('what') == 'summary']
+        if p.returncode != 0 or not summ:
+            return {'error': (p.stderr or p.stdout)[-300:]}
+        out = dict(summ[-1])
+        out.pop('what', None)
+        out['dcn_per_scale'] = [{k: ln[k] for k in ('C', 'hw', 'dcn_ref_ext_ms', 'dcn_torchvision_ms', 'glue_ref_ms',
+                                                    'ours_fused_ms', 'rel_diff_vs_torchvision')}
+                                for ln in lines if ln.get('what') == 'dcn']
+        out['note'] = ('reference route = what a wdmwhh/MRefSR user runs on this GPU today (stock PyTorch ops; DCN = the '
+                       "faster of the reference's own extension built for sm_100a and torchvision); same inputs")
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {'error': repr(e)[:300]}
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference(args)
+    out_stream = _guard_stdout()
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -345,9 +382,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     dist = None
     if world > 1:
-        # keep stdout to the single JSON line (NCCL_DEBUG=VERSION/WARN/INFO prints a version banner on stdout)
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN', 'INFO'):
-            os.environ.pop('NCCL_DEBUG')
+        # NCCL_DEBUG is left alone: whatever NCCL prints goes to stderr (_guard_stdout), stdout stays one JSON line
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group('nccl', device_id=dev)
@@ -391,6 +426,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = b * world * args.steps / (ms_max / 1e3)
+
+    # ---- sustained: the same step back to back for >= 3 s (the timed region above is a fraction of a second)
+    extras = {}
+    if not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import bench_legs
+        try:
+            extras['sustained'] = bench_legs.sustained_leg(
+                lambda: hot_path_step(M, d, b, r, args.match_mode, args.dcn_mode, fused), b,
+                ClockSampler if rank == 0 else None, local_rank, dev, dist)
+        except Exception as e:  # noqa: BLE001
+            extras['sustained'] = {'error': repr(e)[:200]}
 
     # ---- e2e: same step through the operator API with HOST (pinned) buffers, H2D + D2H inside the timed region
     e2e = None
@@ -482,6 +529,23 @@ def main():
         except Exception as e:  # noqa: BLE001
             full = {'error': repr(e)[:200]}
 
+    # ---- extra legs: BASELINE configs 3 / 4 / 5 and the reference's GPU route, in the driver's record
+    if not args.no_extras:
+        torch.cuda.empty_cache()
+        for name, fn in (('ragged', lambda: bench_legs.ragged_leg(dev, rank, world, dist)),
+                         ('train_step', lambda: bench_legs.train_step_leg(dev, rank, world, dist)),
+                         ('refshard', lambda: bench_legs.refshard_leg(dev, rank, world, dist))):
+            # an exception on one rank only would leave the others in a collective: legs catch nothing themselves,
+            # every rank runs the same code on the same shapes, so a failure is common to all ranks
+            try:
+                extras[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                extras[name] = {'error': repr(e)[:300]}
+            torch.cuda.empty_cache()
+        if world == 1 and rank == 0:
+            torch.cuda.synchronize()
+            extras['gpu_reference'] = gpu_reference_leg(b, r)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -538,7 +602,9 @@ def main():
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (matcher: split-bf16 x3 on tcgen05, fp32 accumulate)',
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 I/O (matcher: split-bf16 x3 operands on tcgen05, fp32 accumulate; dcn: tf32 operands, fp32 '
+                     'accumulate; fusion: fp32)',
             'data': 'synthetic',
             'config': {'workload': 'MRefSR x4 inference alignment hot path, batch %d per GPU, %d refs at 160x160 '
                                    '(BASELINE config 2): %d matcher pairs, DynAgg+DCNv2 x3 scales over %d samples, '
@@ -549,7 +615,9 @@ def main():
                        'dynagg': 'fused gather (conv_out + arg-max map)' if fused else 'materialised offset/mask'},
             'roofline': roofline, 'roofline_all': roof_all, 'kernel_ms_per_step': per_kernel,
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'full_model': full}
-    print(json.dumps(line), flush=True)
+    line.update(extras)
+    out_stream.write(json.dumps(line) + '\n')
+    out_stream.flush()
     if dist is not None:
         dist.destroy_process_group()
 

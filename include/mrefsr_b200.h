@@ -118,6 +118,9 @@ MREFSR_API int mrefsr_dcn_tile_plan(int B, int Ho, int Wo, int* meta, int* coord
  * ref_mrapa_restoration_arch.py:74-76): meta[10] = {served (0: the call falls back to the 256-row kernel), tiles of
  * 128 rows, patch width, patch height, patches per tile, window width, window height, margin, pipeline stages, dynamic
  * shared memory bytes}; coords as above with 128 rows per tile. */
+/* Opt-in switch of that kernel (process-wide; also env MREFSR_DCN_WIN=1 at first use).  Returns the previous setting.
+ * Same results bit for bit either way; see DESIGN.md section 2.2b for when it pays. */
+MREFSR_API int mrefsr_dcn_window_enable(int on);
 MREFSR_API int mrefsr_dcn_win_plan(int B, int C, int H, int W, int Co, int deformable_group, int* meta, int* coords,
                                    size_t max_rows);
 MREFSR_API int mrefsr_modulated_deform_conv_forward(const float* input, const float* weight, const float* bias,
@@ -168,7 +171,12 @@ MREFSR_API int mrefsr_dynagg_dcn_forward(const float* input, const float* weight
 enum {
     MREFSR_DCN_IN_NHWC = 1,
     MREFSR_DCN_OUT_NHWC = 2,
+    MREFSR_DCN_W_PACKED = 4, /* `weight` is the output of mrefsr_dcn_pack_weights (inference: packed once per weight update) */
 };
+/* W[Co][C][kh*kw] (the reference's parameter layout, deform_conv.py:305-309) -> the tcgen05 kernels' B operand
+ * [Co][tap][C], rounded to tf32 (round to nearest, so the tensor core's truncation is exact).  The forward entry
+ * points do this on every call unless MREFSR_DCN_W_PACKED is set; a module whose weights are frozen packs once. */
+MREFSR_API int mrefsr_dcn_pack_weights(const float* weight, float* packed, int Co, int C, int K, void* stream);
 MREFSR_API int mrefsr_dynagg_dcn_forward_ex(const float* input, const float* weight, const float* bias,
                                  const float* conv_out, const int64_t* max_idx, int flow_scale, float* output, int B,
                                  int C, int H, int W, int Co, int deformable_group, int with_bias, int layout_flags,

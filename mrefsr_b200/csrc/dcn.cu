@@ -499,6 +499,8 @@ int mrefsr_dcn_tile_plan(int B, int Ho, int Wo, int* meta, int* coords, size_t m
     return dcn_tc_tile_plan(B, Ho, Wo, meta, coords, max_rows);
 }
 
+int mrefsr_dcn_window_enable(int on) { return dcn_win_set_mode(on); }
+
 int mrefsr_dcn_win_plan(int B, int C, int H, int W, int Co, int deformable_group, int* meta, int* coords,
                         size_t max_rows) {
     MREFSR_CHECK(B > 0 && C > 0 && H > 0 && W > 0 && Co > 0 && deformable_group > 0 && meta, ERR_BAD_ARG,
@@ -660,6 +662,11 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
     return 0;
 }
 
+int mrefsr_dcn_pack_weights(const float* weight, float* packed, int Co, int C, int K, void* stream) {
+    MREFSR_CHECK(weight && packed && Co > 0 && C > 0 && K > 0, ERR_BAD_ARG, "pack_weights: bad arguments");
+    return dcn_pack_weights(weight, packed, Co, C, K, static_cast<cudaStream_t>(stream));
+}
+
 int mrefsr_dynagg_dcn_forward(const float* input, const float* weight, const float* bias, const float* conv_out,
                               const int64_t* max_idx, int flow_scale, float* output, int B, int C, int H, int W, int Co,
                               int deformable_group, int with_bias, void* workspace, size_t workspace_bytes,
@@ -682,7 +689,7 @@ int mrefsr_dynagg_dcn_forward_ex(const float* input, const float* weight, const 
                                  void* workspace, size_t workspace_bytes, void* stream) {
     MREFSR_CHECK(input && weight && conv_out && max_idx && output, ERR_BAD_ARG, "dynagg forward: null pointer argument");
     MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dynagg forward: with_bias set but bias is NULL");
-    MREFSR_CHECK((layout_flags & ~(MREFSR_DCN_IN_NHWC | MREFSR_DCN_OUT_NHWC)) == 0, ERR_BAD_ARG,
+    MREFSR_CHECK((layout_flags & ~(MREFSR_DCN_IN_NHWC | MREFSR_DCN_OUT_NHWC | MREFSR_DCN_W_PACKED)) == 0, ERR_BAD_ARG,
                  "dynagg forward: unknown layout flags 0x%x", layout_flags);
     DcnShape s;
     int rc = dcn_make_shape(&s, B, C, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, deformable_group);
@@ -701,7 +708,7 @@ int mrefsr_dynagg_dcn_forward_multi(const float* input, const float* weight, con
                                     void* workspace, size_t workspace_bytes, void* stream) {
     MREFSR_CHECK(input && weight && conv_out && max_idx && outputs, ERR_BAD_ARG, "dynagg forward: null pointer argument");
     MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dynagg forward: with_bias set but bias is NULL");
-    MREFSR_CHECK((layout_flags & ~(MREFSR_DCN_IN_NHWC | MREFSR_DCN_OUT_NHWC)) == 0, ERR_BAD_ARG,
+    MREFSR_CHECK((layout_flags & ~(MREFSR_DCN_IN_NHWC | MREFSR_DCN_OUT_NHWC | MREFSR_DCN_W_PACKED)) == 0, ERR_BAD_ARG,
                  "dynagg forward: unknown layout flags 0x%x", layout_flags);
     MREFSR_CHECK(n_outputs >= 1 && n_outputs <= 8, ERR_BAD_ARG, "dynagg forward: 1..8 output buffers (got %d)", n_outputs);
     DcnShape s;

@@ -35,6 +35,8 @@ int dcn_forward_fp32(const float* x, const float* w, const float* bias, const fl
 // NCHW -> NHWC copy (dcn_tc.cu), also used by the backward's position-major im2col
 int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st);
 
+int dcn_pack_weights(const float* w, float* wt, int Co, int C, int K, cudaStream_t st);
+
 // several destination buffers for one forward (reference-sharded mode: local + peer copies of the gathered tensor)
 struct DcnOutputs {
     float* ptr[8];

@@ -831,6 +831,13 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
     }
 }
 
+int dcn_pack_weights(const float* w, float* wt, int Co, int C, int K, cudaStream_t st) {
+    dcn_weight_repack_kernel<<<cdiv(Co * C * K, 256), 256, 0, st>>>(w, wt, Co, C, K);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
 int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st) {
     nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 128), B), 256, 0, st>>>(x, xt, C, HW);
     MREFSR_LAUNCH_CHECK();
@@ -965,9 +972,13 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }
-        dcn_weight_repack_kernel<<<cdiv(s.Co * s.C * K, 256), 256, 0, st>>>(w, wt, s.Co, s.C, K);
-        MREFSR_LAUNCH_CHECK();
-        count_launches(1);
+        if (layout_flags & MREFSR_DCN_W_PACKED) {      // packed once by the caller (mrefsr_dcn_pack_weights)
+            MREFSR_CHECK((reinterpret_cast<uintptr_t>(w) & 15) == 0, ERR_BAD_ARG, "dcn forward: packed weights must be 16-byte aligned");
+            wt = const_cast<float*>(w);
+        } else {
+            int prc = dcn_pack_weights(w, wt, s.Co, s.C, K, st);
+            if (prc) return prc;
+        }
     }
     CUtensorMap mapW;
     int rc = make_weight_map(&mapW, wt, s.Co, K * s.C);

@@ -39,7 +39,8 @@ struct DcnTcParams {
     // dcn_win.cu only: per patch a (wx x wy)-pixel window of the NHWC input, mlo pixels of margin on the low side,
     // is staged in shared memory; win_rows = 128-byte rows reserved per patch window (multiple of 8),
     // win_bytes = bytes of one window buffer (all patches of a tile)
-    int wx, wy, mlo, win_rows, win_bytes, npatch, rdepth, dbg;   // rdepth: raw offset / mask ring depth in K steps
+    int wx, wy, mlo, win_rows, win_bytes, npatch, rdepth, dbg;
+    long long* trace;    // debug builds only (MREFSR_DCN_DEBUG)   // rdepth: raw offset / mask ring depth in K steps
 };
 
 // (tile, row within the tile) -> (sample, oy, ox); false for padding rows
@@ -108,6 +109,7 @@ __device__ __forceinline__ int ldg_early_s32(const int* p) {
 // dcn_win.cu: shared-memory window gather.  1: shape not served (caller falls back), 0: launched, < 0: error
 int dcn_win_launch(const CUtensorMap& mapW, const float* xt, const float* off, const float* mask,
                    const long long* max_idx, const float* bias, DcnTcParams prm, cudaStream_t st);
+int dcn_win_set_mode(int on);
 int dcn_win_plan_query(int B, int C, int H, int W, int Co, int DG, int* meta, int* coords, size_t max_rows);
 
 }  // namespace mrefsr

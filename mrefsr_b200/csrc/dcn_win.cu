@@ -40,22 +40,44 @@ namespace mrefsr {
 
 constexpr int W_BM = 128;                         // rows (output positions) per CTA tile
 constexpr int W_A_BYTES = W_BM * 128;             // A stage: 128 rows x 32 fp32
-constexpr int W_GW = 16;                          // gather warps (threads 0..511): one (row, chunk) item each per K step
-constexpr int W_LW = 4;                           // raw-loader warps (thread = tile row)
-constexpr int W_MMA_WARP = W_GW + W_LW;
+#ifndef MREFSR_WIN_NG
+#define MREFSR_WIN_NG 3
+#endif
+constexpr int W_NG_MAX = MREFSR_WIN_NG;           // producer groups = pipeline stages (fewer when shared memory is short);
+                                                  // 3 groups + 2 warps = 14 warps: 4 per SM sub-partition -> 128 registers
+constexpr int W_MMA_WARP = W_NG_MAX * 4;          // 4 warps per group: thread = tile row
 constexpr int W_WIN_WARP = W_MMA_WARP + 1;
-constexpr int W_THREADS = (W_WIN_WARP + 1) * 32;  // 704
-constexpr int W_RS = W_BM + 8;                    // words per plane of a raw-ring entry (+8: the 4 groups of a warp hit 32 banks)
-constexpr int W_TINFO_WORDS = 4 * W_BM;           // per-tile row state: yx, b*H, window origin, flow cell
+constexpr int W_THREADS = (W_WIN_WARP + 1) * 32;
 constexpr int W_SMEM_MAX = 227 * 1024;
 
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {   // never suspends the warp
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // Ablation switches for bottleneck hunting (variant builds only: -DMREFSR_DCN_DEBUG, env MREFSR_DCN_DBG = bit mask;
-// results are wrong by design): 1 gather warps skip corner loads / blend / stores, 2 no MMAs (commits only),
-// 4 raw loaders copy nothing, 8 no weight-tile TMA, 16 no window TMA, 32 no sample decode.
+// results are wrong by design): 1 producers skip corner loads / blend / stores, 2 no MMAs (commits only),
+// 4 no offset / mask loads, 8 no weight-tile TMA, 16 no window TMA, 32 no sample decode, 64 no epilogue stores.
 #ifdef MREFSR_DCN_DEBUG
 #define DBG(bit) (prm.dbg & (bit))
+// MREFSR_DCN_TRACE=1: CTA 0 records clock64() at the events of its K steps 180..243 (16 slots per K step)
+#define TRACE(ev, kb)                                                                             \
+    do {                                                                                          \
+        if (prm.trace && blockIdx.x == 0 && (kb) >= 180 && (kb) < 244)                            \
+            prm.trace[((kb) - 180) * 16 + (ev)] = clock64();                                      \
+    } while (0)
 #else
 #define DBG(bit) (false)
+#define TRACE(ev, kb) do { } while (0)
 #endif
 
 // try_wait with a suspend-time hint: the warp is parked by the hardware for up to `ns` instead of spinning through
@@ -79,15 +101,6 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-// the mbarrier receives one (pre-counted) arrival once all cp.async of this thread issued so far have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // 8 consecutive channels (chunk ch of the slab) of window row `pix`: two 16-byte pieces at the 128-byte-swizzled
 // positions the bulk tensor copy wrote them to (window buffers are 1024-byte aligned, so the swizzle phase of a row
 // is its index modulo 8)
@@ -103,7 +116,7 @@ __device__ __forceinline__ F8 lds_corner(uint32_t win, int pix, int ch) {
 }
 
 // Window of patch p of a tile: sample b and the image coordinates (wy0, wx0) of its first pixel.  Computed identically
-// by the window loader and by the raw loaders.  false: the patch lies beyond the batch (no window).
+// once per tile by the window loader, which publishes the origins in shared memory.  false: the patch lies beyond the batch (no window).
 template <bool FUSED>
 __device__ __forceinline__ bool win_patch_geom(const DcnTcParams& prm, int tile, int p, const float* __restrict__ offset,
                                                const long long* __restrict__ max_idx, int& b, int& wy0, int& wx0) {
@@ -150,7 +163,7 @@ __device__ __forceinline__ void win_epilogue_tile(const DcnTcParams& prm, const 
         uint32_t v[8];
         tmem_ld_32x8(taddr + c0, v);
         tmem_ld_wait();
-        if (ok) {
+        if (ok && !DBG(64)) {
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -175,9 +188,14 @@ __device__ __forceinline__ void win_epilogue_tile(const DcnTcParams& prm, const 
     if (lane == 0) mbar_arrive(tempty_bar);
 }
 
-// Shared memory: [stages x (A 16 KB + B Co*128)] [2 window buffers] [barriers 256 B] [tile info 2 x 2 KB]
-//                [raw ring: rdepth x (3 gs + 1) planes x W_RS words]
-template <bool FUSED>
+template <int GS>
+struct WinRaw {                                   // offset / mask / arg-max words of one tile row for one K step
+    float dy[GS], dx[GS], mk[GS];
+    int mi;
+};
+
+// Shared memory: [NG stages x (A 16 KB + B Co*128)] [2 window buffers] [barriers 256 B] [window origins 4 tiles x 2]
+template <bool FUSED, int GS>
 __global__ void __launch_bounds__(W_THREADS, 1)
 dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
@@ -186,22 +204,17 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const DcnShape& s = prm.s;
-    const int S = prm.stages, RD = prm.rdepth, GS = prm.gs;
-    uint8_t* win = smem + (size_t)S * prm.stage_bytes;                 // two window buffers
+    const int NG = prm.stages;                                         // producer groups, one pipeline stage each
+    uint8_t* win = smem + (size_t)NG * prm.stage_bytes;                // two window buffers
     uint64_t* bars = reinterpret_cast<uint64_t*>(win + 2 * (size_t)prm.win_bytes);
-    uint64_t* full = bars;                    // [S]   A produced (16 gather warps) + B landed (expect_tx)
-    uint64_t* empty = full + 4;               // [S]   stage consumed by the MMAs
+    uint64_t* full = bars;                    // [NG]  A produced (4 warps of the owning group) + B landed (expect_tx)
+    uint64_t* empty = full + 4;               // [NG]  stage consumed by the MMAs
     uint64_t* tfull = empty + 4;              // [2]   accumulator complete
-    uint64_t* tempty = tfull + 2;             // [2]   accumulator drained (4 epilogue warps)
+    uint64_t* tempty = tfull + 2;             // [2]   accumulator drained (4 warps of the draining group)
     uint64_t* win_full = tempty + 2;          // [2]   window landed (expect_tx)
-    uint64_t* win_empty = win_full + 2;       // [2]   window released (16 gather warps)
-    uint64_t* raw_full = win_empty + 2;       // [RD <= 8]  raw words landed (128 loader threads)
-    uint64_t* raw_empty = raw_full + 8;       // [RD <= 8]  raw words consumed (16 gather warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 8);
-    int* tinfo = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);       // [2][4][W_BM]
-    const int raw_planes = 3 * GS + 1;
-    const int raw_words = raw_planes * W_RS;                                            // words per ring entry
-    float* raw = reinterpret_cast<float*>(tinfo + 2 * W_TINFO_WORDS);
+    uint64_t* win_empty = win_full + 2;       // [2]   window released: one arrive per producer warp per K step (4 K)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(win_empty + 2);
+    int* worg_ring = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 192);   // [4 tiles][2 patches]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Co = s.Co, C = s.C, K = prm.taps, P = prm.P;
@@ -210,19 +223,15 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapX);
-        for (int i = 0; i < S; ++i) {
-            mbar_init(&full[i], W_GW + 1);
+        for (int i = 0; i < NG; ++i) {
+            mbar_init(&full[i], 4 + 1);
             mbar_init(&empty[i], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], 4);
             mbar_init(&win_full[a], 1);
-            mbar_init(&win_empty[a], W_GW);
-        }
-        for (int a = 0; a < RD; ++a) {
-            mbar_init(&raw_full[a], W_LW * 32);
-            mbar_init(&raw_empty[a], W_GW);
+            mbar_init(&win_empty[a], 4 * K);
         }
         fence_mbar_init();
     }
@@ -234,265 +243,264 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     const int my_tiles = (prm.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * nkb_tile;   // K steps of this CTA, flattened over its tiles: (tile, slab, tap)
 
-    if (warp < W_GW) {
-        // ------------------------------------------------------------------ gather warps
-        const int tid = threadIdx.x;
-        const int ch = tid & 3;                    // 8-channel chunk within the 32-channel slab
-        const int r0 = tid >> 2;                   // tile row
-        const int gsub = (ch * 8) / prm.cdg;       // deform group within the slab (0 when cdg >= 32)
-        const int pixbase = (r0 >> prm.sub_log) * prm.win_rows;
-        const uint32_t a_off0 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch) ^ (r0 & 7)) << 4);
-        const uint32_t win_u32 = smem_u32(win);
-        const bool is_epi = warp < 4;
-        int ep_done = 0, prod_done = 0;
-        auto poll_epilogue = [&]() {               // non-blocking; warp-uniform
-            if (is_epi && ep_done < prod_done) {
-                const int buf = ep_done & 1;
-                if (mbar_try_wait(&tfull[buf], (ep_done >> 1) & 1)) {
-                    tc_fence_after();
-                    win_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf,
-                                      warp, lane);
-                    ++ep_done;
-                }
-            }
-        };
-        auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
-            while (!mbar_try_wait_hint(bar, parity, is_epi ? 200u : 2000u)) poll_epilogue();
-        };
-        int stage = 0, c_slab = 0, c_tap = 0, c_ti = 0, c_tj = 0, wq = 0, rslot = 0, tiq = 0;
-        uint32_t phase = 0, rphase = 0;
-        int row_yx = -1, row_bH = 0, row_worg = 0, row_qyx = 0;     // per-tile state of this thread's row (from tinfo)
-        const int dx_elems = C, dy_elems = s.W * C;
-        const int wxr = prm.wx;
-        for (int kb = 0; kb < total_kb; ++kb) {
-            poll_epilogue();
-            const float* xs = xt + (c_slab * TBK + ch * 8);
-            const uint32_t wcur = win_u32 + (uint32_t)(wq & 1) * (uint32_t)prm.win_bytes;
-            wait_poll(&raw_full[rslot], rphase);
-            if (c_tap == 0 && c_slab == 0) {       // first K step of a tile: this row's state, written by its raw loader
-                const int* ti = tinfo + (tiq & 1) * W_TINFO_WORDS + r0;
-                row_yx = ti[0];
-                row_bH = ti[W_BM];
-                row_worg = ti[2 * W_BM];
-                row_qyx = ti[3 * W_BM];
-                ++tiq;
-            }
-            // ---- raw words of (row, deform group, tap)
-            const float* rw = raw + rslot * raw_words + gsub * 3 * W_RS + r0;
-            const float raw_dy = rw[0], raw_dx = rw[W_RS], raw_mk = rw[2 * W_RS];
-            const int raw_mi = __float_as_int(raw[rslot * raw_words + 3 * GS * W_RS + r0]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[rslot]);
-            // ---- sample decode: same arithmetic as dcn_tc_split_kernel's (bit for bit) + the window test
-            int bf = ~pixbase;
-            float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-            if (!DBG(32)) {
-                const bool row_ok = row_yx >= 0;
-                float y = (float)((row_yx >> 16) * s.sh - s.ph + c_ti * s.dh);
-                float x = (float)((row_yx & 0xffff) * s.sw - s.pw + c_tj * s.dw);
-                if (FUSED) {
-                    float fly = 0.f, flx = 0.f;
-                    const int fy = (row_qyx >> 16) - c_ti, fx = (row_qyx & 0xffff) - c_tj;
-                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
-                        const int my = (int)__umulhi((unsigned)raw_mi, prm.wp_magic), mx = raw_mi - my * prm.wp;
-                        fly = (float)((my - fy) * prm.flow_scale);
-                        flx = (float)((mx - fx) * prm.flow_scale);
+    if (warp < W_MMA_WARP) {
+        // ------------------------------------------------------------------ producer groups
+        // Group g (4 warps, thread = tile row) produces the K steps kb = g (mod NG) into stage g: raw offset / mask
+        // words from registers (loaded two of its own K steps ahead) -> sample decode of the GS deform groups of the
+        // slab -> per 8-channel chunk 8 LDS.128 (window) or 4 LDG.256 (global), blend, round to tf32, two swizzled
+        // 16-byte stores -> arrive.  One barrier round per NG K steps and a whole 128-byte A row per thread, so the
+        // fixed cost of a round (three waits, fence, arrive: ~1000 clocks measured) is paid once per row, not once per
+        // 32-byte item, and the NG groups overlap each other's latency.  Group it % NG drains accumulator `it`.
+        const int g = warp >> 2;
+        if (g < NG) {
+            const int erow = (warp & 3) * 32 + lane;
+            const int my_patch = erow >> prm.sub_log;
+            const int pixbase = my_patch * prm.win_rows;
+            const uint32_t a_row = (uint32_t)erow * 128u;
+            const uint32_t a_swz = (uint32_t)(erow & 7);
+            const uint32_t win_u32 = smem_u32(win);
+            const unsigned kw_magic = 65536u / (unsigned)s.kw + 1u;    // tap / kw == (tap * kw_magic) >> 16 for tap < 256
+            const int dx_elems = C, dy_elems = s.W * C;
+            // ---- epilogue duty: tiles it = g, g + NG, ...
+            int ep_next = g, c_ti = 0;             // c_ti: tiles whose K steps of this group are all produced
+            auto poll_epilogue = [&]() {           // non-blocking; warp-uniform
+                if (ep_next < c_ti) {
+                    const int buf = ep_next & 1;
+                    if (mbar_test_wait(&tfull[buf], (ep_next >> 1) & 1)) {
+                        tc_fence_after();
+                        win_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_next * (int)gridDim.x,
+                                          buf, warp & 3, lane);
+                        ep_next += NG;
                     }
-                    y += raw_dy + fly;
-                    x += raw_dx + flx;
-                } else {
-                    y += raw_dy;
-                    x += raw_dx;
                 }
-                const bool in = row_ok && y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W;
-                const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-raw_mk)) : (mask ? raw_mk : 1.f);
-                const float fy0 = floorf(y), fx0 = floorf(x);
-                const int y0 = (int)fy0, x0 = (int)fx0;
-                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
-                const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
-                const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
-                int base = ((row_bH + yc) * s.W + xc) * C;
-                base |= (tx0 && tx1) ? 1 : 0;
-                base |= (ty0 && ty1) ? 2 : 0;
-                const int ry = y0 - (row_worg >> 16), rx = x0 - ((row_worg << 16) >> 16);
-                const bool hit = in && ry >= 0 && rx >= 0 && ry <= prm.wy - 2 && rx <= prm.wx - 2;
-                const int pix = pixbase + ry * prm.wx + rx;
-                const float hym = hy * mk, lym = ly * mk;
-                bf = hit ? ~pix : (in ? base : ~pixbase);
-                w0 = (in && ty0 && tx0) ? hym * hx : 0.f;
-                w1 = (in && ty0 && tx1) ? hym * lx : 0.f;
-                w2 = (in && ty1 && tx0) ? lym * hx : 0.f;
-                w3 = (in && ty1 && tx1) ? lym * lx : 0.f;
-            }
-            if (c_tap == 0) wait_poll(&win_full[wq & 1], (uint32_t)(wq >> 1) & 1u);
-            wait_poll(&empty[stage], phase ^ 1);
-            uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
-            if (tid == 0) {       // weight tile of this K step (TMA, lands on the same full barrier)
-                if (DBG(8)) {
-                    mbar_arrive(&full[stage]);
-                } else {
-                    mbar_expect_tx(&full[stage], Co * 128);
-                    tma_load_3d(A + W_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
-                }
-            }
-            if (!DBG(1)) {
-                F8 v0, v1, v2, v3;
-                if (bf < 0) {                      // all four corners inside the staged window
-                    const int pix = ~bf;
-                    v0 = lds_corner(wcur, pix, ch);
-                    v1 = lds_corner(wcur, pix + 1, ch);
-                    v2 = lds_corner(wcur, pix + wxr, ch);
-                    v3 = lds_corner(wcur, pix + wxr + 1, ch);
-                } else {                           // through L1, as dcn_tc_split_kernel
-                    const unsigned i0 = (unsigned)(bf & ~3);
-                    const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
-                    const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
-                    const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
-                    v0 = ldg8(xs + i0);
-                    v1 = ldg8(xs + i1);
-                    v2 = ldg8(xs + i2);
-                    v3 = ldg8(xs + i3);
-                }
-                const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
-                             p3 = make_float2(w3, w3);
-                float2 o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float2 a = __fmul2_rn(p0, v0.v[e]);
-                    a = __ffma2_rn(p1, v1.v[e], a);
-                    a = __ffma2_rn(p2, v2.v[e], a);
-                    a = __ffma2_rn(p3, v3.v[e], a);
-                    o[e] = make_float2(tf32_round_bits(a.x), tf32_round_bits(a.y));
-                }
-                *reinterpret_cast<float4*>(A + a_off0) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-                *reinterpret_cast<float4*>(A + (a_off0 ^ 16u)) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&full[stage]);
-                if (c_tap == K - 1) mbar_arrive(&win_empty[wq & 1]);   // last tap of the slab: window may be refilled
-            }
-            if (++stage == S) {
-                stage = 0;
-                phase ^= 1;
-            }
-            if (++rslot == RD) {
-                rslot = 0;
-                rphase ^= 1;
-            }
-            if (++c_tj == s.kw) {
-                c_tj = 0;
-                ++c_ti;
-            }
-            if (++c_tap == K) {
-                c_tap = c_ti = c_tj = 0;
-                ++wq;
-                if (++c_slab == prm.n_slabs) {
-                    c_slab = 0;
-                    ++prod_done;      // every K step of this tile has been produced by this warp
-                }
-            }
-        }
-        while (is_epi && ep_done < prod_done) {    // drain the remaining accumulators
-            const int buf = ep_done & 1;
-            mbar_wait_backoff(&tfull[buf], (ep_done >> 1) & 1, 64);
-            tc_fence_after();
-            win_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf, warp, lane);
-            ++ep_done;
-        }
-    } else if (warp < W_MMA_WARP) {
-        // ------------------------------------------------------------------ raw loaders (thread = tile row)
-        // Per K step: cp.async of this row's offset / mask words (GS deform groups of the slab, one tap) and, in fused
-        // mode, of the arg-max word of the row's flow cell for this tap, into ring entry kb % RD.  Completion: one
-        // cp.async.mbarrier arrive per thread.  At the first K step of a tile the thread also publishes the row's tile
-        // state (coordinates, window origin) with ordinary stores, which an asynchronous arrive would not order, so
-        // that step waits for its copies and arrives normally.
-        const int erow = (warp - W_GW) * 32 + lane;
-        const int my_patch = erow >> prm.sub_log;
-        const uint32_t raw_u32 = smem_u32(raw);
-        int rslot = 0, l_tap = 0, l_ti = 0, l_tj = 0, l_slab = 0, l_tile = blockIdx.x, tiq = 0;
-        uint32_t rphase = 0;
-        int row_yx = -1, row_qyx = 0, row_idx0 = 0;
-        const float* row_off = offset;
-        const float* row_msk = mask;
-        for (int kb = 0; kb < total_kb; ++kb) {
-            bool tile_start = false;
-            if (l_tap == 0 && l_slab == 0) {
-                tile_start = true;
-                int b = 0, oy = 0, ox = 0, pb = 0, wy0 = 0, wx0 = 0, worg = 0, bH = 0;
-                row_yx = -1;
-                row_qyx = 0;
-                if (win_patch_geom<FUSED>(prm, l_tile, my_patch, offset, max_idx, pb, wy0, wx0))
-                    worg = (int)(((unsigned)wy0 << 16) | ((unsigned)wx0 & 0xffffu));
-                if (dcn_row_coords(prm, l_tile, erow, b, oy, ox)) {
+            };
+            auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
+                while (!mbar_try_wait(bar, parity)) poll_epilogue();
+            };
+            // ---- load cursor: the K step whose raw words are loaded next, and the row's state in that tile
+            int l_kb = g, l_tile = blockIdx.x, l_slab = 0, l_tap = g;
+            int n_yx = -1, n_bH = 0, n_qyx = 0, n_idx0 = 0;
+            const float* row_off = offset;
+            const float* row_msk = mask;
+            auto load_rows = [&](int tile) {
+                int b = 0, oy = 0, ox = 0;
+                n_yx = -1;
+                if (dcn_row_coords(prm, tile, erow, b, oy, ox)) {
                     const int p = oy * s.Wo + ox;
-                    row_yx = (oy << 16) | ox;
-                    bH = b * s.H;
+                    n_yx = (oy << 16) | ox;
+                    n_bH = b * s.H;
                     if (FUSED) {
                         row_off = offset + (size_t)b * 3 * s.DG * K * P + p;
-                        row_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
-                        row_idx0 = b * prm.hp * prm.wp;
+                        n_qyx = ((oy / prm.flow_scale) << 16) | (ox / prm.flow_scale);
+                        n_idx0 = b * prm.hp * prm.wp;
                     } else {
                         row_off = offset + (size_t)b * 2 * s.DG * K * P + p;
                         if (mask) row_msk = mask + (size_t)b * s.DG * K * P + p;
                     }
                 }
-                int* ti = tinfo + (tiq & 1) * W_TINFO_WORDS + erow;
-                ti[0] = row_yx;
-                ti[W_BM] = bH;
-                ti[2 * W_BM] = worg;
-                ti[3 * W_BM] = row_qyx;
-                ++tiq;
-            }
-            mbar_wait(&raw_empty[rslot], rphase ^ 1);
-            if (row_yx >= 0 && !DBG(4)) {
-                const uint32_t dst = raw_u32 + (uint32_t)(rslot * raw_words + erow) * 4u;
-                const int dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
-                for (int g = 0; g < GS; ++g) {
-                    const int dgi = dg0 + g;
-                    const uint32_t d = dst + (uint32_t)(g * 3 * W_RS) * 4u;
-                    if (!FUSED) {
-                        const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
-                        cp_async4(d, row_off + o);
-                        cp_async4(d + W_RS * 4u, row_off + o + (unsigned)P);
-                        if (mask) cp_async4(d + 2 * W_RS * 4u, row_msk + (unsigned)((dgi * K + l_tap) * P));
-                    } else {
-                        const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
-                        cp_async4(d, row_off + o);
-                        cp_async4(d + W_RS * 4u, row_off + o + (unsigned)P);
-                        cp_async4(d + 2 * W_RS * 4u, row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));
+            };
+            typedef WinRaw<GS> Raw;
+            auto load_raw = [&](Raw& rr) {         // rr <- raw words of K step l_kb; cursor += NG
+                if (n_yx >= 0 && !DBG(4)) {
+                    const int dg0 = (prm.cdg >= TBK) ? (l_slab * TBK) / prm.cdg : l_slab * (TBK / prm.cdg);
+#pragma unroll
+                    for (int gi = 0; gi < GS; ++gi) {
+                        const int dgi = dg0 + gi;
+                        if (!FUSED) {
+                            const unsigned o = (unsigned)((dgi * 2 * K + 2 * l_tap) * P);
+                            rr.dy[gi] = ldg_early(row_off + o);
+                            rr.dx[gi] = ldg_early(row_off + o + (unsigned)P);
+                            rr.mk[gi] = mask ? ldg_early(row_msk + (unsigned)((dgi * K + l_tap) * P)) : 1.f;
+                        } else {
+                            const unsigned o = (unsigned)(2 * (dgi * K + l_tap) * P);
+                            rr.dy[gi] = ldg_early(row_off + o);
+                            rr.dx[gi] = ldg_early(row_off + o + (unsigned)P);
+                            rr.mk[gi] = ldg_early(row_off + (unsigned)((2 * s.DG * K + dgi * K + l_tap) * P));
+                        }
+                    }
+                    if (FUSED) {
+                        const int l_ti = (int)(((unsigned)l_tap * kw_magic) >> 16), l_tj = l_tap - l_ti * s.kw;
+                        const int fy = (n_qyx >> 16) - l_ti, fx = (n_qyx & 0xffff) - l_tj;
+                        if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp)
+                            rr.mi = ldg_early_s32(reinterpret_cast<const int*>(max_idx + (n_idx0 + fy * prm.wp + fx)));
                     }
                 }
+                l_kb += NG;
+                l_tap += NG;
+                if (l_tap >= K) {
+                    l_tap -= K;
+                    if (++l_slab == prm.n_slabs) {
+                        l_slab = 0;
+                        l_tile += gridDim.x;
+                        if (l_kb < total_kb) load_rows(l_tile);
+                    }
+                }
+            };
+            Raw ra, rb;
+            ra.mi = rb.mi = 0;
+#pragma unroll
+            for (int gi = 0; gi < GS; ++gi) ra.dy[gi] = ra.dx[gi] = ra.mk[gi] = rb.dy[gi] = rb.dx[gi] = rb.mk[gi] = 0.f;
+            if (g < total_kb) {
+                load_rows(l_tile);
+                load_raw(ra);
+            }
+            int c_yx = n_yx, c_bH = n_bH, c_qyx = n_qyx;               // the row's state in the tile being produced
+            if (l_kb < total_kb) load_raw(rb);
+            int c_slab = 0, c_tap = g, c_wq = 0, waited_wq = -1;       // c_wq: window index (tile, slab) of K step kb
+            uint32_t phase = 0;
+            bool new_tile = false;
+
+            auto produce = [&](Raw& rr, int kb) {
+                const bool tr = (warp & 3) == 0 && lane == 0;
+                if (tr) TRACE(0, kb);
+                poll_epilogue();
+                if (new_tile) {                    // first K step of this group in a new tile (the load cursor is in it)
+                    new_tile = false;
+                    c_yx = n_yx;
+                    c_bH = n_bH;
+                    c_qyx = n_qyx;
+                }
+                if (waited_wq != c_wq) {           // first use of this window by this thread (also orders worg_ring)
+                    wait_poll(&win_full[c_wq & 1], (uint32_t)(c_wq >> 1) & 1u);
+                    waited_wq = c_wq;
+                }
+                if (tr) TRACE(1, kb);
+                const int worg = worg_ring[(c_ti & 3) * 2 + my_patch];
+                const uint32_t wcur = win_u32 + (uint32_t)(c_wq & 1) * (uint32_t)prm.win_bytes;
+                const float* xs = xt + c_slab * TBK;
+                // ---- per-row constants of the sample decode
+                const bool row_ok = c_yx >= 0;
+                const int d_ti = (int)(((unsigned)c_tap * kw_magic) >> 16), d_tj = c_tap - d_ti * s.kw;
+                const float ybase = (float)((c_yx >> 16) * s.sh - s.ph + d_ti * s.dh);
+                const float xbase = (float)((c_yx & 0xffff) * s.sw - s.pw + d_tj * s.dw);
+                float fly = 0.f, flx = 0.f;
                 if (FUSED) {
-                    const int fy = (row_qyx >> 16) - l_ti, fx = (row_qyx & 0xffff) - l_tj;
-                    if (fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp)
-                        cp_async4(dst + (uint32_t)(3 * GS * W_RS) * 4u, max_idx + (row_idx0 + fy * prm.wp + fx));   // low word
+                    const int fy = (c_qyx >> 16) - d_ti, fx = (c_qyx & 0xffff) - d_tj;
+                    if (row_ok && fy >= 0 && fx >= 0 && fy < prm.hp && fx < prm.wp) {
+                        const int my = (int)__umulhi((unsigned)rr.mi, prm.wp_magic), mx = rr.mi - my * prm.wp;
+                        fly = (float)((my - fy) * prm.flow_scale);
+                        flx = (float)((mx - fx) * prm.flow_scale);
+                    }
                 }
-            }
-            if (tile_start) {
-                cp_async_wait_all();
-                mbar_arrive(&raw_full[rslot]);
-            } else {
-                cp_async_arrive_noinc(&raw_full[rslot]);
-            }
-            if (++rslot == RD) {
-                rslot = 0;
-                rphase ^= 1;
-            }
-            if (++l_tj == s.kw) {
-                l_tj = 0;
-                ++l_ti;
-            }
-            if (++l_tap == K) {
-                l_tap = l_ti = l_tj = 0;
-                if (++l_slab == prm.n_slabs) {
-                    l_slab = 0;
-                    l_tile += gridDim.x;
+                const int wy0 = worg >> 16, wx0 = (worg << 16) >> 16;
+                if (tr) TRACE(2, kb);
+                wait_poll(&empty[g], phase ^ 1);
+                if (tr) TRACE(3, kb);
+                uint8_t* A = smem + (size_t)g * prm.stage_bytes;
+                if ((warp & 3) == 0 && lane == 0) {   // weight tile of this K step (TMA, lands on the same full barrier)
+                    if (DBG(8)) {
+                        mbar_arrive(&full[g]);
+                    } else {
+                        mbar_expect_tx(&full[g], Co * 128);
+                        tma_load_3d(A + W_A_BYTES, &mapW, &full[g], c_tap * C + c_slab * TBK, 0, 0);
+                    }
                 }
+#pragma unroll
+                for (int gi = 0; gi < GS; ++gi) {
+                    // ---- sample decode of deform group gi of the slab: same arithmetic as dcn_tc_split_kernel's
+                    // (bit for bit) + the window test
+                    int bf = ~pixbase;
+                    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                    if (!DBG(32)) {
+                        const float y = ybase + (FUSED ? rr.dy[gi] + fly : rr.dy[gi]);
+                        const float x = xbase + (FUSED ? rr.dx[gi] + flx : rr.dx[gi]);
+                        const bool in = row_ok && y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W;
+                        const float mk = FUSED ? __fdividef(1.f, 1.f + __expf(-rr.mk[gi])) : rr.mk[gi];
+                        const float fy0 = floorf(y), fx0 = floorf(x);
+                        const int y0 = (int)fy0, x0 = (int)fx0;
+                        const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                        const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
+                        const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
+                        int base = ((c_bH + yc) * s.W + xc) * C;
+                        base |= (tx0 && tx1) ? 1 : 0;
+                        base |= (ty0 && ty1) ? 2 : 0;
+                        const int ry = y0 - wy0, rx = x0 - wx0;
+                        const bool hit = in && ry >= 0 && rx >= 0 && ry <= prm.wy - 2 && rx <= prm.wx - 2;
+                        const int pix = pixbase + ry * prm.wx + rx;
+                        const float hym = hy * mk, lym = ly * mk;
+                        bf = hit ? ~pix : (in ? base : ~pixbase);
+                        w0 = (in && ty0 && tx0) ? hym * hx : 0.f;
+                        w1 = (in && ty0 && tx1) ? hym * lx : 0.f;
+                        w2 = (in && ty1 && tx0) ? lym * hx : 0.f;
+                        w3 = (in && ty1 && tx1) ? lym * lx : 0.f;
+                    }
+                    if (DBG(1)) continue;
+                    const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
+                                 p3 = make_float2(w3, w3);
+#pragma unroll
+                    for (int cc = 0; cc < 4 / GS; ++cc) {  // the 8-channel chunks of this deform group within the slab
+                        const int ch = gi * (4 / GS) + cc;
+                        F8 v0, v1, v2, v3;
+                        if (bf < 0) {                      // all four corners inside the staged window
+                            const int pix = ~bf;
+                            v0 = lds_corner(wcur, pix, ch);
+                            v1 = lds_corner(wcur, pix + 1, ch);
+                            v2 = lds_corner(wcur, pix + prm.wx, ch);
+                            v3 = lds_corner(wcur, pix + prm.wx + 1, ch);
+                        } else {                           // through L1, as dcn_tc_split_kernel
+                            const unsigned i0 = (unsigned)(bf & ~3) + ch * 8;
+                            const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
+                            const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
+                            const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+                            v0 = ldg8(xs + i0);
+                            v1 = ldg8(xs + i1);
+                            v2 = ldg8(xs + i2);
+                            v3 = ldg8(xs + i3);
+                        }
+                        float2 o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 a = __fmul2_rn(p0, v0.v[e]);
+                            a = __ffma2_rn(p1, v1.v[e], a);
+                            a = __ffma2_rn(p2, v2.v[e], a);
+                            a = __ffma2_rn(p3, v3.v[e], a);
+                            o[e] = make_float2(tf32_round_bits(a.x), tf32_round_bits(a.y));
+                        }
+                        const uint32_t c0 = a_row + (((uint32_t)(2 * ch) ^ a_swz) << 4);
+                        *reinterpret_cast<float4*>(A + c0) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                        *reinterpret_cast<float4*>(A + (c0 ^ 16u)) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+                    }
+                }
+                if (tr) TRACE(4, kb);
+                // ---- the raw set is consumed: refill it for this group's K step after next
+                if (l_kb < total_kb) load_raw(rr);
+                if (tr) TRACE(5, kb);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&full[g]);
+                    mbar_arrive(&win_empty[c_wq & 1]);     // this warp is done with the window for this K step
+                }
+                if (tr) TRACE(6, kb);
+                phase ^= 1;
+                c_tap += NG;
+                if (c_tap >= K) {
+                    c_tap -= K;
+                    ++c_wq;
+                    if (++c_slab == prm.n_slabs) {
+                        c_slab = 0;
+                        ++c_ti;
+                        new_tile = true;
+                    }
+                }
+            };
+            for (int kb = g; kb < total_kb; kb += NG) {
+                produce(ra, kb);           // leaves ra reloading for kb + 2 NG
+                Raw t = ra;                // one copy of the produce code (instruction cache): rotate the two raw sets
+                ra = rb;
+                rb = t;
+            }
+            // tiles this group did not produce a last K step for still count as produced once the loop is over
+            c_ti = my_tiles;
+            while (ep_next < my_tiles) {           // drain the remaining accumulators of this group
+                const int buf = ep_next & 1;
+                mbar_wait_backoff(&tfull[buf], (ep_next >> 1) & 1, 64);
+                tc_fence_after();
+                win_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_next * (int)gridDim.x, buf,
+                                  warp & 3, lane);
+                ep_next += NG;
             }
         }
-        cp_async_wait_all();
     } else if (warp == W_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
@@ -501,12 +509,14 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
-                mbar_wait_backoff(&tempty[buf], ((it >> 1) & 1) ^ 1, 32);
+                mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + buf * Co;
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < nkb_tile; ++kb) {
-                    mbar_wait_backoff(&full[stage], phase, 20);
+                    TRACE(8, it * nkb_tile + kb);
+                    mbar_wait(&full[stage], phase);
+                    TRACE(9, it * nkb_tile + kb);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * prm.stage_bytes);
                     const uint32_t sb = sa + W_A_BYTES;
@@ -517,7 +527,8 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                         accumulate = 1;
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == S) {
+                    TRACE(10, it * nkb_tile + kb);
+                    if (++stage == NG) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -529,9 +540,9 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     } else {
         // ------------------------------------------------------------------ window loader
         if (lane == 0) {
-            int wq = 0;
+            int wq = 0, ti = 0;
             const uint32_t patch_bytes = (uint32_t)prm.wx * prm.wy * 128u;
-            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++ti) {
                 int pb0 = 0, wy00 = 0, wx00 = 0, pb1 = 0, wy01 = 0, wx01 = 0;
                 const bool pv0 = win_patch_geom<FUSED>(prm, tile, 0, offset, max_idx, pb0, wy00, wx00);
                 const bool pv1 = prm.npatch > 1 && win_patch_geom<FUSED>(prm, tile, 1, offset, max_idx, pb1, wy01, wx01);
@@ -540,6 +551,10 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                     const int buf = wq & 1;
                     uint8_t* dst = win + (size_t)buf * prm.win_bytes;
                     mbar_wait_backoff(&win_empty[buf], (((uint32_t)wq >> 1) & 1u) ^ 1u, 64);
+                    if (slab == 0) {       // published before the tile's first window: ordered by win_full
+                        worg_ring[(ti & 3) * 2] = (int)(((unsigned)wy00 << 16) | ((unsigned)wx00 & 0xffffu));
+                        worg_ring[(ti & 3) * 2 + 1] = (int)(((unsigned)wy01 << 16) | ((unsigned)wx01 & 0xffffu));
+                    }
                     if (DBG(16)) {
                         mbar_arrive(&win_full[buf]);
                         continue;
@@ -561,19 +576,25 @@ dcn_win_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// MREFSR_DCN_WIN=0|1 (tuning knob; default 1): shared-memory window gather (this file) for eligible shapes
+// MREFSR_DCN_WIN=0|1 (default 0) or mrefsr_dcn_window_enable(): route eligible shapes to this kernel.  Opt-in: measured
+// on B200 (profiles/r02_dcn_window.md) it is bit-identical to dcn_tc_split_kernel but not faster -- the corner fetch
+// stops being the limiter and instruction issue / per-K-step hand-off latency take over.
+static int g_win_mode = -1;
 static int dcn_win_mode() {
-    static int mode = -1;
-    if (mode < 0) {
+    if (g_win_mode < 0) {
         const char* e = getenv("MREFSR_DCN_WIN");
-        mode = (e && e[0] == '0') ? 0 : 1;
+        g_win_mode = (e && e[0] == '1') ? 1 : 0;
     }
-    return mode;
+    return g_win_mode;
+}
+int dcn_win_set_mode(int on) {
+    const int prev = dcn_win_mode();
+    g_win_mode = on ? 1 : 0;
+    return prev;
 }
 
 static size_t dcn_win_smem_bytes(const DcnTcParams& prm) {
-    return (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256 + 2 * W_TINFO_WORDS * 4 +
-           (size_t)prm.rdepth * (3 * prm.gs + 1) * W_RS * 4;
+    return (size_t)prm.stages * prm.stage_bytes + 2 * (size_t)prm.win_bytes + 256;
 }
 
 // 128-row tiles as patches; fills the tile / window geometry of prm.  false: shape not served by this kernel.
@@ -603,11 +624,12 @@ static bool dcn_win_plan(DcnTcParams& prm) {
     prm.npatch = 1 << prm.subs_log;
     prm.tiles = (int)best;
     prm.stage_bytes = W_A_BYTES + s.Co * 128;
-    static const int cfg[4][3] = {{3, 3, 8}, {3, 3, 6}, {3, 2, 8}, {2, 2, 8}};   // (margin, stages, ring depth), most wanted first
-    for (int k = 0; k < 4; ++k) {
+    static const int cfg[5][2] = {{3, 4}, {3, 3}, {2, 3}, {3, 2}, {2, 2}};   // (margin, groups = stages), most wanted first
+    for (int k = 0; k < 5; ++k) {
         prm.mlo = cfg[k][0];
         prm.stages = cfg[k][1];
-        prm.rdepth = cfg[k][2];
+        if (prm.stages > W_NG_MAX) continue;
+        prm.rdepth = 0;
         prm.wx = (1 << prm.tx_log) + 2 + 2 * prm.mlo;
         prm.wy = (1 << prm.ty_log) + 2 + 2 * prm.mlo;
         prm.win_rows = (prm.wx * prm.wy + 7) / 8 * 8;
@@ -629,7 +651,7 @@ int dcn_win_plan_query(int B, int C, int H, int W, int Co, int DG, int* meta, in
     prm.total_rows = B * prm.P;
     prm.cdg = C / DG;
     prm.gs = prm.cdg >= TBK ? 1 : TBK / prm.cdg;
-    const bool ok = dcn_tc_eligible(prm.s) && dcn_win_mode() != 0 && dcn_win_plan(prm);
+    const bool ok = dcn_tc_eligible(prm.s) && dcn_win_plan(prm);
     for (int i = 0; i < 10; ++i) meta[i] = 0;
     if (!ok) return 0;
     meta[0] = 1;
@@ -667,6 +689,13 @@ int dcn_win_launch(const CUtensorMap& mapW, const float* xt, const float* off, c
     prm.nbuf = 2;
 #ifdef MREFSR_DCN_DEBUG
     prm.dbg = getenv("MREFSR_DCN_DBG") ? atoi(getenv("MREFSR_DCN_DBG")) : 0;
+    prm.trace = nullptr;
+    static long long* trace_buf = nullptr;
+    if (getenv("MREFSR_DCN_TRACE")) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 64 * 16 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 64 * 16 * sizeof(long long), st);
+        prm.trace = trace_buf;
+    }
 #endif
     CUtensorMap mapX;
     int rc = make_tensor_map_4d(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, xt, (uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H,
@@ -676,16 +705,40 @@ int dcn_win_launch(const CUtensorMap& mapW, const float* xt, const float* off, c
     int grid = sm_count();
     if (grid > prm.tiles) grid = prm.tiles;
     ScopedTiming tm(MREFSR_K_DCN_FWD, st);
-#define MREFSR_LAUNCH_WIN(F)                                                                                        \
+#define MREFSR_LAUNCH_WIN(F, G)                                                                                     \
     do {                                                                                                            \
-        auto kern = dcn_win_kernel<F>;                                                                              \
+        auto kern = dcn_win_kernel<F, G>;                                                                           \
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<grid, W_THREADS, smem, st>>>(mapW, mapX, xt, off, F ? nullptr : mask, F ? max_idx : nullptr, bias, prm); \
     } while (0)
-    if (prm.fused) MREFSR_LAUNCH_WIN(true);
-    else MREFSR_LAUNCH_WIN(false);
+    if (prm.fused) {
+        if (prm.gs == 1) MREFSR_LAUNCH_WIN(true, 1);
+        else if (prm.gs == 2) MREFSR_LAUNCH_WIN(true, 2);
+        else MREFSR_LAUNCH_WIN(true, 4);
+    } else {
+        if (prm.gs == 1) MREFSR_LAUNCH_WIN(false, 1);
+        else if (prm.gs == 2) MREFSR_LAUNCH_WIN(false, 2);
+        else MREFSR_LAUNCH_WIN(false, 4);
+    }
 #undef MREFSR_LAUNCH_WIN
     MREFSR_LAUNCH_CHECK();
+#ifdef MREFSR_DCN_DEBUG
+    if (prm.trace) {
+        static long long host[64 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, prm.trace, sizeof(host), cudaMemcpyDeviceToHost);
+        long long t0 = host[8] ? host[8] : host[0];
+        fprintf(stderr, "TRACE C=%d Co=%d ng=%d  (clocks relative to the MMA thread's step 180; P0 begin, P1 window ok, P2 "
+                        "decode consts, P3 stage free, P4 gathered, P5 raw reloaded, P6 arrived | M8 wait full, M9 full ok, M10 committed)\n",
+                s.C, s.Co, prm.stages);
+        for (int k = 0; k < 64; ++k) {
+            fprintf(stderr, "kb %3d g%d:", 180 + k, (180 + k) % prm.stages);
+            for (int e = 0; e < 11; ++e)
+                if (e < 7 || e >= 8) fprintf(stderr, " %s%d=%6lld", e < 8 ? "P" : "M", e, host[k * 16 + e] ? host[k * 16 + e] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     count_launches(1);
     return 0;
 }

@@ -31,6 +31,34 @@ def set_default_mode(mode):
     _default_mode = _MODES[mode] if isinstance(mode, str) else int(mode)
 
 
+_packed_cache = {}       # id(weight) -> (weakref, version, data_ptr, packed tensor)
+
+
+def packed_weight(weight):
+    """tf32-rounded [Co][tap][C] copy of a DCN weight for the tcgen05 kernels (mrefsr_dcn_pack_weights), cached per
+    weight tensor and invalidated by torch's version counter (any in-place update, optimizer step or load_state_dict
+    bumps it), by a changed storage address, or when the tensor dies.  Inference packs each weight once instead of on
+    every forward; tensors that require grad are never cached (training updates them every step)."""
+    import weakref
+    if weight.requires_grad and torch.is_grad_enabled():
+        return None
+    key = id(weight)
+    hit = _packed_cache.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3]
+    w = weight.detach().contiguous().float()
+    co, c, kh, kw = w.shape
+    packed = torch.empty(co, kh * kw * c, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = _lib.lib().mrefsr_dcn_pack_weights(_lib.ptr(w), _lib.ptr(packed), co, c, kh * kw, _lib.stream_ptr(w.device))
+    _lib.check(rc, 'mrefsr_dcn_pack_weights')
+    if len(_packed_cache) > 256:
+        for k in [k for k, v in _packed_cache.items() if v[0]() is None]:
+            del _packed_cache[k]
+    _packed_cache[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), packed)
+    return packed
+
+
 def _out_hw(h, w, kh, kw, stride, padding, dilation):
     ho = (h + 2 * padding[0] - (dilation[0] * (kh - 1) + 1)) // stride[0] + 1
     wo = (w + 2 * padding[1] - (dilation[1] * (kw - 1) + 1)) // stride[1] + 1
@@ -135,6 +163,9 @@ def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, defor
     out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device,
                       memory_format=torch.channels_last if out_channels_last else torch.contiguous_format)
     flags = (1 if in_cl else 0) | (2 if out_channels_last else 0)
+    pk = packed_weight(weight)
+    if pk is not None:
+        wgt, flags = pk, flags | 4
     with torch.cuda.device(x.device):
         nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, DCN_TF32, 0)
         ws, ws_bytes = _lib.workspace(nbytes, x.device)

@@ -47,7 +47,7 @@ def similarity_volume(feat_input, feat_ref, patch_size=3, input_stride=1, ref_st
 
 def feature_match_index_oracle(feat_input, feat_ref, patch_size=3, input_stride=1, ref_stride=1,
                                is_norm=True, norm_input=False, dtype=None, use_conv=False,
-                               return_gap=False):
+                               return_gap=False, chunk=None):
     """CPU restatement of feature_match_index (ref_map_util.py:26-86).
 
     Returns (max_idx int64 [h', w'], max_val [h', w']) and, if return_gap, the
@@ -58,6 +58,34 @@ def feature_match_index_oracle(feat_input, feat_ref, patch_size=3, input_stride=
     c, h, w = feat_input.shape
     ho = (h - patch_size) // input_stride + 1
     wo = (w - patch_size) // input_stride + 1
+    if chunk and not use_conv:
+        # same quantity, evaluated for `chunk` input positions at a time so that the [N_ref, N_in] matrix of the
+        # native validation shapes (125^2 / 128^2 feature grids: 2 GB in fp64) never exists in full
+        k = c * patch_size * patch_size
+        p_ref = sample_patches_oracle(feat_ref.to(dtype), patch_size, ref_stride).reshape(k, -1)
+        p_in = sample_patches_oracle(feat_input.to(dtype), patch_size, input_stride).reshape(k, -1)
+        if is_norm:
+            p_ref = p_ref / (p_ref.norm(p=2, dim=0) + 1e-5)
+        p_ref_t = p_ref.t().contiguous()
+        idxs, vals, gaps = [], [], []
+        for lo in range(0, p_in.shape[1], chunk):
+            blk = p_in[:, lo:lo + chunk]
+            sim = p_ref_t @ blk
+            if norm_input:
+                sim = sim / (blk.norm(p=2, dim=0) + 1e-5)
+            v, i = sim.max(dim=0)
+            idxs.append(i)
+            vals.append(v)
+            if return_gap:
+                if sim.shape[0] > 1:
+                    t2 = sim.topk(2, dim=0).values
+                    gaps.append(t2[0] - t2[1])
+                else:
+                    gaps.append(torch.full_like(v, float('inf')))
+        out = (torch.cat(idxs).view(ho, wo), torch.cat(vals).view(ho, wo))
+        if return_gap:
+            out = out + (torch.cat(gaps).view(ho, wo),)
+        return out
     if use_conv:
         # literally the reference's evaluation order: conv2d with ref patches as filters
         fr = feat_ref.to(dtype)

@@ -344,8 +344,8 @@ print('HASH', h.hexdigest())
 
 
 def test_kernel_variants_agree_bit_for_bit():
-    """The shared-memory window kernel (default), the role-split 256-row kernel (MREFSR_DCN_WIN=0), the 17-warp kernel
-    (+ MREFSR_DCN_SPLIT=0) and the linear tile mapping (+ MREFSR_DCN_TILE=linear) are the same arithmetic in a
+    """The role-split 256-row kernel (default), the shared-memory window kernel (MREFSR_DCN_WIN=1), the 17-warp kernel
+    (MREFSR_DCN_SPLIT=0) and the linear tile mapping (MREFSR_DCN_TILE=linear) are the same arithmetic in a
     different schedule / through a different corner-fetch path: identical bits, fused and operator entry points,
     1 / 2 / 4 deform groups per slab, random flows (window misses: global-memory corners) and coherent flows (window
     hits, windows hanging over the image border).  The knobs are read once per process, hence the subprocesses."""
@@ -354,10 +354,9 @@ def test_kernel_variants_agree_bit_for_bit():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hashes = {}
-    for name, env in (('window', {}), ('split+2d', {'MREFSR_DCN_WIN': '0'}),
-                      ('17-warp', {'MREFSR_DCN_WIN': '0', 'MREFSR_DCN_SPLIT': '0'}),
-                      ('linear', {'MREFSR_DCN_WIN': '0', 'MREFSR_DCN_TILE': 'linear'})):
-        e = dict(os.environ)
+    for name, env in (('split+2d', {}), ('window', {'MREFSR_DCN_WIN': '1'}), ('17-warp', {'MREFSR_DCN_SPLIT': '0'}),
+                      ('linear', {'MREFSR_DCN_TILE': 'linear'})):
+        e = {k: v for k, v in os.environ.items() if not k.startswith('MREFSR_DCN_')}
         e.update(env)
         r = subprocess.run([sys.executable, '-c', _VARIANT_SCRIPT % root], env=e, capture_output=True, text=True,
                            timeout=600)
@@ -366,6 +365,15 @@ def test_kernel_variants_agree_bit_for_bit():
         assert lines, (name, r.stdout[-500:], r.stderr[-500:])
         hashes[name] = lines[-1]
     assert len(set(hashes.values())) == 1, hashes
+
+
+@pytest.fixture
+def window_kernel():
+    """Route eligible DCN calls to the shared-memory window kernel (opt-in) for the duration of a test."""
+    from mrefsr_b200 import _lib
+    prev = _lib.lib().mrefsr_dcn_window_enable(1)
+    yield
+    _lib.lib().mrefsr_dcn_window_enable(prev)
 
 
 def _win_served(b, c, h, w, co, dg):
@@ -379,7 +387,7 @@ def _win_served(b, c, h, w, co, dg):
 @pytest.mark.parametrize('cfg', [dict(b=3, c=64, h=48, w=64, s=4), dict(b=2, c=128, h=40, w=48, s=2),
                                  dict(b=2, c=256, h=24, w=40, s=1), dict(b=2, c=64, h=75, w=75, s=1)])
 @pytest.mark.parametrize('flow', ['translate', 'piecewise', 'border'])
-def test_window_gather_vs_oracle(cfg, flow):
+def test_window_gather_vs_oracle(cfg, flow, window_kernel):
     """Shared-memory window gather (csrc/dcn_win.cu) against the oracle on the flows it was built for: a common
     translation + small learned residual ('translate': every corner from the window), two regions with different
     translations ('piecewise': patches on the seam mix window and global-memory corners), and translations that push
@@ -421,3 +429,39 @@ def test_window_gather_vs_oracle(cfg, flow):
     out2 = D.dcn_forward_raw(x.to(DEV), off.to(DEV), mask.to(DEV), wgt.to(DEV), bias.to(DEV), (1, 1), (1, 1), (1, 1), 1,
                              dg, mode='tf32')
     assert rel_err(out2, ref) <= TOL
+
+
+@pytest.mark.parametrize('cfg', [dict(b=2, c=64, hw=160, s=4), dict(b=1, c=128, hw=150, s=2), dict(b=1, c=64, hw=300, s=4),
+                                 dict(b=1, c=256, hw=75, s=1), dict(b=1, c=128, hw=256, s=2)])
+@pytest.mark.parametrize('kernel', ['default', 'window'])
+def test_native_grids_vs_oracle(cfg, kernel):
+    """Fused DynAgg + DCNv2 at the grids of the BASELINE configurations: 160^2 (config 2, large scale), 75 / 150 / 300
+    (config 3: LMR 300x300, incl. the 75-wide grid that the 256-row kernel maps linearly because patches would pad it
+    by 14 %), 256^2 (config 4's middle scale), against the plain-C oracle (oracle/dcn_ref.c, OpenMP) fed with the
+    oracle's own pre-offsets and DynAgg glue.  Both corner-fetch mechanisms."""
+    from mrefsr_b200 import _lib
+    from oracle.dcn import modulated_deform_conv_c
+    b, c, hw, s = (cfg[k] for k in ('b', 'c', 'hw', 's'))
+    dg = 8
+    g = torch.Generator().manual_seed(hw + c)
+    hc = hw // s
+    hp = hc - 2
+    ys, xs = torch.meshgrid(torch.arange(hp), torch.arange(hp), indexing='ij')
+    coherent = (ys + 3).clamp(0, hp - 1) * hp + (xs - 2).clamp(0, hp - 1)
+    rnd = torch.randint(0, hp * hp, (hp, hp), generator=g)
+    max_idx = torch.stack([torch.where(xs < hp // 2, coherent, rnd) for _ in range(b)])   # half translation, half random
+    x = torch.randn(b, c, hw, hw, generator=g)
+    conv_out = torch.randn(b, 3 * dg * 9, hw, hw, generator=g) * 0.5
+    wgt = torch.randn(c, c, 3, 3, generator=g) * (c * 9) ** -0.5
+    bias = torch.randn(c, generator=g) * 0.1
+    key = {1: 'relu3_1', 2: 'relu2_1', 4: 'relu1_1'}[s]
+    pre = torch.stack([oracle.pre_offsets_oracle(max_idx[i])[key] for i in range(b)], 0)
+    off, mask = oracle.dynagg_offsets_oracle(conv_out, pre, dg)
+    ref = modulated_deform_conv_c(x, off, mask, wgt, bias, 1, 1, 1, 1, dg)
+    prev = _lib.lib().mrefsr_dcn_window_enable(1 if kernel == 'window' else 0)
+    try:
+        out = D.dynagg_dcn_forward(x.to(DEV), conv_out.to(DEV), max_idx.to(DEV), s, wgt.to(DEV), bias.to(DEV), dg)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().mrefsr_dcn_window_enable(prev)
+    assert rel_err(out, ref) <= TOL

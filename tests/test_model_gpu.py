@@ -123,8 +123,6 @@ def test_graphed_forward_equals_eager(golden, pipeline):
     assert torch.equal(host_out, eager2.cpu())
 
 
-@pytest.mark.xfail(strict=False, reason='BASELINE config 1 literally (160x160, 5 references): fixture generated at the end '
-                                        'of round 1 after the GPU budget was spent; first hardware run pending')
 def test_config1_literal_sample_matches_reference(golden, pipeline):
     """BASELINE config 1: one CUFED5-shaped sample, 160x160 HR, 5 references, the reference's fp32 CPU forward
     (tests/golden/make_golden.py::gen_full_model('full_model_cfg1'); inputs are 8-bit images stored as uint8)."""

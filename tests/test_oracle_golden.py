@@ -28,6 +28,18 @@ def test_matcher_oracle_matches_reference(golden, case, use_conv):
         assert torch.equal(idx, ref_idx)
 
 
+@pytest.mark.parametrize('case', ['rand', 'zeropad', 'raw', 'strided'])
+def test_matcher_oracle_chunked_equals_full(golden, case):
+    """The chunked evaluation used at the native validation shapes (125^2 / 128^2 grids) is the same function."""
+    g = golden('matcher')
+    kw = eval(str(g(f'{case}.kw')))
+    full = oracle.feature_match_index_oracle(g(f'{case}.fi'), g(f'{case}.fr'), return_gap=True, dtype=torch.float64, **kw)
+    part = oracle.feature_match_index_oracle(g(f'{case}.fi'), g(f'{case}.fr'), return_gap=True, dtype=torch.float64,
+                                             chunk=7, **kw)
+    assert torch.equal(full[0], part[0])
+    assert (full[1] - part[1]).abs().max() < 1e-12 and (full[2] - part[2]).abs().max() < 1e-12
+
+
 def test_matcher_shift_known_answer(golden):
     g = golden('matcher')
     idx = g('shift.idx')
