@@ -23,13 +23,13 @@ const char* get_error() { return g_err; }
 
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
-int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
+int sm_count() {   // of the CURRENT device (a process may drive several GPUs)
+    static std::atomic<int> cached[64];
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64 && (n = cached[dev].load(std::memory_order_relaxed)) > 0) return n;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    cached = n;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
     return n;
 }
 
@@ -124,23 +124,26 @@ void timing_end(int id, cudaStream_t st) {
 
 // ---------------------------------------------------------------- device arena for the *_host entry points
 static std::mutex g_arena_mu;
-static void* g_arena = nullptr;
-static size_t g_arena_bytes = 0;
+static void* g_arena[64] = {nullptr};       // one arena per device: memory of device 0 is no use to a call on device 1
+static size_t g_arena_bytes[64] = {0};
 
 int arena_get(size_t bytes, void** out) {
+    int dev = 0;
+    MREFSR_CUDA(cudaGetDevice(&dev));
+    MREFSR_CHECK(dev >= 0 && dev < 64, ERR_UNSUPPORTED, "arena: device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_arena_mu);
-    if (bytes > g_arena_bytes) {
-        if (g_arena) {
+    if (bytes > g_arena_bytes[dev]) {
+        if (g_arena[dev]) {
             cudaDeviceSynchronize();
-            cudaFree(g_arena);
-            g_arena = nullptr;
-            g_arena_bytes = 0;
+            cudaFree(g_arena[dev]);
+            g_arena[dev] = nullptr;
+            g_arena_bytes[dev] = 0;
         }
         size_t want = align_up(bytes + bytes / 8, (size_t)1 << 21);
-        MREFSR_CUDA(cudaMalloc(&g_arena, want));
-        g_arena_bytes = want;
+        MREFSR_CUDA(cudaMalloc(&g_arena[dev], want));
+        g_arena_bytes[dev] = want;
     }
-    *out = g_arena;
+    *out = g_arena[dev];
     return 0;
 }
 
@@ -176,11 +179,16 @@ int mrefsr_timing_read(double* ms_out, unsigned long long* launches_out, int n) 
 }
 void mrefsr_arena_release(void) {
     std::lock_guard<std::mutex> lk(mrefsr::g_arena_mu);
-    if (mrefsr::g_arena) {
-        cudaDeviceSynchronize();
-        cudaFree(mrefsr::g_arena);
-        mrefsr::g_arena = nullptr;
-        mrefsr::g_arena_bytes = 0;
-    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int dev = 0; dev < 64; ++dev)
+        if (mrefsr::g_arena[dev]) {
+            cudaSetDevice(dev);
+            cudaDeviceSynchronize();
+            cudaFree(mrefsr::g_arena[dev]);
+            mrefsr::g_arena[dev] = nullptr;
+            mrefsr::g_arena_bytes[dev] = 0;
+        }
+    cudaSetDevice(cur);
 }
 }

@@ -118,6 +118,10 @@ def dynagg_dcn_forward_into(input, conv_out, max_idx, flow_scale, weight, bias, 
     co, dg = wgt.shape[0], deformable_groups
     if tuple(co_.shape) != (b, 3 * dg * 9, h, w):
         raise RuntimeError('conv_out shape %s, expected %s' % (tuple(co_.shape), (b, 3 * dg * 9, h, w)))
+    if mi.dtype != torch.int64 or tuple(mi.shape) != (b, h // flow_scale - 2, w // flow_scale - 2):
+        raise RuntimeError('max_idx must be int64 [%d,%d,%d]' % (b, h // flow_scale - 2, w // flow_scale - 2))
+    if tuple(wgt.shape[1:]) != (c, 3, 3):
+        raise RuntimeError('weight shape %s, expected [Co,%d,3,3]' % (tuple(wgt.shape), c))
     if not 1 <= len(out_ptrs) <= 8:
         raise ValueError('1..8 destination buffers')
     arr = (ctypes.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
@@ -160,6 +164,8 @@ def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, defor
         raise RuntimeError('conv_out shape %s, expected %s' % (tuple(co_.shape), (b, 3 * dg * 9, h, w)))
     if mi.dtype != torch.int64 or tuple(mi.shape) != (b, h // flow_scale - 2, w // flow_scale - 2):
         raise RuntimeError('max_idx must be int64 [%d,%d,%d]' % (b, h // flow_scale - 2, w // flow_scale - 2))
+    if tuple(wgt.shape[1:]) != (c, 3, 3):
+        raise RuntimeError('weight shape %s, expected [Co,%d,3,3]' % (tuple(wgt.shape), c))
     out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device,
                       memory_format=torch.channels_last if out_channels_last else torch.contiguous_format)
     flags = (1 if in_cl else 0) | (2 if out_channels_last else 0)

@@ -75,6 +75,11 @@ class DynAgg(ModulatedDeformConv2d):
         matcher's shifted flow at this scale, but offsets / masks / pre-offsets never touch HBM."""
         from .dcn import dynagg_dcn_forward
         from . import trunk as T
+        if not (tuple(self.kernel_size) == (3, 3) and tuple(self.stride) == (1, 1) and tuple(self.padding) == (1, 1)
+                and tuple(self.dilation) == (1, 1) and self.groups == 1):
+            raise NotImplementedError('forward_fused serves the configuration MRefSR uses (3x3, stride 1, padding 1, '
+                                      'dilation 1, groups 1: ref_mrapa_restoration_arch.py:146-158); use forward() with '
+                                      'materialised pre-offsets for anything else')
         feat = x[1] if self.extra_offset_mask else x
         if self.extra_offset_mask:
             x = x[0]

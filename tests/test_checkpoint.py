@@ -69,6 +69,34 @@ def test_load_pipeline_loads_the_two_networks_the_reference_loads(tmp_path):
     C.save_network(a.net_g, pg)
     C.save_network(a.net_extractor, pe)
     rep = C.load_pipeline(b, net_g=pg, net_extractor=pe)
+    assert rep.pop('random_init') == ['net_map']     # its VGG19 comes from torchvision in the reference: load_pipeline(vgg19=...)
     assert set(rep) == {'net_g', 'net_extractor'} and all(not v['missing'] and not v['unexpected'] for v in rep.values())
     assert _same(a.net_g, b.net_g) and _same(a.net_extractor, b.net_extractor)
     assert len(a.net_g.state_dict()) == 350          # the reference's net_g key count (tests/test_abi.py checks the names)
+
+
+def test_torchvision_vgg_weights_map_onto_the_mirrors():
+    """net_map's VGG19 and the extractor towers take torchvision's ImageNet files (what the reference builds with
+    pretrained=True, vgg_arch.py:103-108 / contras_multi_extractor_arch.py:24-25): i-th convolution -> i-th convolution,
+    and load_pipeline reports which networks stay random."""
+    import torchvision
+    from mrefsr_b200.models import MRefSRPipeline
+    torch.manual_seed(0)
+    tv19 = torchvision.models.vgg19(weights=None).state_dict()
+    tv16 = torchvision.models.vgg16(weights=None).state_dict()
+    pipe = MRefSRPipeline()
+    rep = C.load_pipeline(pipe)
+    assert rep['random_init'] == ['net_extractor', 'net_map', 'net_g']
+    rep = C.load_pipeline(pipe, vgg19=tv19, vgg16=tv16)
+    assert rep['random_init'] == ['net_g']
+    sd = pipe.net_map.vgg.state_dict()
+    # torchvision vgg19.features: conv1_1 = 0, conv1_2 = 2, conv2_1 = 5, conv2_2 = 7, conv3_1 = 10
+    for idx, name in ((0, 'conv1_1'), (2, 'conv1_2'), (5, 'conv2_1'), (7, 'conv2_2'), (10, 'conv3_1')):
+        assert torch.equal(sd['vgg_net.%s.weight' % name], tv19['features.%d.weight' % idx])
+        assert torch.equal(sd['vgg_net.%s.bias' % name], tv19['features.%d.bias' % idx])
+    for tower in (pipe.net_extractor.feature_extraction_image1, pipe.net_extractor.feature_extraction_image2):
+        sd = tower.state_dict()
+        assert torch.equal(sd['model.conv3_1.weight'], tv16['features.10.weight'])
+        assert torch.equal(sd['model.conv1_1.bias'], tv16['features.0.bias'])
+    with pytest.raises(RuntimeError):
+        C.load_torchvision_vgg(pipe.net_map.vgg, {'features.0.weight': torch.zeros(8, 3, 3, 3), 'features.0.bias': torch.zeros(8)})

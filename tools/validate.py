@@ -8,8 +8,8 @@ Builds MRefSRPipeline (channels-last trunk), loads the reference's checkpoints i
 MultiRefCUFEDSet with batch size 1 as the reference's validation loader does, and prints per-image and average PSNR /
 PSNR_Y / SSIM_Y; `--save-dir` writes the SR images.  `--synthetic N` replaces the dataset by N generated CUFED5-shaped
 samples (no files needed).  Needs a GPU (the pipeline has no CPU path); its parts -- sample preparation, metrics, the
-loop, checkpoint IO -- are covered by the CPU tests (tests/test_data.py, tests/test_checkpoint.py).  Status: not yet
-exercised on hardware at 500x500 (round 1 ran out of GPU budget before this tool existed).
+loop, checkpoint IO -- are covered by the CPU tests (tests/test_data.py, tests/test_checkpoint.py).  Exercised on a B200
+with --synthetic 3 (500x500 padded samples, 161 ms / image in the network; gpurun_out r02a).
 """
 import argparse
 import os
@@ -42,6 +42,8 @@ def main():
     ap.add_argument('--dataroot')
     ap.add_argument('--net-g')
     ap.add_argument('--net-extractor')
+    ap.add_argument('--vgg19', help="torchvision's ImageNet vgg19 file (vgg19-dcbb9e9d.pth) for net_map's feature taps")
+    ap.add_argument('--vgg16', help="torchvision's ImageNet vgg16 file, used for the extractor when --net-extractor is not given")
     ap.add_argument('--param-key', default='params')
     ap.add_argument('--crop-border', type=int, default=4)
     ap.add_argument('--save-dir')
@@ -54,11 +56,16 @@ def main():
     from mrefsr_b200.models import MRefSRPipeline
     torch.manual_seed(args.seed)
     net = MRefSRPipeline().eval()
-    rep = checkpoint.load_pipeline(net, net_g=args.net_g, net_extractor=args.net_extractor, param_key=args.param_key)
+    rep = checkpoint.load_pipeline(net, net_g=args.net_g, net_extractor=args.net_extractor, param_key=args.param_key,
+                                   vgg19=args.vgg19, vgg16=args.vgg16)
     for name, r in rep.items():
-        print('loaded %s: %d missing, %d unexpected keys' % (name, len(r['missing']), len(r['unexpected'])))
-    if not rep:
-        print('no checkpoints given: random-init weights (metrics are only a plumbing check)')
+        if name != 'random_init':
+            print('loaded %s: %s' % (name, ', '.join('%d %s' % (len(v), k) for k, v in r.items())))
+    if rep['random_init']:
+        print('WARNING: %s left at RANDOM initial weights -- the PSNR / SSIM below are a plumbing check, not a '
+              'quality measurement (the reference takes the VGG19 of net_map from torchvision: pass --vgg19)'
+              % ', '.join(rep['random_init']), file=sys.stderr)
+        print('WARNING: random-init networks: %s' % ', '.join(rep['random_init']))
     net = net.to('cuda').channels_last_()
     if args.synthetic:
         samples = synthetic_samples(args.synthetic)
