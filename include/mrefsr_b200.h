@@ -173,6 +173,17 @@ enum {
     MREFSR_DCN_OUT_NHWC = 2,
     MREFSR_DCN_W_PACKED = 4, /* `weight` is the output of mrefsr_dcn_pack_weights (inference: packed once per weight update) */
 };
+/* The plain GEMM of the DCN backward on tcgen05 (csrc/gemm_tc.cu; TF32 operands, fp32 accumulate), exported for tests:
+ *   D[m][n] = sum_k A[m][k] * B[n][k],   A [M x K] and B [N x K] row-major (k contiguous), D row-major with pitch ldd.
+ * reduce == 0: `batch` independent products, operands / outputs a_batch_stride / b_batch_stride / d_stride elements
+ *   apart (a_batch_stride == 0: one A for all) -- columns = W^T . grad_output, deform_conv_cuda.cpp:623-626;
+ * reduce != 0: ONE product summed over the batch as well as over k, computed as `splits` partial sums written to
+ *   D + split * d_stride (the caller adds them in split order: deterministic) -- grad_weight += grad_output .
+ *   columns^T, deform_conv_cuda.cpp:659-664.
+ * Pitches and batch strides must be multiples of 4 floats and the bases 16-byte aligned (TMA). */
+MREFSR_API int mrefsr_gemm_tf32_nt(const float* A, int lda, long long a_batch_stride, const float* B, int ldb,
+                                   long long b_batch_stride, float* D, int ldd, long long d_stride, int M, int N, int K,
+                                   int batch, int reduce, int splits, void* stream);
 /* W[Co][C][kh*kw] (the reference's parameter layout, deform_conv.py:305-309) -> the tcgen05 kernels' B operand
  * [Co][tap][C], rounded to tf32 (round to nearest, so the tensor core's truncation is exact).  The forward entry
  * points do this on every call unless MREFSR_DCN_W_PACKED is set; a module whose weights are frozen packs once. */

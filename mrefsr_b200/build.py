@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-cudart', 'static', '-lcublas']
+    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-cudart', 'static']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

@@ -268,6 +268,10 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 // with cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda.
 int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
                        uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle);
+// same with explicit row / plane pitches in bytes (multiples of 16)
+int make_tensor_map_3d_strided(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
+                               uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
+                               uint32_t box1, CUtensorMapSwizzle swizzle);
 // 4-D tiled tensor map [d3][d2][d1][d0] (d0 contiguous, densely packed), box = box0 x box1 x box2 x 1; out-of-bounds
 // elements of a box (negative or too large coordinates) are filled with zeros.
 int make_tensor_map_4d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,

@@ -10,7 +10,6 @@
 //     (deform_conv_cuda.cpp:612-672) is batched over chunks of samples sized to a bounded workspace.
 #include "common.cuh"
 #include "dcn_tc.cuh"
-#include <cublas_v2.h>
 #include "../../include/mrefsr_b200.h"
 
 namespace mrefsr {
@@ -255,9 +254,9 @@ __global__ void dcn_im2col_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
-// (4a') position-major columns for the library-GEMM path: colP[bl][p][tap*C + c] from the NHWC copy of the input.
-// One thread = (position, tap, 8-channel chunk): one sample decode, four 256-bit corner loads, one 32-byte store;
-// lanes = consecutive positions (coalesced offset / mask reads).  The planar kernel above issues 8x the L1 sectors.
+// (4a') columns from the NHWC copy of the input.  One thread = (position, tap, 8-channel chunk): one sample decode, four
+// 256-bit corner loads; lanes = consecutive positions (coalesced offset / mask reads).  The planar kernel above issues
+// 8x the L1 sectors.
 struct __align__(32) Col8 {
     float v[8];
 };
@@ -268,9 +267,12 @@ __device__ __forceinline__ Col8 ldg_col8(const float* p) {
         : "l"(p));
     return r;
 }
+// written as planes colT[bl][tap*C + c][p] (k = position contiguous: the B operand of the
+// tcgen05 grad_weight GEMM).  Lanes = consecutive positions, so each of the 8 scalar stores of a thread is a coalesced
+// 128-byte warp store into its channel plane.
 __global__ void __launch_bounds__(256)
-dcn_im2col_nhwc_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
-                       float* __restrict__ colP, const DcnShape s, int b0, int nb) {
+dcn_im2col_planes_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
+                         float* __restrict__ colT, const DcnShape s, int b0, int nb) {
     const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG, C8 = s.C >> 3;
     const size_t total = (size_t)nb * K * C8 * P;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -299,13 +301,37 @@ dcn_im2col_nhwc_kernel(const float* __restrict__ xt, const float* __restrict__ o
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = w0 * v0.v[e] + w1 * v1.v[e] + w2 * v2.v[e] + w3 * v3.v[e];
         }
-        float* dst = colP + ((size_t)bl * P + p) * ((size_t)K * s.C) + (size_t)tap * s.C + c0;
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        float* dst = colT + ((size_t)bl * K * s.C + (size_t)tap * s.C + c0) * P + p;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[(size_t)e * P] = to_tf32(o[e]);     // GEMM operand: the tensor core's read truncates
     }
 }
 
-// grad_weight[oc][c][tap] += gwT[oc][tap*C + c]   (the library GEMM above works in the tap-major column order)
+// W[oc][m] -> WT[m][oc]   (A operand of the columns GEMM: rows m = c*K + tap, k = oc contiguous)
+__global__ void dcn_weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int Co, int MK) {
+    const int total = Co * MK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int oc = i % Co, m = i / Co;
+        wT[i] = to_tf32(__ldg(w + (size_t)oc * MK + m));
+    }
+}
+
+// tf32-rounded copy (GEMM operand whose natural layout is already the one the GEMM wants)
+__global__ void dcn_round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = to_tf32(__ldg(src + i));
+}
+
+// gwT[i] += sum over the splits of part[s][i], in split order (deterministic)
+__global__ void dcn_split_sum_kernel(const float* __restrict__ part, float* __restrict__ gwT, int n, int splits) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float a = gwT[i];
+        for (int sp = 0; sp < splits; ++sp) a += part[(size_t)sp * n + i];
+        gwT[i] = a;
+    }
+}
+
+// grad_weight[oc][c][tap] += gwT[oc][tap*C + c]   (the grad_weight GEMM works in the tap-major column order)
 __global__ void dcn_gw_permute_add_kernel(const float* __restrict__ gwT, float* __restrict__ gw, int Co, int C, int K) {
     const int total = Co * C * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -439,28 +465,7 @@ int dcn_make_shape(DcnShape* s, int B, int C, int H, int W, int Co, int kh, int 
     return 0;
 }
 
-// ---- plain GEMMs of the backward pass: cuBLAS (TF32 tensor cores unless the caller asks for exact fp32).
-// One handle per host thread and device, created on first use; the stream is set per call.
-static cublasHandle_t cublas_handle(cudaStream_t st, bool tf32) {
-    static thread_local cublasHandle_t handles[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!handles[dev] && cublasCreate(&handles[dev]) != CUBLAS_STATUS_SUCCESS) {
-        handles[dev] = nullptr;
-        return nullptr;
-    }
-    cublasSetStream(handles[dev], st);
-    cublasSetMathMode(handles[dev], tf32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH);
-    return handles[dev];
-}
-#define MREFSR_CUBLAS(call)                                                                             \
-    do {                                                                                                \
-        cublasStatus_t cs_ = (call);                                                                    \
-        if (cs_ != CUBLAS_STATUS_SUCCESS) {                                                             \
-            ::mrefsr::set_error("cuBLAS call failed with status %d (%s:%d)", (int)cs_, __FILE__, __LINE__); \
-            return -102;                                                                                \
-        }                                                                                               \
-    } while (0)
+constexpr int BWD_MAX_SPLITS = 32;     // split-K pieces of the grad_weight GEMM (partial sums in the workspace)
 
 static int bwd_chunk(const DcnShape& s) {
     const size_t per = (size_t)s.C * s.kh * s.kw * s.Ho * s.Wo * 4;
@@ -516,9 +521,12 @@ size_t mrefsr_dcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, in
     if (dcn_make_shape(&s, B, C, H, W, Co, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, group,
                        deformable_group))
         return 0;
-    if (backward)   // gcol + col chunks, NHWC copy of the input, tap-major grad_weight scratch
+    if (backward)   // gcol + col chunks, NHWC copies of the input and of grad_output, W^T, tap-major grad_weight scratch
+                    // and the split-K partial sums of the grad_weight GEMM
         return 2 * align_up((size_t)bwd_chunk(s) * C * kh * kw * s.Ho * s.Wo * 4, 1024) +
-               align_up((size_t)B * C * H * W * 4, 1024) + align_up((size_t)Co * C * kh * kw * 4, 1024) + 1024;
+               align_up((size_t)B * C * H * W * 4, 1024) + 2 * align_up((size_t)B * Co * s.Ho * s.Wo * 4, 1024) +
+               2 * align_up((size_t)Co * C * kh * kw * 4, 1024) +
+               align_up((size_t)BWD_MAX_SPLITS * Co * C * kh * kw * 4, 1024) + 1024;
     return dcn_tc_workspace_bytes(s, mode) + 1024;
 }
 
@@ -553,8 +561,10 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
                                           int with_bias, int mode, void* workspace, size_t workspace_bytes,
                                           void* stream) {
     MREFSR_CHECK(input && weight && offset && grad_output, ERR_BAD_ARG, "dcn backward: null pointer argument");
-    // MREFSR_DCN_FP32: exact-fp32 CUDA-core GEMMs of this file; otherwise the two plain GEMMs go to cuBLAS (TF32)
-    const bool lib_gemm = mode != MREFSR_DCN_FP32;
+    // MREFSR_DCN_FP32: exact-fp32 CUDA-core GEMMs of this file; otherwise the two plain GEMMs run on tcgen05
+    // (gemm_tc.cu, TF32 operands, fp32 accumulate) whenever the operand pitches allow TMA (group 1, Co % 4 == 0 for
+    // the columns GEMM, output positions % 4 == 0 for the grad_weight GEMM)
+    const bool tc_gemm = mode != MREFSR_DCN_FP32;
     MREFSR_CHECK(grad_offset || !grad_mask, ERR_BAD_ARG, "dcn backward: grad_mask requires grad_offset");
     MREFSR_CHECK(!with_bias || grad_bias, ERR_BAD_ARG, "dcn backward: with_bias set but grad_bias is NULL");
     DcnShape s;
@@ -566,37 +576,50 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
     const int nbmax = bwd_chunk(s);
     const size_t buf = align_up((size_t)nbmax * C * K * P * 4, 1024);
     const size_t xt_bytes = align_up((size_t)B * C * H * W * 4, 1024), gwt_bytes = align_up((size_t)Co * C * K * 4, 1024);
-    // position-major im2col + one library GEMM per sample for grad_weight (needs whole 8-channel chunks per group)
-    const bool nhwc_cols = lib_gemm && grad_weight && group == 1 && C % 8 == 0 && (C / deformable_group) % 8 == 0 &&
-                           (size_t)B * C * H * W < ((size_t)1 << 31);
-    const size_t need = 2 * buf + (nhwc_cols ? xt_bytes + gwt_bytes : 0);
+    const size_t got_bytes = align_up((size_t)B * Co * P * 4, 1024);
+    const size_t part_bytes = align_up((size_t)BWD_MAX_SPLITS * Co * C * K * 4, 1024);
+    const bool small_enough = (size_t)B * C * H * W < ((size_t)1 << 31) && (size_t)B * Co * P < ((size_t)1 << 31);
+    // columns GEMM on tcgen05: gcol[bl] (MK x P) = W^T (MK x Co) . gout[b] (Co x P); B operand = gout position-major
+    const bool tc_gcol = tc_gemm && (grad_input || grad_offset) && group == 1 && Co % 4 == 0 && small_enough;
+    // grad_weight GEMM on tcgen05: gwT (Co x K*C, tap-major) += gout[b] (Co x P) . colT[bl]^T, k = positions
+    const bool tc_gw = tc_gemm && grad_weight && group == 1 && C % 8 == 0 && (C / deformable_group) % 8 == 0 && P % 4 == 0 &&
+                       small_enough;
+    const size_t need = 2 * buf + xt_bytes + 2 * got_bytes + 2 * gwt_bytes + part_bytes;
     MREFSR_CHECK(workspace && workspace_bytes >= need, ERR_WORKSPACE, "dcn backward: workspace too small (%zu < %zu)",
                  workspace_bytes, need);
-    MREFSR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 31) == 0, ERR_WORKSPACE, "dcn backward: workspace must be 32-byte aligned");
-    float* gcol = static_cast<float*>(workspace);
-    float* col = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + buf);
-    float* xt = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * buf);
-    float* gwT = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * buf + xt_bytes);
-    if (nhwc_cols) {
+    MREFSR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, ERR_WORKSPACE, "dcn backward: workspace must be 1024-byte aligned");
+    uint8_t* wsp = static_cast<uint8_t*>(workspace);
+    float* gcol = reinterpret_cast<float*>(wsp);
+    float* col = reinterpret_cast<float*>(wsp + buf);
+    float* xt = reinterpret_cast<float*>(wsp + 2 * buf);
+    float* goutT = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes);
+    float* gwT = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes);
+    float* wT = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes + gwt_bytes);
+    float* part = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes + 2 * gwt_bytes);
+    float* goutR = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes + 2 * gwt_bytes + part_bytes);
+    if (tc_gw) {
         rc = dcn_nchw_to_nhwc(input, xt, B, C, H * W, st);
         if (rc) return rc;
         MREFSR_CUDA(cudaMemsetAsync(gwT, 0, (size_t)Co * C * K * 4, st));
+        dcn_round_tf32_kernel<<<grid_for((size_t)B * Co * P), 256, 0, st>>>(grad_output, goutR, (size_t)B * Co * P);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
+    }
+    if (tc_gcol) {
+        rc = dcn_nchw_to_nhwc(grad_output, goutT, B, Co, P, st, true);
+        if (rc) return rc;
+        dcn_weight_transpose_kernel<<<cdiv(Co * MK, 256), 256, 0, st>>>(weight, wT, Co, MK);
+        MREFSR_LAUNCH_CHECK();
+        count_launches(1);
     }
     if (grad_input) MREFSR_CUDA(cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * 4, st));
     for (int b0 = 0; b0 < B; b0 += nbmax) {
         const int nb = (B - b0 < nbmax) ? B - b0 : nbmax;
-        if ((grad_input || grad_offset) && lib_gemm) {
-            // gcol[bl] (MK x P) = W_g^T (MK x opg) . gout[b, g] (opg x P)   (deform_conv_cuda.cpp:623-626), row-major
-            // operands handed to column-major cuBLAS as their transposes
-            cublasHandle_t h = cublas_handle(st, true);
-            MREFSR_CHECK(h, -102, "dcn backward: cuBLAS handle creation failed");
-            const float one = 1.f, zero = 0.f;
-            for (int gi = 0; gi < group; ++gi)
-                MREFSR_CUBLAS(cublasSgemmStridedBatched(
-                    h, CUBLAS_OP_N, CUBLAS_OP_T, P, MK, opg, &one, grad_output + ((size_t)b0 * Co + (size_t)gi * opg) * P, P,
-                    (long long)Co * P, weight + (size_t)gi * opg * MK, MK, 0, &zero, gcol + (size_t)gi * MK * P, P,
-                    (long long)C * K * P, nb));
-            count_launches(group);
+        if (tc_gcol) {
+            // (deform_conv_cuda.cpp:623-626), all samples of the chunk in one launch
+            rc = gemm_tf32_nt(wT, Co, 0, goutT + (size_t)b0 * P * Co, Co, (long long)P * Co, gcol, P, (long long)MK * P, MK, P,
+                              Co, nb, 0, 1, st);
+            if (rc) return rc;
         } else if (grad_input || grad_offset) {
             dcn_bwd_gcol_kernel<<<dim3(cdiv(P, DT), group * cdiv(MK, DT), nb), 256, 0, st>>>(weight, grad_output, gcol, s, b0);
             MREFSR_LAUNCH_CHECK();
@@ -613,43 +636,36 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }
-        if (grad_weight && nhwc_cols) {
-            dcn_im2col_nhwc_kernel<<<grid_for((size_t)nb * K * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
+        if (tc_gw) {
+            // recomputed columns (deform_conv_cuda.cpp:647-650) as planes colT[bl][tap*C + c][p], then the chunk's share
+            // of grad_weight (:659-664) as one split-K GEMM whose partial sums are added up in a fixed order
+            dcn_im2col_planes_kernel<<<grid_for((size_t)nb * K * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
-            // gwT (Co x K*C, tap-major) += gout[b] (Co x P) . colP[bl] (P x K*C)
-            cublasHandle_t h = cublas_handle(st, true);
-            MREFSR_CHECK(h, -102, "dcn backward: cuBLAS handle creation failed");
-            const float one = 1.f;
-            for (int bl = 0; bl < nb; ++bl)
-                MREFSR_CUBLAS(cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, K * C, Co, P, &one, col + (size_t)bl * P * K * C, K * C,
-                                          grad_output + (size_t)(b0 + bl) * Co * P, P, &one, gwT, K * C));
-            count_launches(1 + nb);
+            count_launches(1);
+            const long long all_kb = (long long)nb * cdiv(P, 32);
+            const int tiles = cdiv(Co, 128) * cdiv(K * C, 128);
+            int splits = cdiv(2 * sm_count(), tiles);
+            if (splits > BWD_MAX_SPLITS) splits = BWD_MAX_SPLITS;
+            if (splits > all_kb) splits = (int)all_kb;
+            if (splits < 1) splits = 1;
+            rc = gemm_tf32_nt(goutR + (size_t)b0 * Co * P, P, (long long)Co * P, col, P, (long long)K * C * P, part, K * C,
+                              (long long)Co * K * C, Co, K * C, P, nb, 1, splits, st);
+            if (rc) return rc;
+            dcn_split_sum_kernel<<<cdiv(Co * C * K, 256), 256, 0, st>>>(part, gwT, Co * C * K, splits);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
         } else if (grad_weight) {
             dcn_im2col_kernel<<<grid_for((size_t)nb * C * K * P), 256, 0, st>>>(input, offset, mask, col, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
-            if (lib_gemm) {
-                // gW_g (opg x MK) += gout[b, g] (opg x P) . col[bl]^T (P x MK)   (deform_conv_cuda.cpp:659-666)
-                cublasHandle_t h = cublas_handle(st, true);
-                MREFSR_CHECK(h, -102, "dcn backward: cuBLAS handle creation failed");
-                const float one = 1.f;
-                for (int bl = 0; bl < nb; ++bl)
-                    for (int gi = 0; gi < group; ++gi)
-                        MREFSR_CUBLAS(cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, MK, opg, P, &one,
-                                                  col + ((size_t)bl * C * K + (size_t)gi * MK) * P, P,
-                                                  grad_output + ((size_t)(b0 + bl) * Co + (size_t)gi * opg) * P, P, &one,
-                                                  grad_weight + (size_t)gi * opg * MK, MK));
-                count_launches(nb * group);
-            } else {
-                const int pchunks = cdiv(P, WCHUNK);
-                dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
-                    grad_output, col, grad_weight, s, b0, pchunks);
-                MREFSR_LAUNCH_CHECK();
-                count_launches(1);
-            }
+            const int pchunks = cdiv(P, WCHUNK);
+            dcn_bwd_weight_kernel<<<dim3(group * cdiv(MK, DT), cdiv(opg, DT), nb * pchunks), 256, 0, st>>>(
+                grad_output, col, grad_weight, s, b0, pchunks);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
         }
     }
-    if (nhwc_cols) {
+    if (tc_gw) {
         dcn_gw_permute_add_kernel<<<cdiv(Co * C * K, 256), 256, 0, st>>>(gwT, grad_weight, Co, C, K);
         MREFSR_LAUNCH_CHECK();
         count_launches(1);
@@ -660,6 +676,15 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
         count_launches(1);
     }
     return 0;
+}
+
+int mrefsr_gemm_tf32_nt(const float* A, int lda, long long a_batch_stride, const float* B, int ldb, long long b_batch_stride,
+                        float* D, int ldd, long long d_stride, int M, int N, int K, int batch, int reduce, int splits,
+                        void* stream) {
+    MREFSR_CHECK(A && B && D, ERR_BAD_ARG, "gemm: null pointer argument");
+    MREFSR_CHECK(!reduce || splits >= 1, ERR_BAD_ARG, "gemm: reduce mode needs splits >= 1");
+    return gemm_tf32_nt(A, lda, a_batch_stride, B, ldb, b_batch_stride, D, ldd, d_stride, M, N, K, batch, reduce, splits,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int mrefsr_dcn_pack_weights(const float* weight, float* packed, int Co, int C, int K, void* stream) {

@@ -33,7 +33,13 @@ int dcn_forward_fp32(const float* x, const float* w, const float* bias, const fl
                      const DcnShape& s, cudaStream_t st);
 
 // NCHW -> NHWC copy (dcn_tc.cu), also used by the backward's position-major im2col
-int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st);
+int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st, bool round_tf32 = false);
+
+// tcgen05 TF32 GEMM D = A . B^T of the backward pass (gemm_tc.cu)
+bool gemm_tc_operands_ok(const void* A, int lda, long long a_batch_stride, const void* B, int ldb, long long b_batch_stride);
+int gemm_tf32_nt(const float* A, int lda, long long a_batch_stride, const float* B, int ldb, long long b_batch_stride,
+                 float* D, int ldd, long long d_stride, int M, int N, int K, int batch, int reduce, int splits,
+                 cudaStream_t st);
 
 int dcn_pack_weights(const float* w, float* wt, int Co, int C, int K, cudaStream_t st);
 

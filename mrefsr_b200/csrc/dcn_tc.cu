@@ -54,6 +54,7 @@ namespace mrefsr {
 // NCHW -> NHWC (fp32): tile = 32 pixels x up to 128 channels per CTA (256 threads).  Loads: lane = pixel (128-byte
 // coalesced, 16 independent loads per thread in flight); stores: one float4 (4 channels) per lane, 512 bytes
 // contiguous per warp.  grid (ceil(HW/32), ceil(C/128), B)
+template <bool ROUND>     // ROUND: values rounded to tf32 on the way (operands of the tcgen05 GEMMs, whose reads truncate)
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
     __shared__ float tile[128][33];
@@ -65,7 +66,8 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int cl = warp + 8 * i, c = c0 + cl;
-        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+        const float v = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+        tile[cl][lane] = ROUND ? to_tf32(v) : v;
     }
     __syncthreads();
 #pragma unroll
@@ -838,8 +840,9 @@ int dcn_pack_weights(const float* w, float* wt, int Co, int C, int K, cudaStream
     return 0;
 }
 
-int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st) {
-    nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(C, 128), B), 256, 0, st>>>(x, xt, C, HW);
+int dcn_nchw_to_nhwc(const float* x, float* xt, int B, int C, int HW, cudaStream_t st, bool round_tf32) {
+    if (round_tf32) nchw_to_nhwc_kernel<true><<<dim3(cdiv(HW, 32), cdiv(C, 128), B), 256, 0, st>>>(x, xt, C, HW);
+    else nchw_to_nhwc_kernel<false><<<dim3(cdiv(HW, 32), cdiv(C, 128), B), 256, 0, st>>>(x, xt, C, HW);
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;
@@ -968,7 +971,7 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
             MREFSR_CHECK((reinterpret_cast<uintptr_t>(x) & 31) == 0, ERR_BAD_ARG, "dcn forward: NHWC input must be 32-byte aligned");
             xt = const_cast<float*>(x);
         } else {
-            nchw_to_nhwc_kernel<<<dim3(cdiv(HW, 32), cdiv(s.C, 128), s.B), 256, 0, st>>>(x, xt, s.C, HW);
+            nchw_to_nhwc_kernel<false><<<dim3(cdiv(HW, 32), cdiv(s.C, 128), s.B), 256, 0, st>>>(x, xt, s.C, HW);
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }

@@ -66,6 +66,24 @@ int make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_byt
     return 0;
 }
 
+int make_tensor_map_3d_strided(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
+                               uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
+                               uint32_t box1, CUtensorMapSwizzle swizzle) {
+    PFN_encodeTiled fn = encode_fn();
+    MREFSR_CHECK(fn != nullptr, ERR_NOT_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MREFSR_CHECK(r == CUDA_SUCCESS, ERR_BAD_ARG,
+                 "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu strides %llu / %llu box %u x %u", (int)r,
+                 (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                 (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1);
+    return 0;
+}
+
 int make_tensor_map_4d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t d0,
                        uint64_t d1, uint64_t d2, uint64_t d3, uint32_t box0, uint32_t box1, uint32_t box2,
                        CUtensorMapSwizzle swizzle) {

@@ -465,3 +465,37 @@ def test_native_grids_vs_oracle(cfg, kernel):
     finally:
         _lib.lib().mrefsr_dcn_window_enable(prev)
     assert rel_err(out, ref) <= TOL
+
+
+@pytest.mark.parametrize('shape', [dict(M=576, N=1600, K=64, batch=3), dict(M=130, N=70, K=36, batch=2),
+                                   dict(M=2304, N=6400, K=256, batch=1), dict(M=64, N=576, K=25600, batch=2, reduce=True, splits=30),
+                                   dict(M=256, N=2304, K=1600, batch=5, reduce=True, splits=4),
+                                   dict(M=96, N=200, K=100, batch=3, reduce=True, splits=7)])
+def test_backward_gemm_on_tcgen05(shape):
+    """csrc/gemm_tc.cu, the GEMM behind both products of the DCN backward (deform_conv_cuda.cpp:623-626, :659-664),
+    through its C-ABI test entry against torch in fp64: TF32 operands, fp32 accumulation -> 1e-3 of the result's
+    scale.  Ragged tiles (M, N, K not multiples of the 128 x 128 x 32 tile), a shared A operand, and the split-K
+    reduce mode whose partial sums must add up to the batch-summed product."""
+    from mrefsr_b200 import _lib
+    M_, N_, K_, batch = (shape[k] for k in ('M', 'N', 'K', 'batch'))
+    reduce, splits = shape.get('reduce', False), shape.get('splits', 1)
+    g = torch.Generator().manual_seed(M_ + N_)
+    lda = (K_ + 3) // 4 * 4 + 4                      # pitches larger than K: padding columns must never be read as data
+    a = torch.randn(batch if reduce else 1, M_, lda, generator=g).to(DEV)
+    b = torch.randn(batch, N_, lda, generator=g).to(DEV)
+    n_out = splits if reduce else batch
+    ldd = N_ + 3
+    d = torch.full((n_out, M_, ldd), float('nan'), device=DEV)
+    rc = _lib.lib().mrefsr_gemm_tf32_nt(_lib.ptr(a), lda, M_ * lda if reduce else 0, _lib.ptr(b), lda, N_ * lda, _lib.ptr(d), ldd,
+                                        M_ * ldd, M_, N_, K_, batch, int(reduce), splits, _lib.stream_ptr(a.device))
+    _lib.check(rc, 'mrefsr_gemm_tf32_nt')
+    torch.cuda.synchronize()
+    a64, b64 = a[..., :K_].double().cpu(), b[..., :K_].double().cpu()
+    assert torch.isnan(d[..., N_:]).all()             # nothing written beyond the N columns
+    if reduce:
+        ref = torch.einsum('zmk,znk->mn', a64, b64)
+        out = d[..., :N_].double().cpu().sum(0)
+    else:
+        ref = torch.einsum('mk,znk->zmn', a64[0], b64)
+        out = d[..., :N_].double().cpu()
+    assert float((out - ref).abs().max() / ref.abs().max()) <= 1e-3

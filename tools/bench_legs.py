@@ -160,7 +160,7 @@ def train_step_leg(dev, rank, world, dist, batch=12, refs=5, hr=160, steps=3, bf
     pipe.net_map.eval()
     for p in list(pipe.net_extractor.parameters()) + list(pipe.net_map.parameters()):
         p.requires_grad_(False)
-    net_g = pipe.net_g.train()
+    net_g = pipe.net_g.train().to(memory_format=torch.channels_last)     # cuDNN's native layout for the plain convolutions
     for name in ('small', 'medium', 'large'):      # zero-init in the reference: give every backward path a signal
         getattr(net_g.dyn_agg_restore, f'{name}_dyn_agg').conv_offset_mask.weight.data.normal_(0, 1e-3)
     model = torch.nn.parallel.DistributedDataParallel(net_g, device_ids=[dev.index]) if world > 1 else net_g
@@ -181,7 +181,7 @@ def train_step_leg(dev, rank, world, dist, batch=12, refs=5, hr=160, steps=3, bf
                 rfs.append(rf)
         opt.zero_grad(set_to_none=True)
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
-            out = model(lq, pres, rfs)
+            out = model(lq.contiguous(memory_format=torch.channels_last), pres, rfs)
         loss = torch.nn.functional.l1_loss(out.float(), gt)
         loss.backward()
         opt.step()
@@ -200,7 +200,7 @@ def train_step_leg(dev, rank, world, dist, batch=12, refs=5, hr=160, steps=3, bf
     del pipe, model, opt
     torch.cuda.empty_cache()
     return {'config': 'BASELINE config 5: stage-3 restoration training step, batch %d per GPU, %d refs @%d^2, L1 loss, '
-                      'Adam, %s, %d GPU(s)%s' % (batch, refs, hr, 'bf16 autocast convolutions' if bf16 else 'fp32',
+                      'Adam, %s, channels_last net_g, %d GPU(s)%s' % (batch, refs, hr, 'bf16 autocast convolutions' if bf16 else 'fp32',
                                                  world, ' (DDP)' if world > 1 else ''),
             'ms_per_step': ms, 'images_per_s': batch * world / (ms / 1e3), 'losses': [round(v, 5) for v in losses],
             'all_grads_finite': finite}
