@@ -206,6 +206,18 @@ MREFSR_API int mrefsr_dynagg_dcn_forward_multi(const float* input, const float* 
                                     int with_bias, int layout_flags, float out_slope, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* Same with PIXEL-SLAB routing: output row oy is stored to outputs[oy / slab_rows] only (buffers in RANK order, each
+ * [n, R, Co, slab_rows, W] NCHW planes, slot as above).  Each rank of the reference-sharded mode then holds every
+ * reference's aligned features for ITS rows, runs the fusion (softmax over references,
+ * ref_mrapa_restoration_arch.py:321-335) on 1/N of the pixels and all-gathers the fused result: the exchange of SURVEY
+ * 8e as an all-to-all inside the DCN epilogue, N times fewer bytes per GPU than the all-gather of aligned features. */
+MREFSR_API int mrefsr_dynagg_dcn_forward_slabs(const float* input, const float* weight, const float* bias,
+                                    const float* conv_out, const int64_t* max_idx, int flow_scale,
+                                    float* const* outputs, int n_outputs, int slab_rows, int dst_group, int dst_stride,
+                                    int dst_offset, int B, int C, int H, int W, int Co, int deformable_group,
+                                    int with_bias, int layout_flags, float out_slope, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Trunk glue (the plain-convolution network either side of the path; convolutions
  * themselves stay cuDNN).  One streaming pass instead of torch's bias-add / activation /

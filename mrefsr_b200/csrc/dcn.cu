@@ -747,6 +747,35 @@ int mrefsr_dynagg_dcn_forward_multi(const float* input, const float* weight, con
     m.group = dst_group;
     m.stride = dst_stride;
     m.offset = dst_offset;
+    m.slab_rows = 0;
+    return dcn_forward_tc_impl(input, weight, with_bias ? bias : nullptr, conv_out, nullptr,
+                               reinterpret_cast<const long long*>(max_idx), flow_scale, nullptr, s, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream), layout_flags, out_slope, &m);
+}
+
+int mrefsr_dynagg_dcn_forward_slabs(const float* input, const float* weight, const float* bias, const float* conv_out,
+                                    const int64_t* max_idx, int flow_scale, float* const* outputs, int n_outputs,
+                                    int slab_rows, int dst_group, int dst_stride, int dst_offset, int B, int C, int H,
+                                    int W, int Co, int deformable_group, int with_bias, int layout_flags, float out_slope,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    MREFSR_CHECK(input && weight && conv_out && max_idx && outputs, ERR_BAD_ARG, "dynagg forward: null pointer argument");
+    MREFSR_CHECK(!with_bias || bias, ERR_BAD_ARG, "dynagg forward: with_bias set but bias is NULL");
+    MREFSR_CHECK((layout_flags & ~(MREFSR_DCN_IN_NHWC | MREFSR_DCN_W_PACKED)) == 0, ERR_BAD_ARG,
+                 "dynagg forward (slabs): unknown or unsupported layout flags 0x%x", layout_flags);
+    MREFSR_CHECK(n_outputs >= 1 && n_outputs <= 8 && slab_rows >= 1, ERR_BAD_ARG,
+                 "dynagg forward (slabs): 1..8 output buffers and slab_rows >= 1 (got %d, %d)", n_outputs, slab_rows);
+    DcnShape s;
+    int rc = dcn_make_shape(&s, B, C, H, W, Co, 3, 3, 1, 1, 1, 1, 1, 1, 1, deformable_group);
+    if (rc) return rc;
+    MREFSR_CHECK(dcn_tc_eligible(s), ERR_UNSUPPORTED,
+                 "dynagg forward: needs C %% 32 == 0, (C/deformable_group) %% 8 == 0, Co %% 32 == 0, Co <= 256");
+    DcnOutputs m;
+    for (int k = 0; k < 8; ++k) m.ptr[k] = k < n_outputs ? outputs[k] : nullptr;
+    m.n = n_outputs;
+    m.group = dst_group;
+    m.stride = dst_stride;
+    m.offset = dst_offset;
+    m.slab_rows = slab_rows;
     return dcn_forward_tc_impl(input, weight, with_bias ? bias : nullptr, conv_out, nullptr,
                                reinterpret_cast<const long long*>(max_idx), flow_scale, nullptr, s, workspace,
                                workspace_bytes, static_cast<cudaStream_t>(stream), layout_flags, out_slope, &m);

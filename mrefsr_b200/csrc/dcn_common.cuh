@@ -47,6 +47,7 @@ int dcn_pack_weights(const float* w, float* wt, int Co, int C, int K, cudaStream
 struct DcnOutputs {
     float* ptr[8];
     int n, group, stride, offset;   // sample b -> slot (b / group) * stride + offset + b % group  (group 0: slot b)
+    int slab_rows;                  // > 0: output row oy goes to buffer oy / slab_rows only ([slots, Co, slab_rows, Wo])
 };
 
 // tcgen05 (TF32) forward, dcn_tc.cu

@@ -28,6 +28,10 @@ struct DcnTcParams {
     // (b / dst_group) * dst_stride + dst_offset + b % dst_group  (dst_group == 0: slot b).
     float* outs[8];
     int n_outs, dst_group, dst_stride, dst_offset;
+    // dst_slab_rows > 0 (NCHW outputs only): pixel-slab routing -- output row oy belongs to buffer oy / dst_slab_rows
+    // ALONE, which holds [slots, Co, dst_slab_rows, Wo]: each rank of the reference-sharded mode then receives only
+    // the rows it fuses (an all-to-all folded into the epilogue instead of an all-gather)
+    int dst_slab_rows;
     int out_nhwc;        // epilogue writes [B, Ho, Wo, Co] instead of [B, Co, Ho, Wo]
     float out_slope;     // leaky-ReLU slope applied to the output (1: none)
     unsigned wp_magic;   // ceil(2^32 / wp): idx / wp == umulhi(idx, wp_magic) for idx < hp * wp  (hp * wp * wp < 2^32)

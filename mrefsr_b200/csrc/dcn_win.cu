@@ -156,7 +156,14 @@ __device__ __forceinline__ void win_epilogue_tile(const DcnTcParams& prm, const 
     const int p = ok ? oy * prm.s.Wo + ox : 0;
     if (!ok) b = 0;
     const int bd = prm.dst_group ? (b / prm.dst_group) * prm.dst_stride + prm.dst_offset + b % prm.dst_group : b;
-    const size_t o_off = prm.out_nhwc ? ((size_t)bd * P + p) * Co : (size_t)bd * Co * P + p;
+    int k_lo = 0, k_hi = prm.n_outs, Pd = P;      // destination buffers of this row, plane size there
+    size_t o_off = prm.out_nhwc ? ((size_t)bd * P + p) * Co : (size_t)bd * Co * P + p;
+    if (prm.dst_slab_rows) {
+        k_lo = oy / prm.dst_slab_rows;
+        k_hi = k_lo + 1;
+        Pd = prm.dst_slab_rows * prm.s.Wo;
+        o_off = (size_t)bd * Co * Pd + (size_t)(oy - k_lo * prm.dst_slab_rows) * prm.s.Wo + ox;
+    }
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * Co;
 #pragma unroll 1
     for (int c0 = 0; c0 < Co; c0 += 8) {
@@ -171,14 +178,14 @@ __device__ __forceinline__ void win_epilogue_tile(const DcnTcParams& prm, const 
                 f[e] = f[e] > 0.f ? f[e] : f[e] * prm.out_slope;
             }
 #pragma unroll 1
-            for (int k = 0; k < prm.n_outs; ++k) {
+            for (int k = k_lo; k < k_hi; ++k) {
                 float* o = prm.outs[k] + o_off;
                 if (prm.out_nhwc) {
                     *reinterpret_cast<float4*>(o + c0) = make_float4(f[0], f[1], f[2], f[3]);
                     *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * P] = f[e];
+                    for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * Pd] = f[e];
                 }
             }
         }

@@ -98,11 +98,13 @@ def dcn_forward_raw(input, offset, mask, weight, bias, stride, padding, dilation
 
 
 def dynagg_dcn_forward_into(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups, out_ptrs,
-                            dst_group, dst_stride, dst_offset, out_slope=1.0):
+                            dst_group, dst_stride, dst_offset, out_slope=1.0, slab_rows=0):
     """Fused DynAgg forward whose epilogue stores straight into several gathered buffers [n, R, Co, H, W] (NCHW
     planes): `out_ptrs` are device addresses of this GPU's and the peers' copies (see parallel.PeerGatherBuffer);
     sample b lands in slot (b // dst_group) * dst_stride + dst_offset + b % dst_group.  Returns nothing: the data is
-    in the buffers once the kernel and the caller's cross-GPU barrier have completed."""
+    in the buffers once the kernel and the caller's cross-GPU barrier have completed.
+    slab_rows > 0: pixel-slab routing -- `out_ptrs` are the ranks' buffers IN RANK ORDER, each [n, R, Co, slab_rows, W],
+    and output row oy goes to buffer oy // slab_rows only (parallel.PeerSlabBuffer)."""
     import ctypes
     from .trunk import to_nchw
     _lib.require_cuda(input, conv_out, max_idx, weight, bias)
@@ -128,12 +130,21 @@ def dynagg_dcn_forward_into(input, conv_out, max_idx, flow_scale, weight, bias, 
     with torch.cuda.device(x.device):
         nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, DCN_TF32, 0)
         ws, ws_bytes = _lib.workspace(nbytes, x.device)
-        rc = lib.mrefsr_dynagg_dcn_forward_multi(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
-                                                 int(flow_scale), ctypes.cast(arr, ctypes.c_void_p), len(out_ptrs),
-                                                 int(dst_group), int(dst_stride), int(dst_offset), b, c, h, w, co, dg,
-                                                 int(bs is not None), 1 if in_cl else 0, float(out_slope), ws, ws_bytes,
-                                                 _lib.stream_ptr(x.device))
-    _lib.check(rc, 'mrefsr_dynagg_dcn_forward_multi')
+        if slab_rows:
+            if slab_rows * len(out_ptrs) < h:
+                raise ValueError('slab_rows * buffers must cover the %d output rows' % h)
+            rc = lib.mrefsr_dynagg_dcn_forward_slabs(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
+                                                     int(flow_scale), ctypes.cast(arr, ctypes.c_void_p), len(out_ptrs),
+                                                     int(slab_rows), int(dst_group), int(dst_stride), int(dst_offset), b, c,
+                                                     h, w, co, dg, int(bs is not None), 1 if in_cl else 0, float(out_slope),
+                                                     ws, ws_bytes, _lib.stream_ptr(x.device))
+        else:
+            rc = lib.mrefsr_dynagg_dcn_forward_multi(_lib.ptr(x), _lib.ptr(wgt), _lib.ptr(bs), _lib.ptr(co_), _lib.ptr(mi),
+                                                     int(flow_scale), ctypes.cast(arr, ctypes.c_void_p), len(out_ptrs),
+                                                     int(dst_group), int(dst_stride), int(dst_offset), b, c, h, w, co, dg,
+                                                     int(bs is not None), 1 if in_cl else 0, float(out_slope), ws, ws_bytes,
+                                                     _lib.stream_ptr(x.device))
+    _lib.check(rc, 'mrefsr_dynagg_dcn_forward_slabs' if slab_rows else 'mrefsr_dynagg_dcn_forward_multi')
 
 
 def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups, out_slope=1.0,

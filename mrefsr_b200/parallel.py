@@ -191,6 +191,7 @@ class PeerGatherBuffer:
         rank = dist.get_rank(self.group)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.ptrs = [ptrs[rank]] + [p for i, p in enumerate(ptrs) if i != rank]     # local copy first
+        self.ptrs_by_rank = ptrs
         if len(self.ptrs) > 8:
             raise RuntimeError('PeerGatherBuffer: at most 8 ranks per group')
 
@@ -200,3 +201,47 @@ class PeerGatherBuffer:
     def finish(self):
         self.hdl.barrier(channel=1)
         return self.buf
+
+
+class PeerSlabBuffer(PeerGatherBuffer):
+    """Pixel-slab variant of the exchange: every GPU owns H / world consecutive output rows and its buffer
+    [n, R, C, H / world, W] receives, from every rank's DCN epilogue, those rows of that rank's references
+    (dcn.dynagg_dcn_forward_into(..., out_ptrs=buf.ptrs_by_rank, slab_rows=buf.slab_rows)).  Each GPU then fuses its
+    slab over all R references and `all_gather_slabs` reassembles the fused result: 1/world of the fusion work and
+    ~1/world of the exchanged bytes of the all-gather of aligned features.
+
+        buf = PeerSlabBuffer(n, R, C, H, W, device)
+        buf.begin(); dynagg_dcn_forward_into(..., buf.ptrs_by_rank, r_local, R, lo, slab_rows=buf.slab_rows)
+        slab = buf.finish()              # [n, R, C, H / world, W]: all references, this rank's rows
+    """
+
+    def __init__(self, n, n_refs, channels, height, width, device, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError('PeerSlabBuffer needs an initialised process group')
+        world = dist.get_world_size(group)
+        if height % world:
+            raise RuntimeError('PeerSlabBuffer: %d rows do not split evenly over %d ranks' % (height, world))
+        self.slab_rows = height // world
+        super().__init__((n, n_refs, channels, self.slab_rows, width), device, group)
+
+
+def slab_of(t, rank, world, dim=2):
+    """This rank's consecutive rows of a full-height tensor (dim = the height axis)."""
+    rows = t.shape[dim] // world
+    return t.narrow(dim, rank * rows, rows).contiguous()
+
+
+def all_gather_slabs(slab, group=None):
+    """[n, C, H / world, W] per rank -> [n, C, H, W] on every rank (rows in rank order)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return slab
+    world = dist.get_world_size(group)
+    n, c, hs, w = slab.shape
+    recv = slab.new_empty((world, n, c, hs, w))
+    if slab.is_cuda:
+        dist.all_gather_into_tensor(recv.view(-1), slab.contiguous().view(-1), group=group)
+    else:
+        parts = [torch.empty_like(slab) for _ in range(world)]
+        dist.all_gather(parts, slab.contiguous(), group=group)
+        recv = torch.stack(parts, 0)
+    return recv.permute(1, 2, 0, 3, 4).reshape(n, c, world * hs, w)

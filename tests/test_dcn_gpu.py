@@ -276,6 +276,37 @@ def test_dynagg_dcn_forward_into_several_buffers():
         assert bool((t[:, :lo] == -7.0).all()) and bool((t[:, lo + r_local:] == -7.0).all())   # other slots untouched
 
 
+@pytest.mark.parametrize('kernel', ['default', 'window'])
+def test_dynagg_dcn_forward_into_pixel_slabs(kernel):
+    """Pixel-slab routing of the reference-sharded mode: output row oy is stored to buffer oy // slab_rows only, at
+    the global reference slot; four local buffers stand in for four ranks.  Reassembling the slabs must give exactly
+    the plain forward, and nothing else may be written."""
+    from mrefsr_b200 import _lib
+    from mrefsr_b200.dcn import dynagg_dcn_forward, dynagg_dcn_forward_into
+    g = torch.Generator().manual_seed(22)
+    n, r_local, R, lo, c, h, w, dg, s, ranks = 1, 2, 8, 4, 64, 32, 48, 8, 2, 4
+    b = n * r_local
+    x = torch.randn(b, c, h, w, generator=g).to(DEV)
+    conv_out = torch.randn(b, 3 * dg * 9, h, w, generator=g).to(DEV)
+    hp, wp = h // s - 2, w // s - 2
+    max_idx = torch.randint(0, hp * wp, (b, hp, wp), generator=g).to(DEV)
+    wgt = (torch.randn(c, c, 3, 3, generator=g) * 0.05).to(DEV)
+    bias = torch.randn(c, generator=g).to(DEV)
+    prev = _lib.lib().mrefsr_dcn_window_enable(1 if kernel == 'window' else 0)
+    try:
+        want = dynagg_dcn_forward(x, conv_out, max_idx, s, wgt, bias, dg).view(r_local, n, c, h, w).transpose(0, 1)
+        hs = h // ranks
+        bufs = [torch.full((n, R, c, hs, w), -7.0, device=DEV) for _ in range(ranks)]
+        dynagg_dcn_forward_into(x, conv_out, max_idx, s, wgt, bias, dg, [t.data_ptr() for t in bufs], r_local, R, lo,
+                                slab_rows=hs)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().mrefsr_dcn_window_enable(prev)
+    for k, t in enumerate(bufs):
+        assert torch.equal(t[:, lo:lo + r_local], want[:, :, :, k * hs:(k + 1) * hs])
+        assert bool((t[:, :lo] == -7.0).all()) and bool((t[:, lo + r_local:] == -7.0).all())
+
+
 @pytest.mark.parametrize('scale', [1.0, 3e5, 1e-6, float('inf')])
 @pytest.mark.parametrize('nhwc', [False, True])
 def test_input_dynamic_range(scale, nhwc):

@@ -54,7 +54,11 @@ def _worker(rank, world, port, n_refs, out):
         parts = [None] * world
         dist.all_gather_object(parts, mine.tolist())
         ok3 = sum(parts, []) == b.tolist()
-        out[rank] = bool(ok1 and ok2 and ok3)
+        # pixel-slab exchange: each rank fuses its rows of every reference; all_gather_slabs reassembles the rows
+        fused_full = full.sum(1)                                   # stand-in for the fusion over references
+        mine_rows = P.slab_of(full, rank, world, dim=3).sum(1)     # what this rank computes from its slab
+        ok4 = torch.equal(P.all_gather_slabs(mine_rows), fused_full)
+        out[rank] = bool(ok1 and ok2 and ok3 and ok4)
     finally:
         dist.destroy_process_group()
 

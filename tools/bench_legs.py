@@ -78,7 +78,9 @@ def refshard_leg(dev, rank, world, dist, hw=512, n_refs=8, steps=2):
     """BASELINE config 4: the alignment path on one 512x512 image with 8 references split across the ranks.  Two
     exchange mechanisms are timed back to back on the same inputs: NCCL all-gather of the aligned features per scale
     (parallel.all_gather_refs) and the DCN epilogue storing its tiles straight into every GPU's gathered tensor over
-    NVLink (mrefsr_dynagg_dcn_forward_multi + parallel.PeerGatherBuffer); outputs are compared bit for bit."""
+    NVLink (mrefsr_dynagg_dcn_forward_multi + parallel.PeerGatherBuffer), and the pixel-slab exchange (each tile stored
+    only to the GPU that owns its rows, fusion of 1 / world of the pixels per GPU, all-gather of the fused result:
+    mrefsr_dynagg_dcn_forward_slabs + parallel.PeerSlabBuffer); outputs are compared bit for bit."""
     import mrefsr_b200 as M
     from mrefsr_b200 import parallel as P
     from mrefsr_b200.dcn import dynagg_dcn_forward, dynagg_dcn_forward_into
@@ -99,6 +101,22 @@ def refshard_leg(dev, rank, world, dist, hw=512, n_refs=8, steps=2):
     cs = {c: torch.stack([conv[c][r] for r in mine], 0).flatten(0, 1).to(dev) for c, s in scales}
     del feat_ref, x, conv
     peer = {c: P.PeerGatherBuffer((n, R, c, h * s, h * s), dev) for c, s in scales} if world > 1 else {}
+    slabs = {c: P.PeerSlabBuffer(n, R, c, h * s, h * s, dev) for c, s in scales} if world > 1 else {}
+    emb_t_slab = {c: P.slab_of(emb_t[c], rank, world) for c, s in scales} if world > 1 else {}
+
+    def run_slabs():
+        """pixel-slab exchange: every rank receives all references for ITS rows (from the DCN epilogues), fuses 1/world
+        of the pixels and all-gathers the fused result"""
+        idx, _ = M.feature_match_index_batched(feat_in, fr, is_norm=True, norm_input=True, normalize_pixels=True, in_div=1)
+        outs = []
+        for c, s in scales:
+            pg = slabs[c]
+            pg.begin()
+            dynagg_dcn_forward_into(xs[c], cs[c], idx, s, wgt[c], bias[c], 8, pg.ptrs_by_rank, len(mine), R, mine[0],
+                                    slab_rows=pg.slab_rows)
+            emb = pg.finish().flatten(0, 1)                                            # [n*R, C, H/world, W]
+            outs.append(P.all_gather_slabs(M.mrapa_attention(emb_t_slab[c], emb, emb.repeat(1, 2, 1, 1), R)))
+        return outs
 
     def run(fused_gather):
         idx, _ = M.feature_match_index_batched(feat_in, fr, is_norm=True, norm_input=True, normalize_pixels=True, in_div=1)
@@ -119,31 +137,35 @@ def refshard_leg(dev, rank, world, dist, hw=512, n_refs=8, steps=2):
 
     res = {}
     outs = {}
-    for name, fg in (('nccl_all_gather', False), ('peer_store_epilogue', True)):
-        if fg and world == 1:
+    for name, fg in (('nccl_all_gather', False), ('peer_store_epilogue', True), ('peer_store_pixel_slabs', None)):
+        if fg is not False and world == 1:
             continue
+        fn = run_slabs if fg is None else (lambda fg=fg: run(fg))
         for _ in range(2):
-            outs[name] = run(fg)
+            outs[name] = fn()
         _barrier(dist)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            outs[name] = run(fg)
+            outs[name] = fn()
         e1.record()
         _barrier(dist)
         res[name] = _max_over_ranks(e0.elapsed_time(e1) / steps, dev, dist)
     same = None
-    if len(outs) == 2:
-        same = all(torch.equal(a, b) for a, b in zip(outs['nccl_all_gather'], outs['peer_store_epilogue']))
+    if len(outs) > 1:
+        same = all(torch.equal(a, b) for name in outs if name != 'nccl_all_gather'
+                   for a, b in zip(outs['nccl_all_gather'], outs[name]))
     checksum = float(sum(o.double().sum() for o in outs['nccl_all_gather']))
     ex_bytes = sum(4 * c * (h * s) ** 2 * n * (R - len(mine)) for c, s in scales)       # received per GPU per image
+    # pixel slabs: (R - r_local) references x 1/world of the rows in, then (world - 1)/world of the fused 2C planes
+    ex_slabs = sum(4 * c * (h * s) ** 2 * n * ((R - len(mine)) + 2 * (world - 1)) // world for c, s in scales)
     best = min(res.values())
     out = {'config': 'BASELINE config 4: %dx%d HR, %d references sharded over %d GPU(s), aligned features exchanged per '
                      'scale, fusion on every rank; alignment path only, inputs resident' % (hw, hw, R, world),
-           'ms_per_image': res, 'images_per_s': 1e3 / best, 'exchange_bytes_received_per_gpu': ex_bytes,
-           'exchange_gb_per_s_per_gpu_at_best': ex_bytes / 1e9 / (best / 1e3) if world > 1 else 0.0,
+           'ms_per_image': res, 'images_per_s': 1e3 / best,
+           'exchange_bytes_received_per_gpu': {'all_gather_of_aligned_features': ex_bytes, 'pixel_slabs': ex_slabs},
            'mechanisms_bit_identical': same, 'checksum': checksum}
-    del peer, outs
+    del peer, slabs, outs
     torch.cuda.empty_cache()
     return out
 
