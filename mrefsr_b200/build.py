@@ -58,5 +58,47 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_EXT_DIR = os.path.join(HERE, 'torch_ext')
+TORCH_EXT = os.path.join(TORCH_EXT_DIR, 'deform_conv_ext.so')
+
+
+def build_torch_ext(force=False, verbose=False):
+    """The torch extension module `deform_conv_ext` (csrc/torch_ext/deform_conv_ext.cpp): the reference's five pybind
+    exports on top of libmrefsr_b200.so -- the file that replaces the reference's own deform_conv_ext build.  Built
+    in-tree (mrefsr_b200/torch_ext/deform_conv_ext.so, git-ignored) so that it travels to the GPU box; it finds the
+    kernel library through an $ORIGIN-relative rpath."""
+    src = os.path.join(CSRC, 'torch_ext', 'deform_conv_ext.cpp')
+    build(force=False)
+    if (not force and os.path.exists(TORCH_EXT) and os.path.getmtime(TORCH_EXT) >= os.path.getmtime(src) and
+            os.path.getmtime(TORCH_EXT) >= os.path.getmtime(os.path.join(HERE, '..', 'include', 'mrefsr_b200.h'))):
+        return TORCH_EXT
+    os.makedirs(TORCH_EXT_DIR, exist_ok=True)
+    bdir = os.path.join(TORCH_EXT_DIR, 'build')
+    os.makedirs(bdir, exist_ok=True)
+    os.environ.setdefault('MAX_JOBS', '4')
+    os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+    from torch.utils.cpp_extension import load
+    load(name='deform_conv_ext', sources=[src], build_directory=bdir, is_python_module=False, verbose=verbose,
+         with_cuda=True, extra_cflags=['-O2'],
+         extra_ldflags=['-L' + LIBDIR, '-lmrefsr_b200', # ninja ($$) and the shell (quotes) both see this string before the linker does
+                        "-Wl,-rpath,'$$ORIGIN/../lib'", "-Wl,-rpath,'$$ORIGIN/../../lib'", '-Wl,--no-as-needed'])
+    os.replace(os.path.join(bdir, 'deform_conv_ext.so'), TORCH_EXT)
+    return TORCH_EXT
+
+
+def load_torch_ext():
+    """Import the built extension module (raises with the build command if it is missing: no fallback)."""
+    import importlib.util
+    if not os.path.exists(TORCH_EXT):
+        raise RuntimeError('mrefsr_b200: %s is missing -- build it with `python -m mrefsr_b200.build --torch-ext`' % TORCH_EXT)
+    import torch  # noqa: F401  (libtorch symbols must be loaded first)
+    spec = importlib.util.spec_from_file_location('deform_conv_ext', TORCH_EXT)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    if '--torch-ext' in sys.argv:
+        print(build_torch_ext(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

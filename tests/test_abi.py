@@ -176,3 +176,21 @@ def test_missing_library_fails_loudly_with_the_build_command():
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
     assert 'RAISED' in r.stdout and 'python -m mrefsr_b200.build' in r.stdout and 'no CPU / PyTorch fallback' in r.stdout
+
+
+def test_torch_extension_module_exports_the_reference_names():
+    """The module that replaces the reference's deform_conv_ext build: importable without a GPU, the five pybind exports
+    of basicsr/ops/dcn/src/deform_conv_ext.cpp:150-164, and the reference's CPU-tensor error (:124)."""
+    from mrefsr_b200 import build as B
+    B.build_torch_ext()
+    m = B.load_torch_ext()
+    for name in ('deform_conv_forward', 'deform_conv_backward_input', 'deform_conv_backward_parameters',
+                 'modulated_deform_conv_forward', 'modulated_deform_conv_backward'):
+        assert callable(getattr(m, name)), name
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match='not implemented on CPU'):
+        m.modulated_deform_conv_forward(z(1, 8, 4, 4), z(8, 8, 3, 3), z(8), z(0), z(1, 18, 4, 4), z(1, 9, 4, 4), z(1, 8, 4, 4),
+                                        z(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, True)
+    with pytest.raises(RuntimeError, match='not implemented on CPU'):
+        m.deform_conv_forward(z(1, 8, 4, 4), z(8, 8, 3, 3), z(1, 18, 4, 4), z(1, 8, 4, 4), z(0), z(0), 3, 3, 1, 1, 1, 1, 1, 1,
+                              1, 1, 1)

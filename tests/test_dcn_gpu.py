@@ -254,6 +254,50 @@ def test_against_reference_cuda_extension():
     assert rel_err(mine, out1) <= TOL
 
 
+def test_torch_extension_module_is_call_compatible_with_the_reference_extension():
+    """mrefsr_b200/torch_ext/deform_conv_ext.so -- the pybind module that replaces the reference's deform_conv_ext build
+    (csrc/torch_ext/deform_conv_ext.cpp) -- and the reference's own extension (oracle/_ref, checker) are driven with the
+    SAME argument lists, the way basicsr/ops/dcn/deform_conv.py:147-170 calls them: caller-allocated output, size-0
+    `ones` / `columns` scratch, zero-initialised gradients, grad_weight / grad_bias accumulated."""
+    import importlib.util
+    from mrefsr_b200 import build as B
+    ours = B.load_torch_ext()
+    spec = importlib.util.spec_from_file_location('deform_conv_ext_ref', _REF_SO)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    x, off, mask, wgt, bias = (t.to(DEV) for t in _rand_problem(2, 64, 24, 20, 64, 8, 33, off_scale=3.0))
+    empty = x.new_empty(0)
+    outs, grads = {}, {}
+    go = torch.randn(2, 64, 24, 20, generator=torch.Generator().manual_seed(2)).to(DEV)
+    for name, ext in (('ours', ours), ('ref', ref)):
+        out = x.new_empty(2, 64, 24, 20)
+        ext.modulated_deform_conv_forward(x, wgt, bias, empty, off, mask, out, empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, 8, True)
+        outs[name] = out
+        g = [torch.zeros_like(t) for t in (x, wgt, bias, off, mask)]
+        g[1].fill_(0.5)                                        # pre-existing content: grad_weight / grad_bias accumulate
+        g[2].fill_(-1.0)
+        ext.modulated_deform_conv_backward(x, wgt, bias, empty, off, mask, empty, g[0], g[1], g[2], g[3], g[4], go, 3, 3,
+                                           1, 1, 1, 1, 1, 1, 1, 8, True)
+        grads[name] = g
+    assert rel_err(outs['ours'], outs['ref']) <= TOL
+    for a, b, name in zip(grads['ours'], grads['ref'], ('input', 'weight', 'bias', 'offset', 'mask')):
+        assert rel_err(a, b) <= TOL, name
+    # DCNv1 export, the reference's (W, H) argument order; int return value 1
+    o1, o2 = x.new_empty(2, 64, 24, 20), x.new_empty(2, 64, 24, 20)
+    assert ours.deform_conv_forward(x, wgt, off, o1, empty, empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, 8, 2) == 1
+    ref.deform_conv_forward(x, wgt, off, o2, empty, empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, 8, 2)
+    assert rel_err(o1, o2) <= TOL
+    # fp16 tensors are accepted like the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF (computed in fp32 here)
+    oh = x.new_empty(2, 64, 24, 20).half()
+    ours.modulated_deform_conv_forward(x.half(), wgt.half(), bias.half(), empty, off.half(), mask.half(), oh, empty, 3, 3,
+                                       1, 1, 1, 1, 1, 1, 1, 8, True)
+    assert rel_err(oh.float(), outs['ref']) <= 2e-2
+    # the reference's error behaviour: kernel-shape mismatch -> RuntimeError
+    with pytest.raises(RuntimeError, match="kernel shape won't match"):
+        ours.modulated_deform_conv_forward(x, wgt, bias, empty, off, mask, x.new_empty(2, 64, 24, 20), empty, 5, 5, 1, 1, 1,
+                                           1, 1, 1, 1, 8, True)
+
+
 def test_dynagg_dcn_forward_into_several_buffers():
     """Epilogue of the reference-sharded mode: every tile stored to each destination buffer, at the global reference
     slot of the gathered [n, R, C, H, W] tensor (here two local buffers stand in for the peers' copies)."""
