@@ -11,6 +11,10 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+
 #include "../../../include/mrefsr_b200.h"
 
 namespace {
@@ -31,8 +35,28 @@ Workspace make_workspace(size_t bytes, const at::Tensor& like) {
   return w;
 }
 
+// Error messages are formatted here and handed to TORCH_CHECK as ONE C string: with this image's torch 2.11 headers and
+// gcc 13 the variadic c10::str(...) path of TORCH_CHECK crashes inside an extension module (reproduced with a
+// three-line module), the single-string path does not.
+[[noreturn]] void fail(const char* fmt, ...) {
+  static thread_local char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  TORCH_CHECK(false, buf);
+  abort();  // not reached
+}
+
 void check_rc(int rc, const char* what) {
-  TORCH_CHECK(rc == 0, what, " failed (", rc, "): ", mrefsr_last_error());
+  if (rc != 0) fail("%s failed (%d): %s", what, rc, mrefsr_last_error());
+}
+
+void check_kernel(int kernel_h, int kernel_w, int kh, int kw, int C, int channels_kernel, int group) {
+  if (kh != kernel_h || kw != kernel_w)   // deform_conv_cuda.cpp:511-513
+    fail("Input shape and kernel shape won't match: (%d x %d vs %d x %d).", kernel_h, kernel_w, kh, kw);
+  if (C != channels_kernel * group)       // deform_conv_cuda.cpp:514-516
+    fail("Input shape and kernel channels won't match: (%d vs %d).", C, channels_kernel * group);
 }
 
 // fp32 contiguous view of a tensor the kernels read (the reference dispatches on the scalar type; the sm_100a kernels
@@ -43,8 +67,8 @@ void write_back(at::Tensor dst, const at::Tensor& src) {
   if (dst.data_ptr() != src.data_ptr()) dst.view(src.sizes()).copy_(src);
 }
 
-}  // namespace
-
+// The exported functions have internal linkage: the reference's own extension defines functions with exactly these
+// names and signatures, and two such modules in one process (the parity tests load both) must not interpose each other.
 void modulated_deform_conv_forward(at::Tensor input, at::Tensor weight, at::Tensor bias, at::Tensor ones, at::Tensor offset,
                                    at::Tensor mask, at::Tensor output, at::Tensor columns, int kernel_h, int kernel_w,
                                    const int stride_h, const int stride_w, const int pad_h, const int pad_w,
@@ -56,17 +80,14 @@ void modulated_deform_conv_forward(at::Tensor input, at::Tensor weight, at::Tens
   at::DeviceGuard guard(input.device());
   const int B = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
   const int Co = weight.size(0), channels_kernel = weight.size(1), kh = weight.size(2), kw = weight.size(3);
-  TORCH_CHECK(kh == kernel_h && kw == kernel_w, "Input shape and kernel shape won't match: (", kernel_h, " x ", kernel_w,
-              " vs ", kh, " x ", kw, ").");
-  TORCH_CHECK(C == channels_kernel * group, "Input shape and kernel channels won't match: (", C, " vs ",
-              channels_kernel * group, ").");
+  check_kernel(kernel_h, kernel_w, kh, kw, C, channels_kernel, group);
   const int Ho = (H + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
   const int Wo = (W + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
   at::Tensor x = f32(input), w = f32(weight), off = f32(offset), msk = f32(mask);
   at::Tensor b = with_bias ? f32(bias) : at::Tensor();
   // the reference resizes `output` itself (output.view({B, Co, Ho, Wo}).zero_()); the caller allocated it with that shape
-  TORCH_CHECK(output.numel() == (int64_t)B * Co * Ho * Wo, "output has ", output.numel(), " elements, expected ",
-              (int64_t)B * Co * Ho * Wo);
+  if (output.numel() != (int64_t)B * Co * Ho * Wo)
+    fail("output has %lld elements, expected %lld", (long long)output.numel(), (long long)B * Co * Ho * Wo);
   at::Tensor out = (output.scalar_type() == at::kFloat && output.is_contiguous())
                        ? output
                        : at::empty({B, Co, Ho, Wo}, x.options());
@@ -94,10 +115,7 @@ void modulated_deform_conv_backward(at::Tensor input, at::Tensor weight, at::Ten
   at::DeviceGuard guard(input.device());
   const int B = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
   const int Co = weight.size(0), channels_kernel = weight.size(1), kh = weight.size(2), kw = weight.size(3);
-  TORCH_CHECK(kh == kernel_h && kw == kernel_w, "Input shape and kernel shape won't match: (", kernel_h, " x ", kernel_w,
-              " vs ", kh, " x ", kw, ").");
-  TORCH_CHECK(C == channels_kernel * group, "Input shape and kernel channels won't match: (", C, " vs ",
-              channels_kernel * group, ").");
+  check_kernel(kernel_h, kernel_w, kh, kw, C, channels_kernel, group);
   at::Tensor x = f32(input), w = f32(weight), off = f32(offset), msk = f32(mask), go = f32(grad_output);
   // gradients: grad_weight / grad_bias ACCUMULATE into the caller's (zero-initialised) tensors as the reference's
   // addmm_ with beta = 1 does (deform_conv_cuda.cpp:659-671); the others are overwritten
@@ -195,6 +213,8 @@ int deform_conv_backward_parameters(at::Tensor input, at::Tensor offset, at::Ten
   gradWeight.add_(gw.view_as(gradWeight).to(gradWeight.scalar_type()), scale);     // accumulates, like the reference
   return 1;
 }
+
+}  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("deform_conv_forward", &deform_conv_forward, "deform forward");
