@@ -118,6 +118,9 @@ __device__ __forceinline__ void dcn_epilogue_tile(const DcnTcParams& prm, const 
             uint32_t v[8];
             tmem_ld_32x8(taddr + c0, v);
             tmem_ld_wait();
+#ifdef MREFSR_DCN_DEBUG
+            if (prm.dbg & 16) continue;              // ablation 16: no epilogue stores
+#endif
             if (ok) {
                 float f[8];
 #pragma unroll
@@ -167,6 +170,9 @@ __device__ __forceinline__ void dcn_mma_issuer(const DcnTcParams& prm, uint8_t* 
             const uint32_t sb = sa + T_A_BYTES;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
+#ifdef MREFSR_DCN_DEBUG
+                if (prm.dbg & 8) continue;           // ablation 8: no MMAs
+#endif
                 const uint64_t db = umma_desc_sw128(sb + kk * 32, 0);
                 umma_tf32(tacc, umma_desc_sw128(sa + kk * 32, 0), db, idesc, accumulate);
                 umma_tf32(tacc + Co, umma_desc_sw128(sa + 128 * 128 + kk * 32, 0), db, idesc, accumulate);
@@ -641,7 +647,18 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
                 const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
                 const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
                 const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+#ifdef MREFSR_DCN_DEBUG   // ablation (variant builds only): 1 = no corner loads (the blend runs on the table words)
+                F8 v0, v1, v2, v3;
+                if (prm.dbg & 32) continue;          // ablation 32: no table reads used, no blend, no A-tile stores
+                if (prm.dbg & 1) {
+                    v0.v[0] = v0.v[1] = v0.v[2] = v0.v[3] = make_float2(w0, w1);
+                    v1 = v2 = v3 = v0;
+                } else {
+                    v0 = ldg8(xs + i0), v1 = ldg8(xs + i1), v2 = ldg8(xs + i2), v3 = ldg8(xs + i3);
+                }
+#else
                 const F8 v0 = ldg8(xs + i0), v1 = ldg8(xs + i1), v2 = ldg8(xs + i2), v3 = ldg8(xs + i3);
+#endif
                 const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
                              p3 = make_float2(w3, w3);
                 float2 o[4];
@@ -719,7 +736,11 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
             rr.yx = row_yx;
             rr.bH = row_bH;
             rr.r.fyx = -1;
+#ifdef MREFSR_DCN_DEBUG
+            if (row_yx >= 0 && !(prm.dbg & 2)) {     // ablation 2: no offset / mask loads
+#else
             if (row_yx >= 0) {
+#endif
 #pragma unroll
                 for (int g = 0; g < GS; ++g) {
                     {
@@ -778,6 +799,16 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
             // row are independent straight-line chains the scheduler can interleave; same arithmetic as
             // dcn_tc_kernel's decode, bit for bit.
             const bool row_ok = rr.yx >= 0;
+#ifdef MREFSR_DCN_DEBUG
+            if (prm.dbg & 4) {                       // ablation 4: no sample decode (constant table entries)
+#pragma unroll
+                for (int g = 0; g < GS; ++g) {
+                    const int e = g * TAB_STRIDE;
+                    tb[e] = 0;
+                    tw[e] = tw[e + tab_n] = tw[e + 2 * tab_n] = tw[e + 3 * tab_n] = 0.25f;
+                }
+            } else
+#endif
 #pragma unroll
             for (int g = 0; g < GS; ++g) {
                 {
@@ -1005,11 +1036,20 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     prm.stage_bytes = T_A_BYTES + s.Co * 128;
     const bool split = dcn_split_mode() != 0;
     const size_t table_bytes = (size_t)(split ? S_NTAB : T_NTAB) * 5 * prm.gs * (TBM + 4) * 4;
-    prm.stages = (int)((T_SMEM_BUDGET - (int)table_bytes) / prm.stage_bytes);
+    int smem_budget = T_SMEM_BUDGET;
+#ifdef MREFSR_DCN_DEBUG
+    if (getenv("MREFSR_DCN_SMEM_KB")) smem_budget = atoi(getenv("MREFSR_DCN_SMEM_KB")) * 1024;   // tuning experiments
+#endif
+    prm.stages = (int)((smem_budget - (int)table_bytes) / prm.stage_bytes);
     if (prm.stages > 4) prm.stages = 4;
     if (prm.stages < 2) prm.stages = 2;
     prm.nbuf = (2 * s.Co * 2 <= 512) ? 2 : 1;
     prm.fused = max_idx != nullptr;
+    prm.dbg = 0;
+    prm.trace = nullptr;
+#ifdef MREFSR_DCN_DEBUG
+    prm.dbg = getenv("MREFSR_DCN_DBG") ? atoi(getenv("MREFSR_DCN_DBG")) : 0;
+#endif
     for (int k = 0; k < 8; ++k) prm.outs[k] = nullptr;
     if (multi) {
         MREFSR_CHECK(multi->n >= 1 && multi->n <= 8, ERR_BAD_ARG, "dcn forward: 1..8 output buffers (got %d)", multi->n);
