@@ -271,6 +271,12 @@ MREFSR_API int mrefsr_mrapa_attention_nhwc(const float* q_raw, const float* k_ra
                                 const float* bias_k, const float* bias_v, const float* slope_q, int slope_q_n,
                                 const float* slope_k, int slope_k_n, float q_scale, float* out, int n, int t, int C,
                                 int Cv, int h, int w, void* stream);
+/* bf16 tensors in and out (inference; the north star's "bf16 tolerance stated separately"): same kernel, half the bytes,
+ * logits / softmax / weighted sum in fp32, output rounded to nearest even.  Tolerance against the fp64 oracle evaluated on
+ * the SAME bf16-rounded inputs: 4e-3 of the output scale (one bf16 rounding of the result = 2^-9 relative).  Needs t <= 8,
+ * h*w % 4 == 0, 8-byte aligned tensors. */
+MREFSR_API int mrefsr_mrapa_attention_forward_bf16(const void* emb_t, const void* emb, const void* ass, void* out, int n,
+                                                   int t, int C, int Cv, int h, int w, void* stream);
 MREFSR_API int mrefsr_mrapa_attention_backward(const float* emb_t, const float* emb, const float* ass, const float* prob,
                                     const float* grad_out, float* grad_emb_t, float* grad_emb, float* grad_ass,
                                     int n, int t, int C, int Cv, int h, int w, void* stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
     'mrefsr_layout_convert': (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'mrefsr_attn_modulate': (c_int, [_P] * 5 + [_I] * 4 + [_P]),
     'mrefsr_mrapa_attention_forward': (c_int, [_P] * 5 + [_I] * 6 + [_P]),
+    'mrefsr_mrapa_attention_forward_bf16': (c_int, [_P] * 4 + [_I] * 6 + [_P]),
     'mrefsr_mrapa_attention_nhwc': (c_int, [_P] * 7 + [_I, _P, _I, ctypes.c_float, _P] + [_I] * 6 + [_P]),
     'mrefsr_mrapa_attention_backward': (c_int, [_P] * 8 + [_I] * 6 + [_P]),
     'mrefsr_feature_match_batched_host': (c_int, [_P, _P] + [_I] * 15 + [_P, _P, _P]),

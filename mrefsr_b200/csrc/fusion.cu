@@ -82,11 +82,27 @@ mrapa_fwd_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb,
 // Vectorised forward: each lane owns 4 consecutive pixels (one 16-byte load per plane and lane, 512 bytes per
 // warp-level load), CTA = 128 pixels x 8 warps.  Needs HW % 4 == 0 and 16-byte aligned tensors.
 __device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+// four consecutive pixels of one channel plane, streamed: fp32 (16 bytes) or bf16 (8 bytes) in memory, fp32 in registers
+__device__ __forceinline__ float4 ldcs4(const __nv_bfloat16* p) {
+    const uint2 r = __ldcs(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void stcs4(__nv_bfloat16* p, float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);   // round to nearest even
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    __stcs(reinterpret_cast<uint2*>(p), r);
+}
 
-template <int TMAX>   // TMAX == t exactly: no dead accumulators, so 3 CTAs (24 warps) fit per SM
+// IO = float: the reference's precision.  IO = __nv_bfloat16: bf16 tensors in and out (half the bytes of this
+// HBM-bound kernel), logits / softmax / weighted sum still in fp32.
+template <int TMAX, typename IO>   // TMAX == t exactly: no dead accumulators, so 3 CTAs (24 warps) fit per SM
 __global__ void __launch_bounds__(FW * 32, 3)
-mrapa_fwd_vec4_kernel(const float* __restrict__ emb_t, const float* __restrict__ emb, const float* __restrict__ ass,
-                      float* __restrict__ out, float* __restrict__ prob, int t, int C, int Cv, int HW) {
+mrapa_fwd_vec4_kernel(const IO* __restrict__ emb_t, const IO* __restrict__ emb, const IO* __restrict__ ass,
+                      IO* __restrict__ out, float* __restrict__ prob, int t, int C, int Cv, int HW) {
     __shared__ float4 part[FW][TMAX][32];
     const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = (blockIdx.x * 32 + lane) * 4;
@@ -95,8 +111,8 @@ mrapa_fwd_vec4_kernel(const float* __restrict__ emb_t, const float* __restrict__
     float4 l[TMAX];
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) l[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* q = emb_t + (size_t)n * C * HW + pc;
-    const float* k = emb + (size_t)n * t * C * HW + pc;
+    const IO* q = emb_t + (size_t)n * C * HW + pc;
+    const IO* k = emb + (size_t)n * t * C * HW + pc;
     const int cper = (C + FW - 1) / FW;
     const int cbeg = warp * cper, cend = min(C, cbeg + cper);
 #pragma unroll 2
@@ -149,8 +165,8 @@ mrapa_fwd_vec4_kernel(const float* __restrict__ emb_t, const float* __restrict__
         for (int i = 0; i < TMAX; ++i)
             if (i < t) *reinterpret_cast<float4*>(prob + ((size_t)n * t + i) * HW + p) = l[i];
     }
-    const float* v = ass + (size_t)n * t * Cv * HW + pc;
-    float* o = out + (size_t)n * Cv * HW + p;
+    const IO* v = ass + (size_t)n * t * Cv * HW + pc;
+    IO* o = out + (size_t)n * Cv * HW + p;
     const int vper = (Cv + FW - 1) / FW;
     const int vbeg = warp * vper, vend = min(Cv, vbeg + vper);
 #pragma unroll 2
@@ -165,7 +181,7 @@ mrapa_fwd_vec4_kernel(const float* __restrict__ emb_t, const float* __restrict__
                 acc.z = fmaf(l[i].z, vv.z, acc.z);
                 acc.w = fmaf(l[i].w, vv.w, acc.w);
             }
-        if (ok) __stcs(reinterpret_cast<float4*>(o + (size_t)c * HW), acc);
+        if (ok) stcs4(o + (size_t)c * HW, acc);
     }
 }
 
@@ -381,7 +397,7 @@ int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const f
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (t <= 8 && HW % 4 == 0 && al16(emb_t) && al16(emb) && al16(ass) && al16(out) && (!prob || al16(prob))) {
         const dim3 g4(cdiv(HW, 128), n);
-#define MREFSR_FWD4(T) mrapa_fwd_vec4_kernel<T><<<g4, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW)
+#define MREFSR_FWD4(T) mrapa_fwd_vec4_kernel<T, float><<<g4, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW)
         switch (t) {
             case 1: MREFSR_FWD4(1); break;
             case 2: MREFSR_FWD4(2); break;
@@ -401,6 +417,39 @@ int mrefsr_mrapa_attention_forward(const float* emb_t, const float* emb, const f
         mrapa_fwd_kernel<8><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
     else
         mrapa_fwd_kernel<16><<<grid, FW * 32, 0, st>>>(emb_t, emb, ass, out, prob, t, C, Cv, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_mrapa_attention_forward_bf16(const void* emb_t, const void* emb, const void* ass, void* out, int n, int t, int C,
+                                        int Cv, int h, int w, void* stream) {
+    MREFSR_CHECK(emb_t && emb && ass && out, ERR_BAD_ARG, "mrapa attention forward (bf16): null pointer argument");
+    int rc = check_args(n, t, C, Cv, h, w);
+    if (rc) return rc;
+    const int HW = h * w;
+    auto al8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+    MREFSR_CHECK(t <= 8 && HW % 4 == 0 && al8(emb_t) && al8(emb) && al8(ass) && al8(out), ERR_UNSUPPORTED,
+                 "mrapa attention forward (bf16): needs t <= 8, h*w %% 4 == 0 and 8-byte aligned tensors");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(emb_t);
+    const __nv_bfloat16* k = static_cast<const __nv_bfloat16*>(emb);
+    const __nv_bfloat16* v = static_cast<const __nv_bfloat16*>(ass);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    const dim3 g4(cdiv(HW, 128), n);
+    ScopedTiming tm(MREFSR_K_FUSION_FWD, st);
+#define MREFSR_FWD4B(T) mrapa_fwd_vec4_kernel<T, __nv_bfloat16><<<g4, FW * 32, 0, st>>>(q, k, v, o, nullptr, t, C, Cv, HW)
+    switch (t) {
+        case 1: MREFSR_FWD4B(1); break;
+        case 2: MREFSR_FWD4B(2); break;
+        case 3: MREFSR_FWD4B(3); break;
+        case 4: MREFSR_FWD4B(4); break;
+        case 5: MREFSR_FWD4B(5); break;
+        case 6: MREFSR_FWD4B(6); break;
+        case 7: MREFSR_FWD4B(7); break;
+        default: MREFSR_FWD4B(8); break;
+    }
+#undef MREFSR_FWD4B
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

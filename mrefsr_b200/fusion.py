@@ -59,8 +59,33 @@ class MRAPAAttentionFunction(Function):
 
 
 def mrapa_attention(emb_t, emb, ass, t):
-    """emb_t [n,C,h,w] (already scaled by C**-0.5), emb [n*t,C,h,w], ass [n*t,Cv,h,w] -> [n,Cv,h,w]."""
+    """emb_t [n,C,h,w] (already scaled by C**-0.5), emb [n*t,C,h,w], ass [n*t,Cv,h,w] -> [n,Cv,h,w].
+    Three bf16 tensors that need no gradient take the bf16-I/O kernel (`mrapa_attention_bf16`)."""
+    if (emb_t.dtype == emb.dtype == ass.dtype == torch.bfloat16 and
+            not (torch.is_grad_enabled() and (emb_t.requires_grad or emb.requires_grad or ass.requires_grad))):
+        return mrapa_attention_bf16(emb_t, emb, ass, t)
     return MRAPAAttentionFunction.apply(emb_t, emb, ass, t)
+
+
+def mrapa_attention_bf16(emb_t, emb, ass, t):
+    """bf16 tensors in, bf16 tensor out (inference): the fusion core is HBM-bound, so halving the bytes halves its time.
+    Logits, softmax over the references and the weighted sum are computed in fp32; the result is rounded to nearest
+    even.  Stated tolerance: 4e-3 of the output scale against the fp64 oracle on the same bf16-rounded inputs
+    (tests/test_fusion_gpu.py::test_bf16_io)."""
+    _lib.require_cuda(emb_t, emb, ass)
+    n, c, h, w = emb_t.shape
+    cv = ass.shape[1]
+    if not all(x.dtype == torch.bfloat16 for x in (emb_t, emb, ass)):
+        raise ValueError('mrapa_attention_bf16: bf16 tensors expected')
+    if tuple(emb.shape) != (n * t, c, h, w) or tuple(ass.shape) != (n * t, cv, h, w):
+        raise ValueError('expected emb_t [n,C,h,w], emb [n*t,C,h,w], ass [n*t,Cv,h,w]')
+    q, k, v = emb_t.contiguous(), emb.contiguous(), ass.contiguous()
+    out = torch.empty(n, cv, h, w, dtype=torch.bfloat16, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().mrefsr_mrapa_attention_forward_bf16(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(out), n, t, c, cv,
+                                                            h, w, _lib.stream_ptr(q.device))
+    _lib.check(rc, 'mrefsr_mrapa_attention_forward_bf16')
+    return out
 
 
 def mrapa_attention_nhwc(q_raw, k_raw, v_raw, t, bias_q=None, bias_k=None, bias_v=None, slope_q=None, slope_k=None,

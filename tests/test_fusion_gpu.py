@@ -103,3 +103,21 @@ def test_nhwc_variant_with_folded_epilogues(c, t):
     got2 = mrapa_attention_nhwc(q_raw.contiguous(memory_format=cl), k_raw.contiguous(memory_format=cl),
                                 v_raw.contiguous(memory_format=cl), t)
     assert rel_err(got2, want2) <= 1e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 5, 64, 128, 40, 40), (1, 8, 128, 256, 16, 24), (1, 3, 256, 512, 8, 12)])
+def test_bf16_io(shape):
+    """bf16 tensors in / out (the north star's separately stated bf16 tolerance): against the fp64 oracle evaluated on the
+    SAME bf16-rounded inputs the result may differ by one bf16 rounding of the output plus fp32 accumulation error:
+    4e-3 of the output scale.  Against the fp32-I/O kernel on those inputs the difference is the output rounding alone."""
+    n, t, c, cv, h, w = shape
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(n, c, h, w, generator=g) * 0.3).bfloat16()
+    k = torch.randn(n * t, c, h, w, generator=g).bfloat16()
+    v = torch.randn(n * t, cv, h, w, generator=g).bfloat16()
+    out = M.mrapa_attention(q.to(DEV), k.to(DEV), v.to(DEV), t)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (n, cv, h, w)
+    ref = oracle.mrapa_attention_oracle(q.float(), k.float(), v.float(), t, dtype=torch.float64)
+    assert rel_err(out.float(), ref) <= 4e-3
+    out32 = M.mrapa_attention(q.float().to(DEV), k.float().to(DEV), v.float().to(DEV), t)
+    assert torch.equal(out, out32.bfloat16())
