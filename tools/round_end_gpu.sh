@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call that refreshes everything measured for a round (TAG = file prefix under gpurun_out/):
 #   GPU tests, reference-route comparison, bench.py (N=1), ncu launch list of the bench, ncu --set full of the DCN launches.
-TAG=${1:-r01s}
+TAG=${1:-r02v}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/${TAG}_pytest.log
 tail -3 gpurun_out/${TAG}_pytest.log
