@@ -31,31 +31,19 @@ def set_default_mode(mode):
     _default_mode = _MODES[mode] if isinstance(mode, str) else int(mode)
 
 
-_packed_cache = {}       # id(weight) -> (weakref, version, data_ptr, packed tensor)
-
-
-def packed_weight(weight):
-    """tf32-rounded [Co][tap][C] copy of a DCN weight for the tcgen05 kernels (mrefsr_dcn_pack_weights), cached per
-    weight tensor and invalidated by torch's version counter (any in-place update, optimizer step or load_state_dict
-    bumps it), by a changed storage address, or when the tensor dies.  Inference packs each weight once instead of on
-    every forward; tensors that require grad are never cached (training updates them every step)."""
-    import weakref
-    if weight.requires_grad and torch.is_grad_enabled():
-        return None
-    key = id(weight)
-    hit = _packed_cache.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
-        return hit[3]
+def pack_weight(weight):
+    """tf32-rounded [Co][tap][C] copy of a DCN weight, the B operand of the tcgen05 kernels (mrefsr_dcn_pack_weights).
+    The forward entry points repack on every call (a few microseconds); a caller whose weights are frozen may pack once
+    and hand the result to `dynagg_dcn_forward(..., weight_packed=...)`.  There is deliberately NO implicit cache:
+    torch's version counter does not see `weight.data.copy_(...)`-style updates, and a stale packing would be a silent
+    wrong answer for a 0.2 % gain."""
+    _lib.require_cuda(weight)
     w = weight.detach().contiguous().float()
     co, c, kh, kw = w.shape
     packed = torch.empty(co, kh * kw * c, dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
         rc = _lib.lib().mrefsr_dcn_pack_weights(_lib.ptr(w), _lib.ptr(packed), co, c, kh * kw, _lib.stream_ptr(w.device))
     _lib.check(rc, 'mrefsr_dcn_pack_weights')
-    if len(_packed_cache) > 256:
-        for k in [k for k, v in _packed_cache.items() if v[0]() is None]:
-            del _packed_cache[k]
-    _packed_cache[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), packed)
     return packed
 
 
@@ -148,14 +136,14 @@ def dynagg_dcn_forward_into(input, conv_out, max_idx, flow_scale, weight, bias, 
 
 
 def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, deformable_groups, out_slope=1.0,
-                       out_channels_last=None):
+                       out_channels_last=None, weight_packed=None):
     """Fused DynAgg forward for inference (no autograd): DCNv2 (3x3, stride 1, pad 1) whose offsets and masks are
     assembled inside the gather from the raw conv_offset_mask output and the matcher's arg-max map
     (ref_mrapa_restoration_arch.py:45-76 + corres_generation_arch.py:30-47, :70-105 for one scale).
     input [B,C,H,W], conv_out [B,3*dg*9,H,W], max_idx int64 [B,H/s-2,W/s-2] -> [B,Co,H,W].
     A torch.channels_last `input` is consumed as it is (it already is the gather layout); the result is
     channels_last when `out_channels_last` (default: follows the input).  out_slope: leaky-ReLU slope applied to the
-    result in the epilogue (1.0 = none)."""
+    result in the epilogue (1.0 = none).  weight_packed: optional `pack_weight(weight)` (skips the per-call repack)."""
     _lib.require_cuda(input, conv_out, max_idx, weight, bias)
     lib = _lib.lib()
     x = input.float()
@@ -180,9 +168,10 @@ def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, defor
     out = torch.empty(b, co, h, w, dtype=torch.float32, device=x.device,
                       memory_format=torch.channels_last if out_channels_last else torch.contiguous_format)
     flags = (1 if in_cl else 0) | (2 if out_channels_last else 0)
-    pk = packed_weight(weight)
-    if pk is not None:
-        wgt, flags = pk, flags | 4
+    if weight_packed is not None:        # pack_weight(weight), made once by a caller whose weights are frozen
+        if tuple(weight_packed.shape) != (co, 9 * c) or weight_packed.dtype != torch.float32 or not weight_packed.is_contiguous():
+            raise RuntimeError('weight_packed must be the result of pack_weight(weight)')
+        wgt, flags = weight_packed, flags | 4
     with torch.cuda.device(x.device):
         nbytes = lib.mrefsr_dcn_workspace_bytes(b, c, h, w, co, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, DCN_TF32, 0)
         ws, ws_bytes = _lib.workspace(nbytes, x.device)

@@ -574,3 +574,20 @@ def test_backward_gemm_on_tcgen05(shape):
         ref = torch.einsum('mk,znk->zmn', a64[0], b64)
         out = d[..., :N_].double().cpu()
     assert float((out - ref).abs().max() / ref.abs().max()) <= 1e-3
+
+
+def test_explicitly_packed_weights_give_the_same_bits():
+    """`pack_weight` + `weight_packed=` (a caller with frozen weights packs once) against the per-call repack; a packed
+    tensor of the wrong shape is refused."""
+    g = torch.Generator().manual_seed(3)
+    b, c, hw, dg, s = 2, 64, 16, 8, 1
+    x = torch.randn(b, c, hw, hw, generator=g).to(DEV)
+    conv_out = (torch.randn(b, 216, hw, hw, generator=g) * 0.5).to(DEV)
+    idx = torch.randint(0, (hw - 2) ** 2, (b, hw - 2, hw - 2), generator=g).to(DEV)
+    bias = torch.zeros(c, device=DEV)
+    w = (torch.randn(c, c, 3, 3, generator=g) * 0.05).to(DEV)
+    y0 = D.dynagg_dcn_forward(x, conv_out, idx, s, w, bias, dg)
+    y1 = D.dynagg_dcn_forward(x, conv_out, idx, s, w, bias, dg, weight_packed=D.pack_weight(w))
+    assert torch.equal(y0, y1)
+    with pytest.raises(RuntimeError):
+        D.dynagg_dcn_forward(x, conv_out, idx, s, w, bias, dg, weight_packed=torch.zeros(c, 8 * c, device=DEV))
