@@ -594,8 +594,23 @@ def main():
             'bound': 'l1-sector gather (microbenchmark of the gather alone, same shapes)', 'floor_ms': floor_ms,
             'achieved_ms': per_kernel['dcn_fwd']['ms_per_step'], 'frac': floor_ms / per_kernel['dcn_fwd']['ms_per_step'],
             'sectors_per_step': 4.0 * 9 * (b * r) * sum(hw * hw * c / 8 for c, hw in SCALES)}
+        # Round 2 (profiles/r02_dcn_window.md): ablating the kernel shows that neither HBM nor the L1 gather bounds it -- a
+        # free corner fetch saves 0.75 of 3.63 ms.  What does is instruction issue and hand-off latency: the operator
+        # needs ~75 instructions per decoded sampling point (position, deform group, tap) and ~70 per gathered
+        # 8-channel item (position, chunk, tap).  That count at 100 % issue rate (4 warp instructions per clock per SM
+        # at the measured SM clock) is the floor reported here.
+        sm_ghz = ((clocks or {}).get('sm_mhz') or 1900.0) / 1e3
+        warp_instr = sum((75.0 * DG + 70.0 * c / 8) * 9 * hw * hw for c, hw in SCALES) * (b * r) / 32.0
+        floor_issue_ms = warp_instr / (148 * 4 * sm_ghz * 1e9) * 1e3
+        roof_all['dcn_fwd']['issue_floor'] = {
+            'bound': 'instruction issue: essential decode + gather instructions at 4 warp-instructions/clk/SM',
+            'warp_instructions_per_step': warp_instr, 'floor_ms': floor_issue_ms,
+            'achieved_ms': per_kernel['dcn_fwd']['ms_per_step'], 'frac': floor_issue_ms / per_kernel['dcn_fwd']['ms_per_step'],
+            'note': 'ablation: pipeline skeleton 0.60 + decode 0.49 + gather 0.58 + epilogue stores 0.25 + MMA 0.14 ms add up '
+                    'serially at the large scale (profiles/r02_dcn_window.md)'}
         if dom == 'dcn_fwd':
             roofline['l1_gather'] = roof_all['dcn_fwd']['l1_gather']
+            roofline['issue_floor'] = roof_all['dcn_fwd']['issue_floor']
 
     # contract: the CPU baseline is timed on rank 0 at N = 1 only (at N > 1 the host cores are shared by the ranks)
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.cpu_images, r)
