@@ -95,10 +95,10 @@ __global__ void dcn_weight_repack_kernel(const float* __restrict__ w, float* __r
 // (Inlined at the four poll sites of the producer loop: an out-of-line call forces spills at the 96-register cap.)
 __device__ __forceinline__ void dcn_epilogue_tile(const DcnTcParams& prm, const float* __restrict__ bias,
                                                   uint32_t tmem_base, uint64_t* tempty_bar, int tile, int buf, int warp,
-                                                  int lane) {
+                                                  int lane, int half_lo = 0, int half_hi = 2) {
     const int Co = prm.s.Co, P = prm.P;
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    for (int half = half_lo; half < half_hi; ++half) {
         int b = 0, oy = 0, ox = 0;
         const bool ok = dcn_row_coords(prm, tile, half * 128 + warp * 32 + lane, b, oy, ox);
         const int p = ok ? oy * prm.s.Wo + ox : 0;
@@ -545,7 +545,12 @@ struct DcnRaw {                                     // inputs of one table row (
     int mi, fyx;
 };
 
-template <bool FUSED, int GS>       // GS = deform groups per 32-channel slab (prm.gs: 1, 2 or 4)
+// ALT (default since round 2; MREFSR_DCN_ALT=0 restores the round-1 schedule): the gather warps work as two groups of
+// eight that take alternate K steps (256 threads cover the 256 rows x 4 chunks of a K step with four items each)
+// instead of all sixteen walking every K step in lock-step: while one group waits for its stage to be consumed, the
+// other gathers.  Same arithmetic, same bits; measured on B200 (profiles/r02x): 3.72 -> 3.36 ms per step on coherent
+// flows, and with the groups decoupled a third stage pays at 16+ channels per deform group (mid scale 0.93 -> 0.84 ms).
+template <bool FUSED, int GS, bool ALT = false>       // GS = deform groups per 32-channel slab (prm.gs: 1, 2 or 4)
 __global__ void __launch_bounds__(S_THREADS, 1)
 dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __restrict__ xt,
                     const float* __restrict__ offset, const float* __restrict__ mask,
@@ -574,16 +579,16 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapW);
         for (int i = 0; i < S; ++i) {
-            mbar_init(&full[i], S_GW + 1);   // one elected arrive per gather warp + the TMA expect_tx arrive
+            mbar_init(&full[i], (ALT ? S_GW / 2 : S_GW) + 1);   // one elected arrive per gather warp + the TMA expect_tx arrive
             mbar_init(&empty[i], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], ALT ? 8 : 4);
         }
         for (int a = 0; a < S_NTAB; ++a) {
             mbar_init(&tab_full[a], S_DW);
-            mbar_init(&tab_empty[a], S_GW);
+            mbar_init(&tab_empty[a], ALT ? S_GW / 2 : S_GW);
         }
         fence_mbar_init();
     }
@@ -595,7 +600,115 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
     const int my_tiles = (prm.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * nkb_tile;   // K steps of this CTA, flattened over its tiles: (tile, slab, tap)
 
-    if (warp < S_GW) {
+    if (ALT && warp < S_GW) {
+        // ------------------------------------------------------------------ gather warps, two groups on alternate K steps
+        const int grp = warp >> 3;                 // this group's K steps: kb = grp (mod 2)
+        const int tg = threadIdx.x & 255;          // thread within the group
+        const int ch = tg & 3;                     // 8-channel chunk within the 32-channel slab
+        const int r0 = tg >> 2;                    // rows r0 + 64 i, i < 4
+        const int gsub = (ch * 8) / prm.cdg;
+        const uint32_t a_off0 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch) ^ (r0 & 7)) << 4);
+        const uint32_t a_off1 = (uint32_t)r0 * 128u + (uint32_t)(((2 * ch + 1) ^ (r0 & 7)) << 4);
+        // epilogue duty: warps 0..3 drain rows 0..127 of a tile, warps 8..11 rows 128..255 (TMEM lane quarter = warp % 4)
+        const bool is_epi = (warp & 7) < 4;
+        int ep_done = 0, prod_done = 0;
+        const int nbuf_mask = prm.nbuf - 1;
+        auto poll_epilogue = [&]() {
+            if (is_epi && ep_done < prod_done) {
+                const int buf = ep_done & nbuf_mask;
+                if (mbar_try_wait(&tfull[buf], (ep_done >> nbuf_mask) & 1)) {
+                    tc_fence_after();
+                    dcn_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf,
+                                      warp & 3, lane, grp, grp + 1);
+                    ++ep_done;
+                }
+            }
+        };
+        auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
+            while (!mbar_try_wait(bar, parity)) poll_epilogue();
+        };
+        int stage = grp % S, c_slab = 0, c_tap = grp;
+        uint32_t phase = 0;
+        while (c_tap >= K) {                       // (K = 1 kernels)
+            c_tap -= K;
+            if (++c_slab == prm.n_slabs) {
+                c_slab = 0;
+                ++prod_done;
+            }
+        }
+        const int dx_elems = C, dy_elems = s.W * C;
+        for (int kb = grp; kb < total_kb; kb += 2) {
+            const int g_slot = kb & (S_NTAB - 1);
+            const uint32_t g_phase = (uint32_t)(kb / S_NTAB) & 1u;
+            poll_epilogue();
+            const float* xs = xt + (c_slab * TBK + ch * 8);
+            const int* tb = tab_base + g_slot * tab_n + gsub * TAB_STRIDE + r0;
+            const float* tw = tab_w + g_slot * 4 * tab_n + gsub * TAB_STRIDE + r0;
+            wait_poll(&tab_full[g_slot], g_phase);
+            wait_poll(&empty[stage], phase ^ 1);
+            uint8_t* A = smem + (size_t)stage * prm.stage_bytes;
+            if (tg == 0) {        // weight tile of this K step (TMA, lands on the same full barrier)
+                mbar_expect_tx(&full[stage], Co * 128);
+                tma_load_3d(A + T_A_BYTES, &mapW, &full[stage], c_tap * C + c_slab * TBK, 0, 0);
+            }
+#pragma unroll 1
+            for (int pr = 0; pr < 2; ++pr) {
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii) {
+                    const int i = pr * 2 + ii;
+                    const int r = 64 * i;
+                    const int bf = tb[r];
+                    const float w0 = tw[r], w1 = tw[r + tab_n], w2 = tw[r + 2 * tab_n], w3 = tw[r + 3 * tab_n];
+                    const unsigned i0 = (unsigned)(bf & ~3);
+                    const unsigned i1 = i0 + ((bf & 1) ? dx_elems : 0);
+                    const unsigned i2 = i0 + ((bf & 2) ? dy_elems : 0);
+                    const unsigned i3 = i2 + ((bf & 1) ? dx_elems : 0);
+                    const F8 v0 = ldg8(xs + i0), v1 = ldg8(xs + i1), v2 = ldg8(xs + i2), v3 = ldg8(xs + i3);
+                    const float2 p0 = make_float2(w0, w0), p1 = make_float2(w1, w1), p2 = make_float2(w2, w2),
+                                 p3 = make_float2(w3, w3);
+                    float2 o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 a = __fmul2_rn(p0, v0.v[e]);
+                        a = __ffma2_rn(p1, v1.v[e], a);
+                        a = __ffma2_rn(p2, v2.v[e], a);
+                        a = __ffma2_rn(p3, v3.v[e], a);
+                        o[e] = make_float2(tf32_round_bits(a.x), tf32_round_bits(a.y));
+                    }
+                    *reinterpret_cast<float4*>(A + a_off0 + i * (64 * 128)) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                    *reinterpret_cast<float4*>(A + a_off1 + i * (64 * 128)) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[stage]);
+                mbar_arrive(&tab_empty[g_slot]);
+            }
+            stage += 2;
+            if (stage >= S) {
+                stage -= S;
+                phase ^= 1;
+            }
+            c_tap += 2;
+            while (c_tap >= K) {
+                c_tap -= K;
+                if (++c_slab == prm.n_slabs) {
+                    c_slab = 0;
+                    ++prod_done;      // this group has produced all of its K steps of the tile
+                }
+            }
+        }
+        prod_done = my_tiles;
+        while (is_epi && ep_done < prod_done) {    // drain the remaining accumulators
+            const int buf = ep_done & nbuf_mask;
+            mbar_wait_backoff(&tfull[buf], (ep_done >> nbuf_mask) & 1, 64);
+            tc_fence_after();
+            dcn_epilogue_tile(prm, bias, tmem_base, &tempty[buf], (int)blockIdx.x + ep_done * (int)gridDim.x, buf, warp & 3,
+                              lane, grp, grp + 1);
+            ++ep_done;
+        }
+    } else if (warp < S_GW) {
         // ------------------------------------------------------------------ gather warps
         const int tid = threadIdx.x;
         const int ch = tid & 3;                    // 8-channel chunk within the 32-channel slab
@@ -1036,7 +1149,10 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     prm.stage_bytes = T_A_BYTES + s.Co * 128;
     const bool split = dcn_split_mode() != 0;
     const size_t table_bytes = (size_t)(split ? S_NTAB : T_NTAB) * 5 * prm.gs * (TBM + 4) * 4;
-    int smem_budget = T_SMEM_BUDGET;
+    // stage ring vs L1: at 8 channels per deform group the gather needs the L1 more than a third stage (2.11 vs 1.91 ms
+    // at the large scale); from 16 channels per group on, the third stage wins once the gather groups alternate
+    int smem_budget = (split && prm.cdg >= 16 && !(getenv("MREFSR_DCN_ALT") && getenv("MREFSR_DCN_ALT")[0] == '0'))
+                          ? 205 * 1024 : T_SMEM_BUDGET;
 #ifdef MREFSR_DCN_DEBUG
     if (getenv("MREFSR_DCN_SMEM_KB")) smem_budget = atoi(getenv("MREFSR_DCN_SMEM_KB")) * 1024;   // tuning experiments
 #endif
@@ -1096,9 +1212,11 @@ int dcn_forward_tc_impl(const float* x, const float* w, const float* bias, const
     if (grid > prm.tiles) grid = prm.tiles;
     ScopedTiming tm(MREFSR_K_DCN_FWD, st);
     if (split) {
+    static int alt_mode = -1;       // MREFSR_DCN_ALT=0: all sixteen gather warps walk every K step (the round-1 schedule)
+    if (alt_mode < 0) alt_mode = (getenv("MREFSR_DCN_ALT") && getenv("MREFSR_DCN_ALT")[0] == '0') ? 0 : 1;
 #define MREFSR_LAUNCH_SPLIT(F, G)                                                                                  \
     do {                                                                                                            \
-        auto kern = dcn_tc_split_kernel<F, G>;                                                                      \
+        auto kern = alt_mode ? dcn_tc_split_kernel<F, G, true> : dcn_tc_split_kernel<F, G, false>;                  \
         MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<grid, S_THREADS, smem, st>>>(mapW, xt, off, F ? nullptr : mask, F ? max_idx : nullptr, bias, prm);   \
     } while (0)

@@ -419,8 +419,9 @@ print('HASH', h.hexdigest())
 
 
 def test_kernel_variants_agree_bit_for_bit():
-    """The role-split 256-row kernel (default), the shared-memory window kernel (MREFSR_DCN_WIN=1), the 17-warp kernel
-    (MREFSR_DCN_SPLIT=0) and the linear tile mapping (MREFSR_DCN_TILE=linear) are the same arithmetic in a
+    """The role-split 256-row kernel with alternating gather groups (default), its lock-step schedule of round 1
+    (MREFSR_DCN_ALT=0), the shared-memory window kernel (MREFSR_DCN_WIN=1), the 17-warp kernel (MREFSR_DCN_SPLIT=0) and
+    the linear tile mapping (MREFSR_DCN_TILE=linear) are the same arithmetic in a
     different schedule / through a different corner-fetch path: identical bits, fused and operator entry points,
     1 / 2 / 4 deform groups per slab, random flows (window misses: global-memory corners) and coherent flows (window
     hits, windows hanging over the image border).  The knobs are read once per process, hence the subprocesses."""
@@ -430,7 +431,8 @@ def test_kernel_variants_agree_bit_for_bit():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hashes = {}
     for name, env in (('split+2d', {}), ('window', {'MREFSR_DCN_WIN': '1'}), ('17-warp', {'MREFSR_DCN_SPLIT': '0'}),
-                      ('linear', {'MREFSR_DCN_TILE': 'linear'})):
+                      ('linear', {'MREFSR_DCN_TILE': 'linear'}), ('lock-step gather warps', {'MREFSR_DCN_ALT': '0'}),
+                      ('lock-step gather warps, linear', {'MREFSR_DCN_ALT': '0', 'MREFSR_DCN_TILE': 'linear'})):
         e = {k: v for k, v in os.environ.items() if not k.startswith('MREFSR_DCN_')}
         e.update(env)
         r = subprocess.run([sys.executable, '-c', _VARIANT_SCRIPT % root], env=e, capture_output=True, text=True,
