@@ -568,7 +568,7 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
     uint64_t* tab_full = tempty + 2;          // [S_NTAB]
     uint64_t* tab_empty = tab_full + S_NTAB;  // [S_NTAB]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_empty + S_NTAB);
-    const int tab_n = prm.gs * TAB_STRIDE;
+    constexpr int tab_n = GS * TAB_STRIDE;      // compile-time: table addresses are register + immediate
     int* tab_base = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
     float* tab_w = reinterpret_cast<float*>(tab_base + S_NTAB * tab_n);
 
@@ -932,18 +932,29 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
                     const float fy0 = floorf(y), fx0 = floorf(x);
                     const int y0 = (int)fy0, x0 = (int)fx0;       // saturating conversions: garbage in, garbage selected away
                     const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
-                    const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
-                    const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
-                    int base = ((rr.bH + yc) * s.W + xc) * C;
-                    base |= (tx0 && tx1) ? 1 : 0;
-                    base |= (ty0 && ty1) ? 2 : 0;
                     const float hym = hy * mk, lym = ly * mk;
+                    // Interior sampling points (all four corners inside the plane: everything but the outermost ring)
+                    // need no clamping and no validity bits; the border rule is a rarely taken fix-up.  Same values
+                    // as the one-formula version bit for bit, ~16 instructions fewer per entry on the common path.
+                    int base = (((rr.bH + y0) * s.W + x0) * C) | 3;
+                    float w0 = hym * hx, w1 = hym * lx, w2 = lym * hx, w3 = lym * lx;
+                    if (in && !((unsigned)y0 < (unsigned)(s.H - 1) && (unsigned)x0 < (unsigned)(s.W - 1))) {
+                        const bool ty0 = y0 >= 0, ty1 = y0 <= s.H - 2, tx0 = x0 >= 0, tx1 = x0 <= s.W - 2;
+                        const int yc = min(max(y0, 0), s.H - 1), xc = min(max(x0, 0), s.W - 1);
+                        base = ((rr.bH + yc) * s.W + xc) * C;
+                        base |= (tx0 && tx1) ? 1 : 0;
+                        base |= (ty0 && ty1) ? 2 : 0;
+                        w0 = (ty0 && tx0) ? w0 : 0.f;
+                        w1 = (ty0 && tx1) ? w1 : 0.f;
+                        w2 = (ty1 && tx0) ? w2 : 0.f;
+                        w3 = (ty1 && tx1) ? w3 : 0.f;
+                    }
                     const int e = g * TAB_STRIDE;
                     tb[e] = in ? base : 0;
-                    tw[e] = (in && ty0 && tx0) ? hym * hx : 0.f;
-                    tw[e + tab_n] = (in && ty0 && tx1) ? hym * lx : 0.f;
-                    tw[e + 2 * tab_n] = (in && ty1 && tx0) ? lym * hx : 0.f;
-                    tw[e + 3 * tab_n] = (in && ty1 && tx1) ? lym * lx : 0.f;
+                    tw[e] = in ? w0 : 0.f;
+                    tw[e + tab_n] = in ? w1 : 0.f;
+                    tw[e + 2 * tab_n] = in ? w2 : 0.f;
+                    tw[e + 3 * tab_n] = in ? w3 : 0.f;
                 }
             }
             __syncwarp();
