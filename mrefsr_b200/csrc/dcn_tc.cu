@@ -625,6 +625,7 @@ dcn_tc_split_kernel(const __grid_constant__ CUtensorMap mapW, const float* __res
             }
         };
         auto wait_poll = [&](uint64_t* bar, uint32_t parity) {
+            // (a nanosleep back-off between polls -- 20 / 50 / 100 ns -- changes nothing: measured, profiles/r02_dcn_window.md)
             while (!mbar_try_wait(bar, parity)) poll_epilogue();
         };
         int stage = grp % S, c_slab = 0, c_tap = grp;
