@@ -267,6 +267,59 @@ __device__ __forceinline__ Col8 ldg_col8(const float* p) {
         : "l"(p));
     return r;
 }
+// (2') grad_offset / grad_mask from the NHWC copy of the input: one thread per (bl, deform group, tap, position) like the
+// planar kernel above, but the group's channels come as 8-channel chunks with four 256-bit corner loads each instead of
+// 32 scalar plane loads per chunk.  One thread owns a whole (group, tap, position): plain stores, deterministic.
+__global__ void __launch_bounds__(256)
+dcn_bwd_coord_nhwc_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
+                          const float* __restrict__ gcol, float* __restrict__ goff, float* __restrict__ gmask,
+                          const DcnShape s, int b0, int nb) {
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG;
+    const size_t total = (size_t)nb * s.DG * K * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int tap = (idx / P) % K;
+        const int dgi = (idx / ((size_t)P * K)) % s.DG;
+        const int bl = idx / ((size_t)P * K * s.DG);
+        const int b = b0 + bl;
+        const int oy = p / s.Wo, ox = p - oy * s.Wo, ti = tap / s.kw, tj = tap - ti * s.kw;
+        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+        const size_t mb = ((size_t)(b * s.DG + dgi) * K + tap) * P + p;
+        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldg(offset + ob);
+        const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldg(offset + ob + P);
+        const float m = mask ? __ldg(mask + mb) : 1.f;
+        float dy = 0.f, dx = 0.f, dm = 0.f;
+        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+            const float fy0 = floorf(y), fx0 = floorf(x);
+            const int y0 = (int)fy0, x0 = (int)fx0;
+            const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+            const float* base = xt + ((size_t)(b * s.H + yc) * s.W + xc) * s.C + dgi * cdg;
+            const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
+            const float va = (ty0 && tx0) ? 1.f : 0.f, vb = (ty0 && tx1) ? 1.f : 0.f, vc = (ty1 && tx0) ? 1.f : 0.f,
+                        vd = (ty1 && tx1) ? 1.f : 0.f;
+            const float* gc = gcol + ((size_t)bl * s.C * K + (size_t)dgi * cdg * K + tap) * P + p;
+            for (int c0 = 0; c0 < cdg; c0 += 8) {
+                const Col8 v0 = ldg_col8(base + c0), v1 = ldg_col8(base + c0 + dxo), v2 = ldg_col8(base + c0 + dyo),
+                           v3 = ldg_col8(base + c0 + dyo + dxo);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float a = va * v0.v[e], bq = vb * v1.v[e], cq = vc * v2.v[e], d = vd * v3.v[e];
+                    const float g = __ldg(gc + (size_t)(c0 + e) * K * P);
+                    const float v = hy * hx * a + hy * lx * bq + ly * hx * cq + ly * lx * d;
+                    dm += g * v;
+                    dy += g * m * (hx * (cq - a) + lx * (d - bq));
+                    dx += g * m * (hy * (bq - a) + ly * (d - cq));
+                }
+            }
+        }
+        goff[ob] = dy;
+        goff[ob + P] = dx;
+        if (gmask) gmask[mb] = dm;
+    }
+}
+
 // written as planes colT[bl][tap*C + c][p] (k = position contiguous: the B operand of the
 // tcgen05 grad_weight GEMM).  Lanes = consecutive positions, so each of the 8 scalar stores of a thread is a coalesced
 // 128-byte warp store into its channel plane.
@@ -447,6 +500,43 @@ __global__ void dynagg_offsets_kernel(const float* __restrict__ conv_out, const 
     }
 }
 
+// The same pass, four positions per thread (16-byte accesses, no integer division in the loop): grid.y = (sample, plane).
+// Same arithmetic per element as the scalar kernel; used when P % 4 == 0 and the tensors are 16-byte aligned.
+__global__ void __launch_bounds__(256)
+dynagg_offsets_vec4_kernel(const float* __restrict__ conv_out, const float* __restrict__ pre, float* __restrict__ offset,
+                           float* __restrict__ mask, float* __restrict__ abs_sum, int dg, int K, int P) {
+    const int OC = 2 * dg * K, MC = dg * K, TC = OC + MC;
+    const int b = blockIdx.y / TC, ch = blockIdx.y - b * TC;
+    const float4* src = reinterpret_cast<const float4*>(conv_out + ((size_t)b * TC + ch) * P);
+    const int P4 = P >> 2;
+    float local = 0.f;
+    if (ch < OC) {
+        const int k = (ch >> 1) % K;
+        const int comp = (ch & 1) ? 0 : 1;       // even plane = y = pre[..., 1], odd plane = x = pre[..., 0]
+        const float4* pv = reinterpret_cast<const float4*>(pre + ((size_t)b * K + k) * P * 2);   // (x, y) pairs of 2 positions
+        float4* dst = reinterpret_cast<float4*>(offset + ((size_t)b * OC + ch) * P);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+            const float4 v = __ldcs(src + i);
+            const float4 p0 = __ldg(pv + 2 * i), p1 = __ldg(pv + 2 * i + 1);
+            const float a0 = comp ? p0.y : p0.x, a1 = comp ? p0.w : p0.z, a2 = comp ? p1.y : p1.x, a3 = comp ? p1.w : p1.z;
+            dst[i] = make_float4(v.x + a0, v.y + a1, v.z + a2, v.w + a3);
+            local += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+        }
+    } else {
+        float4* dst = reinterpret_cast<float4*>(mask + ((size_t)b * MC + (ch - OC)) * P);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+            const float4 v = __ldcs(src + i);
+            dst[i] = make_float4(1.f / (1.f + expf(-v.x)), 1.f / (1.f + expf(-v.y)), 1.f / (1.f + expf(-v.z)),
+                                 1.f / (1.f + expf(-v.w)));
+        }
+    }
+    if (abs_sum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(abs_sum, local);
+    }
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -597,9 +687,13 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
     float* wT = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes + gwt_bytes);
     float* part = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes + 2 * gwt_bytes);
     float* goutR = reinterpret_cast<float*>(wsp + 2 * buf + xt_bytes + got_bytes + 2 * gwt_bytes + part_bytes);
-    if (tc_gw) {
+    // grad_offset / grad_mask from the NHWC copy (four 256-bit corner loads per 8-channel chunk instead of 32 scalar loads)
+    const bool nhwc_coord = tc_gemm && grad_offset && C % 8 == 0 && (C / deformable_group) % 8 == 0 && small_enough;
+    if (tc_gw || nhwc_coord) {
         rc = dcn_nchw_to_nhwc(input, xt, B, C, H * W, st);
         if (rc) return rc;
+    }
+    if (tc_gw) {
         MREFSR_CUDA(cudaMemsetAsync(gwT, 0, (size_t)Co * C * K * 4, st));
         dcn_round_tf32_kernel<<<grid_for((size_t)B * Co * P), 256, 0, st>>>(grad_output, goutR, (size_t)B * Co * P);
         MREFSR_LAUNCH_CHECK();
@@ -625,7 +719,12 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }
-        if (grad_offset) {
+        if (grad_offset && nhwc_coord) {
+            dcn_bwd_coord_nhwc_kernel<<<grid_for((size_t)nb * deformable_group * K * P), 256, 0, st>>>(
+                xt, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
+        } else if (grad_offset) {
             dcn_bwd_coord_kernel<<<grid_for((size_t)nb * deformable_group * K * P), 256, 0, st>>>(
                 input, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
@@ -788,7 +887,15 @@ int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t total = (size_t)B * 3 * dg * K * H * W;
     ScopedTiming tm(MREFSR_K_GLUE, st);
-    dynagg_offsets_kernel<<<grid_for(total), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, B, dg, K, H * W);
+    const int P = H * W;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (P % 4 == 0 && al16(conv_out) && al16(pre_offset) && al16(offset) && al16(mask) && (size_t)B * 3 * dg * K <= 65535) {
+        int gx = cdiv(P / 4, 256);
+        if (gx > 8) gx = 8;
+        dynagg_offsets_vec4_kernel<<<dim3(gx, B * 3 * dg * K), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, dg, K, P);
+    } else {
+        dynagg_offsets_kernel<<<grid_for(total), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, B, dg, K, P);
+    }
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

@@ -39,6 +39,13 @@
 // cp.async.bulk.prefetch.L2 of the input, deeper stage rings at the expense of L1 (+8 %), the table decode moved
 // under the corner loads' latency (spills at the register cap: +16 %), cp.async staging of the raw offsets (+5 %).
 //
+// Round 2 (profiles/r02_dcn_window.md): an ablation of dcn_tc_split_kernel showed that its parts -- pipeline skeleton,
+// decode, gather, epilogue stores, MMAs -- add up almost serially and that a FREE corner fetch would save only a fifth of
+// its time, i.e. the kernel is bound by instruction issue and hand-off latency, not by the L1 sector rate.  The gather
+// warps therefore no longer walk every K step in lock-step: they work as two groups of eight on alternate K steps
+// (template flag ALT, default), a third pipeline stage is used where a deform group has >= 16 channels, and the decode
+// handles interior sampling points without clamps / validity bits: 0.55 / 0.88 / 1.96 ms per launch, same bits.
+//
 // Offsets / masks come either as materialised tensors (the reference operator API) or -- fused DynAgg mode --
 // straight from the raw conv_offset_mask output plus the matcher's arg-max map: offset = conv + s*flow shifted
 // by the tap, mask = sigmoid(conv) (basicsr/archs/ref_mrapa_restoration_arch.py:55-68 and

@@ -593,3 +593,23 @@ def test_explicitly_packed_weights_give_the_same_bits():
     assert torch.equal(y0, y1)
     with pytest.raises(RuntimeError):
         D.dynagg_dcn_forward(x, conv_out, idx, s, w, bias, dg, weight_packed=torch.zeros(c, 8 * c, device=DEV))
+
+
+@pytest.mark.parametrize('hw', [(12, 16), (7, 9), (40, 40), (5, 4)])
+def test_dynagg_glue_both_kernels_vs_oracle(hw):
+    """DynAgg offset / mask assembly (ref_mrapa_restoration_arch.py:55-73): the four-positions-per-thread kernel
+    (h*w % 4 == 0) and the scalar one (other sizes) against the oracle, offsets bit-exact, and the mean-|learned offset|
+    statistic the reference computes with a host sync (:70-71)."""
+    from mrefsr_b200.dynagg import DynAggOffsetsFunction
+    h, w = hw
+    b, dg, k = 3, 8, 9
+    g = torch.Generator().manual_seed(h * w)
+    conv_out = torch.randn(b, 3 * dg * k, h, w, generator=g)
+    pre = torch.randint(-20, 21, (b, k, h, w, 2), generator=g).float()
+    stats = torch.zeros(1, device=DEV)
+    off, mask = DynAggOffsetsFunction.apply(conv_out.to(DEV), pre.to(DEV), dg, stats)
+    o_off, o_mask = oracle.dynagg_offsets_oracle(conv_out, pre, dg)
+    assert torch.equal(off.cpu(), o_off)
+    assert (mask.cpu() - o_mask).abs().max() <= 1e-6
+    want = float(conv_out[:, :2 * dg * k].abs().double().sum())
+    assert abs(float(stats.item()) - want) <= 1e-4 * want
