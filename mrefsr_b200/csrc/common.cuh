@@ -224,6 +224,10 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
+// 32 lanes x 2 consecutive fp32 columns (the two look-ahead columns of the matcher's diagonal-sum epilogue)
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (rows of 128 B, 8-row groups 1024 B

@@ -489,10 +489,226 @@ match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 }
 
 // =====================================================================================================
+// 3c. tcgen05 matcher, diagonal form (default): a third of the MMAs of 3b
+// =====================================================================================================
+// The 3x3 patch correlation is a sum along a diagonal of the pixel Gram matrix G[p, q] = <f_in(p), f_ref(q)>:
+//     sim[p, q] = sum_{i, j} G[p + i*w_in + j, q + i*w_ref + j].
+// The tensor core only computes the tap-COLUMN sums H[p, q] = sum_i G[p + i*w_in, q + i*w_ref] (K = 3*C: row-shifted
+// TMA boxes as in 3b, j = 0 only); the three tap-ROW terms are the same H one row and one column further,
+//     sim[p, q] = H[p, q] + H[p+1, q+1] + H[p+2, q+2],
+// and the epilogue adds them: in TMEM a lane is a row and a register a column, so H[p+1, q+1] is the neighbouring
+// lane's next register -- two warp shuffles and two adds per element.  A warp can only reach its own 32 TMEM lanes, so
+// the four 32-lane quarters of the accumulator hold 32-row windows that start 30 rows apart (four 32-row TMA boxes per
+// A tile) and only the first 30 lanes of a warp own an output row: 120 rows per tile.  Likewise an N tile covers 254
+// output columns with 256 accumulator columns.  Accumulation order differs from 3b (fp32 sums over (i, c) in TMEM, then
+// fp32 over j), precision is the same.
+template <int NPASS>
+struct DgCfg {
+    static constexpr int BM = 128, BN = 256, BK = 64;
+    static constexpr int MV = 120, NV = 254;             // output rows / columns owned by a tile
+    static constexpr int WROWS = 30;                     // row distance of consecutive lane quarters
+    static constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+    static constexpr int NSPLIT = (NPASS == 1) ? 1 : 2;  // hi only, or hi + lo
+    static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 8 /*scale,bias*/ + 256 /*barriers*/ + 1024;
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(192, 1)
+match_diag_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                  const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                  const float2* __restrict__ colsb, unsigned long long* __restrict__ keys, const TcParams prm) {
+    using Cfg = DgCfg<NPASS>;
+    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* stage_base = smem;
+    float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_sb) + 2 * BN * 8);
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* empty = bars + STAGES;       // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;   // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slabs = prm.C / Cfg::BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA_hi);
+        tma_prefetch_desc(&mapB_hi);
+        if (NPASS > 1) {
+            tma_prefetch_desc(&mapA_lo);
+            tma_prefetch_desc(&mapB_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x) {
+                const int nt = item % prm.n_tiles;
+                const int mt = (item / prm.n_tiles) % prm.m_tiles;
+                const int pair = item / (prm.n_tiles * prm.m_tiles);
+                const int img = (pair / prm.in_div) % prm.n_in;
+                const int m0 = mt * Cfg::MV, n0 = nt * Cfg::NV;
+                for (int slab = 0; slab < n_slabs; ++slab) {
+                    for (int ti = 0; ti < 3; ++ti) {
+                        const int ra = m0 + ti * prm.w_in, rb = n0 + ti * prm.w_ref;
+                        mbar_wait_backoff(&empty[stage], phase ^ 1, 64);
+                        uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
+                        uint8_t* sbm = sa + Cfg::NSPLIT * Cfg::A_BYTES;
+                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_3d(sbm, &mapB_hi, &full[stage], slab * Cfg::BK, rb, pair);
+                        if (NPASS > 1) tma_load_3d(sbm + Cfg::B_BYTES, &mapB_lo, &full[stage], slab * Cfg::BK, rb, pair);
+#pragma unroll
+                        for (int wq = 0; wq < 4; ++wq) {
+                            tma_load_3d(sa + wq * 4096, &mapA_hi, &full[stage], slab * Cfg::BK, ra + wq * Cfg::WROWS, img);
+                            if (NPASS > 1)
+                                tma_load_3d(sa + Cfg::A_BYTES + wq * 4096, &mapA_lo, &full[stage], slab * Cfg::BK,
+                                            ra + wq * Cfg::WROWS, img);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
+                const int nt = item % prm.n_tiles;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                int ncols = prm.hw_ref - nt * Cfg::NV + 2;     // +2: the look-ahead columns of the last outputs
+                ncols = ncols > BN ? BN : ((ncols + 31) & ~31);
+                const uint32_t idesc = umma_idesc(MREFSR_IDESC_16, Cfg::BM, ncols);
+                mbar_wait_backoff(&tempty[acc], acc_phase ^ 1, 64);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int slab = 0; slab < n_slabs; ++slab) {
+                    for (int ti = 0; ti < 3; ++ti) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + Cfg::NSPLIT * Cfg::A_BYTES;
+#pragma unroll
+                        for (int pass = 0; pass < NPASS; ++pass) {
+                            // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
+                            const uint32_t a0 = sa + ((pass == 2) ? Cfg::A_BYTES : 0);
+                            const uint32_t b0 = sb + ((pass == 1) ? Cfg::B_BYTES : 0);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma_f16(tacc, umma_desc_sw128(a0 + kk * 32, 0), umma_desc_sw128(b0 + kk * 32, 0), idesc,
+                                         accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int et = threadIdx.x - 64;            // 0..127
+        int it = 0;
+        for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
+            const int nt = item % prm.n_tiles;
+            const int mt = (item / prm.n_tiles) % prm.m_tiles;
+            const int pair = item / (prm.n_tiles * prm.m_tiles);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n0 = nt * Cfg::NV;
+            const int nout = min(Cfg::NV, prm.hw_ref - n0);           // output columns of this tile
+            int ncols = prm.hw_ref - n0 + 2;
+            ncols = ncols > BN ? BN : ((ncols + 31) & ~31);           // accumulator columns the MMAs wrote
+            float2* sbuf = s_sb + acc * BN;
+            const float2* gsb = colsb + (size_t)pair * prm.colsb_stride + n0;
+            for (int i = et; i < ncols; i += 128) sbuf[i] = (i < nout) ? gsb[i] : make_float2(0.f, -INFINITY);
+            named_bar_sync(1, 128);
+            mbar_wait_backoff(&tfull[acc], acc_phase, 256);
+            tc_fence_after();
+            float best = -INFINITY;
+            int bestn = 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32], e[2];
+                tmem_ld_32x32(taddr + c0, v);
+                if (c0 + 32 < ncols) {
+                    tmem_ld_32x2(taddr + c0 + 32, e);
+                } else {
+                    e[0] = e[1] = 0u;
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const uint32_t x1 = (k + 1 < 32) ? v[(k + 1) & 31] : e[0];
+                    const uint32_t x2 = (k + 2 < 32) ? v[(k + 2) & 31] : e[(k + 2) & 1];
+                    const float h1 = __uint_as_float(__shfl_down_sync(0xffffffffu, x1, 1));
+                    const float h2 = __uint_as_float(__shfl_down_sync(0xffffffffu, x2, 2));
+                    const float sum = (__uint_as_float(v[k]) + h1) + h2;
+                    const float2 s = sbuf[c0 + k];
+                    const float val = fmaf(sum, s.x, s.y);
+                    if (val > best) {
+                        best = val;
+                        bestn = c0 + k;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            const int m = mt * Cfg::MV + q * Cfg::WROWS + lane;
+            if (lane < Cfg::WROWS && m < prm.hw_in && best > -INFINITY)
+                atomicMax(keys + (size_t)pair * prm.key_stride + m, pack_key(best, (uint32_t)(n0 + bestn)));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// =====================================================================================================
 // host side
 // =====================================================================================================
 struct MatchPlan {
-    int mode, strip, base_offset_mode;
+    int mode, strip, base_offset_mode, diag;
     int hw_in, hw_ref, ho, wo, ho_ref, wo_ref;
     int key_stride, colsb_stride;
     size_t off_keys, off_sumsq_in, off_sumsq_ref, off_rownorm, off_colsb, off_a0, off_a1, off_b0, off_b1, total;
@@ -512,6 +728,7 @@ static int make_plan(MatchPlan* pl, int n_in, int n_pairs, int C, int h_in, int 
     pl->mode = mode;
     pl->strip = (mode_flags & MREFSR_MATCH_FLAG_NO_STRIP) ? 1 : 3;
     pl->base_offset_mode = (mode_flags & MREFSR_MATCH_FLAG_BASE_OFFSET) ? 1 : 0;
+    pl->diag = (mode_flags & (MREFSR_MATCH_FLAG_NO_DIAG | MREFSR_MATCH_FLAG_NO_STRIP | MREFSR_MATCH_FLAG_BASE_OFFSET)) ? 0 : 1;
     pl->hw_in = h_in * w_in;
     pl->hw_ref = h_ref * w_ref;
     pl->ho = (h_in - ps) / s_in + 1;
@@ -594,6 +811,49 @@ static int launch_tc(const MatchPlan& pl, uint8_t* ws, int n_in, int n_pairs, in
     return 0;
 }
 
+template <int NPASS>
+static int launch_diag(const MatchPlan& pl, uint8_t* ws, int n_in, int n_pairs, int in_div, int C, int w_in, int w_ref,
+                       cudaStream_t st) {
+    using Cfg = DgCfg<NPASS>;
+    static_assert(Cfg::STAGES >= 2, "need at least a double-buffered pipeline");
+    CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+    const CUtensorMapDataType dt = MREFSR_TMAP_16;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    int rc;
+    void* a_hi = ws + pl.off_a0;
+    void* b_hi = ws + pl.off_b0;
+    void* a_lo = (NPASS > 1) ? ws + pl.off_a1 : a_hi;
+    void* b_lo = (NPASS > 1) ? ws + pl.off_b1 : b_hi;
+    if ((rc = make_tensor_map_3d(&mA_hi, dt, 2, a_hi, C, pl.hw_in, n_in, 64, 32, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mA_lo, dt, 2, a_lo, C, pl.hw_in, n_in, 64, 32, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB_hi, dt, 2, b_hi, C, pl.hw_ref, n_pairs, 64, Cfg::BN, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB_lo, dt, 2, b_lo, C, pl.hw_ref, n_pairs, 64, Cfg::BN, sw))) return rc;
+    TcParams prm;
+    prm.n_pairs = n_pairs;
+    prm.in_div = in_div;
+    prm.n_in = n_in;
+    prm.C = C;
+    prm.hw_in = (pl.hw_in / w_in - 3) * w_in + (w_in - 2);      // pixel-linear indices up to the last valid origin
+    prm.w_in = w_in;
+    prm.hw_ref = (pl.hw_ref / w_ref - 3) * w_ref + (w_ref - 2);
+    prm.w_ref = w_ref;
+    prm.m_tiles = cdiv(prm.hw_in, Cfg::MV);
+    prm.n_tiles = cdiv(prm.hw_ref, Cfg::NV);
+    prm.total_items = n_pairs * prm.m_tiles * prm.n_tiles;
+    prm.key_stride = pl.key_stride;
+    prm.colsb_stride = pl.colsb_stride;
+    prm.base_offset_mode = 0;
+    auto kern = match_diag_kernel<NPASS>;
+    MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int grid = sm_count();
+    if (grid > prm.total_items) grid = prm.total_items;
+    kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, reinterpret_cast<const float2*>(ws + pl.off_colsb),
+                                              reinterpret_cast<unsigned long long*>(ws + pl.off_keys), prm);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
 static int run_match(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div, int C, int h_in,
                      int w_in, int h_ref, int w_ref, int ps, int s_in, int s_ref, int is_norm, int norm_input,
                      int normalize_pixels, int mode_flags, long long* max_idx, float* max_val, void* workspace,
@@ -653,7 +913,10 @@ static int run_match(const float* feat_in, const float* feat_ref, int n_in, int 
         MREFSR_LAUNCH_CHECK();
         count_launches(1);
     } else {
-        if (pl.strip == 3) {
+        if (pl.diag) {
+            rc = x3 ? launch_diag<3>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st)
+                    : launch_diag<1>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st);
+        } else if (pl.strip == 3) {
             rc = x3 ? launch_tc<3, 3>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st)
                     : launch_tc<3, 1>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st);
         } else {
