@@ -54,6 +54,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // grid (ceil(HW/32), n_img), block 256, dynamic smem C*33 floats.
+// Phase 1: the block's 32 pixels x C channels through a padded shared-memory tile, sixteen independent 128-byte row
+// loads in flight per warp (the pass is HBM-bound; a dependent load-store loop leaves the memory system idle).
+// Phase 2: one warp per pixel, the pixel's channels (pairs 2*lane + 64*k) in registers from one tile read: sum of
+// squares, optional normalisation, hi / lo split and the stores -- no second trip through shared memory.
+template <int CPL>   // channel pairs per lane = C / 64 (0: generic loop over the tile for other channel counts)
 __global__ void __launch_bounds__(256)
 match_prep_kernel(const float* __restrict__ src, int C, int HW, int normalize, float* __restrict__ dst_f32,
                   bf16* __restrict__ dst_hi, bf16* __restrict__ dst_lo, float* __restrict__ pix_sumsq) {
@@ -62,46 +67,107 @@ match_prep_kernel(const float* __restrict__ src, int C, int HW, int normalize, f
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const float* s = src + (size_t)img * C * HW;
     const int p = p0 + lane;
-    for (int c = warp; c < C; c += nwarps) tile[c * 33 + lane] = (p < HW) ? __ldg(s + (size_t)c * HW + p) : 0.f;
+    constexpr int U = 16;
+#pragma unroll 1
+    for (int c0 = warp; c0 < C; c0 += nwarps * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u * nwarps;
+            v[u] = (p < HW && c < C) ? __ldg(s + (size_t)c * HW + p) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u * nwarps;
+            if (c < C) tile[c * 33 + lane] = v[u];
+        }
+    }
     __syncthreads();
     for (int pp = warp; pp < 32; pp += nwarps) {
-        float ss = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            float v = tile[c * 33 + pp];
-            ss += v * v;
-        }
-        ss = warp_sum(ss);
-        if (normalize) {
-            // F.normalize(dim=0): x / max(||x||_2, 1e-12)  (corres_generation_arch.py:57-59)
-            const float denom = fmaxf(sqrtf(ss), 1e-12f);
-            float ss2 = 0.f;
-            for (int c = lane; c < C; c += 32) {
-                float v = tile[c * 33 + pp] / denom;
-                tile[c * 33 + pp] = v;
-                ss2 += v * v;
-            }
-            ss = warp_sum(ss2);
-        }
         const int q = p0 + pp;
-        if (q < HW) {
+        if (CPL > 0) {
+            float2 v[CPL > 0 ? CPL : 1];
+            float ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int c = 2 * lane + 64 * k;
+                v[k].x = tile[c * 33 + pp];
+                v[k].y = tile[(c + 1) * 33 + pp];
+                ss = fmaf(v[k].x, v[k].x, ss);
+                ss = fmaf(v[k].y, v[k].y, ss);
+            }
+            ss = warp_sum(ss);
+            if (normalize) {
+                // F.normalize(dim=0): x / max(||x||_2, 1e-12)  (corres_generation_arch.py:57-59)
+                const float denom = fmaxf(sqrtf(ss), 1e-12f);
+                float ss2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    v[k].x = v[k].x / denom;
+                    v[k].y = v[k].y / denom;
+                    ss2 = fmaf(v[k].x, v[k].x, ss2);
+                    ss2 = fmaf(v[k].y, v[k].y, ss2);
+                }
+                ss = warp_sum(ss2);
+            }
+            if (q >= HW) continue;
             if (lane == 0) pix_sumsq[(size_t)img * HW + q] = ss;
             const size_t row = ((size_t)img * HW + q) * C;
-            if (dst_f32) {
-                for (int c = lane; c < C; c += 32) dst_f32[row + c] = tile[c * 33 + pp];
-            }
-            if (dst_hi) {
-                for (int c = lane * 2; c < C; c += 64) {
-                    const float v0 = tile[c * 33 + pp], v1 = tile[(c + 1) * 33 + pp];
-                    const bf16 h0 = MREFSR_TO16(v0), h1 = MREFSR_TO16(v1);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int c = 2 * lane + 64 * k;
+                if (dst_f32) *reinterpret_cast<float2*>(dst_f32 + row + c) = v[k];
+                if (dst_hi) {
+                    const bf16 h0 = MREFSR_TO16(v[k].x), h1 = MREFSR_TO16(v[k].y);
                     bf16x2 hh;
                     hh.x = h0;
                     hh.y = h1;
                     *reinterpret_cast<bf16x2*>(dst_hi + row + c) = hh;
                     if (dst_lo) {
                         bf16x2 ll;
-                        ll.x = MREFSR_TO16(v0 - MREFSR_FROM16(h0));
-                        ll.y = MREFSR_TO16(v1 - MREFSR_FROM16(h1));
+                        ll.x = MREFSR_TO16(v[k].x - MREFSR_FROM16(h0));
+                        ll.y = MREFSR_TO16(v[k].y - MREFSR_FROM16(h1));
                         *reinterpret_cast<bf16x2*>(dst_lo + row + c) = ll;
+                    }
+                }
+            }
+        } else {
+            float ss = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                float v = tile[c * 33 + pp];
+                ss += v * v;
+            }
+            ss = warp_sum(ss);
+            if (normalize) {
+                const float denom = fmaxf(sqrtf(ss), 1e-12f);
+                float ss2 = 0.f;
+                for (int c = lane; c < C; c += 32) {
+                    float v = tile[c * 33 + pp] / denom;
+                    tile[c * 33 + pp] = v;
+                    ss2 += v * v;
+                }
+                ss = warp_sum(ss2);
+            }
+            if (q < HW) {
+                if (lane == 0) pix_sumsq[(size_t)img * HW + q] = ss;
+                const size_t row = ((size_t)img * HW + q) * C;
+                if (dst_f32) {
+                    for (int c = lane; c < C; c += 32) dst_f32[row + c] = tile[c * 33 + pp];
+                }
+                if (dst_hi) {
+                    for (int c = lane * 2; c < C; c += 64) {
+                        const float v0 = tile[c * 33 + pp], v1 = tile[(c + 1) * 33 + pp];
+                        const bf16 h0 = MREFSR_TO16(v0), h1 = MREFSR_TO16(v1);
+                        bf16x2 hh;
+                        hh.x = h0;
+                        hh.y = h1;
+                        *reinterpret_cast<bf16x2*>(dst_hi + row + c) = hh;
+                        if (dst_lo) {
+                            bf16x2 ll;
+                            ll.x = MREFSR_TO16(v0 - MREFSR_FROM16(h0));
+                            ll.y = MREFSR_TO16(v1 - MREFSR_FROM16(h1));
+                            *reinterpret_cast<bf16x2*>(dst_lo + row + c) = ll;
+                        }
                     }
                 }
             }
@@ -877,15 +943,17 @@ static int run_match(const float* feat_in, const float* feat_ref, int n_in, int 
     timing_begin(MREFSR_K_MATCH_PREP, st);
     const size_t prep_smem = (size_t)C * 33 * sizeof(float);
     MREFSR_CHECK(prep_smem <= 200 * 1024, ERR_UNSUPPORTED, "matcher: C = %d too large for the prep tile", C);
+    auto prep = (C == 256) ? match_prep_kernel<4> : (C == 128) ? match_prep_kernel<2> : (C == 64) ? match_prep_kernel<1>
+                                                                                                  : match_prep_kernel<0>;
     if (prep_smem > 48 * 1024)
-        MREFSR_CUDA(cudaFuncSetAttribute(match_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+        MREFSR_CUDA(cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
     const bool f32 = pl.mode == MREFSR_MATCH_FP32, x3 = pl.mode == MREFSR_MATCH_TC_BF16X3;
-    match_prep_kernel<<<dim3(cdiv(pl.hw_in, 32), n_in), 256, prep_smem, st>>>(
+    prep<<<dim3(cdiv(pl.hw_in, 32), n_in), 256, prep_smem, st>>>(
         feat_in, C, pl.hw_in, normalize_pixels, f32 ? reinterpret_cast<float*>(ws + pl.off_a0) : nullptr,
         f32 ? nullptr : reinterpret_cast<bf16*>(ws + pl.off_a0), x3 ? reinterpret_cast<bf16*>(ws + pl.off_a1) : nullptr,
         reinterpret_cast<float*>(ws + pl.off_sumsq_in));
     MREFSR_LAUNCH_CHECK();
-    match_prep_kernel<<<dim3(cdiv(pl.hw_ref, 32), n_pairs), 256, prep_smem, st>>>(
+    prep<<<dim3(cdiv(pl.hw_ref, 32), n_pairs), 256, prep_smem, st>>>(
         feat_ref, C, pl.hw_ref, normalize_pixels, f32 ? reinterpret_cast<float*>(ws + pl.off_b0) : nullptr,
         f32 ? nullptr : reinterpret_cast<bf16*>(ws + pl.off_b0), x3 ? reinterpret_cast<bf16*>(ws + pl.off_b1) : nullptr,
         reinterpret_cast<float*>(ws + pl.off_sumsq_ref));

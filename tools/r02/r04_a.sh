@@ -11,3 +11,8 @@ j = json.load(open('gpurun_out/${T}_bench.json'))
 print(j['value'], j['ms_per_step'], json.dumps(j['kernel_ms_per_step']))
 PY
 tail -3 gpurun_out/${T}_bench.err
+if [ -n "$NCU_MATCH" ]; then
+ncu --set full --import-source on --clock-control none -k regex:match_diag -s 2 -c 1 -o gpurun_out/${T}_match_full -f \
+  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-full-model --no-extras > gpurun_out/${T}_ncu_match.log 2>&1
+ls -la gpurun_out/${T}_match_full*
+fi
