@@ -72,6 +72,7 @@ enum {
 #define MREFSR_MATCH_FLAG_NO_STRIP 0x100      /* one tap per pipeline stage (no row-shifted descriptors) */
 #define MREFSR_MATCH_FLAG_BASE_OFFSET 0x200   /* encode (addr>>7)&7 in the descriptor base-offset field */
 #define MREFSR_MATCH_FLAG_NO_DIAG 0x400       /* all nine taps as MMAs (round-1 kernel) instead of the diagonal form */
+#define MREFSR_MATCH_FLAG_NO_BSTRIP 0x800     /* diagonal form: reload the reference rows per tap row (no shared strip) */
 
 MREFSR_API size_t mrefsr_match_workspace_bytes(int n_in, int n_pairs, int C, int h_in, int w_in, int h_ref, int w_ref,
                                     int mode);

@@ -363,6 +363,7 @@ struct TcParams {
     int m_tiles, n_tiles, total_items;
     int key_stride, colsb_stride;
     int base_offset_mode;
+    int strip_rows, b_bytes, stage_bytes, stages;   // match_diag_strip_kernel: runtime stage geometry
 };
 
 template <int STRIP, int NPASS>
@@ -568,6 +569,69 @@ match_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 // A tile) and only the first 30 lanes of a warp own an output row: 120 rows per tile.  Likewise an N tile covers 254
 // output columns with 256 accumulator columns.  Accumulation order differs from 3b (fp32 sums over (i, c) in TMEM, then
 // fp32 over j), precision is the same.
+constexpr int DG_BN = 256, DG_MV = 120, DG_NV = 254, DG_WROWS = 30;
+
+// Epilogue warps (2..5) of the diagonal-form kernels: per item, sim = H[p, q] + H[p+1, q+1] + H[p+2, q+2] from the
+// accumulator (lane = row, register = column: two shuffles per element), scaled by the column's (1/norm, mask),
+// running (max, first index) per row, one 64-bit atomicMax per row.
+__device__ __forceinline__ void diag_epilogue(const TcParams& prm, const float2* __restrict__ colsb,
+                                              unsigned long long* __restrict__ keys, float2* s_sb, uint64_t* tfull,
+                                              uint64_t* tempty, uint32_t tmem_base, int warp, int lane) {
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;            // 0..127
+    int it = 0;
+    for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
+        const int nt = item % prm.n_tiles;
+        const int mt = (item / prm.n_tiles) % prm.m_tiles;
+        const int pair = item / (prm.n_tiles * prm.m_tiles);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int n0 = nt * DG_NV;
+        const int nout = min(DG_NV, prm.hw_ref - n0);           // output columns of this tile
+        int ncols = prm.hw_ref - n0 + 2;
+        ncols = ncols > DG_BN ? DG_BN : ((ncols + 31) & ~31);           // accumulator columns the MMAs wrote
+        float2* sbuf = s_sb + acc * DG_BN;
+        const float2* gsb = colsb + (size_t)pair * prm.colsb_stride + n0;
+        for (int i = et; i < ncols; i += 128) sbuf[i] = (i < nout) ? gsb[i] : make_float2(0.f, -INFINITY);
+        named_bar_sync(1, 128);
+        mbar_wait_backoff(&tfull[acc], acc_phase, 256);
+        tc_fence_after();
+        float best = -INFINITY;
+        int bestn = 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * DG_BN;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32], e[2];
+            tmem_ld_32x32(taddr + c0, v);
+            if (c0 + 32 < ncols) {
+                tmem_ld_32x2(taddr + c0 + 32, e);
+            } else {
+                e[0] = e[1] = 0u;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const uint32_t x1 = (k + 1 < 32) ? v[(k + 1) & 31] : e[0];
+                const uint32_t x2 = (k + 2 < 32) ? v[(k + 2) & 31] : e[(k + 2) & 1];
+                const float h1 = __uint_as_float(__shfl_down_sync(0xffffffffu, x1, 1));
+                const float h2 = __uint_as_float(__shfl_down_sync(0xffffffffu, x2, 2));
+                const float sum = (__uint_as_float(v[k]) + h1) + h2;
+                const float2 s = sbuf[c0 + k];
+                const float val = fmaf(sum, s.x, s.y);
+                if (val > best) {
+                    best = val;
+                    bestn = c0 + k;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        const int m = mt * DG_MV + q * DG_WROWS + lane;
+        if (lane < DG_WROWS && m < prm.hw_in && best > -INFINITY)
+            atomicMax(keys + (size_t)pair * prm.key_stride + m, pack_key(best, (uint32_t)(n0 + bestn)));
+    }
+}
+
 template <int NPASS>
 struct DgCfg {
     static constexpr int BM = 128, BN = 256, BK = 64;
@@ -707,60 +771,188 @@ match_diag_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;                     // TMEM lane quarter this warp may access
-        const int et = threadIdx.x - 64;            // 0..127
-        int it = 0;
-        for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
-            const int nt = item % prm.n_tiles;
-            const int mt = (item / prm.n_tiles) % prm.m_tiles;
-            const int pair = item / (prm.n_tiles * prm.m_tiles);
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            const int n0 = nt * Cfg::NV;
-            const int nout = min(Cfg::NV, prm.hw_ref - n0);           // output columns of this tile
-            int ncols = prm.hw_ref - n0 + 2;
-            ncols = ncols > BN ? BN : ((ncols + 31) & ~31);           // accumulator columns the MMAs wrote
-            float2* sbuf = s_sb + acc * BN;
-            const float2* gsb = colsb + (size_t)pair * prm.colsb_stride + n0;
-            for (int i = et; i < ncols; i += 128) sbuf[i] = (i < nout) ? gsb[i] : make_float2(0.f, -INFINITY);
-            named_bar_sync(1, 128);
-            mbar_wait_backoff(&tfull[acc], acc_phase, 256);
-            tc_fence_after();
-            float best = -INFINITY;
-            int bestn = 0;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                uint32_t v[32], e[2];
-                tmem_ld_32x32(taddr + c0, v);
-                if (c0 + 32 < ncols) {
-                    tmem_ld_32x2(taddr + c0 + 32, e);
-                } else {
-                    e[0] = e[1] = 0u;
-                }
-                tmem_ld_wait();
+        diag_epilogue(prm, colsb, keys, s_sb, tfull, tempty, tmem_base, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ---- 3d. diagonal form with the three tap rows of B taken from ONE shared-memory strip ---------------------------
+// match_diag_kernel is bound by the L2 -> shared-memory feed (64 B/clk/SM wanted, ~42 available with all SMs pulling):
+// per 64-channel slab it loads the 256 reference rows three times, once per tap row i, each time w_ref rows further.
+// Here a stage is a 32-channel slab (64-byte rows, SWIZZLE_64B) whose B side is the strip of 256 + 2*w_ref rows that
+// covers all three tap rows; the MMAs of tap row i start i*w_ref rows into it (descriptor start address, swizzle on
+// absolute address bits as for the row-shifted descriptors of 3b).  A side: the 4 x 32-row windows of each tap row as
+// before.  Bytes per MMA drop 1.6x (39 B/clk/SM).  A stage completes in two halves (tap row 0 + the first 256 strip
+// rows; the rest) so that the first MMAs start before the whole stage has landed.  Served when two stages fit
+// (w_ref <= 104); wider grids use match_diag_kernel.
+constexpr int DS_BK = 32, DS_ROWB = 64;                       // channels / bytes per shared-memory row
+constexpr int DS_A_BYTES = 3 * 128 * DS_ROWB;                 // three tap rows x 128 lanes
+constexpr int DS_MAX_STAGES = 4;
+
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;   // 8-row groups 512 B apart
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;          // SWIZZLE_64B
+    return d;
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(192, 1)
+match_diag_strip_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                        const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                        const __grid_constant__ CUtensorMap mapB2_hi, const __grid_constant__ CUtensorMap mapB2_lo,
+                        const float2* __restrict__ colsb, unsigned long long* __restrict__ keys, const TcParams prm) {
+    constexpr int NSPLIT = (NPASS == 1) ? 1 : 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    const int STAGES = prm.stages;
+    uint8_t* stage_base = smem;
+    float2* s_sb = reinterpret_cast<float2*>(smem + STAGES * prm.stage_bytes);  // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_sb) + 2 * DG_BN * 8);
+    uint64_t* full0 = bars;                              // [DS_MAX_STAGES] tap row 0 + strip rows 0..255
+    uint64_t* full1 = bars + DS_MAX_STAGES;              // [DS_MAX_STAGES] tap rows 1, 2 + the rest of the strip
+    uint64_t* empty = bars + 2 * DS_MAX_STAGES;          // [DS_MAX_STAGES]
+    uint64_t* tfull = bars + 3 * DS_MAX_STAGES;          // [2]
+    uint64_t* tempty = tfull + 2;                        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slabs = prm.C / DS_BK;
+    const int tail_rows = prm.strip_rows - 256;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA_hi);
+        tma_prefetch_desc(&mapB_hi);
+        tma_prefetch_desc(&mapB2_hi);
+        if (NPASS > 1) {
+            tma_prefetch_desc(&mapA_lo);
+            tma_prefetch_desc(&mapB_lo);
+            tma_prefetch_desc(&mapB2_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full0[s], 1);
+            mbar_init(&full1[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x) {
+                const int nt = item % prm.n_tiles;
+                const int mt = (item / prm.n_tiles) % prm.m_tiles;
+                const int pair = item / (prm.n_tiles * prm.m_tiles);
+                const int img = (pair / prm.in_div) % prm.n_in;
+                const int m0 = mt * DG_MV, n0 = nt * DG_NV;
+                for (int slab = 0; slab < n_slabs; ++slab) {
+                    const int c0 = slab * DS_BK;
+                    mbar_wait_backoff(&empty[stage], phase ^ 1, 64);
+                    uint8_t* sa = stage_base + stage * prm.stage_bytes;
+                    uint8_t* sbm = sa + NSPLIT * DS_A_BYTES;
+                    // first half: strip rows 0..255 and tap row 0 of A
+                    mbar_expect_tx(&full0[stage], NSPLIT * (256 * DS_ROWB + 128 * DS_ROWB));
+                    tma_load_3d(sbm, &mapB_hi, &full0[stage], c0, n0, pair);
+                    if (NPASS > 1) tma_load_3d(sbm + prm.b_bytes, &mapB_lo, &full0[stage], c0, n0, pair);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const uint32_t x1 = (k + 1 < 32) ? v[(k + 1) & 31] : e[0];
-                    const uint32_t x2 = (k + 2 < 32) ? v[(k + 2) & 31] : e[(k + 2) & 1];
-                    const float h1 = __uint_as_float(__shfl_down_sync(0xffffffffu, x1, 1));
-                    const float h2 = __uint_as_float(__shfl_down_sync(0xffffffffu, x2, 2));
-                    const float sum = (__uint_as_float(v[k]) + h1) + h2;
-                    const float2 s = sbuf[c0 + k];
-                    const float val = fmaf(sum, s.x, s.y);
-                    if (val > best) {
-                        best = val;
-                        bestn = c0 + k;
+                    for (int wq = 0; wq < 4; ++wq) {
+                        tma_load_3d(sa + wq * 2048, &mapA_hi, &full0[stage], c0, m0 + wq * DG_WROWS, img);
+                        if (NPASS > 1)
+                            tma_load_3d(sa + DS_A_BYTES + wq * 2048, &mapA_lo, &full0[stage], c0, m0 + wq * DG_WROWS, img);
+                    }
+                    // second half: the rest of the strip and tap rows 1, 2 of A
+                    mbar_expect_tx(&full1[stage], NSPLIT * (tail_rows * DS_ROWB + 2 * 128 * DS_ROWB));
+                    tma_load_3d(sbm + 256 * DS_ROWB, &mapB2_hi, &full1[stage], c0, n0 + 256, pair);
+                    if (NPASS > 1)
+                        tma_load_3d(sbm + prm.b_bytes + 256 * DS_ROWB, &mapB2_lo, &full1[stage], c0, n0 + 256, pair);
+#pragma unroll
+                    for (int ti = 1; ti < 3; ++ti) {
+#pragma unroll
+                        for (int wq = 0; wq < 4; ++wq) {
+                            const int ra = m0 + ti * prm.w_in + wq * DG_WROWS;
+                            tma_load_3d(sa + ti * 8192 + wq * 2048, &mapA_hi, &full1[stage], c0, ra, img);
+                            if (NPASS > 1)
+                                tma_load_3d(sa + DS_A_BYTES + ti * 8192 + wq * 2048, &mapA_lo, &full1[stage], c0, ra, img);
+                        }
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            const int m = mt * Cfg::MV + q * Cfg::WROWS + lane;
-            if (lane < Cfg::WROWS && m < prm.hw_in && best > -INFINITY)
-                atomicMax(keys + (size_t)pair * prm.key_stride + m, pack_key(best, (uint32_t)(n0 + bestn)));
         }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < prm.total_items; item += gridDim.x, ++it) {
+                const int nt = item % prm.n_tiles;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                int ncols = prm.hw_ref - nt * DG_NV + 2;     // +2: the look-ahead columns of the last outputs
+                ncols = ncols > DG_BN ? DG_BN : ((ncols + 31) & ~31);
+                const uint32_t idesc = umma_idesc(MREFSR_IDESC_16, 128, ncols);
+                mbar_wait_backoff(&tempty[acc], acc_phase ^ 1, 64);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * DG_BN;
+                uint32_t accumulate = 0;
+                for (int slab = 0; slab < n_slabs; ++slab) {
+                    const uint32_t sa = smem_u32(stage_base + stage * prm.stage_bytes);
+                    const uint32_t sb = sa + NSPLIT * DS_A_BYTES;
+#pragma unroll
+                    for (int ti = 0; ti < 3; ++ti) {
+                        if (ti == 0) mbar_wait(&full0[stage], phase);
+                        if (ti == 1) mbar_wait(&full1[stage], phase);
+                        if (ti < 2) tc_fence_after();
+                        const uint32_t brow = sb + (uint32_t)(ti * prm.w_ref) * DS_ROWB;
+#pragma unroll
+                        for (int pass = 0; pass < NPASS; ++pass) {
+                            // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
+                            const uint32_t a0 = sa + ((pass == 2) ? DS_A_BYTES : 0) + ti * 8192;
+                            const uint32_t b0 = brow + ((pass == 1) ? prm.b_bytes : 0);
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {
+                                umma_f16(tacc, umma_desc_sw64(a0 + kk * 32), umma_desc_sw64(b0 + kk * 32), idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        diag_epilogue(prm, colsb, keys, s_sb, tfull, tempty, tmem_base, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -774,7 +966,7 @@ match_diag_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
 // host side
 // =====================================================================================================
 struct MatchPlan {
-    int mode, strip, base_offset_mode, diag;
+    int mode, strip, base_offset_mode, diag, bstrip;
     int hw_in, hw_ref, ho, wo, ho_ref, wo_ref;
     int key_stride, colsb_stride;
     size_t off_keys, off_sumsq_in, off_sumsq_ref, off_rownorm, off_colsb, off_a0, off_a1, off_b0, off_b1, total;
@@ -794,6 +986,7 @@ static int make_plan(MatchPlan* pl, int n_in, int n_pairs, int C, int h_in, int 
     pl->mode = mode;
     pl->strip = (mode_flags & MREFSR_MATCH_FLAG_NO_STRIP) ? 1 : 3;
     pl->base_offset_mode = (mode_flags & MREFSR_MATCH_FLAG_BASE_OFFSET) ? 1 : 0;
+    pl->bstrip = (mode_flags & MREFSR_MATCH_FLAG_NO_BSTRIP) ? 0 : 1;
     pl->diag = (mode_flags & (MREFSR_MATCH_FLAG_NO_DIAG | MREFSR_MATCH_FLAG_NO_STRIP | MREFSR_MATCH_FLAG_BASE_OFFSET)) ? 0 : 1;
     pl->hw_in = h_in * w_in;
     pl->hw_ref = h_ref * w_ref;
@@ -920,6 +1113,71 @@ static int launch_diag(const MatchPlan& pl, uint8_t* ws, int n_in, int n_pairs, 
     return 0;
 }
 
+// stage geometry of match_diag_strip_kernel; false when two stages do not fit
+static bool diag_strip_geometry(int npass, int w_ref, TcParams* prm, int* smem_bytes) {
+    const int nsplit = (npass == 1) ? 1 : 2;
+    const int strip_rows = 256 + (int)align_up((size_t)2 * w_ref, 16);
+    if (strip_rows - 256 > 256) return false;
+    const int b_bytes = strip_rows * DS_ROWB;
+    const int stage_bytes = nsplit * (DS_A_BYTES + b_bytes);
+    int stages = (208 * 1024) / stage_bytes;
+    if (stages < 2) return false;
+    if (stages > DS_MAX_STAGES) stages = DS_MAX_STAGES;
+    prm->strip_rows = strip_rows;
+    prm->b_bytes = b_bytes;
+    prm->stage_bytes = stage_bytes;
+    prm->stages = stages;
+    *smem_bytes = stages * stage_bytes + 2 * DG_BN * 8 + 256 + 1024;
+    return true;
+}
+
+template <int NPASS>
+static int launch_diag_strip(const MatchPlan& pl, uint8_t* ws, int n_in, int n_pairs, int in_div, int C, int w_in,
+                             int w_ref, cudaStream_t st) {
+    CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mB2_hi, mB2_lo;
+    const CUtensorMapDataType dt = MREFSR_TMAP_16;
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    TcParams prm;
+    int smem_bytes = 0;
+    MREFSR_CHECK(diag_strip_geometry(NPASS, w_ref, &prm, &smem_bytes), ERR_UNSUPPORTED, "matcher: strip geometry");
+    int rc;
+    void* a_hi = ws + pl.off_a0;
+    void* b_hi = ws + pl.off_b0;
+    void* a_lo = (NPASS > 1) ? ws + pl.off_a1 : a_hi;
+    void* b_lo = (NPASS > 1) ? ws + pl.off_b1 : b_hi;
+    const int tail = prm.strip_rows - 256;
+    if ((rc = make_tensor_map_3d(&mA_hi, dt, 2, a_hi, C, pl.hw_in, n_in, DS_BK, 32, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mA_lo, dt, 2, a_lo, C, pl.hw_in, n_in, DS_BK, 32, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB_hi, dt, 2, b_hi, C, pl.hw_ref, n_pairs, DS_BK, 256, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB_lo, dt, 2, b_lo, C, pl.hw_ref, n_pairs, DS_BK, 256, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB2_hi, dt, 2, b_hi, C, pl.hw_ref, n_pairs, DS_BK, tail, sw))) return rc;
+    if ((rc = make_tensor_map_3d(&mB2_lo, dt, 2, b_lo, C, pl.hw_ref, n_pairs, DS_BK, tail, sw))) return rc;
+    prm.n_pairs = n_pairs;
+    prm.in_div = in_div;
+    prm.n_in = n_in;
+    prm.C = C;
+    prm.hw_in = (pl.hw_in / w_in - 3) * w_in + (w_in - 2);      // pixel-linear indices up to the last valid origin
+    prm.w_in = w_in;
+    prm.hw_ref = (pl.hw_ref / w_ref - 3) * w_ref + (w_ref - 2);
+    prm.w_ref = w_ref;
+    prm.m_tiles = cdiv(prm.hw_in, DG_MV);
+    prm.n_tiles = cdiv(prm.hw_ref, DG_NV);
+    prm.total_items = n_pairs * prm.m_tiles * prm.n_tiles;
+    prm.key_stride = pl.key_stride;
+    prm.colsb_stride = pl.colsb_stride;
+    prm.base_offset_mode = 0;
+    auto kern = match_diag_strip_kernel<NPASS>;
+    MREFSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int grid = sm_count();
+    if (grid > prm.total_items) grid = prm.total_items;
+    kern<<<grid, 192, smem_bytes, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, mB2_hi, mB2_lo,
+                                         reinterpret_cast<const float2*>(ws + pl.off_colsb),
+                                         reinterpret_cast<unsigned long long*>(ws + pl.off_keys), prm);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
 static int run_match(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div, int C, int h_in,
                      int w_in, int h_ref, int w_ref, int ps, int s_in, int s_ref, int is_norm, int norm_input,
                      int normalize_pixels, int mode_flags, long long* max_idx, float* max_val, void* workspace,
@@ -981,7 +1239,12 @@ static int run_match(const float* feat_in, const float* feat_ref, int n_in, int 
         MREFSR_LAUNCH_CHECK();
         count_launches(1);
     } else {
-        if (pl.diag) {
+        TcParams probe;
+        int probe_smem = 0;
+        if (pl.diag && pl.bstrip && diag_strip_geometry(x3 ? 3 : 1, w_ref, &probe, &probe_smem)) {
+            rc = x3 ? launch_diag_strip<3>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st)
+                    : launch_diag_strip<1>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st);
+        } else if (pl.diag) {
             rc = x3 ? launch_diag<3>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st)
                     : launch_diag<1>(pl, ws, n_in, n_pairs, in_div, C, w_in, w_ref, st);
         } else if (pl.strip == 3) {

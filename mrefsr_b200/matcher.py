@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 MATCH_AUTO, MATCH_TC_BF16X3, MATCH_TC_BF16, MATCH_FP32 = 0, 1, 2, 3
-FLAG_NO_STRIP, FLAG_BASE_OFFSET, FLAG_NO_DIAG = 0x100, 0x200, 0x400
+FLAG_NO_STRIP, FLAG_BASE_OFFSET, FLAG_NO_DIAG, FLAG_NO_BSTRIP = 0x100, 0x200, 0x400, 0x800
 _MODES = {'auto': MATCH_AUTO, 'bf16x3': MATCH_TC_BF16X3, 'bf16': MATCH_TC_BF16, 'fp32': MATCH_FP32}
 
 

@@ -9,7 +9,7 @@ from tests.util import match_parity, unit_features
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 CASES = ['rand', 'shift', 'zeropad', 'raw', 'nonorm', 'strided', 'c256']
-TC_MODES = [MM.MATCH_TC_BF16X3, MM.MATCH_TC_BF16X3 | MM.FLAG_NO_DIAG, MM.MATCH_TC_BF16X3 | MM.FLAG_NO_STRIP]
+TC_MODES = [MM.MATCH_TC_BF16X3, MM.MATCH_TC_BF16X3 | MM.FLAG_NO_BSTRIP, MM.MATCH_TC_BF16X3 | MM.FLAG_NO_DIAG, MM.MATCH_TC_BF16X3 | MM.FLAG_NO_STRIP]
 
 
 def _run(fi, fr, kw, mode):
