@@ -151,6 +151,11 @@ MREFSR_API int mrefsr_modulated_deform_conv_backward(const float* input, const f
  *     replaces  basicsr/archs/ref_mrapa_restoration_arch.py:55-73 */
 MREFSR_API int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float* offset, float* mask,
                           float* abs_sum, int B, int dg, int K, int H, int W, void* stream);
+/* Its backward (training): grad_conv_out [B, 3*dg*K, H, W] = [grad_offset, grad_mask * mask * (1 - mask)]
+ * (the autograd of the chunk / cat / sigmoid sequence at ref_mrapa_restoration_arch.py:55-68; the pre-offsets carry no
+ * gradient), one pass. */
+MREFSR_API int mrefsr_dynagg_offsets_backward(const float* grad_offset, const float* grad_mask, const float* mask,
+                                   float* grad_conv_out, int B, int dg, int K, int H, int W, void* stream);
 
 /* Fused DynAgg forward (inference): DCNv2 whose offsets / masks are assembled inside the gather from the raw
  * conv_offset_mask output and the matcher's arg-max map, so neither the pre-offset tensors nor offset / mask

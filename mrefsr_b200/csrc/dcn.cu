@@ -537,6 +537,47 @@ dynagg_offsets_vec4_kernel(const float* __restrict__ conv_out, const float* __re
     }
 }
 
+// Backward of the glue: grad of the raw conv_offset_mask output = [grad_offset, grad_mask * m * (1 - m)] (the pre-offsets are
+// constants; d sigmoid = m (1 - m)), one pass with 16-byte accesses instead of torch's mul / mul / cat.  grid.y = (sample, plane).
+__global__ void __launch_bounds__(256)
+dynagg_offsets_bwd_vec4_kernel(const float* __restrict__ g_offset, const float* __restrict__ g_mask,
+                               const float* __restrict__ mask, float* __restrict__ g_conv, int dg, int K, int P) {
+    const int OC = 2 * dg * K, MC = dg * K, TC = OC + MC;
+    const int b = blockIdx.y / TC, ch = blockIdx.y - b * TC;
+    float4* dst = reinterpret_cast<float4*>(g_conv + ((size_t)b * TC + ch) * P);
+    const int P4 = P >> 2;
+    if (ch < OC) {
+        const float4* src = reinterpret_cast<const float4*>(g_offset + ((size_t)b * OC + ch) * P);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) dst[i] = __ldcs(src + i);
+    } else {
+        const float4* gm = reinterpret_cast<const float4*>(g_mask + ((size_t)b * MC + (ch - OC)) * P);
+        const float4* mk = reinterpret_cast<const float4*>(mask + ((size_t)b * MC + (ch - OC)) * P);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+            const float4 g = __ldcs(gm + i), m = __ldcs(mk + i);
+            dst[i] = make_float4(g.x * m.x * (1.f - m.x), g.y * m.y * (1.f - m.y), g.z * m.z * (1.f - m.z),
+                                 g.w * m.w * (1.f - m.w));
+        }
+    }
+}
+__global__ void dynagg_offsets_bwd_kernel(const float* __restrict__ g_offset, const float* __restrict__ g_mask,
+                                          const float* __restrict__ mask, float* __restrict__ g_conv, int B, int dg, int K,
+                                          int P) {
+    const int OC = 2 * dg * K, MC = dg * K, TC = OC + MC;
+    const size_t total = (size_t)B * TC * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int ch = (idx / P) % TC;
+        const int b = idx / ((size_t)P * TC);
+        if (ch < OC) {
+            g_conv[idx] = g_offset[((size_t)b * OC + ch) * P + p];
+        } else {
+            const size_t mi = ((size_t)b * MC + (ch - OC)) * P + p;
+            const float m = mask[mi];
+            g_conv[idx] = g_mask[mi] * m * (1.f - m);
+        }
+    }
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -895,6 +936,29 @@ int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float*
         dynagg_offsets_vec4_kernel<<<dim3(gx, B * 3 * dg * K), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, dg, K, P);
     } else {
         dynagg_offsets_kernel<<<grid_for(total), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, B, dg, K, P);
+    }
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_dynagg_offsets_backward(const float* grad_offset, const float* grad_mask, const float* mask, float* grad_conv_out,
+                                   int B, int dg, int K, int H, int W, void* stream) {
+    MREFSR_CHECK(grad_offset && grad_mask && mask && grad_conv_out && B > 0 && dg > 0 && K > 0 && H > 0 && W > 0, ERR_BAD_ARG,
+                 "dynagg_offsets_backward: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t total = (size_t)B * 3 * dg * K * H * W;
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    const int P = H * W;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (P % 4 == 0 && al16(grad_offset) && al16(grad_mask) && al16(mask) && al16(grad_conv_out) &&
+        (size_t)B * 3 * dg * K <= 65535) {
+        int gx = cdiv(P / 4, 256);
+        if (gx > 8) gx = 8;
+        dynagg_offsets_bwd_vec4_kernel<<<dim3(gx, B * 3 * dg * K), 256, 0, st>>>(grad_offset, grad_mask, mask, grad_conv_out, dg,
+                                                                                  K, P);
+    } else {
+        dynagg_offsets_bwd_kernel<<<grid_for(total), 256, 0, st>>>(grad_offset, grad_mask, mask, grad_conv_out, B, dg, K, P);
     }
     MREFSR_LAUNCH_CHECK();
     count_launches(1);

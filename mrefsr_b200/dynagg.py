@@ -47,6 +47,68 @@ class DynAggOffsetsFunction(Function):
         return g.to(ctx.in_dtype), None, None, None
 
 
+class DynAggDCNFunction(Function):
+    """Training path of DynAgg.forward as ONE autograd node: (x, conv_out, pre_offset, weight, bias) -> DCNv2 output.
+
+    Same arithmetic as DynAggOffsetsFunction followed by ModulatedDeformConvFunction (the reference's operator
+    boundaries, ref_mrapa_restoration_arch.py:55-76), but offsets / masks and their gradients stay fp32 tensors of this
+    node instead of crossing two Function boundaries: under bf16 autocast that boundary costs eight cast passes over the
+    216-plane tensor per call, and the glue backward (mul, mul, cat) is one kernel.  3x3 / stride 1 / padding 1 /
+    dilation 1 / groups 1 only (what MRefSR uses); DynAgg.forward falls back to the two Functions otherwise."""
+
+    @staticmethod
+    def forward(ctx, x, conv_out, pre_offset, weight, bias, dg, stats):
+        from .dcn import dcn_forward_raw, _nchw
+        _lib.require_cuda(x, conv_out, pre_offset, weight, bias)
+        ctx.conv_dtype, ctx.x_dtype, ctx.dg = conv_out.dtype, x.dtype, dg
+        ctx.conv_cl = conv_out.dim() == 4 and not conv_out.is_contiguous() and \
+            conv_out.is_contiguous(memory_format=torch.channels_last)
+        ctx.with_bias = bias is not None
+        ctx.w_dtype = weight.dtype
+        x32, co = _nchw(x), _nchw(conv_out)
+        pre = pre_offset.contiguous().float()
+        b, ch, h, w = co.shape
+        k = pre.shape[1]
+        if ch != 3 * dg * k or tuple(pre.shape) != (b, k, h, w, 2):
+            raise ValueError('expected conv_out [B,3*dg*K,H,W] and pre_offset [B,K,H,W,2]')
+        offset = torch.empty(b, 2 * dg * k, h, w, dtype=torch.float32, device=co.device)
+        mask = torch.empty(b, dg * k, h, w, dtype=torch.float32, device=co.device)
+        with torch.cuda.device(co.device):
+            rc = _lib.lib().mrefsr_dynagg_offsets(_lib.ptr(co), _lib.ptr(pre), _lib.ptr(offset), _lib.ptr(mask),
+                                                  _lib.ptr(stats), b, dg, k, h, w, _lib.stream_ptr(co.device))
+        _lib.check(rc, 'mrefsr_dynagg_offsets')
+        wgt = weight.contiguous().float()
+        bs = bias.contiguous().float() if bias is not None else None
+        ctx.save_for_backward(x32, offset, mask, wgt)
+        out = dcn_forward_raw(x32, offset, mask, wgt, bs, (1, 1), (1, 1), (1, 1), 1, dg)
+        return out.to(x.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        from .dcn import dcn_backward_raw, _nchw
+        x32, offset, mask, wgt = ctx.saved_tensors
+        need_conv = ctx.needs_input_grad[1]
+        gi, go, gm, gw, gb = dcn_backward_raw(x32, offset, mask, wgt, _nchw(grad_output), (1, 1), (1, 1), (1, 1), 1, ctx.dg,
+                                              ctx.with_bias, need_input=ctx.needs_input_grad[0], need_offset=need_conv,
+                                              need_weight=ctx.needs_input_grad[3])
+        g_conv = None
+        if need_conv:
+            b, mc, h, w = mask.shape
+            k = mc // ctx.dg
+            g_conv = torch.empty(b, 3 * mc, h, w, dtype=torch.float32, device=mask.device)
+            with torch.cuda.device(mask.device):
+                rc = _lib.lib().mrefsr_dynagg_offsets_backward(_lib.ptr(go), _lib.ptr(gm), _lib.ptr(mask), _lib.ptr(g_conv), b,
+                                                               ctx.dg, k, h, w, _lib.stream_ptr(mask.device))
+            _lib.check(rc, 'mrefsr_dynagg_offsets_backward')
+            if ctx.conv_cl or ctx.conv_dtype != torch.float32:
+                g_conv = g_conv.to(dtype=ctx.conv_dtype,
+                                   memory_format=torch.channels_last if ctx.conv_cl else torch.contiguous_format)
+        cast = (lambda t, dt: None if t is None else t.to(dt))
+        return (cast(gi, ctx.x_dtype), g_conv, None, cast(gw, ctx.w_dtype),
+                gb if ctx.with_bias and ctx.needs_input_grad[4] else None, None, None)
+
+
 class DynAgg(ModulatedDeformConv2d):
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation=1, groups=1,
@@ -57,6 +119,7 @@ class DynAgg(ModulatedDeformConv2d):
         self.conv_offset_mask = nn.Conv2d(self.in_channels, channels_, kernel_size=self.kernel_size,
                                           stride=self.stride, padding=self.padding, bias=True)
         self.init_offset()
+        self.fused_autograd = True       # forward(): one autograd node (DynAggDCNFunction) instead of the two operator Functions
         self._stats = None
         self._stats_count = 0
 
@@ -99,6 +162,10 @@ class DynAgg(ModulatedDeformConv2d):
         if self._stats is None or self._stats.device != out.device:
             self._stats = torch.zeros(1, dtype=torch.float32, device=out.device)
         self._stats.zero_()
+        if self.fused_autograd and (tuple(self.kernel_size) == (3, 3) and tuple(self.stride) == (1, 1) and
+                                    tuple(self.padding) == (1, 1) and tuple(self.dilation) == (1, 1) and self.groups == 1):
+            self._stats_count = out.numel() // 3 * 2
+            return DynAggDCNFunction.apply(x, out, pre_offset, self.weight, self.bias, self.deform_groups, self._stats)
         offset, mask = DynAggOffsetsFunction.apply(out, pre_offset, self.deform_groups, self._stats)
         self._stats_count = offset.numel()
         return modulated_deform_conv2d(x, offset, mask, self.weight, self.bias, self.stride, self.padding,

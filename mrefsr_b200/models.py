@@ -163,8 +163,42 @@ class DynamicAggregationRestoration(nn.Module):
             cache[key] = (ver, w[:, :n_x].contiguous(memory_format=fmt), w[:, n_x:].contiguous(memory_format=fmt))
         return cache[key][1], cache[key][2]
 
+    batch_refs = True    # forward(): run the R references of a scale as one batch (same arithmetic per sample)
+
+    def _forward_refs_batched(self, x, pre_offset_list, img_ref_feat_list):
+        """forward() with the Python loop over references folded into the batch dimension (autograd-capable: this is
+        the training path).  Per scale: the references' features / pre-offsets stacked [B, R] -> B*R, conv1 split by
+        input channels so that its x half runs once per image instead of once per (image, reference) and no
+        repeat / cat of x is materialised, ONE offset-conv / DynAgg / lrelu chain over B*R samples, and the fusion head
+        on the stacked tensor (MRAPAFusion.forward would stack the list again)."""
+        r = len(img_ref_feat_list)
+        for name, key in self._SCALES:
+            conv1, conv2 = getattr(self, f'{name}_offset_conv1'), getattr(self, f'{name}_offset_conv2')
+            agg = getattr(self, f'{name}_dyn_agg')
+            feat = torch.stack([f[key] for f in img_ref_feat_list], 1).flatten(0, 1)          # [B*R, C, H, W]
+            pre = torch.stack([p[key] for p in pre_offset_list], 1).flatten(0, 1)             # [B*R, 9, H, W, 2]
+            feat_c = feat           # the DCN reads planes (NCHW); the convolution takes the trunk's layout
+            if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+                feat_c = feat.contiguous(memory_format=torch.channels_last)
+            nx = x.shape[1]
+            ox = F.conv2d(x, conv1.weight[:, :nx], None, conv1.stride, conv1.padding)         # once per image
+            of = F.conv2d(feat_c, conv1.weight[:, nx:], conv1.bias, conv1.stride, conv1.padding)
+            o = (of.unflatten(0, (-1, r)) + ox.unsqueeze(1)).flatten(0, 1)
+            if T.layout_of(of) == 1:
+                o = o.contiguous(memory_format=torch.channels_last)
+            o = self.lrelu(o)
+            o = self.lrelu(conv2(o))
+            y = self.lrelu(agg([feat, o], pre))                                               # [B*R, C, H, W]
+            h = getattr(self, f'head_{name}').forward_stacked(x, y, r)
+            h = getattr(self, f'body_{name}')(h) + x
+            x = getattr(self, f'tail_{name}')(h)
+        return x
+
     def forward(self, x, pre_offset_list, img_ref_feat_list):
         """Reference contract: lists over references of pre_offset / VGG feature dicts."""
+        if (self.batch_refs and len(img_ref_feat_list) > 1 and len(pre_offset_list) == len(img_ref_feat_list) and
+                all(f[k].shape == img_ref_feat_list[0][k].shape for f in img_ref_feat_list for _, k in self._SCALES)):
+            return self._forward_refs_batched(x, pre_offset_list, img_ref_feat_list)
         for name, key in self._SCALES:
             conv1, conv2 = getattr(self, f'{name}_offset_conv1'), getattr(self, f'{name}_offset_conv2')
             agg = getattr(self, f'{name}_dyn_agg')

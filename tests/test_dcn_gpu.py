@@ -175,6 +175,56 @@ def test_dynagg_module_golden(golden):
         assert m.last_offset_abs_mean() is not None
 
 
+def _dynagg_module_run(fused, bf16, x, feat0, pre, gout, c, dg):
+    torch.manual_seed(5)
+    m = M.DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True).to(DEV)
+    m.conv_offset_mask.weight.data.normal_(0, 0.02)
+    m.conv_offset_mask.bias.data.normal_(0, 0.3)
+    m.fused_autograd = fused
+    feat = feat0.clone().requires_grad_(True)
+    f_in = feat
+    if bf16:
+        m.conv_offset_mask.to(memory_format=torch.channels_last)
+        f_in = feat.contiguous(memory_format=torch.channels_last)
+    with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+        y = m([x, f_in], pre)
+    y.float().backward(gout)
+    assert m.last_offset_abs_mean() is not None
+    return (y.float().detach(), feat.grad, m.conv_offset_mask.weight.grad, m.conv_offset_mask.bias.grad, m.weight.grad,
+            m.bias.grad)
+
+
+def test_dynagg_fused_autograd_node_matches_the_two_functions():
+    """DynAgg.forward as one autograd node (DynAggDCNFunction) against the reference operator boundaries
+    (DynAggOffsetsFunction -> ModulatedDeformConvFunction): same output and the same gradients for the offset
+    convolution, the DCN weight / bias and the feature that feeds the offset convolution, in fp32.  Then with the offset
+    convolution under bf16 autocast in channels-last (the config-5 training step): there the two-Function path rounds
+    offsets / masks and their gradients to bf16 at its boundaries and the fused node does not, and the offset gradient is
+    discontinuous across pixel cells, so the check is statistical -- the fused node must be at least as close (relative
+    L2) to the fp32 result as the two-Function path is."""
+    g = torch.Generator().manual_seed(31)
+    b, c, h, w, dg = 2, 64, 20, 24, 8
+    x = torch.randn(b, c, h, w, generator=g).to(DEV)
+    feat0 = torch.randn(b, c, h, w, generator=g).to(DEV)
+    pre = (torch.randn(b, 9, h, w, 2, generator=g) * 2).to(DEV)
+    gout = torch.randn(b, c, h, w, generator=g).to(DEV)
+    names = ('y', 'g_feat', 'g_com_w', 'g_com_b', 'g_weight', 'g_bias')
+    truth = _dynagg_module_run(False, False, x, feat0, pre, gout, c, dg)
+    fused32 = _dynagg_module_run(True, False, x, feat0, pre, gout, c, dg)
+    for a, r_, name in zip(fused32, truth, names):
+        assert a.shape == r_.shape and a.dtype == r_.dtype, name
+        assert rel_err(a, r_) <= 1e-5, (name, rel_err(a, r_))
+
+    def rel_l2(a, r_):
+        return float((a.double() - r_.double()).norm() / r_.double().norm().clamp_min(1e-30))
+    two16 = _dynagg_module_run(False, True, x, feat0, pre, gout, c, dg)
+    fused16 = _dynagg_module_run(True, True, x, feat0, pre, gout, c, dg)
+    for a, o, r_, name in zip(fused16, two16, truth, names):
+        assert a.shape == r_.shape and a.dtype == r_.dtype, name
+        e_fused, e_two = rel_l2(a, r_), rel_l2(o, r_)
+        assert e_fused <= max(1.25 * e_two, 1e-3) and e_fused <= 0.15, (name, e_fused, e_two)   # bf16 offset conv: ~0.03 px
+
+
 def test_dynagg_glue_golden(golden):
     from mrefsr_b200.dynagg import DynAggOffsetsFunction
     g = golden('dynagg')

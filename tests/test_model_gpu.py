@@ -142,3 +142,41 @@ def test_config1_literal_sample_matches_reference(golden, pipeline):
     rel_l2, rel_max = _err(sr, sr_ref, base)
     assert rel_l2 <= 1e-3, (rel_l2, rel_max)
     assert float((sr.cpu() - sr_ref.cpu()).abs().max()) <= 1e-3
+
+
+def test_training_forward_with_batched_references_equals_the_loop():
+    """MRAPARestorationNet.forward (the training path, autograd on): the references of a scale run as one batch
+    (DynamicAggregationRestoration._forward_refs_batched: split offset_conv1, one DynAgg node over B*R samples, fusion head
+    on the stacked tensor) against the reference's Python loop over references (ref_mrapa_restoration_arch.py:213-259):
+    same SR image, same gradients."""
+    from mrefsr_b200.models import MRAPARestorationNet
+    g = torch.Generator().manual_seed(9)
+    b, r, h = 2, 3, 12
+    net = MRAPARestorationNet(ngf=64, n_blocks=1, groups=8)
+    refill_parameters(net, 4)
+    net = net.to(DEV).train()
+    lq = torch.rand(b, 3, h, h, generator=g).to(DEV)
+    feats = [{'relu3_1': torch.randn(b, 256, h, h, generator=g).to(DEV),
+              'relu2_1': torch.randn(b, 128, 2 * h, 2 * h, generator=g).to(DEV),
+              'relu1_1': torch.randn(b, 64, 4 * h, 4 * h, generator=g).to(DEV)} for _ in range(r)]
+    pres = [{'relu3_1': (torch.randn(b, 9, h, h, 2, generator=g) * 2).to(DEV),
+             'relu2_1': (torch.randn(b, 9, 2 * h, 2 * h, 2, generator=g) * 4).to(DEV),
+             'relu1_1': (torch.randn(b, 9, 4 * h, 4 * h, 2, generator=g) * 8).to(DEV)} for _ in range(r)]
+    gt = torch.rand(b, 3, 4 * h, 4 * h, generator=g).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    res = {}
+    try:
+        for batched in (False, True):
+            net.dyn_agg_restore.batch_refs = batched
+            net.zero_grad(set_to_none=True)
+            out = net(lq, pres, feats)
+            torch.nn.functional.l1_loss(out, gt).backward()
+            res[batched] = (out.detach(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert float((res[True][0] - res[False][0]).abs().max()) <= 1e-4
+    assert res[True][1].keys() == res[False][1].keys() and len(res[True][1]) > 50
+    for k in res[False][1]:
+        a, c = res[True][1][k].double(), res[False][1][k].double()
+        assert float((a - c).norm() / c.norm().clamp_min(1e-12)) <= 2e-3, k
