@@ -255,6 +255,22 @@ MREFSR_API int mrefsr_bias_act(float* x, const float* bias, const float* slope_d
                     float scale, void* stream);
 MREFSR_API int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B, int C, int HW,
                           int to_channels_last, void* stream);
+/* Training path of the same epilogue, channels-last activations [rows = B*H*W, C], dtype 0 = fp32 / 1 = bf16 (the
+ * reference's training step runs these as separate torch kernels: bias add, activation, their backward, and a reduction
+ * over grad_output for every convolution's bias gradient -- basicsr/archs/arch_util.py:88-117 under autograd).
+ *   forward:  x = act(x + bias[c]) * scale + residual   in place (residual may be NULL; act NONE or LEAKY)
+ *   backward: grad_in = grad_out * act'(y) * scale (y = the forward's output; only read for LEAKY, which then requires
+ *             residual == NULL and scale > 0 in the forward), grad_bias[c] = sum over rows of grad_in, in one pass;
+ *             grad_in may be NULL when only the bias gradient is wanted.  partial: fp32 scratch of
+ *             mrefsr_bias_act_train_blocks() * C entries (partial sums are added in a fixed order: deterministic).
+ *   mrefsr_bias_act_train_supported: 1 when C fits the 16-byte channel vectors of these kernels. */
+MREFSR_API int mrefsr_bias_act_train_supported(int C, int dtype);
+MREFSR_API int mrefsr_bias_act_train_blocks(void);
+MREFSR_API int mrefsr_bias_act_train_forward(void* x, const float* bias, const void* residual, long long rows, int C,
+                                  int dtype, int act, float slope, float scale, void* stream);
+MREFSR_API int mrefsr_bias_act_train_backward(const void* grad_out, const void* y, void* grad_in, float* grad_bias,
+                                   float* partial, long long rows, int C, int dtype, int act, float slope,
+                                   float scale, void* stream);
 /* 2x2 / stride-2 max pooling, channels-last [B,H,W,C] -> [B,H/2,W/2,C] (VGG pool1 / pool2), C % 4 == 0, H, W even. */
 MREFSR_API int mrefsr_maxpool2x2_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,

@@ -40,6 +40,11 @@ SIGNATURES = {
     'mrefsr_dynagg_offsets': (c_int, [_P] * 5 + [_I] * 5 + [_P]),
     'mrefsr_dynagg_offsets_backward': (c_int, [_P] * 4 + [_I] * 5 + [_P]),
     'mrefsr_bias_act': (c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, ctypes.c_float, _P]),
+    'mrefsr_bias_act_train_supported': (c_int, [_I, _I]),
+    'mrefsr_bias_act_train_blocks': (c_int, []),
+    'mrefsr_bias_act_train_forward': (c_int, [_P, _P, _P, ctypes.c_longlong, _I, _I, _I, ctypes.c_float, ctypes.c_float, _P]),
+    'mrefsr_bias_act_train_backward': (c_int, [_P, _P, _P, _P, _P, ctypes.c_longlong, _I, _I, _I, ctypes.c_float,
+                                               ctypes.c_float, _P]),
     'mrefsr_maxpool2x2_nhwc': (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     'mrefsr_layout_convert': (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'mrefsr_attn_modulate': (c_int, [_P] * 5 + [_I] * 4 + [_P]),

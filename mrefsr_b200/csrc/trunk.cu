@@ -239,6 +239,124 @@ maxpool2_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, lon
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---------------------------------------------------------------------------------------------------------
+// Training path of the same epilogue (channels-last activations, fp32 or bf16 -- the config-5 step runs the plain
+// convolutions under bf16 autocast).  torch computes a convolution's bias gradient as a separate reduction over
+// grad_output (0.09 ms per [12, 64, 160, 160] tensor, 10 ms of a 102 ms step) after a separate activation-backward
+// pass; here  grad_in = grad_out * act'(y) * scale  and  grad_bias = sum_rows grad_in  are one pass, and the forward
+//     y = act(x + bias[c]) * scale + residual
+// is one in-place pass over the convolution's (bias-free) output.  Rows = B*H*W pixels, C channels fastest.
+// A thread owns one 16-byte channel vector (4 fp32 / 8 bf16) and walks rows; per-channel sums go through shared
+// memory to one partial row per CTA, a second tiny kernel adds the partial rows in a fixed order (deterministic).
+template <typename T>
+struct TrainVec;
+template <>
+struct TrainVec<float> {
+    static constexpr int W = 4;
+    __device__ static void load(const float* p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+    __device__ static void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct TrainVec<__nv_bfloat16> {
+    static constexpr int W = 8;
+    __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_train_fwd_kernel(T* __restrict__ x, const float* __restrict__ bias, const T* __restrict__ residual, long long nvec,
+                          int cvec, int act, float slope, float scale) {
+    constexpr int W = TrainVec<T>::W;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int c = (int)(i % cvec) * W;
+        float v[W], r[W];
+        TrainVec<T>::load(x + i * W, v);
+        if (residual) TrainVec<T>::load(residual + i * W, r);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            float t = v[k] + (bias ? __ldg(bias + c + k) : 0.f);
+            if (act == MREFSR_ACT_LEAKY) t = t > 0.f ? t : t * slope;
+            v[k] = t * scale + (residual ? r[k] : 0.f);
+        }
+        TrainVec<T>::store(x + i * W, v);
+    }
+}
+
+// grad_in may be NULL (no activation and scale 1: grad_in == grad_out, only the bias gradient is wanted)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_train_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ y, T* __restrict__ gin,
+                          float* __restrict__ partial, long long rows, int C, int act, float slope, float scale) {
+    constexpr int W = TrainVec<T>::W;
+    __shared__ float red[256 * W];
+    const int cvec = C / W, rpb = 256 / cvec;          // rows per CTA per iteration (cvec divides 256)
+    const int cv = threadIdx.x % cvec, r0 = threadIdx.x / cvec;
+    float acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k] = 0.f;
+    for (long long row = (long long)blockIdx.x * rpb + r0; row < rows; row += (long long)gridDim.x * rpb) {
+        const long long o = row * C + (long long)cv * W;
+        float g[W], yy[W];
+        TrainVec<T>::load(gout + o, g);
+        if (act == MREFSR_ACT_LEAKY) {
+            TrainVec<T>::load(y + o, yy);
+#pragma unroll
+            for (int k = 0; k < W; ++k) g[k] = (yy[k] > 0.f ? g[k] : g[k] * slope);
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            g[k] *= scale;
+            acc[k] += g[k];
+        }
+        if (gin) TrainVec<T>::store(gin + o, g);
+    }
+#pragma unroll
+    for (int k = 0; k < W; ++k) red[threadIdx.x * W + k] = acc[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int v = c / W, k = c - v * W;
+        float sum = 0.f;
+        for (int r = 0; r < rpb; ++r) sum += red[(r * cvec + v) * W + k];
+        partial[(size_t)blockIdx.x * C + c] = sum;
+    }
+}
+
+__global__ void bias_grad_sum_kernel(const float* __restrict__ partial, float* __restrict__ gbias, int nblocks, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sum = 0.f;
+    for (int b = 0; b < nblocks; ++b) sum += partial[(size_t)b * C + c];
+    gbias[c] = sum;
+}
+
+static bool train_shape_ok(int C, int dtype) {
+    const int W = dtype ? 8 : 4;
+    return C % W == 0 && C / W <= 256 && 256 % (C / W) == 0;
+}
+
 }  // namespace mrefsr
 
 using namespace mrefsr;
@@ -352,6 +470,70 @@ int mrefsr_maxpool2x2_nhwc(const float* src, float* dst, int B, int C, int H, in
     maxpool2_nhwc_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, total4, C / 4, W / 2, H / 2, W);
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int mrefsr_bias_act_train_supported(int C, int dtype) { return train_shape_ok(C, dtype) ? 1 : 0; }
+
+int mrefsr_bias_act_train_blocks(void) { return 2 * sm_count(); }
+
+int mrefsr_bias_act_train_forward(void* x, const float* bias, const void* residual, long long rows, int C, int dtype, int act,
+                                  float slope, float scale, void* stream) {
+    MREFSR_CHECK(x && rows > 0 && C > 0, ERR_BAD_ARG, "bias_act_train_forward: bad arguments");
+    MREFSR_CHECK(dtype == 0 || dtype == 1, ERR_BAD_ARG, "bias_act_train_forward: dtype must be 0 (fp32) or 1 (bf16)");
+    MREFSR_CHECK(act == MREFSR_ACT_NONE || act == MREFSR_ACT_LEAKY, ERR_BAD_ARG, "bias_act_train_forward: activation %d", act);
+    MREFSR_CHECK(train_shape_ok(C, dtype), ERR_UNSUPPORTED, "bias_act_train_forward: C = %d not served", C);
+    MREFSR_CHECK(al16(x) && (!residual || al16(residual)), ERR_BAD_ARG, "bias_act_train_forward: 16-byte alignment");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    const int W = dtype ? 8 : 4;
+    const long long nvec = rows * C / W;
+    long long blocks = (nvec + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) blocks = 1;
+    if (dtype)
+        bias_act_train_fwd_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(
+            static_cast<__nv_bfloat16*>(x), bias, static_cast<const __nv_bfloat16*>(residual), nvec, C / W, act, slope, scale);
+    else
+        bias_act_train_fwd_kernel<float><<<(int)blocks, 256, 0, st>>>(static_cast<float*>(x), bias,
+                                                                      static_cast<const float*>(residual), nvec, C / W, act,
+                                                                      slope, scale);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_bias_act_train_backward(const void* grad_out, const void* y, void* grad_in, float* grad_bias, float* partial,
+                                   long long rows, int C, int dtype, int act, float slope, float scale, void* stream) {
+    MREFSR_CHECK(grad_out && grad_bias && partial && rows > 0 && C > 0, ERR_BAD_ARG, "bias_act_train_backward: bad arguments");
+    MREFSR_CHECK(dtype == 0 || dtype == 1, ERR_BAD_ARG, "bias_act_train_backward: dtype must be 0 (fp32) or 1 (bf16)");
+    MREFSR_CHECK(act == MREFSR_ACT_NONE || (act == MREFSR_ACT_LEAKY && y), ERR_BAD_ARG,
+                 "bias_act_train_backward: activation %d (leaky needs the forward output)", act);
+    MREFSR_CHECK(train_shape_ok(C, dtype), ERR_UNSUPPORTED, "bias_act_train_backward: C = %d not served", C);
+    MREFSR_CHECK(al16(grad_out) && (!y || al16(y)) && (!grad_in || al16(grad_in)), ERR_BAD_ARG,
+                 "bias_act_train_backward: 16-byte alignment");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    const int W = dtype ? 8 : 4, rpb = 256 / (C / W);
+    long long blocks = (rows + rpb - 1) / rpb;
+    const int cap = 2 * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (dtype)
+        bias_act_train_bwd_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(grad_out), static_cast<const __nv_bfloat16*>(y),
+            static_cast<__nv_bfloat16*>(grad_in), partial, rows, C, act, slope, scale);
+    else
+        bias_act_train_bwd_kernel<float><<<(int)blocks, 256, 0, st>>>(static_cast<const float*>(grad_out),
+                                                                      static_cast<const float*>(y), static_cast<float*>(grad_in),
+                                                                      partial, rows, C, act, slope, scale);
+    MREFSR_LAUNCH_CHECK();
+    bias_grad_sum_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, grad_bias, (int)blocks, C);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(2);
     return 0;
 }
 

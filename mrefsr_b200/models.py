@@ -73,6 +73,12 @@ class ResidualBlockNoBN(nn.Module):
         if T.fast_ok(x):    # inference: conv -> [bias + ReLU] -> conv -> [bias, * res_scale, + x], two epilogue passes
             t = T.conv_bias_act(x, self.conv1, T.ACT_LEAKY, 0.0)
             return T.conv_bias_act(t, self.conv2, T.ACT_NONE, residual=x, scale=self.res_scale)
+        if T.train_ok(x):   # training: bias / ReLU / residual epilogues and their backward (+ bias gradients) fused
+            t = T.conv_bias_act_train(x, self.conv1, T.ACT_LEAKY, 0.0)
+            if t is not None:
+                out = T.conv_bias_act_train(t, self.conv2, T.ACT_NONE, residual=x, scale=self.res_scale)
+                if out is not None:
+                    return out
         return x + self.conv2(self.relu(self.conv1(x))) * self.res_scale
 
 
@@ -129,6 +135,10 @@ class ContentExtractor(nn.Module):
     def forward(self, x):
         if T.fast_ok(x):
             return self.body(T.conv_bias_act(x, self.conv_first, T.ACT_LEAKY, 0.1))
+        if T.train_ok(x):
+            t = T.conv_bias_act_train(x, self.conv_first, T.ACT_LEAKY, 0.1)
+            if t is not None:
+                return self.body(t)
         return self.body(self.lrelu(self.conv_first(x)))
 
 
@@ -187,7 +197,8 @@ class DynamicAggregationRestoration(nn.Module):
             if T.layout_of(of) == 1:
                 o = o.contiguous(memory_format=torch.channels_last)
             o = self.lrelu(o)
-            o = self.lrelu(conv2(o))
+            o2 = T.conv_bias_act_train(o, conv2, T.ACT_LEAKY, 0.1)
+            o = o2 if o2 is not None else self.lrelu(conv2(o))
             y = self.lrelu(agg([feat, o], pre))                                               # [B*R, C, H, W]
             h = getattr(self, f'head_{name}').forward_stacked(x, y, r)
             h = getattr(self, f'body_{name}')(h) + x

@@ -181,3 +181,90 @@ def run_sequential(seq, x, taps=None, out=None):
             out[name] = x
         i += 1
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training path of the same epilogue (autograd on): channels-last fp32 / bf16 activations
+# ---------------------------------------------------------------------------------------------------------------------
+_CL = torch.channels_last
+TRAIN_FUSED = True      # False: modules keep their ordinary torch expressions under autograd (cross-check / A-B)
+
+
+def train_ok(*tensors):
+    """True when the fused TRAINING epilogue applies: autograd on, dense channels-last CUDA tensors of one dtype
+    (fp32, or bf16 under autocast), channel count the 16-byte channel vectors of csrc/trunk.cu can serve."""
+    if not TRAIN_FUSED or not torch.is_grad_enabled() or not tensors:
+        return False
+    dt = tensors[0].dtype
+    if dt not in (torch.float32, torch.bfloat16):
+        return False
+    for t in tensors:
+        if not (t.is_cuda and t.dim() == 4 and t.dtype == dt and layout_of(t) == 1):
+            return False
+    return True
+
+
+class BiasActFunction(torch.autograd.Function):
+    """y = act(x + bias[c]) * scale + residual on a convolution's bias-free output, in place; backward = ONE pass that
+    produces grad_x = grad_y * act'(y) * scale and grad_bias (torch: activation backward, then a reduction over
+    grad_output per convolution).  act: ACT_NONE or ACT_LEAKY (ReLU = slope 0)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, act, slope, residual, scale):
+        lib = _lib.lib()
+        b, c, h, w = x.shape
+        dt = 1 if x.dtype == torch.bfloat16 else 0
+        if act == ACT_LEAKY and (residual is not None or scale <= 0):
+            raise ValueError('BiasActFunction: an activation excludes residual / non-positive scale')
+        with torch.cuda.device(x.device):
+            rc = lib.mrefsr_bias_act_train_forward(_lib.ptr(x), _lib.ptr(bias), _lib.ptr(residual), b * h * w, c, dt, act,
+                                                   float(slope), float(scale), _lib.stream_ptr(x.device))
+        _lib.check(rc, 'mrefsr_bias_act_train_forward')
+        ctx.mark_dirty(x)
+        ctx.act, ctx.slope, ctx.scale, ctx.has_res = act, float(slope), float(scale), residual is not None
+        ctx.bias_dtype = bias.dtype
+        if act == ACT_LEAKY:
+            ctx.save_for_backward(x)
+        return x
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        lib = _lib.lib()
+        if layout_of(g) != 1:
+            g = g.contiguous(memory_format=_CL)
+        y = ctx.saved_tensors[0] if ctx.act == ACT_LEAKY else None
+        if y is not None and y.dtype != g.dtype:
+            g = g.to(y.dtype)
+        b, c, h, w = g.shape
+        dt = 1 if g.dtype == torch.bfloat16 else 0
+        plain = ctx.act == ACT_NONE and ctx.scale == 1.0
+        gin = g if plain else torch.empty_like(g, memory_format=_CL)
+        gb = torch.empty(c, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            part = torch.empty(lib.mrefsr_bias_act_train_blocks() * c, dtype=torch.float32, device=g.device)
+            rc = lib.mrefsr_bias_act_train_backward(_lib.ptr(g), _lib.ptr(y), None if plain else _lib.ptr(gin), _lib.ptr(gb),
+                                                    _lib.ptr(part), b * h * w, c, dt, ctx.act, ctx.slope, ctx.scale,
+                                                    _lib.stream_ptr(g.device))
+        _lib.check(rc, 'mrefsr_bias_act_train_backward')
+        return gin, gb.to(ctx.bias_dtype), None, None, (g if ctx.has_res else None), None
+
+
+def conv_bias_act_train(x, conv, act=ACT_NONE, slope=0.0, residual=None, scale=1.0):
+    """Training-path conv -> [bias, activation, * scale, + residual]: the convolution runs bias-free (cuDNN, autocast as
+    usual) and the epilogue is BiasActFunction.  Returns None when the shapes / layouts are not served (the caller keeps
+    its ordinary nn.Module expression)."""
+    if conv.bias is None or not train_ok(x):
+        return None
+    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    dt = 1 if y.dtype == torch.bfloat16 else 0
+    if not train_ok(y) or not _lib.lib().mrefsr_bias_act_train_supported(y.shape[1], dt):
+        y = y + conv.bias.view(1, -1, 1, 1).to(y.dtype)          # same arithmetic through torch
+        if act == ACT_LEAKY:
+            y = F.leaky_relu(y, slope)
+        y = y * scale if scale != 1.0 else y
+        return y + residual if residual is not None else y
+    if residual is not None and not (train_ok(residual) and residual.dtype == y.dtype and residual.shape == y.shape):
+        y = BiasActFunction.apply(y, conv.bias, act, slope, None, scale)
+        return y + residual
+    return BiasActFunction.apply(y, conv.bias, act, slope, residual, scale)

@@ -197,3 +197,74 @@ def test_maxpool2x2_nhwc():
     assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, want)
     odd = torch.randn(1, 6, 9, 9, device=DEV).contiguous(memory_format=torch.channels_last)     # torch path
     assert torch.equal(T.maxpool2x2(odd, torch.nn.MaxPool2d(2, 2)), F.max_pool2d(odd, 2, 2))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', ['leaky', 'relu', 'residual', 'residual_scaled', 'bias_only'])
+@pytest.mark.parametrize('shape', [(3, 64, 10, 12), (2, 256, 5, 7), (1, 8, 3, 3)])
+def test_bias_act_training_function(dtype, case, shape):
+    """BiasActFunction (training epilogue: in-place forward, one-pass backward with the bias gradient) against the torch
+    expression it replaces, channels-last fp32 and bf16."""
+    if not M._lib.lib().mrefsr_bias_act_train_supported(shape[1], 1 if dtype == torch.bfloat16 else 0):
+        pytest.skip('channel count not served by the 16-byte channel vectors')
+    g = torch.Generator().manual_seed(3)
+    cl = torch.channels_last
+    x0 = torch.randn(*shape, generator=g).to(DEV, dtype).contiguous(memory_format=cl)
+    r0 = torch.randn(*shape, generator=g).to(DEV, dtype).contiguous(memory_format=cl)
+    b0 = torch.randn(shape[1], generator=g).to(DEV)
+    go = torch.randn(*shape, generator=g).to(DEV, dtype).contiguous(memory_format=cl)
+    act, slope, scale, use_res = {'leaky': (T.ACT_LEAKY, 0.1, 1.0, False), 'relu': (T.ACT_LEAKY, 0.0, 1.0, False),
+                                  'residual': (T.ACT_NONE, 0.0, 1.0, True), 'residual_scaled': (T.ACT_NONE, 0.0, 0.5, True),
+                                  'bias_only': (T.ACT_NONE, 0.0, 1.0, False)}[case]
+
+    def run(fused):
+        x = x0.clone().requires_grad_(True)
+        r = r0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True)
+        pre = x * 1.0                      # a non-leaf the Function may overwrite (a convolution's output in the network)
+        if fused:
+            y = T.BiasActFunction.apply(pre, b, act, slope, r if use_res else None, scale)
+        else:
+            y = pre.float() + b.view(1, -1, 1, 1)
+            if dtype == torch.bfloat16:
+                y = y.to(dtype).float()    # torch rounds the bias add to bf16 before the activation
+            if act == T.ACT_LEAKY:
+                y = F.leaky_relu(y, slope)
+            y = y * scale
+            if use_res:
+                y = y + r.float()
+            y = y.to(dtype)
+        y.backward(go)
+        return y.detach().float(), x.grad.float(), b.grad.float(), (r.grad.float() if use_res else None)
+
+    a, c = run(True), run(False)
+    tol = 1e-6 if dtype == torch.float32 else 1.6e-2
+    for u, v, name in zip(a, c, ('y', 'gx', 'gb', 'gr')):
+        if v is None:
+            assert u is None
+            continue
+        assert rel_err(u, v) <= tol, (name, rel_err(u, v))
+
+
+def test_resblock_training_path_matches_torch():
+    """ResidualBlockNoBN / ContentExtractor under autograd in channels-last: fused epilogues (T.TRAIN_FUSED) against the
+    ordinary nn.Module expressions, outputs and every parameter gradient."""
+    torch.manual_seed(0)
+    net = ContentExtractor(n_blocks=2).to(DEV).to(memory_format=torch.channels_last).train()
+    x = torch.randn(2, 3, 20, 24, device=DEV).contiguous(memory_format=torch.channels_last)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    res = {}
+    try:
+        for fused in (False, True):
+            T.TRAIN_FUSED = fused
+            net.zero_grad(set_to_none=True)
+            y = net(x)
+            y.square().mean().backward()
+            res[fused] = (y.detach(), {k: p.grad.clone() for k, p in net.named_parameters()})
+    finally:
+        T.TRAIN_FUSED = True
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    assert rel_err(res[True][0], res[False][0]) <= 1e-5
+    for k in res[False][1]:
+        assert rel_err(res[True][1][k], res[False][1][k]) <= 1e-4, k
