@@ -151,17 +151,20 @@ class MRAPAFusion(nn.Module):
         if T.fast_ok(target, refs):
             return self._forward_fused_glue(target, refs, t, h_input, w_input)
         # multi-ref attention: one fused kernel instead of 3 permute copies + 2 batched matmuls (:321-335)
+        # (autograd path; T.conv_act = conv -> [bias, lrelu] with the fused training epilogue where it applies)
         emb_t = self.conv_emb1(target) * self.scale
         emb = self.conv_emb2(refs)
-        ass = self.conv_ass(refs)
+        ass = T.conv_act(refs, self.conv_ass)
         refs = mrapa_attention(emb_t, emb, ass, t)
+        if T.layout_of(target) == 1 and T.layout_of(refs) != 1:      # keep a channels-last trunk channels-last
+            refs = refs.contiguous(memory_format=torch.channels_last)
         # spatial attention (:338-344)
-        attn = self.lrelu(self.spatial_attn(torch.cat([target, refs], dim=1)))
-        attn_mul = self.spatial_attn_mul2(self.lrelu(self.spatial_attn_mul1(attn)))
-        attn_add = self.spatial_attn_add2(self.lrelu(self.spatial_attn_add1(attn)))
+        attn = T.conv_act(torch.cat([target, refs.to(target.dtype)], dim=1), self.spatial_attn, T.ACT_LEAKY, 0.1)
+        attn_mul = T.conv_act(T.conv_act(attn, self.spatial_attn_mul1, T.ACT_LEAKY, 0.1), self.spatial_attn_mul2)
+        attn_add = T.conv_act(T.conv_act(attn, self.spatial_attn_add1, T.ACT_LEAKY, 0.1), self.spatial_attn_add2)
         attn_mul = torch.sigmoid(attn_mul)
         refs = refs * attn_mul * 2 + attn_add
-        feat = self.lrelu(self.feat_fusion(torch.cat([target, refs], dim=1)))
+        feat = T.conv_act(torch.cat([target, refs.to(target.dtype)], dim=1), self.feat_fusion, T.ACT_LEAKY, 0.1)
         return feat[:, :, :h_input, :w_input]
 
     def _forward_fused_glue(self, target, refs, t, h_input, w_input):

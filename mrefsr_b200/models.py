@@ -202,7 +202,15 @@ class DynamicAggregationRestoration(nn.Module):
             y = self.lrelu(agg([feat, o], pre))                                               # [B*R, C, H, W]
             h = getattr(self, f'head_{name}').forward_stacked(x, y, r)
             h = getattr(self, f'body_{name}')(h) + x
-            x = getattr(self, f'tail_{name}')(h)
+            tail = getattr(self, f'tail_{name}')
+            if T.train_ok(h):
+                if name == 'large':     # conv -> lrelu -> conv
+                    x = T.conv_act(T.conv_act(h, tail[0], T.ACT_LEAKY, 0.1), tail[2])
+                else:                   # conv -> pixel shuffle -> lrelu == conv -> lrelu -> pixel shuffle
+                    x = F.pixel_shuffle(T.conv_act(h, tail[0], T.ACT_LEAKY, 0.1), 2).contiguous(
+                        memory_format=torch.channels_last)
+            else:
+                x = tail(h)
         return x
 
     def forward(self, x, pre_offset_list, img_ref_feat_list):

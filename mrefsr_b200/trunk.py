@@ -268,3 +268,13 @@ def conv_bias_act_train(x, conv, act=ACT_NONE, slope=0.0, residual=None, scale=1
         y = BiasActFunction.apply(y, conv.bias, act, slope, None, scale)
         return y + residual
     return BiasActFunction.apply(y, conv.bias, act, slope, residual, scale)
+
+
+def conv_act(x, conv, act=ACT_NONE, slope=0.0):
+    """act(conv(x)) for the autograd path: the fused training epilogue where it applies, the torch expression otherwise."""
+    if train_ok(x):
+        y = conv_bias_act_train(x, conv, act, slope)
+        if y is not None:
+            return y
+    y = conv(x)
+    return F.leaky_relu(y, slope) if act == ACT_LEAKY else y

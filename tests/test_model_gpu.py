@@ -177,6 +177,9 @@ def test_training_forward_with_batched_references_equals_the_loop():
         torch.backends.cudnn.allow_tf32 = old
     assert float((res[True][0] - res[False][0]).abs().max()) <= 1e-4
     assert res[True][1].keys() == res[False][1].keys() and len(res[True][1]) > 50
+    gmax = max(float(v.double().norm()) for v in res[False][1].values())
     for k in res[False][1]:
         a, c = res[True][1][k].double(), res[False][1][k].double()
-        assert float((a - c).norm() / c.norm().clamp_min(1e-12)) <= 5e-3, k     # TF32 DCN / GEMMs, different batch chunking
+        # TF32 DCN / GEMMs and a different batch chunking: relative to the parameter's own gradient, plus a floor for
+        # the few parameters whose gradient is a sum of cancelling terms (PReLU slopes)
+        assert float((a - c).norm()) <= 5e-3 * float(c.norm()) + 1e-4 * gmax, k
