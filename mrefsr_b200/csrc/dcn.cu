@@ -270,53 +270,58 @@ __device__ __forceinline__ Col8 ldg_col8(const float* p) {
 // (2') grad_offset / grad_mask from the NHWC copy of the input: one thread per (bl, deform group, tap, position) like the
 // planar kernel above, but the group's channels come as 8-channel chunks with four 256-bit corner loads each instead of
 // 32 scalar plane loads per chunk.  One thread owns a whole (group, tap, position): plain stores, deterministic.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dcn_bwd_coord_nhwc_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
                           const float* __restrict__ gcol, float* __restrict__ goff, float* __restrict__ gmask,
                           const DcnShape s, int b0, int nb) {
+    // thread = (bl, deform group, position), the taps are a loop: the nine sampling points of a position lie within a
+    // few pixels of each other, so their corners meet in L1 (a thread per tap re-fetched every sector from L2 per tap)
     const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG;
-    const size_t total = (size_t)nb * s.DG * K * P;
+    const size_t total = (size_t)nb * s.DG * P;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int p = idx % P;
-        const int tap = (idx / P) % K;
-        const int dgi = (idx / ((size_t)P * K)) % s.DG;
-        const int bl = idx / ((size_t)P * K * s.DG);
+        const int dgi = (idx / P) % s.DG;
+        const int bl = idx / ((size_t)P * s.DG);
         const int b = b0 + bl;
-        const int oy = p / s.Wo, ox = p - oy * s.Wo, ti = tap / s.kw, tj = tap - ti * s.kw;
-        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
-        const size_t mb = ((size_t)(b * s.DG + dgi) * K + tap) * P + p;
-        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldg(offset + ob);
-        const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldg(offset + ob + P);
-        const float m = mask ? __ldg(mask + mb) : 1.f;
-        float dy = 0.f, dx = 0.f, dm = 0.f;
-        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
-            const float fy0 = floorf(y), fx0 = floorf(x);
-            const int y0 = (int)fy0, x0 = (int)fx0;
-            const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
-            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
-            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
-            const float* base = xt + ((size_t)(b * s.H + yc) * s.W + xc) * s.C + dgi * cdg;
-            const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
-            const float va = (ty0 && tx0) ? 1.f : 0.f, vb = (ty0 && tx1) ? 1.f : 0.f, vc = (ty1 && tx0) ? 1.f : 0.f,
-                        vd = (ty1 && tx1) ? 1.f : 0.f;
-            const float* gc = gcol + ((size_t)bl * s.C * K + (size_t)dgi * cdg * K + tap) * P + p;
-            for (int c0 = 0; c0 < cdg; c0 += 8) {
-                const Col8 v0 = ldg_col8(base + c0), v1 = ldg_col8(base + c0 + dxo), v2 = ldg_col8(base + c0 + dyo),
-                           v3 = ldg_col8(base + c0 + dyo + dxo);
+        const int oy = p / s.Wo, ox = p - oy * s.Wo;
+        const float* xb = xt + (size_t)b * s.H * s.W * s.C + dgi * cdg;
+        for (int tap = 0; tap < K; ++tap) {
+            const int ti = tap / s.kw, tj = tap - ti * s.kw;
+            const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+            const size_t mb = ((size_t)(b * s.DG + dgi) * K + tap) * P + p;
+            const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldcs(offset + ob);
+            const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldcs(offset + ob + P);
+            const float m = mask ? __ldcs(mask + mb) : 1.f;
+            float dy = 0.f, dx = 0.f, dm = 0.f;
+            if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+                const float fy0 = floorf(y), fx0 = floorf(x);
+                const int y0 = (int)fy0, x0 = (int)fx0;
+                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+                const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+                const float* base = xb + ((size_t)yc * s.W + xc) * s.C;
+                const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
+                const float va = (ty0 && tx0) ? 1.f : 0.f, vb = (ty0 && tx1) ? 1.f : 0.f, vc = (ty1 && tx0) ? 1.f : 0.f,
+                            vd = (ty1 && tx1) ? 1.f : 0.f;
+                const float* gc = gcol + ((size_t)bl * s.C * K + (size_t)dgi * cdg * K + tap) * P + p;
+                for (int c0 = 0; c0 < cdg; c0 += 8) {
+                    const Col8 v0 = ldg_col8(base + c0), v1 = ldg_col8(base + c0 + dxo), v2 = ldg_col8(base + c0 + dyo),
+                               v3 = ldg_col8(base + c0 + dyo + dxo);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float a = va * v0.v[e], bq = vb * v1.v[e], cq = vc * v2.v[e], d = vd * v3.v[e];
-                    const float g = __ldg(gc + (size_t)(c0 + e) * K * P);
-                    const float v = hy * hx * a + hy * lx * bq + ly * hx * cq + ly * lx * d;
-                    dm += g * v;
-                    dy += g * m * (hx * (cq - a) + lx * (d - bq));
-                    dx += g * m * (hy * (bq - a) + ly * (d - cq));
+                    for (int e = 0; e < 8; ++e) {
+                        const float a = va * v0.v[e], bq = vb * v1.v[e], cq = vc * v2.v[e], d = vd * v3.v[e];
+                        const float g = __ldcs(gc + (size_t)(c0 + e) * K * P);      // read once: keep it out of the corners' L1
+                        const float v = hy * hx * a + hy * lx * bq + ly * hx * cq + ly * lx * d;
+                        dm += g * v;
+                        dy += g * m * (hx * (cq - a) + lx * (d - bq));
+                        dx += g * m * (hy * (bq - a) + ly * (d - cq));
+                    }
                 }
             }
+            __stcs(goff + ob, dy);
+            __stcs(goff + ob + P, dx);
+            if (gmask) __stcs(gmask + mb, dm);
         }
-        goff[ob] = dy;
-        goff[ob + P] = dx;
-        if (gmask) gmask[mb] = dm;
     }
 }
 
@@ -326,41 +331,44 @@ dcn_bwd_coord_nhwc_kernel(const float* __restrict__ xt, const float* __restrict_
 __global__ void __launch_bounds__(256)
 dcn_im2col_planes_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
                          float* __restrict__ colT, const DcnShape s, int b0, int nb) {
+    // thread = (bl, 8-channel chunk, position), taps as a loop (their corners meet in L1, as in the coordinate kernel)
     const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG, C8 = s.C >> 3;
-    const size_t total = (size_t)nb * K * C8 * P;
+    const size_t total = (size_t)nb * C8 * P;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int p = idx % P;
         const int j = (idx / P) % C8;
-        const int tap = (idx / ((size_t)P * C8)) % K;
-        const int bl = idx / ((size_t)P * C8 * K);
+        const int bl = idx / ((size_t)P * C8);
         const int b = b0 + bl, c0 = j * 8, dgi = c0 / cdg;
-        const int oy = p / s.Wo, ox = p - oy * s.Wo, ti = tap / s.kw, tj = tap - ti * s.kw;
-        const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
-        const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldg(offset + ob);
-        const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldg(offset + ob + P);
-        const float m = mask ? __ldg(mask + ((size_t)(b * s.DG + dgi) * K + tap) * P + p) : 1.f;
-        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
-            const float fy0 = floorf(y), fx0 = floorf(x);
-            const int y0 = (int)fy0, x0 = (int)fx0;
-            const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
-            const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
-            const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
-            const float* base = xt + ((size_t)(b * s.H + yc) * s.W + xc) * s.C + c0;
-            const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
-            const float w0 = (ty0 && tx0) ? hy * hx * m : 0.f, w1 = (ty0 && tx1) ? hy * lx * m : 0.f;
-            const float w2 = (ty1 && tx0) ? ly * hx * m : 0.f, w3 = (ty1 && tx1) ? ly * lx * m : 0.f;
-            const Col8 v0 = ldg_col8(base), v1 = ldg_col8(base + dxo), v2 = ldg_col8(base + dyo), v3 = ldg_col8(base + dyo + dxo);
+        const int oy = p / s.Wo, ox = p - oy * s.Wo;
+        const float* xb = xt + (size_t)b * s.H * s.W * s.C + c0;
+        for (int tap = 0; tap < K; ++tap) {
+            const int ti = tap / s.kw, tj = tap - ti * s.kw;
+            const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+            const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldg(offset + ob);
+            const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldg(offset + ob + P);
+            const float m = mask ? __ldg(mask + ((size_t)(b * s.DG + dgi) * K + tap) * P + p) : 1.f;
+            float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+                const float fy0 = floorf(y), fx0 = floorf(x);
+                const int y0 = (int)fy0, x0 = (int)fx0;
+                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+                const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+                const float* base = xb + ((size_t)yc * s.W + xc) * s.C;
+                const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
+                const float w0 = (ty0 && tx0) ? hy * hx * m : 0.f, w1 = (ty0 && tx1) ? hy * lx * m : 0.f;
+                const float w2 = (ty1 && tx0) ? ly * hx * m : 0.f, w3 = (ty1 && tx1) ? ly * lx * m : 0.f;
+                const Col8 v0 = ldg_col8(base), v1 = ldg_col8(base + dxo), v2 = ldg_col8(base + dyo), v3 = ldg_col8(base + dyo + dxo);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = w0 * v0.v[e] + w1 * v1.v[e] + w2 * v2.v[e] + w3 * v3.v[e];
+                for (int e = 0; e < 8; ++e) o[e] = w0 * v0.v[e] + w1 * v1.v[e] + w2 * v2.v[e] + w3 * v3.v[e];
+            }
+            float* dst = colT + ((size_t)bl * K * s.C + (size_t)tap * s.C + c0) * P + p;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) __stcs(dst + (size_t)e * P, to_tf32(o[e]));     // GEMM operand: the tensor core's read truncates
         }
-        float* dst = colT + ((size_t)bl * K * s.C + (size_t)tap * s.C + c0) * P + p;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) dst[(size_t)e * P] = to_tf32(o[e]);     // GEMM operand: the tensor core's read truncates
     }
 }
 
-// W[oc][m] -> WT[m][oc]   (A operand of the columns GEMM: rows m = c*K + tap, k = oc contiguous)
 __global__ void dcn_weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int Co, int MK) {
     const int total = Co * MK;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -761,7 +769,7 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
             count_launches(1);
         }
         if (grad_offset && nhwc_coord) {
-            dcn_bwd_coord_nhwc_kernel<<<grid_for((size_t)nb * deformable_group * K * P), 256, 0, st>>>(
+            dcn_bwd_coord_nhwc_kernel<<<grid_for((size_t)nb * deformable_group * P), 256, 0, st>>>(
                 xt, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
@@ -779,7 +787,7 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
         if (tc_gw) {
             // recomputed columns (deform_conv_cuda.cpp:647-650) as planes colT[bl][tap*C + c][p], then the chunk's share
             // of grad_weight (:659-664) as one split-K GEMM whose partial sums are added up in a fixed order
-            dcn_im2col_planes_kernel<<<grid_for((size_t)nb * K * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
+            dcn_im2col_planes_kernel<<<grid_for((size_t)nb * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
             const long long all_kb = (long long)nb * cdiv(P, 32);
