@@ -200,6 +200,10 @@ class DynamicAggregationRestoration(nn.Module):
             o2 = T.conv_bias_act_train(o, conv2, T.ACT_LEAKY, 0.1)
             o = o2 if o2 is not None else self.lrelu(conv2(o))
             y = self.lrelu(agg([feat, o], pre))                                               # [B*R, C, H, W]
+            if T.layout_of(o) == 1 and (y.dtype != o.dtype or T.layout_of(y) != 1):
+                # hand the aligned features to the fusion head in the trunk's dtype / layout once, instead of one cast
+                # (autocast) and one layout conversion (cuDNN) per convolution that reads them
+                y = y.to(dtype=o.dtype, memory_format=torch.channels_last)
             h = getattr(self, f'head_{name}').forward_stacked(x, y, r)
             h = getattr(self, f'body_{name}')(h) + x
             tail = getattr(self, f'tail_{name}')
