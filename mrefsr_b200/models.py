@@ -330,13 +330,31 @@ class MRefSRPipeline(nn.Module):
         ref_feats = self.net_map.vgg(img_refs.flatten(0, 1))
         return self.net_g.forward_batched(img_in_lq, max_idx, ref_feats, r)
 
-    def forward_ragged(self, samples, max_batch=16):
+    def forward_ragged(self, samples, max_batch=16, graphs=False):
         """Images with different reference counts / sizes (LMR-shaped groups, BASELINE config 3): samples[i] =
         (lq [3,h,w], up [3,H,W], refs [R_i,3,H,W]); images sharing (R, H, W) go through one batched `forward`.
         Returns the SR images in input order (parallel.run_ragged; shard a ragged batch over ranks with
-        parallel.shard_ragged first)."""
+        parallel.shard_ragged first).
+
+        graphs=True replays one captured CUDA graph per shape class (batch, R, H, W) instead of launching the ~700
+        kernels of a forward eagerly: the groups of a ragged batch are small (1-3 images), so the eager path is bound
+        by the host.  Graphs are captured on first use and kept (`clear_graphs()` drops them -- call it after the
+        weights were re-allocated or updated through anything but in-place writes)."""
         from .parallel import run_ragged
-        return run_ragged(self, samples, max_batch)
+        if not graphs:
+            return run_ragged(self, samples, max_batch)
+        cache = self.__dict__.setdefault('_ragged_graphs', {})
+
+        def fwd(lq, up, refs):
+            key = (tuple(lq.shape), tuple(up.shape), tuple(refs.shape), str(lq.device))
+            g = cache.get(key)
+            if g is None:
+                g = cache[key] = self.graphed(lq, up, refs)
+            return g(lq, up, refs).clone()      # the graph's static output is overwritten by its next replay
+        return run_ragged(fwd, samples, max_batch)
+
+    def clear_graphs(self):
+        self.__dict__.pop('_ragged_graphs', None)
 
     def graphed(self, img_in_lq, img_in_up, img_refs, warmup=3):
         """Capture `forward` for these shapes into a CUDA graph and return a GraphedForward runner.  The forward is
@@ -355,7 +373,19 @@ class MRefSRPipeline(nn.Module):
             pre, rf = self.net_map(f, ref)
             pres.append(pre)
             rfs.append(rf)
-        return self.net_g(img_in_lq, pres, rfs)
+        # the cross-check keeps the reference's structure: Python loop over references, DynAgg as the two operator Functions
+        dar = self.net_g.dyn_agg_restore
+        aggs = [getattr(dar, f'{n}_dyn_agg') for n in ('small', 'medium', 'large')]
+        saved = (dar.batch_refs, [a.fused_autograd for a in aggs])
+        dar.batch_refs = False
+        for a in aggs:
+            a.fused_autograd = False
+        try:
+            return self.net_g(img_in_lq, pres, rfs)
+        finally:
+            dar.batch_refs = saved[0]
+            for a, v in zip(aggs, saved[1]):
+                a.fused_autograd = v
 
 
 class GraphedForward:

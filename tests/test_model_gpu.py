@@ -183,3 +183,26 @@ def test_training_forward_with_batched_references_equals_the_loop():
         # TF32 DCN / GEMMs and a different batch chunking: relative to the parameter's own gradient, plus a floor for
         # the few parameters whose gradient is a sum of cancelling terms (PReLU slopes)
         assert float((a - c).norm()) <= 5e-3 * float(c.norm()) + 1e-4 * gmax, k
+
+
+def test_forward_ragged_eager_and_graph_replay(pipeline):
+    """BASELINE config 3 shape class: images with different reference counts.  forward_ragged buckets them by
+    (R, H, W); with graphs=True each bucket replays a captured CUDA graph.  Both must return, in input order, what a
+    plain forward on each image alone returns."""
+    g = torch.Generator().manual_seed(12)
+    H = 48
+    samples = []
+    for r in (2, 3, 2, 1):
+        lq = torch.rand(3, H // 4, H // 4, generator=g)
+        up = torch.nn.functional.interpolate(lq[None], scale_factor=4, mode='bicubic', align_corners=False)[0]
+        samples.append((lq.to(DEV), up.to(DEV), torch.rand(r, 3, H, H, generator=g).to(DEV)))
+    alone = [pipeline(lq[None], up[None], refs[None])[0] for lq, up, refs in samples]
+    eager = pipeline.forward_ragged(samples)
+    graphed = pipeline.forward_ragged(samples, graphs=True)
+    again = pipeline.forward_ragged(samples, graphs=True)          # second call: replay only
+    pipeline.clear_graphs()
+    for a, e, gr, ag in zip(alone, eager, graphed, again):
+        assert e.shape == a.shape == gr.shape
+        # batch 1 vs batch 2 of the same bucket may pick different cuDNN algorithms
+        assert float((e - a).abs().max()) <= 2e-3
+        assert float((gr - e).abs().max()) <= 1e-5 and torch.equal(gr, ag)

@@ -53,24 +53,36 @@ def ragged_leg(dev, rank, world, dist, images_per_gpu=6, hr=300, steps=2):
         up = torch.nn.functional.interpolate(lq[None], scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)[0]
         refs = torch.rand(counts[i], 3, hr, hr, generator=gl)
         samples.append((lq.to(dev), up.to(dev), refs.to(dev)))
+    res = {}
     with torch.no_grad():
-        out = net.forward_ragged(samples)          # warm-up (cuDNN autotune, workspaces)
-        _barrier(dist)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = net.forward_ragged(samples)
-        e1.record()
-        _barrier(dist)
-    ms = _max_over_ranks(e0.elapsed_time(e1) / steps, dev, dist)
+        for mode in ('eager', 'graphs'):
+            kw = {'graphs': mode == 'graphs'}
+            out = net.forward_ragged(samples, **kw)          # warm-up (cuDNN autotune, workspaces, graph capture)
+            _barrier(dist)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = net.forward_ragged(samples, **kw)
+            e1.record()
+            _barrier(dist)
+            res[mode] = (_max_over_ranks(e0.elapsed_time(e1) / steps, dev, dist), [o.clone() for o in out])
+    ms = res['graphs'][0]
+    out = res['graphs'][1]
+    same = max(float((a - b).abs().max()) for a, b in zip(res['eager'][1], res['graphs'][1])) if out else 0.0
     ok = all(o.shape == (3, hr, hr) and bool(torch.isfinite(o).all()) for o in out)
-    del net, samples, out
+    eager_ms = res['eager'][0]
+    net.clear_graphs()
+    del net, samples, out, res
     torch.cuda.empty_cache()
     return {'config': 'BASELINE config 3: LMR-shaped groups, %dx%d HR, 2-6 references per image, %d images per step '
                       'batch-sharded over %d GPU(s) by reference-count cost, no collective' % (hr, hr, n, world),
             'images_per_s': n / (ms / 1e3), 'ms_per_step': ms, 'images_per_step': n, 'ref_counts': counts,
             'images_on_rank0': len(mine), 'outputs_finite': ok,
-            'note': 'whole network (cuDNN convolutions + this library), eager forward_ragged, inputs resident'}
+            'eager_ms_per_step': eager_ms, 'eager_images_per_s': n / (eager_ms / 1e3),
+            'max_abs_diff_graphs_vs_eager': same,
+            'note': 'whole network (cuDNN convolutions + this library), forward_ragged(graphs=True): one CUDA graph per '
+                    'shape class (batch, R, H, W), captured before the timed region; eager_* = the same call launched '
+                    'eagerly (host-bound); inputs resident'}
 
 
 # ----------------------------------------------------------------------------------------------------------
