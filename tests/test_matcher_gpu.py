@@ -69,6 +69,27 @@ def test_shapes_vs_oracle(shape):
     assert r['n_bad'] == 0 and r['val_err'] <= 1e-3, r
 
 
+@pytest.mark.parametrize('w_ref', [3, 8, 33, 40, 75, 96, 97, 104, 130, 259])
+def test_diagonal_form_across_reference_widths(w_ref):
+    """The diagonal-form kernels take row offsets i * w_ref into their tiles: the strip variant as shared-memory
+    descriptor offsets (any w_ref up to 96, odd ones included: swizzle on absolute address bits), the plain variant as
+    TMA coordinates (wider grids).  Every variant against the oracle, and the variants against each other, at widths on
+    both sides of the strip limit, with an input grid of a different width and tiles that end inside a row."""
+    h_ref, h_in, w_in, c = 7, 9, 21, 64
+    fi, fr = unit_features(1, c, h_in, w_in, 100 + w_ref)[0], unit_features(1, c, h_ref, w_ref, 200 + w_ref)[0]
+    kw = dict(is_norm=True, norm_input=True)
+    outs = []
+    for mode in TC_MODES:
+        idx, val = _run(fi, fr, kw, mode)
+        r = match_parity(idx, val, fi, fr, kw)
+        assert r['n_bad'] == 0 and r['val_err'] <= 1e-3, (mode, r)
+        outs.append((idx.cpu(), val.cpu()))
+    for idx, val in outs[1:]:
+        same = idx == outs[0][0]
+        assert int((~same).sum()) <= r['n_lowgap']
+        assert float((val - outs[0][1]).abs().max()) <= 1e-5
+
+
 def test_different_input_and_ref_sizes():
     fi, fr = unit_features(1, 64, 12, 20, 5)[0], unit_features(1, 64, 30, 17, 6)[0]
     kw = dict(is_norm=True, norm_input=True)
