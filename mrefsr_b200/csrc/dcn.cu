@@ -608,7 +608,7 @@ constexpr int BWD_MAX_SPLITS = 32;     // split-K pieces of the grad_weight GEMM
 
 static int bwd_chunk(const DcnShape& s) {
     const size_t per = (size_t)s.C * s.kh * s.kw * s.Ho * s.Wo * 4;
-    size_t nb = ((size_t)256 << 20) / per;
+    size_t nb = ((size_t)1024 << 20) / per;     // two scratch tensors of <= 1 GiB (columns, their gradient): fewer, larger launches
     if (nb < 1) nb = 1;
     if (nb > (size_t)s.B) nb = s.B;
     return (int)nb;
