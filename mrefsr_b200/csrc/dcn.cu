@@ -523,19 +523,42 @@ dynagg_offsets_vec4_kernel(const float* __restrict__ conv_out, const float* __re
         const int comp = (ch & 1) ? 0 : 1;       // even plane = y = pre[..., 1], odd plane = x = pre[..., 0]
         const float4* pv = reinterpret_cast<const float4*>(pre + ((size_t)b * K + k) * P * 2);   // (x, y) pairs of 2 positions
         float4* dst = reinterpret_cast<float4*>(offset + ((size_t)b * OC + ch) * P);
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+        // two float4 per thread and iteration: six independent 16-byte loads in flight (the pass is HBM-bound)
+        const int step = gridDim.x * blockDim.x;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += 2 * step) {
+            const int i2 = i + step;
+            const bool two = i2 < P4;
             const float4 v = __ldcs(src + i);
             const float4 p0 = __ldg(pv + 2 * i), p1 = __ldg(pv + 2 * i + 1);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f), q0 = w, q1 = w;
+            if (two) {
+                w = __ldcs(src + i2);
+                q0 = __ldg(pv + 2 * i2);
+                q1 = __ldg(pv + 2 * i2 + 1);
+            }
             const float a0 = comp ? p0.y : p0.x, a1 = comp ? p0.w : p0.z, a2 = comp ? p1.y : p1.x, a3 = comp ? p1.w : p1.z;
-            dst[i] = make_float4(v.x + a0, v.y + a1, v.z + a2, v.w + a3);
+            __stcs(dst + i, make_float4(v.x + a0, v.y + a1, v.z + a2, v.w + a3));
             local += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+            if (two) {
+                const float b0 = comp ? q0.y : q0.x, b1 = comp ? q0.w : q0.z, b2 = comp ? q1.y : q1.x, b3 = comp ? q1.w : q1.z;
+                __stcs(dst + i2, make_float4(w.x + b0, w.y + b1, w.z + b2, w.w + b3));
+                local += fabsf(w.x) + fabsf(w.y) + fabsf(w.z) + fabsf(w.w);
+            }
         }
     } else {
         float4* dst = reinterpret_cast<float4*>(mask + ((size_t)b * MC + (ch - OC)) * P);
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+        const int step = gridDim.x * blockDim.x;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += 2 * step) {
+            const int i2 = i + step;
+            const bool two = i2 < P4;
             const float4 v = __ldcs(src + i);
-            dst[i] = make_float4(1.f / (1.f + expf(-v.x)), 1.f / (1.f + expf(-v.y)), 1.f / (1.f + expf(-v.z)),
-                                 1.f / (1.f + expf(-v.w)));
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (two) w = __ldcs(src + i2);
+            __stcs(dst + i, make_float4(1.f / (1.f + expf(-v.x)), 1.f / (1.f + expf(-v.y)), 1.f / (1.f + expf(-v.z)),
+                                        1.f / (1.f + expf(-v.w))));
+            if (two)
+                __stcs(dst + i2, make_float4(1.f / (1.f + expf(-w.x)), 1.f / (1.f + expf(-w.y)), 1.f / (1.f + expf(-w.z)),
+                                             1.f / (1.f + expf(-w.w))));
         }
     }
     if (abs_sum) {
@@ -939,8 +962,9 @@ int mrefsr_dynagg_offsets(const float* conv_out, const float* pre_offset, float*
     const int P = H * W;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (P % 4 == 0 && al16(conv_out) && al16(pre_offset) && al16(offset) && al16(mask) && (size_t)B * 3 * dg * K <= 65535) {
-        int gx = cdiv(P / 4, 256);
-        if (gx > 8) gx = 8;
+        int gx = cdiv(P / 4, 256 * 2);
+        if (gx > 4) gx = 4;
+        if (gx < 1) gx = 1;
         dynagg_offsets_vec4_kernel<<<dim3(gx, B * 3 * dg * K), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, dg, K, P);
     } else {
         dynagg_offsets_kernel<<<grid_for(total), 256, 0, st>>>(conv_out, pre_offset, offset, mask, abs_sum, B, dg, K, P);

@@ -344,12 +344,15 @@ bias_act_train_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ y, T
     }
 }
 
+// one warp per channel: lanes stride over the partial rows, then a shuffle tree -- a fixed order (deterministic)
 __global__ void bias_grad_sum_kernel(const float* __restrict__ partial, float* __restrict__ gbias, int nblocks, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     float sum = 0.f;
-    for (int b = 0; b < nblocks; ++b) sum += partial[(size_t)b * C + c];
-    gbias[c] = sum;
+    for (int b = lane; b < nblocks; b += 32) sum += partial[(size_t)b * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) gbias[c] = sum;
 }
 
 static bool train_shape_ok(int C, int dtype) {
@@ -531,7 +534,7 @@ int mrefsr_bias_act_train_backward(const void* grad_out, const void* y, void* gr
                                                                       static_cast<const float*>(y), static_cast<float*>(grad_in),
                                                                       partial, rows, C, act, slope, scale);
     MREFSR_LAUNCH_CHECK();
-    bias_grad_sum_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, grad_bias, (int)blocks, C);
+    bias_grad_sum_kernel<<<cdiv(C * 32, 256), 256, 0, st>>>(partial, grad_bias, (int)blocks, C);
     MREFSR_LAUNCH_CHECK();
     count_launches(2);
     return 0;
