@@ -312,12 +312,12 @@ bias_act_train_bwd_kernel(const T* __restrict__ gout, const T* __restrict__ y, T
                           float* __restrict__ partial, long long rows, int C, int act, float slope, float scale) {
     constexpr int W = TrainVec<T>::W;
     __shared__ float red[256 * W];
-    const int cvec = C / W, rpb = 256 / cvec;          // rows per CTA per iteration (cvec divides 256)
+    const int cvec = C / W, rpb = 256 / cvec;          // rows per CTA per iteration; threads beyond rpb * cvec idle
     const int cv = threadIdx.x % cvec, r0 = threadIdx.x / cvec;
     float acc[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) acc[k] = 0.f;
-    for (long long row = (long long)blockIdx.x * rpb + r0; row < rows; row += (long long)gridDim.x * rpb) {
+    for (long long row = (long long)blockIdx.x * rpb + r0; r0 < rpb && row < rows; row += (long long)gridDim.x * rpb) {
         const long long o = row * C + (long long)cv * W;
         float g[W], yy[W];
         TrainVec<T>::load(gout + o, g);
@@ -357,7 +357,7 @@ __global__ void bias_grad_sum_kernel(const float* __restrict__ partial, float* _
 
 static bool train_shape_ok(int C, int dtype) {
     const int W = dtype ? 8 : 4;
-    return C % W == 0 && C / W <= 256 && 256 % (C / W) == 0;
+    return C % W == 0 && C / W <= 256;
 }
 
 }  // namespace mrefsr

@@ -154,11 +154,12 @@ class DynAgg(ModulatedDeformConv2d):
                                   out_slope=out_slope)
 
     def forward(self, x, pre_offset):
+        from . import trunk as T
         if self.extra_offset_mask:
-            out = self.conv_offset_mask(x[1])
+            out = T.conv_act(x[1], self.conv_offset_mask)       # (training: bias add and its gradient fused)
             x = x[0]
         else:
-            out = self.conv_offset_mask(x)
+            out = T.conv_act(x, self.conv_offset_mask)
         if self._stats is None or self._stats.device != out.device:
             self._stats = torch.zeros(1, dtype=torch.float32, device=out.device)
         self._stats.zero_()

@@ -201,7 +201,7 @@ def test_maxpool2x2_nhwc():
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('case', ['leaky', 'relu', 'residual', 'residual_scaled', 'bias_only'])
-@pytest.mark.parametrize('shape', [(3, 64, 10, 12), (2, 256, 5, 7), (1, 8, 3, 3)])
+@pytest.mark.parametrize('shape', [(3, 64, 10, 12), (2, 256, 5, 7), (1, 8, 3, 3), (2, 216, 9, 11)])
 def test_bias_act_training_function(dtype, case, shape):
     """BiasActFunction (training epilogue: in-place forward, one-pass backward with the bias gradient) against the torch
     expression it replaces, channels-last fp32 and bf16."""
