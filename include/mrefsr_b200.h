@@ -271,6 +271,11 @@ MREFSR_API int mrefsr_bias_act_train_forward(void* x, const float* bias, const v
 MREFSR_API int mrefsr_bias_act_train_backward(const void* grad_out, const void* y, void* grad_in, float* grad_bias,
                                    float* partial, long long rows, int C, int dtype, int act, float slope,
                                    float scale, void* stream);
+/* The two conversions of the training path under bf16 autocast, one pass each (torch: a cast, then a strided copy):
+ * to_channels_last_bf16 = 0: bf16 channels-last [B,HW,C] -> fp32 planes [B,C,HW];  1: fp32 planes -> bf16 channels-last
+ * (round to nearest even).  C % 4 == 0. */
+MREFSR_API int mrefsr_layout_convert_bf16(const void* src, void* dst, int B, int C, int HW, int to_channels_last_bf16,
+                               void* stream);
 /* 2x2 / stride-2 max pooling, channels-last [B,H,W,C] -> [B,H/2,W/2,C] (VGG pool1 / pool2), C % 4 == 0, H, W even. */
 MREFSR_API int mrefsr_maxpool2x2_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,

@@ -214,6 +214,64 @@ nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst,
     }
 }
 
+// The same two conversions with a dtype change on the way (training under bf16 autocast: the plain convolutions produce
+// and consume bf16 channels-last tensors, the alignment kernels fp32 planes): one pass instead of torch's cast followed
+// by the transpose.  bf16 side: 4 channels = 8 bytes per lane.
+__global__ void __launch_bounds__(256)
+nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[128][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const __nv_bfloat16* s = src + (size_t)b * C * HW;
+    float* d = dst + (size_t)b * C * HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+        if (pp < HW && c < C) {
+            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(s + (size_t)pp * C + c));
+            tile[lane * 4][pl] = __uint_as_float(v.x << 16);
+            tile[lane * 4 + 1][pl] = __uint_as_float(v.x & 0xffff0000u);
+            tile[lane * 4 + 2][pl] = __uint_as_float(v.y << 16);
+            tile[lane * 4 + 3][pl] = __uint_as_float(v.y & 0xffff0000u);
+        }
+    }
+    __syncthreads();
+    const int p = p0 + lane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int cl = warp + 8 * i, c = c0 + cl;
+        if (c < C && p < HW) d[(size_t)c * HW + p] = tile[cl][lane];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[128][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* s = src + (size_t)b * C * HW;
+    __nv_bfloat16* d = dst + (size_t)b * C * HW;
+    const int p = p0 + lane;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int cl = warp + 8 * i, c = c0 + cl;
+        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+        if (pp < HW && c < C) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(tile[lane * 4][pl], tile[lane * 4 + 1][pl]);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(tile[lane * 4 + 2][pl], tile[lane * 4 + 3][pl]);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(d + (size_t)pp * C + c) = o;
+        }
+    }
+}
+
 // 2x2 / stride 2 max pooling on channels-last data (VGG pool1 / pool2, vgg_arch.py:141-161): float4 over channels,
 // every access a contiguous row segment.  torch's max_pool_forward_nhwc takes 1.7 ms for the six calls of a batch-16
 // forward; this is the streaming rate.
@@ -455,6 +513,24 @@ int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B
         nchw_to_nhwc_conv_kernel<<<grid, 256, 0, st>>>(src, dst, bias, C, HW);
     else
         nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(src, dst, bias, C, HW);
+    MREFSR_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int mrefsr_layout_convert_bf16(const void* src, void* dst, int B, int C, int HW, int to_channels_last_bf16, void* stream) {
+    MREFSR_CHECK(src && dst && src != dst, ERR_BAD_ARG, "layout_convert_bf16: bad pointers");
+    MREFSR_CHECK(B > 0 && C > 0 && HW > 0 && C % 4 == 0, ERR_BAD_ARG, "layout_convert_bf16: needs C %% 4 == 0 (B=%d C=%d HW=%d)", B, C, HW);
+    MREFSR_CHECK((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, ERR_BAD_ARG,
+                 "layout_convert_bf16: tensors must be 8-byte aligned");
+    MREFSR_CHECK(B <= 65535 && cdiv(C, 128) <= 65535, ERR_BAD_ARG, "layout_convert_bf16: batch too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScopedTiming tm(MREFSR_K_GLUE, st);
+    const dim3 grid(cdiv(HW, 32), cdiv(C, 128), B);
+    if (to_channels_last_bf16)
+        nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), C, HW);
+    else
+        nhwc_bf16_to_nchw_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), C, HW);
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

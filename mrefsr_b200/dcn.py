@@ -184,8 +184,8 @@ def dynagg_dcn_forward(input, conv_out, max_idx, flow_scale, weight, bias, defor
 
 def _nchw(t):
     """dense NCHW fp32 view / copy of an activation (channels-last tensors go through the tiled transpose kernel)."""
-    from .trunk import to_nchw
-    return to_nchw(t.float())
+    from .trunk import to_nchw_f32
+    return to_nchw_f32(t)
 
 
 class ModulatedDeformConvFunction(Function):

@@ -102,8 +102,8 @@ class DynAggDCNFunction(Function):
                                                                ctx.dg, k, h, w, _lib.stream_ptr(mask.device))
             _lib.check(rc, 'mrefsr_dynagg_offsets_backward')
             if ctx.conv_cl or ctx.conv_dtype != torch.float32:
-                g_conv = g_conv.to(dtype=ctx.conv_dtype,
-                                   memory_format=torch.channels_last if ctx.conv_cl else torch.contiguous_format)
+                from .trunk import from_nchw_f32
+                g_conv = from_nchw_f32(g_conv, ctx.conv_dtype, ctx.conv_cl)
         cast = (lambda t, dt: None if t is None else t.to(dt))
         return (cast(gi, ctx.x_dtype), g_conv, None, cast(gw, ctx.w_dtype),
                 gb if ctx.with_bias and ctx.needs_input_grad[4] else None, None, None)

@@ -22,7 +22,8 @@ class MRAPAAttentionFunction(Function):
     def forward(ctx, emb_t, emb, ass, t):
         _lib.require_cuda(emb_t, emb, ass)
         ctx.in_dtype = emb_t.dtype
-        q, k, v = (T.to_nchw(x.float()) for x in (emb_t, emb, ass))
+        ctx.in_cl = tuple(T.is_channels_last(x) for x in (emb_t, emb, ass))
+        q, k, v = (T.to_nchw_f32(x) for x in (emb_t, emb, ass))
         n, c, h, w = q.shape
         if k.shape[0] != n * t or k.shape[1] != c or v.shape[0] != n * t or k.shape[2:] != q.shape[2:] \
                 or v.shape[2:] != q.shape[2:]:
@@ -39,13 +40,13 @@ class MRAPAAttentionFunction(Function):
         if need:
             ctx.save_for_backward(q, k, v, prob)
         ctx.t = t
-        return out.to(emb_t.dtype)
+        return T.from_nchw_f32(out, emb_t.dtype, ctx.in_cl[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
         q, k, v, prob = ctx.saved_tensors
-        go = T.to_nchw(grad_out.float())
+        go = T.to_nchw_f32(grad_out)
         n, c, h, w = q.shape
         cv = v.shape[1]
         gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
@@ -54,8 +55,9 @@ class MRAPAAttentionFunction(Function):
                                                             _lib.ptr(go), _lib.ptr(gq), _lib.ptr(gk), _lib.ptr(gv), n,
                                                             ctx.t, c, cv, h, w, _lib.stream_ptr(q.device))
         _lib.check(rc, 'mrefsr_mrapa_attention_backward')
-        dt = ctx.in_dtype
-        return gq.to(dt), gk.to(dt), gv.to(dt), None
+        dt = ctx.in_dtype      # gradients go back in the dtype AND layout the inputs came in (bf16 channels-last: one pass)
+        return (T.from_nchw_f32(gq, dt, ctx.in_cl[0]), T.from_nchw_f32(gk, dt, ctx.in_cl[1]),
+                T.from_nchw_f32(gv, dt, ctx.in_cl[2]), None)
 
 
 def mrapa_attention(emb_t, emb, ass, t):

@@ -83,6 +83,44 @@ def to_nchw(t):
     return t.contiguous()
 
 
+def _bf16_convertible(t):
+    return (t.is_cuda and t.dim() == 4 and t.shape[1] % 4 == 0 and t.shape[0] <= 65535 and t.numel() > 0 and
+            (not t.requires_grad or not torch.is_grad_enabled()))
+
+
+def to_nchw_f32(t):
+    """Dense fp32 NCHW tensor with the values of t (what the alignment kernels read).  A bf16 channels-last tensor --
+    a convolution's output under autocast -- is converted in ONE pass (torch: a cast, then a strided copy)."""
+    if t.dtype == torch.bfloat16 and layout_of(t) == 1 and not t.is_contiguous() and _bf16_convertible(t):
+        b, c, h, w = t.shape
+        out = torch.empty(b, c, h, w, dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            rc = _lib.lib().mrefsr_layout_convert_bf16(_lib.ptr(t), _lib.ptr(out), b, c, h * w, 0, _lib.stream_ptr(t.device))
+        _lib.check(rc, 'mrefsr_layout_convert_bf16')
+        return out
+    return to_nchw(t.float())
+
+
+def from_nchw_f32(t, dtype, channels_last):
+    """The way back for gradients: dense fp32 NCHW `t` as a tensor of `dtype` in the given layout (one pass to bf16
+    channels-last; otherwise torch's conversions)."""
+    if (dtype == torch.bfloat16 and channels_last and t.dtype == torch.float32 and t.is_contiguous() and
+            _bf16_convertible(t)):
+        b, c, h, w = t.shape
+        out = torch.empty(b, c, h, w, dtype=torch.bfloat16, device=t.device, memory_format=torch.channels_last)
+        with torch.cuda.device(t.device):
+            rc = _lib.lib().mrefsr_layout_convert_bf16(_lib.ptr(t), _lib.ptr(out), b, c, h * w, 1, _lib.stream_ptr(t.device))
+        _lib.check(rc, 'mrefsr_layout_convert_bf16')
+        return out
+    if channels_last and dtype == torch.float32:
+        return to_nhwc(t)
+    return t.to(dtype=dtype, memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+
+
+def is_channels_last(t):
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
 def conv_bias_to_nchw(x, conv):
     """conv(x) + bias as a dense NCHW tensor.  From a channels-last convolution the bias rides on the layout
     conversion (one pass instead of two); otherwise it is the ordinary conv + bias epilogue."""

@@ -121,3 +121,27 @@ def test_bf16_io(shape):
     assert rel_err(out.float(), ref) <= 4e-3
     out32 = M.mrapa_attention(q.float().to(DEV), k.float().to(DEV), v.float().to(DEV), t)
     assert torch.equal(out, out32.bfloat16())
+
+
+def test_bf16_channels_last_training_path():
+    """The autograd Function on bf16 channels-last tensors (the convolutions' outputs under autocast): values and
+    gradients equal the fp32 NCHW run on the same bf16-rounded inputs up to the bf16 rounding of outputs / gradients, and
+    gradients come back bf16 channels-last (the layout the producing convolutions' backward wants)."""
+    n, t, c, cv, h, w = 2, 5, 64, 128, 12, 20
+    g = torch.Generator().manual_seed(9)
+    cl = torch.channels_last
+    q = (torch.randn(n, c, h, w, generator=g) * 0.3).to(DEV).bfloat16()
+    k = torch.randn(n * t, c, h, w, generator=g).to(DEV).bfloat16()
+    v = torch.randn(n * t, cv, h, w, generator=g).to(DEV).bfloat16()
+    go = torch.randn(n, cv, h, w, generator=g).to(DEV).bfloat16()
+    a = [x.contiguous(memory_format=cl).requires_grad_(True) for x in (q, k, v)]
+    out = M.mrapa_attention(a[0], a[1], a[2], t)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=cl)
+    out.backward(go.contiguous(memory_format=cl))
+    r = [x.float().requires_grad_(True) for x in (q, k, v)]
+    ref = M.mrapa_attention(r[0], r[1], r[2], t)
+    ref.backward(go.float())
+    assert rel_err(out.float(), ref) <= 8e-3
+    for x, y, name in zip(a, r, ('emb_t', 'emb', 'ass')):
+        assert x.grad.dtype == torch.bfloat16 and x.grad.is_contiguous(memory_format=cl), name
+        assert rel_err(x.grad.float(), y.grad) <= 8e-3, name

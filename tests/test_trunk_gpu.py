@@ -268,3 +268,20 @@ def test_resblock_training_path_matches_torch():
     assert rel_err(res[True][0], res[False][0]) <= 1e-5
     for k in res[False][1]:
         assert rel_err(res[True][1][k], res[False][1][k]) <= 1e-4, k
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 9, 13), (1, 216, 16, 16), (3, 8, 5, 5), (2, 260, 4, 7)])
+def test_layout_convert_bf16_one_pass(shape):
+    """bf16 channels-last <-> fp32 NCHW in one pass (training under autocast) against torch's two-step conversion:
+    exact both ways (bf16 -> fp32 is exact; fp32 -> bf16 rounds to nearest even like torch)."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(*shape, generator=g).to(DEV)
+    xb = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    a = T.to_nchw_f32(xb)
+    assert a.dtype == torch.float32 and a.is_contiguous() and torch.equal(a, xb.float().contiguous())
+    b = T.from_nchw_f32(x, torch.bfloat16, True)
+    assert b.dtype == torch.bfloat16 and b.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(b, x.to(torch.bfloat16))
+    # other combinations fall back to torch's conversions with the same values
+    assert torch.equal(T.to_nchw_f32(x), x)
+    assert torch.equal(T.from_nchw_f32(x, torch.float32, True), x)
