@@ -276,6 +276,11 @@ MREFSR_API int mrefsr_bias_act_train_backward(const void* grad_out, const void* 
  * (round to nearest even).  C % 4 == 0. */
 MREFSR_API int mrefsr_layout_convert_bf16(const void* src, void* dst, int B, int C, int HW, int to_channels_last_bf16,
                                void* stream);
+/* The same with a leaky ReLU folded in (the activation after DynAgg, ref_mrapa_restoration_arch.py:229):
+ * to_channels_last_bf16 = 1: dst = lrelu(src, slope) on the way out;  0: dst = src * (gate > 0 ? 1 : slope), gate = the
+ * activation's bf16 channels-last OUTPUT (its backward on the way in; gate may be NULL). */
+MREFSR_API int mrefsr_layout_convert_bf16_act(const void* src, void* dst, const void* gate, float slope, int B, int C, int HW,
+                                   int to_channels_last_bf16, void* stream);
 /* 2x2 / stride-2 max pooling, channels-last [B,H,W,C] -> [B,H/2,W/2,C] (VGG pool1 / pool2), C % 4 == 0, H, W even. */
 MREFSR_API int mrefsr_maxpool2x2_nhwc(const float* src, float* dst, int B, int C, int H, int W, void* stream);
 MREFSR_API int mrefsr_attn_modulate(float* refs, const float* attn_mul, const float* attn_add, const float* bias_mul,

@@ -48,6 +48,7 @@ SIGNATURES = {
     'mrefsr_maxpool2x2_nhwc': (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     'mrefsr_layout_convert': (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'mrefsr_layout_convert_bf16': (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    'mrefsr_layout_convert_bf16_act': (c_int, [_P, _P, _P, ctypes.c_float, _I, _I, _I, _I, _P]),
     'mrefsr_attn_modulate': (c_int, [_P] * 5 + [_I] * 4 + [_P]),
     'mrefsr_mrapa_attention_forward': (c_int, [_P] * 5 + [_I] * 6 + [_P]),
     'mrefsr_mrapa_attention_forward_bf16': (c_int, [_P] * 4 + [_I] * 6 + [_P]),

@@ -217,8 +217,11 @@ nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst,
 // The same two conversions with a dtype change on the way (training under bf16 autocast: the plain convolutions produce
 // and consume bf16 channels-last tensors, the alignment kernels fp32 planes): one pass instead of torch's cast followed
 // by the transpose.  bf16 side: 4 channels = 8 bytes per lane.
+// gate != NULL (same shape / layout as src): dst = src * (gate > 0 ? 1 : slope) -- the backward of a leaky ReLU whose output
+// is `gate`, folded into the conversion of the incoming gradient
 __global__ void __launch_bounds__(256)
-nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                             const __nv_bfloat16* __restrict__ gate, float slope, int C, int HW) {
     __shared__ float tile[128][33];
     const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -229,10 +232,20 @@ nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __res
         const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
         if (pp < HW && c < C) {
             const uint2 v = __ldcs(reinterpret_cast<const uint2*>(s + (size_t)pp * C + c));
-            tile[lane * 4][pl] = __uint_as_float(v.x << 16);
-            tile[lane * 4 + 1][pl] = __uint_as_float(v.x & 0xffff0000u);
-            tile[lane * 4 + 2][pl] = __uint_as_float(v.y << 16);
-            tile[lane * 4 + 3][pl] = __uint_as_float(v.y & 0xffff0000u);
+            float f0 = __uint_as_float(v.x << 16), f1 = __uint_as_float(v.x & 0xffff0000u);
+            float f2 = __uint_as_float(v.y << 16), f3 = __uint_as_float(v.y & 0xffff0000u);
+            if (gate) {
+                const uint2 g = __ldcs(reinterpret_cast<const uint2*>(gate + (size_t)b * C * HW + (size_t)pp * C + c));
+                // bf16 sign / zero test on the raw bits: positive and non-zero <=> (bits & 0x7fff) != 0 and sign clear
+                f0 = ((g.x & 0x8000u) || !(g.x & 0x7fffu)) ? f0 * slope : f0;
+                f1 = ((g.x & 0x80000000u) || !(g.x & 0x7fff0000u)) ? f1 * slope : f1;
+                f2 = ((g.y & 0x8000u) || !(g.y & 0x7fffu)) ? f2 * slope : f2;
+                f3 = ((g.y & 0x80000000u) || !(g.y & 0x7fff0000u)) ? f3 * slope : f3;
+            }
+            tile[lane * 4][pl] = f0;
+            tile[lane * 4 + 1][pl] = f1;
+            tile[lane * 4 + 2][pl] = f2;
+            tile[lane * 4 + 3][pl] = f3;
         }
     }
     __syncthreads();
@@ -244,8 +257,9 @@ nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __res
     }
 }
 
+// slope != 1: a leaky ReLU applied on the way (dst = lrelu(src))
 __global__ void __launch_bounds__(256)
-nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, float slope, int C, int HW) {
     __shared__ float tile[128][33];
     const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -255,7 +269,8 @@ nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __res
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int cl = warp + 8 * i, c = c0 + cl;
-        tile[cl][lane] = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+        float v = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
+        tile[cl][lane] = v > 0.f ? v : v * slope;
     }
     __syncthreads();
 #pragma unroll
@@ -519,7 +534,14 @@ int mrefsr_layout_convert(const float* src, float* dst, const float* bias, int B
 }
 
 int mrefsr_layout_convert_bf16(const void* src, void* dst, int B, int C, int HW, int to_channels_last_bf16, void* stream) {
+    return mrefsr_layout_convert_bf16_act(src, dst, nullptr, 1.f, B, C, HW, to_channels_last_bf16, stream);
+}
+
+int mrefsr_layout_convert_bf16_act(const void* src, void* dst, const void* gate, float slope, int B, int C, int HW,
+                                   int to_channels_last_bf16, void* stream) {
     MREFSR_CHECK(src && dst && src != dst, ERR_BAD_ARG, "layout_convert_bf16: bad pointers");
+    MREFSR_CHECK(!gate || (!to_channels_last_bf16 && (reinterpret_cast<uintptr_t>(gate) & 7) == 0), ERR_BAD_ARG,
+                 "layout_convert_bf16: gate is an 8-byte aligned bf16 channels-last tensor of the gradient direction only");
     MREFSR_CHECK(B > 0 && C > 0 && HW > 0 && C % 4 == 0, ERR_BAD_ARG, "layout_convert_bf16: needs C %% 4 == 0 (B=%d C=%d HW=%d)", B, C, HW);
     MREFSR_CHECK((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, ERR_BAD_ARG,
                  "layout_convert_bf16: tensors must be 8-byte aligned");
@@ -528,9 +550,11 @@ int mrefsr_layout_convert_bf16(const void* src, void* dst, int B, int C, int HW,
     ScopedTiming tm(MREFSR_K_GLUE, st);
     const dim3 grid(cdiv(HW, 32), cdiv(C, 128), B);
     if (to_channels_last_bf16)
-        nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), C, HW);
+        nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), slope,
+                                                           C, HW);
     else
-        nhwc_bf16_to_nchw_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), C, HW);
+        nhwc_bf16_to_nchw_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst),
+                                                           static_cast<const __nv_bfloat16*>(gate), slope, C, HW);
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

@@ -57,7 +57,10 @@ class DynAggDCNFunction(Function):
     dilation 1 / groups 1 only (what MRefSR uses); DynAgg.forward falls back to the two Functions otherwise."""
 
     @staticmethod
-    def forward(ctx, x, conv_out, pre_offset, weight, bias, dg, stats):
+    def forward(ctx, x, conv_out, pre_offset, weight, bias, dg, stats, out_slope=1.0, out_like_conv=False):
+        """out_slope != 1: a leaky ReLU on the output (the activation MRefSR applies after DynAgg,
+        ref_mrapa_restoration_arch.py:229) as part of this node; out_like_conv: return the output in conv_out's dtype and
+        layout (the trunk's) instead of x's -- both ride on the one conversion pass of the result."""
         from .dcn import dcn_forward_raw, _nchw
         _lib.require_cuda(x, conv_out, pre_offset, weight, bias)
         ctx.conv_dtype, ctx.x_dtype, ctx.dg = conv_out.dtype, x.dtype, dg
@@ -79,17 +82,36 @@ class DynAggDCNFunction(Function):
         _lib.check(rc, 'mrefsr_dynagg_offsets')
         wgt = weight.contiguous().float()
         bs = bias.contiguous().float() if bias is not None else None
-        ctx.save_for_backward(x32, offset, mask, wgt)
         out = dcn_forward_raw(x32, offset, mask, wgt, bs, (1, 1), (1, 1), (1, 1), 1, dg)
-        return out.to(x.dtype)
+        ctx.out_slope = float(out_slope)
+        from .trunk import from_nchw_f32
+        if out_like_conv:
+            res = from_nchw_f32(out, conv_out.dtype, ctx.conv_cl, slope=ctx.out_slope)
+        else:
+            if ctx.out_slope != 1.0:
+                out = torch.nn.functional.leaky_relu_(out, ctx.out_slope)
+            res = out.to(x.dtype)
+        if ctx.out_slope != 1.0:
+            ctx.save_for_backward(x32, offset, mask, wgt, res)
+        else:
+            ctx.save_for_backward(x32, offset, mask, wgt)
+        return res
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
         from .dcn import dcn_backward_raw, _nchw
-        x32, offset, mask, wgt = ctx.saved_tensors
+        from .trunk import to_nchw_f32
+        if ctx.out_slope != 1.0:
+            x32, offset, mask, wgt, res = ctx.saved_tensors
+            if grad_output.dtype != res.dtype:
+                grad_output = grad_output.to(res.dtype)
+            g32 = to_nchw_f32(grad_output, gate=res, slope=ctx.out_slope)
+        else:
+            x32, offset, mask, wgt = ctx.saved_tensors
+            g32 = _nchw(grad_output)
         need_conv = ctx.needs_input_grad[1]
-        gi, go, gm, gw, gb = dcn_backward_raw(x32, offset, mask, wgt, _nchw(grad_output), (1, 1), (1, 1), (1, 1), 1, ctx.dg,
+        gi, go, gm, gw, gb = dcn_backward_raw(x32, offset, mask, wgt, g32, (1, 1), (1, 1), (1, 1), 1, ctx.dg,
                                               ctx.with_bias, need_input=ctx.needs_input_grad[0], need_offset=need_conv,
                                               need_weight=ctx.needs_input_grad[3])
         g_conv = None
@@ -106,7 +128,7 @@ class DynAggDCNFunction(Function):
                 g_conv = from_nchw_f32(g_conv, ctx.conv_dtype, ctx.conv_cl)
         cast = (lambda t, dt: None if t is None else t.to(dt))
         return (cast(gi, ctx.x_dtype), g_conv, None, cast(gw, ctx.w_dtype),
-                gb if ctx.with_bias and ctx.needs_input_grad[4] else None, None, None)
+                gb if ctx.with_bias and ctx.needs_input_grad[4] else None, None, None, None, None)
 
 
 class DynAgg(ModulatedDeformConv2d):
@@ -153,7 +175,9 @@ class DynAgg(ModulatedDeformConv2d):
         return dynagg_dcn_forward(x, out, max_idx, flow_scale, self.weight, self.bias, self.deform_groups,
                                   out_slope=out_slope)
 
-    def forward(self, x, pre_offset):
+    def forward(self, x, pre_offset, out_slope=1.0, out_like_conv=False):
+        """Reference signature forward(x, pre_offset).  out_slope / out_like_conv (fused autograd node only): apply the
+        leaky ReLU that follows DynAgg in MRefSR and return the result in the offset convolution's dtype / layout."""
         from . import trunk as T
         if self.extra_offset_mask:
             out = T.conv_act(x[1], self.conv_offset_mask)       # (training: bias add and its gradient fused)
@@ -166,7 +190,10 @@ class DynAgg(ModulatedDeformConv2d):
         if self.fused_autograd and (tuple(self.kernel_size) == (3, 3) and tuple(self.stride) == (1, 1) and
                                     tuple(self.padding) == (1, 1) and tuple(self.dilation) == (1, 1) and self.groups == 1):
             self._stats_count = out.numel() // 3 * 2
-            return DynAggDCNFunction.apply(x, out, pre_offset, self.weight, self.bias, self.deform_groups, self._stats)
+            return DynAggDCNFunction.apply(x, out, pre_offset, self.weight, self.bias, self.deform_groups, self._stats,
+                                           out_slope, out_like_conv)
+        if out_slope != 1.0 or out_like_conv:
+            raise NotImplementedError('out_slope / out_like_conv need the fused autograd node (3x3, stride 1, padding 1)')
         offset, mask = DynAggOffsetsFunction.apply(out, pre_offset, self.deform_groups, self._stats)
         self._stats_count = offset.numel()
         return modulated_deform_conv2d(x, offset, mask, self.weight, self.bias, self.stride, self.padding,

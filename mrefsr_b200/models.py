@@ -199,11 +199,13 @@ class DynamicAggregationRestoration(nn.Module):
             o = self.lrelu(o)
             o2 = T.conv_bias_act_train(o, conv2, T.ACT_LEAKY, 0.1)
             o = o2 if o2 is not None else self.lrelu(conv2(o))
-            y = self.lrelu(agg([feat, o], pre))                                               # [B*R, C, H, W]
-            if T.layout_of(o) == 1 and (y.dtype != o.dtype or T.layout_of(y) != 1):
-                # hand the aligned features to the fusion head in the trunk's dtype / layout once, instead of one cast
-                # (autocast) and one layout conversion (cuDNN) per convolution that reads them
-                y = y.to(dtype=o.dtype, memory_format=torch.channels_last)
+            if agg.fused_autograd and T.layout_of(o) == 1:
+                # the leaky ReLU and the hand-off to the fusion head in the trunk's dtype / layout ride on the DynAgg
+                # node's one conversion pass (instead of an activation pass, then a cast (autocast) and a layout
+                # conversion (cuDNN) per convolution that reads the aligned features)
+                y = agg([feat, o], pre, out_slope=0.1, out_like_conv=True)                    # [B*R, C, H, W]
+            else:
+                y = self.lrelu(agg([feat, o], pre))
             h = getattr(self, f'head_{name}').forward_stacked(x, y, r)
             h = getattr(self, f'body_{name}')(h) + x
             tail = getattr(self, f'tail_{name}')

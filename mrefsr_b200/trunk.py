@@ -88,30 +88,39 @@ def _bf16_convertible(t):
             (not t.requires_grad or not torch.is_grad_enabled()))
 
 
-def to_nchw_f32(t):
+def to_nchw_f32(t, gate=None, slope=1.0):
     """Dense fp32 NCHW tensor with the values of t (what the alignment kernels read).  A bf16 channels-last tensor --
-    a convolution's output under autocast -- is converted in ONE pass (torch: a cast, then a strided copy)."""
-    if t.dtype == torch.bfloat16 and layout_of(t) == 1 and not t.is_contiguous() and _bf16_convertible(t):
+    a convolution's output under autocast -- is converted in ONE pass (torch: a cast, then a strided copy).
+    gate / slope: t * (gate > 0 ? 1 : slope), i.e. the backward of a leaky ReLU whose output is `gate`, on the way."""
+    fast = t.dtype == torch.bfloat16 and layout_of(t) == 1 and not t.is_contiguous() and _bf16_convertible(t)
+    if fast and (gate is None or (gate.dtype == torch.bfloat16 and gate.shape == t.shape and layout_of(gate) == 1
+                                  and not gate.is_contiguous())):
         b, c, h, w = t.shape
         out = torch.empty(b, c, h, w, dtype=torch.float32, device=t.device)
         with torch.cuda.device(t.device):
-            rc = _lib.lib().mrefsr_layout_convert_bf16(_lib.ptr(t), _lib.ptr(out), b, c, h * w, 0, _lib.stream_ptr(t.device))
-        _lib.check(rc, 'mrefsr_layout_convert_bf16')
+            rc = _lib.lib().mrefsr_layout_convert_bf16_act(_lib.ptr(t), _lib.ptr(out), _lib.ptr(gate), float(slope), b, c,
+                                                           h * w, 0, _lib.stream_ptr(t.device))
+        _lib.check(rc, 'mrefsr_layout_convert_bf16_act')
         return out
+    if gate is not None:
+        t = torch.where(gate > 0, t, t * slope)
     return to_nchw(t.float())
 
 
-def from_nchw_f32(t, dtype, channels_last):
-    """The way back for gradients: dense fp32 NCHW `t` as a tensor of `dtype` in the given layout (one pass to bf16
-    channels-last; otherwise torch's conversions)."""
+def from_nchw_f32(t, dtype, channels_last, slope=1.0):
+    """The way back: dense fp32 NCHW `t` as a tensor of `dtype` in the given layout (one pass to bf16 channels-last;
+    otherwise torch's conversions).  slope != 1 applies a leaky ReLU on the way."""
     if (dtype == torch.bfloat16 and channels_last and t.dtype == torch.float32 and t.is_contiguous() and
             _bf16_convertible(t)):
         b, c, h, w = t.shape
         out = torch.empty(b, c, h, w, dtype=torch.bfloat16, device=t.device, memory_format=torch.channels_last)
         with torch.cuda.device(t.device):
-            rc = _lib.lib().mrefsr_layout_convert_bf16(_lib.ptr(t), _lib.ptr(out), b, c, h * w, 1, _lib.stream_ptr(t.device))
-        _lib.check(rc, 'mrefsr_layout_convert_bf16')
+            rc = _lib.lib().mrefsr_layout_convert_bf16_act(_lib.ptr(t), _lib.ptr(out), None, float(slope), b, c, h * w, 1,
+                                                           _lib.stream_ptr(t.device))
+        _lib.check(rc, 'mrefsr_layout_convert_bf16_act')
         return out
+    if slope != 1.0:
+        t = F.leaky_relu(t, slope)
     if channels_last and dtype == torch.float32:
         return to_nhwc(t)
     return t.to(dtype=dtype, memory_format=torch.channels_last if channels_last else torch.contiguous_format)

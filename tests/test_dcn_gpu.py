@@ -225,6 +225,40 @@ def test_dynagg_fused_autograd_node_matches_the_two_functions():
         assert e_fused <= max(1.25 * e_two, 1e-3) and e_fused <= 0.15, (name, e_fused, e_two)   # bf16 offset conv: ~0.03 px
 
 
+@pytest.mark.parametrize('bf16', [False, True])
+def test_dynagg_node_with_folded_activation(bf16):
+    """DynAgg.forward(..., out_slope=0.1, out_like_conv=True): the leaky ReLU that follows DynAgg in MRefSR and the
+    hand-off in the offset convolution's dtype / layout as part of the autograd node, against lrelu(DynAgg.forward(...))
+    converted afterwards -- same values (the bf16 result is rounded once either way) and the same gradients."""
+    g = torch.Generator().manual_seed(41)
+    b, c, h, w, dg = 2, 64, 12, 20, 8
+    x = torch.randn(b, c, h, w, generator=g).to(DEV)
+    feat0 = torch.randn(b, c, h, w, generator=g).to(DEV)
+    pre = (torch.randn(b, 9, h, w, 2, generator=g) * 2).to(DEV)
+    cl = torch.channels_last
+    gout = torch.randn(b, c, h, w, generator=g).to(DEV).contiguous(memory_format=cl)
+    res = {}
+    for folded in (False, True):
+        torch.manual_seed(5)
+        m = M.DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True).to(DEV)
+        m.conv_offset_mask.weight.data.normal_(0, 0.02)
+        m.conv_offset_mask.bias.data.normal_(0, 0.3)
+        m.conv_offset_mask.to(memory_format=cl)
+        feat = feat0.clone().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+            f_in = feat.contiguous(memory_format=cl)
+            if folded:
+                y = m([x, f_in], pre, out_slope=0.1, out_like_conv=True)
+            else:
+                y = torch.nn.functional.leaky_relu(m([x, f_in], pre), 0.1)
+                y = y.to(dtype=torch.bfloat16 if bf16 else torch.float32, memory_format=cl)
+        assert y.dtype == (torch.bfloat16 if bf16 else torch.float32) and y.is_contiguous(memory_format=cl)
+        y.backward(gout.to(y.dtype))
+        res[folded] = (y.float().detach(), feat.grad, m.conv_offset_mask.weight.grad, m.weight.grad, m.bias.grad)
+    for a, r_, name in zip(res[True], res[False], ('y', 'g_feat', 'g_com_w', 'g_weight', 'g_bias')):
+        assert rel_err(a, r_) <= (1e-5 if not bf16 else 1e-5), (name, rel_err(a, r_))
+
+
 def test_dynagg_glue_golden(golden):
     from mrefsr_b200.dynagg import DynAggOffsetsFunction
     g = golden('dynagg')
