@@ -325,6 +325,69 @@ dcn_bwd_coord_nhwc_kernel(const float* __restrict__ xt, const float* __restrict_
     }
 }
 
+// (2') + (4a') in one pass: the coordinate gradients and the recomputed columns need the same corners of the same sampling
+// points, so when a backward wants both (grad_offset / grad_mask and grad_weight: every training step of MRefSR) one kernel
+// gathers them once.  Thread = (bl, deform group, position), taps as a loop; columns are written as planes
+// colT[bl][tap*C + c][p], rounded to tf32 (the grad_weight GEMM's B operand), exactly where dcn_im2col_planes_kernel puts them.
+__global__ void __launch_bounds__(256, 2)
+dcn_bwd_coord_cols_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
+                          const float* __restrict__ gcol, float* __restrict__ goff, float* __restrict__ gmask,
+                          float* __restrict__ colT, const DcnShape s, int b0, int nb) {
+    const int K = s.kh * s.kw, P = s.Ho * s.Wo, cdg = s.C / s.DG;
+    const size_t total = (size_t)nb * s.DG * P;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int p = idx % P;
+        const int dgi = (idx / P) % s.DG;
+        const int bl = idx / ((size_t)P * s.DG);
+        const int b = b0 + bl;
+        const int oy = p / s.Wo, ox = p - oy * s.Wo;
+        const float* xb = xt + (size_t)b * s.H * s.W * s.C + dgi * cdg;
+        for (int tap = 0; tap < K; ++tap) {
+            const int ti = tap / s.kw, tj = tap - ti * s.kw;
+            const size_t ob = ((size_t)(b * s.DG + dgi) * 2 * K + 2 * tap) * P + p;
+            const size_t mb = ((size_t)(b * s.DG + dgi) * K + tap) * P + p;
+            const float y = (float)(oy * s.sh - s.ph + ti * s.dh) + __ldcs(offset + ob);
+            const float x = (float)(ox * s.sw - s.pw + tj * s.dw) + __ldcs(offset + ob + P);
+            const float m = mask ? __ldcs(mask + mb) : 1.f;
+            float dy = 0.f, dx = 0.f, dm = 0.f;
+            float* ct = colT + ((size_t)bl * K * s.C + (size_t)tap * s.C + dgi * cdg) * P + p;
+            if (y > -1.f && x > -1.f && y < (float)s.H && x < (float)s.W) {
+                const float fy0 = floorf(y), fx0 = floorf(x);
+                const int y0 = (int)fy0, x0 = (int)fx0;
+                const float ly = y - fy0, lx = x - fx0, hy = 1.f - ly, hx = 1.f - lx;
+                const bool ty0 = y0 >= 0, ty1 = y0 + 1 <= s.H - 1, tx0 = x0 >= 0, tx1 = x0 + 1 <= s.W - 1;
+                const int yc = ty0 ? y0 : 0, xc = tx0 ? x0 : 0;
+                const float* base = xb + ((size_t)yc * s.W + xc) * s.C;
+                const size_t dxo = (tx0 && tx1) ? s.C : 0, dyo = (ty0 && ty1) ? (size_t)s.W * s.C : 0;
+                const float va = (ty0 && tx0) ? 1.f : 0.f, vb = (ty0 && tx1) ? 1.f : 0.f, vc = (ty1 && tx0) ? 1.f : 0.f,
+                            vd = (ty1 && tx1) ? 1.f : 0.f;
+                const float w0 = va * hy * hx * m, w1 = vb * hy * lx * m, w2 = vc * ly * hx * m, w3 = vd * ly * lx * m;
+                const float* gc = gcol + ((size_t)bl * s.C * K + (size_t)dgi * cdg * K + tap) * P + p;
+                for (int c0 = 0; c0 < cdg; c0 += 8) {
+                    const Col8 v0 = ldg_col8(base + c0), v1 = ldg_col8(base + c0 + dxo), v2 = ldg_col8(base + c0 + dyo),
+                               v3 = ldg_col8(base + c0 + dyo + dxo);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float a = va * v0.v[e], bq = vb * v1.v[e], cq = vc * v2.v[e], d = vd * v3.v[e];
+                        const float g = __ldcs(gc + (size_t)(c0 + e) * K * P);
+                        const float v = hy * hx * a + hy * lx * bq + ly * hx * cq + ly * lx * d;
+                        dm += g * v;
+                        dy += g * m * (hx * (cq - a) + lx * (d - bq));
+                        dx += g * m * (hy * (bq - a) + ly * (d - cq));
+                        // the column exactly as dcn_im2col_planes_kernel computes it (mask and validity folded into the weights)
+                        __stcs(ct + (size_t)(c0 + e) * P, to_tf32(w0 * v0.v[e] + w1 * v1.v[e] + w2 * v2.v[e] + w3 * v3.v[e]));
+                    }
+                }
+            } else {
+                for (int c = 0; c < cdg; ++c) __stcs(ct + (size_t)c * P, 0.f);
+            }
+            __stcs(goff + ob, dy);
+            __stcs(goff + ob + P, dx);
+            if (gmask) __stcs(gmask + mb, dm);
+        }
+    }
+}
+
 // written as planes colT[bl][tap*C + c][p] (k = position contiguous: the B operand of the
 // tcgen05 grad_weight GEMM).  Lanes = consecutive positions, so each of the 8 scalar stores of a thread is a coalesced
 // 128-byte warp store into its channel plane.
@@ -637,6 +700,16 @@ static int bwd_chunk(const DcnShape& s) {
     return (int)nb;
 }
 
+// MREFSR_DCN_BWD_MERGE=0 (tuning knob / cross-check; default 1): separate coordinate-gradient and column kernels
+static bool bwd_merge_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MREFSR_DCN_BWD_MERGE");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 static int grid_for(size_t total) {
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)sm_count() * 32;
@@ -791,7 +864,14 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
             MREFSR_LAUNCH_CHECK();
             count_launches(1);
         }
-        if (grad_offset && nhwc_coord) {
+        // coordinate gradients and recomputed columns from ONE gather when the backward wants both
+        const bool merged = grad_offset && nhwc_coord && tc_gw && bwd_merge_enabled();
+        if (merged) {
+            dcn_bwd_coord_cols_kernel<<<grid_for((size_t)nb * deformable_group * P), 256, 0, st>>>(
+                xt, offset, mask, gcol, grad_offset, grad_mask, col, s, b0, nb);
+            MREFSR_LAUNCH_CHECK();
+            count_launches(1);
+        } else if (grad_offset && nhwc_coord) {
             dcn_bwd_coord_nhwc_kernel<<<grid_for((size_t)nb * deformable_group * P), 256, 0, st>>>(
                 xt, offset, mask, gcol, grad_offset, grad_mask, s, b0, nb);
             MREFSR_LAUNCH_CHECK();
@@ -810,9 +890,11 @@ int mrefsr_modulated_deform_conv_backward(const float* input, const float* weigh
         if (tc_gw) {
             // recomputed columns (deform_conv_cuda.cpp:647-650) as planes colT[bl][tap*C + c][p], then the chunk's share
             // of grad_weight (:659-664) as one split-K GEMM whose partial sums are added up in a fixed order
-            dcn_im2col_planes_kernel<<<grid_for((size_t)nb * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
-            MREFSR_LAUNCH_CHECK();
-            count_launches(1);
+            if (!merged) {
+                dcn_im2col_planes_kernel<<<grid_for((size_t)nb * (C / 8) * P), 256, 0, st>>>(xt, offset, mask, col, s, b0, nb);
+                MREFSR_LAUNCH_CHECK();
+                count_launches(1);
+            }
             const long long all_kb = (long long)nb * cdiv(P, 32);
             const int tiles = cdiv(Co, 128) * cdiv(K * C, 128);
             int splits = cdiv(2 * sm_count(), tiles);
