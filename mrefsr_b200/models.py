@@ -53,6 +53,12 @@ def srntt_init_weights(net, init_gain=0.02):
     net.apply(init_func)
 
 
+def _lib_supports(t):
+    """channel count of a channels-last fp32 / bf16 activation served by the fused training epilogue"""
+    from . import _lib
+    return bool(_lib.lib().mrefsr_bias_act_train_supported(t.shape[1], 1 if t.dtype == torch.bfloat16 else 0))
+
+
 def make_layer(basic_block, num_basic_block, **kwarg):
     return nn.Sequential(*[basic_block(**kwarg) for _ in range(num_basic_block)])
 
@@ -182,17 +188,29 @@ class DynamicAggregationRestoration(nn.Module):
         repeat / cat of x is materialised, ONE offset-conv / DynAgg / lrelu chain over B*R samples, and the fusion head
         on the stacked tensor (MRAPAFusion.forward would stack the list again)."""
         r = len(img_ref_feat_list)
+        keys = [k for _, k in self._SCALES]
+        feats = {k: torch.stack([f[k] for f in img_ref_feat_list], 1).flatten(0, 1) for k in keys}   # [B*R, C, H, W]
+        pres = {k: torch.stack([p[k] for p in pre_offset_list], 1).flatten(0, 1) for k in keys}     # [B*R, 9, H, W, 2]
+        return self._forward_stacked(x, pres, feats, r)
+
+    def _forward_stacked(self, x, pres, feats, r):
+        """The same on tensors that are already stacked over the references: pres / feats = {layer: [B*R, ...]}, pairs laid
+        out [B, R] (what MRefSRPipeline.correspondences returns: no per-reference lists, no re-stacking)."""
         for name, key in self._SCALES:
             conv1, conv2 = getattr(self, f'{name}_offset_conv1'), getattr(self, f'{name}_offset_conv2')
             agg = getattr(self, f'{name}_dyn_agg')
-            feat = torch.stack([f[key] for f in img_ref_feat_list], 1).flatten(0, 1)          # [B*R, C, H, W]
-            pre = torch.stack([p[key] for p in pre_offset_list], 1).flatten(0, 1)             # [B*R, 9, H, W, 2]
+            feat, pre = feats[key], pres[key]
             feat_c = feat           # the DCN reads planes (NCHW); the convolution takes the trunk's layout
             if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
                 feat_c = feat.contiguous(memory_format=torch.channels_last)
             nx = x.shape[1]
             ox = F.conv2d(x, conv1.weight[:, :nx], None, conv1.stride, conv1.padding)         # once per image
-            of = F.conv2d(feat_c, conv1.weight[:, nx:], conv1.bias, conv1.stride, conv1.padding)
+            # the bias rides on the per-image half (1 / R of the elements; its gradient = the fused epilogue's one-pass
+            # reduction over that half's gradient instead of torch's reduction over all B*R samples)
+            fused_bias = conv1.bias is not None and T.train_ok(ox) and _lib_supports(ox)
+            if fused_bias:
+                ox = T.BiasActFunction.apply(ox, conv1.bias, T.ACT_NONE, 0.0, None, 1.0)
+            of = F.conv2d(feat_c, conv1.weight[:, nx:], None if fused_bias else conv1.bias, conv1.stride, conv1.padding)
             o = (of.unflatten(0, (-1, r)) + ox.unsqueeze(1)).flatten(0, 1)
             if T.layout_of(of) == 1:
                 o = o.contiguous(memory_format=torch.channels_last)
@@ -219,8 +237,13 @@ class DynamicAggregationRestoration(nn.Module):
                 x = tail(h)
         return x
 
-    def forward(self, x, pre_offset_list, img_ref_feat_list):
-        """Reference contract: lists over references of pre_offset / VGG feature dicts."""
+    def forward(self, x, pre_offset_list, img_ref_feat_list, n_refs=None):
+        """Reference contract: lists over references of pre_offset / VGG feature dicts.  Also accepted: the same tensors
+        already stacked over the references ({layer: [B*R, ...]} dicts, pairs laid out [B, R]) with n_refs = R."""
+        if isinstance(img_ref_feat_list, dict):
+            if n_refs is None or not isinstance(pre_offset_list, dict):
+                raise ValueError('stacked references: pass two {layer: [B*R, ...]} dicts and n_refs')
+            return self._forward_stacked(x, pre_offset_list, img_ref_feat_list, int(n_refs))
         if (self.batch_refs and len(img_ref_feat_list) > 1 and len(pre_offset_list) == len(img_ref_feat_list) and
                 all(f[k].shape == img_ref_feat_list[0][k].shape for f in img_ref_feat_list for _, k in self._SCALES)):
             return self._forward_refs_batched(x, pre_offset_list, img_ref_feat_list)
@@ -287,9 +310,9 @@ class MRAPARestorationNet(nn.Module):
         for name in ('small', 'medium', 'large'):
             getattr(self.dyn_agg_restore, f'{name}_dyn_agg').init_offset()
 
-    def forward(self, x, pre_offset_list, img_ref_feat_list):
+    def forward(self, x, pre_offset_list, img_ref_feat_list, n_refs=None):
         base = F.interpolate(x, None, 4, 'bilinear', False)
-        return self.dyn_agg_restore(self.content_extractor(x), pre_offset_list, img_ref_feat_list) + base
+        return self.dyn_agg_restore(self.content_extractor(x), pre_offset_list, img_ref_feat_list, n_refs) + base
 
     def forward_batched(self, x, max_idx, ref_feats, n_refs):
         base = F.interpolate(x, None, 4, 'bilinear', False)
@@ -331,6 +354,21 @@ class MRefSRPipeline(nn.Module):
                                                  mode=self.match_mode)
         ref_feats = self.net_map.vgg(img_refs.flatten(0, 1))
         return self.net_g.forward_batched(img_in_lq, max_idx, ref_feats, r)
+
+    @torch.no_grad()
+    def correspondences(self, img_in_up, img_refs):
+        """The frozen half of a training step (MultiRefRestorationModel.optimize_parameters evaluates net_extractor and
+        net_map per reference under no_grad, multi_ref_restoration_model.py:281-294 has the same loop for testing), batched
+        over the references: one extractor pass over B*R reference images, ONE matcher launch for all pairs, one VGG pass.
+        img_in_up [B,3,H,W], img_refs [B,R,3,H,W] -> (pre_offsets, ref_feats, R): {layer: [B*R, 9, s*h, s*w, 2]} and
+        {layer: [B*R, C, s*h, s*w]} with pairs laid out [B, R] -- the stacked form net_g.forward accepts."""
+        b, r = img_refs.shape[:2]
+        f1, f2 = self.net_extractor.forward_batched(img_in_up, img_refs)
+        idx, _ = feature_match_index_batched(f1, f2, 3, 1, 1, True, True, normalize_pixels=True, in_div=r,
+                                             mode=self.match_mode)
+        o1, o2, o4 = pre_offsets(idx)
+        feats = self.net_map.vgg(img_refs.flatten(0, 1))
+        return {'relu3_1': o1, 'relu2_1': o2, 'relu1_1': o4}, {k: feats[k] for k in ('relu3_1', 'relu2_1', 'relu1_1')}, r
 
     def forward_ragged(self, samples, max_batch=16, graphs=False):
         """Images with different reference counts / sizes (LMR-shaped groups, BASELINE config 3): samples[i] =

@@ -178,6 +178,24 @@ def test_training_forward_with_batched_references_equals_the_loop():
     assert float((res[True][0] - res[False][0]).abs().max()) <= 1e-4
     assert res[True][1].keys() == res[False][1].keys() and len(res[True][1]) > 50
     gmax = max(float(v.double().norm()) for v in res[False][1].values())
+    # the same tensors handed over already stacked over the references (what MRefSRPipeline.correspondences returns)
+    keys = ('relu3_1', 'relu2_1', 'relu1_1')
+    feats_s = {k: torch.stack([f[k] for f in feats], 1).flatten(0, 1) for k in keys}
+    pres_s = {k: torch.stack([p[k] for p in pres], 1).flatten(0, 1) for k in keys}
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net.zero_grad(set_to_none=True)
+        out_s = net(lq, pres_s, feats_s, n_refs=r)
+        torch.nn.functional.l1_loss(out_s, gt).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert float((out_s.detach() - res[True][0]).abs().max()) <= 1e-6
+    for k, p in net.named_parameters():
+        if p.grad is not None:      # same code path from here on; cuDNN's weight-gradient kernels are not run-to-run exact
+            a, c = p.grad.double(), res[True][1][k].double()
+            assert float((a - c).norm()) <= 1e-4 * float(c.norm()) + 1e-6 * gmax, k
+    gmax = max(float(v.double().norm()) for v in res[False][1].values())
     for k in res[False][1]:
         a, c = res[True][1][k].double(), res[False][1][k].double()
         # TF32 DCN / GEMMs and a different batch chunking: relative to the parameter's own gradient, plus a floor for
@@ -206,3 +224,27 @@ def test_forward_ragged_eager_and_graph_replay(pipeline):
         # batch 1 vs batch 2 of the same bucket may pick different cuDNN algorithms
         assert float((e - a).abs().max()) <= 2e-3
         assert float((gr - e).abs().max()) <= 1e-5 and torch.equal(gr, ag)
+
+
+def test_correspondences_batched_equals_the_per_reference_loop(pipeline):
+    """MRefSRPipeline.correspondences (one extractor / matcher / VGG pass over all references) against the reference's
+    per-reference loop over net_extractor / net_map: same pre-offsets (integers), same reference features."""
+    g = torch.Generator().manual_seed(21)
+    b, r, H = 2, 3, 48
+    lq = torch.rand(b, 3, H // 4, H // 4, generator=g).to(DEV)
+    up = torch.nn.functional.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False)
+    refs = torch.rand(b, r, 3, H, H, generator=g).to(DEV)
+    pres, feats, n = pipeline.correspondences(up, refs)
+    assert n == r
+    with torch.no_grad():
+        ref_list = list(refs.unbind(1))
+        fl = pipeline.net_extractor(up, ref_list)
+        for k_ref, (f, ref) in enumerate(zip(fl, ref_list)):
+            pre, rf = pipeline.net_map(f, ref)
+            for key in ('relu3_1', 'relu2_1', 'relu1_1'):
+                a = pres[key].unflatten(0, (b, r))[:, k_ref]
+                assert a.shape == pre[key].shape
+                # batch 6 vs batch 2 through cuDNN may flip a near-tie of the arg-max: allow a handful of positions
+                assert float((a != pre[key]).float().mean()) <= 2e-3, key
+                fa = feats[key].unflatten(0, (b, r))[:, k_ref]
+                assert float((fa - rf[key]).abs().max()) <= 1e-3 * float(rf[key].abs().max()), key

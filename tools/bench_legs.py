@@ -205,17 +205,15 @@ def train_step_leg(dev, rank, world, dist, batch=12, refs=5, hr=160, steps=3, bf
     up = torch.nn.functional.interpolate(lq, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
     ref_list = [torch.rand(batch, 3, hr, hr, generator=g).to(dev) for _ in range(refs)]
 
+    refs_stacked = torch.stack(ref_list, 1)                      # [B, R, 3, H, W]
+
     def step():
-        with torch.no_grad():
-            feats = pipe.net_extractor(up, ref_list)
-            pres, rfs = [], []
-            for f, ref in zip(feats, ref_list):
-                pre, rf = pipe.net_map(f, ref)
-                pres.append(pre)
-                rfs.append(rf)
+        # frozen half (extractor, matcher, VGG19 of the references) batched over the references, then net_g on the stacked
+        # tensors: the per-reference loops of the reference's training step, same arithmetic per (image, reference)
+        pres, rfs, n_refs = pipe.correspondences(up, refs_stacked)
         opt.zero_grad(set_to_none=True)
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
-            out = model(lq.contiguous(memory_format=torch.channels_last), pres, rfs)
+            out = model(lq.contiguous(memory_format=torch.channels_last), pres, rfs, n_refs)
         loss = torch.nn.functional.l1_loss(out.float(), gt)
         loss.backward()
         opt.step()

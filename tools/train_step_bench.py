@@ -24,6 +24,7 @@ ap.add_argument('--refs', type=int, default=5)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--hr', type=int, default=160)
 ap.add_argument('--channels-last', action='store_true', help='run net_g in torch.channels_last (cuDNN native layout)')
+ap.add_argument('--per-reference', action='store_true', help='evaluate the frozen nets once per reference (the reference model structure)')
 ap.add_argument('--bf16', action='store_true', help='bf16 autocast for the plain convolutions (hot-path ops stay fp32)')
 args = ap.parse_args()
 
@@ -57,18 +58,25 @@ up = torch.nn.functional.interpolate(lq, scale_factor=4, mode='bicubic', align_c
 refs = [torch.rand(b, 3, H, H, generator=g).to(dev) for _ in range(r)]
 
 
+refs_stacked = torch.stack(refs, 1)                              # [B, R, 3, H, W]
+
+
 def step():
-    with torch.no_grad():
-        feats = pipe.net_extractor(up, refs)
-        pres, rfs = [], []
-        for f, ref in zip(feats, refs):
-            pre, rf = pipe.net_map(f, ref)
-            pres.append(pre)
-            rfs.append(rf)
+    if args.per_reference:      # the reference's own structure: one net_extractor / net_map evaluation per reference
+        with torch.no_grad():
+            feats = pipe.net_extractor(up, refs)
+            pres, rfs = [], []
+            for f, ref in zip(feats, refs):
+                pre, rf = pipe.net_map(f, ref)
+                pres.append(pre)
+                rfs.append(rf)
+        n_refs = None
+    else:                       # the same, batched over the references (one extractor / matcher / VGG pass)
+        pres, rfs, n_refs = pipe.correspondences(up, refs_stacked)
     opt.zero_grad(set_to_none=True)
     x_in = lq.contiguous(memory_format=torch.channels_last) if args.channels_last else lq
     with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.bf16):
-        out = model(x_in, pres, rfs)
+        out = model(x_in, pres, rfs, n_refs)
     loss = torch.nn.functional.l1_loss(out.float(), gt)
     loss.backward()
     opt.step()
