@@ -363,6 +363,9 @@ class MRefSRPipeline(nn.Module):
         img_in_up [B,3,H,W], img_refs [B,R,3,H,W] -> (pre_offsets, ref_feats, R): {layer: [B*R, 9, s*h, s*w, 2]} and
         {layer: [B*R, C, s*h, s*w]} with pairs laid out [B, R] -- the stacked form net_g.forward accepts."""
         b, r = img_refs.shape[:2]
+        if self._channels_last:     # (channels_last_(): the frozen nets run cuDNN's NHWC kernels without layout conversions)
+            img_in_up = img_in_up.contiguous(memory_format=torch.channels_last)
+            img_refs = img_refs.flatten(0, 1).contiguous(memory_format=torch.channels_last).unflatten(0, (b, r))
         f1, f2 = self.net_extractor.forward_batched(img_in_up, img_refs)
         idx, _ = feature_match_index_batched(f1, f2, 3, 1, 1, True, True, normalize_pixels=True, in_div=r,
                                              mode=self.match_mode)

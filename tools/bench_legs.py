@@ -194,7 +194,8 @@ def train_step_leg(dev, rank, world, dist, batch=12, refs=5, hr=160, steps=3, bf
     pipe.net_map.eval()
     for p in list(pipe.net_extractor.parameters()) + list(pipe.net_map.parameters()):
         p.requires_grad_(False)
-    net_g = pipe.net_g.train().to(memory_format=torch.channels_last)     # cuDNN's native layout for the plain convolutions
+    pipe.channels_last_()                    # cuDNN's native layout for the plain convolutions, frozen nets included
+    net_g = pipe.net_g.train()
     for name in ('small', 'medium', 'large'):      # zero-init in the reference: give every backward path a signal
         getattr(net_g.dyn_agg_restore, f'{name}_dyn_agg').conv_offset_mask.weight.data.normal_(0, 1e-3)
     model = torch.nn.parallel.DistributedDataParallel(net_g, device_ids=[dev.index]) if world > 1 else net_g

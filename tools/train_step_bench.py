@@ -43,7 +43,7 @@ for p in list(pipe.net_extractor.parameters()) + list(pipe.net_map.parameters())
     p.requires_grad_(False)
 net_g = pipe.net_g.train()
 if args.channels_last:
-    net_g.to(memory_format=torch.channels_last)
+    pipe.channels_last_()                    # net_g and the frozen nets in torch.channels_last
 # learned offsets start at zero in the reference; give them a little signal so every backward path is exercised
 for name in ('small', 'medium', 'large'):
     getattr(net_g.dyn_agg_restore, f'{name}_dyn_agg').conv_offset_mask.weight.data.normal_(0, 1e-3)
