@@ -236,7 +236,10 @@ def train_step_leg(dev, rank, world, dist, batch=12, refs=5, hr=160, steps=3, bf
                       'Adam, %s, channels_last net_g, %d GPU(s)%s' % (batch, refs, hr, 'bf16 autocast convolutions' if bf16 else 'fp32',
                                                  world, ' (DDP)' if world > 1 else ''),
             'ms_per_step': ms, 'images_per_s': batch * world / (ms / 1e3), 'losses': [round(v, 5) for v in losses],
-            'all_grads_finite': finite}
+            'all_grads_finite': finite,
+            'note': 'whole step inside the timed region: frozen extractor / matcher / VGG19 of the references (evaluated once '
+                    'for all references: MRefSRPipeline.correspondences), net_g forward + backward (cuDNN convolutions; '
+                    'DynAgg / DCNv2 / fusion / bias-activation epilogues = this library), Adam'}
 
 
 # ----------------------------------------------------------------------------------------------------------
