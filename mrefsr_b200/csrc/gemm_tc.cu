@@ -21,7 +21,9 @@ namespace mrefsr {
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 32, G_STAGES = 6;
 constexpr int G_STAGE_BYTES = (G_BM + G_BN) * 128;
-constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + 256 + 1024;
+constexpr int G_EPI_PITCH = 36;                                    // floats per staged row (32 + 4: conflict-free 16-byte accesses)
+constexpr int G_EPI_BYTES = 4 * 32 * G_EPI_PITCH * 4;              // one 32 x 32 staging tile per epilogue warp
+constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + 256 + G_EPI_BYTES + 1024;
 
 struct GemmTcParams {
     int M, N, K;               // per batch item
@@ -46,6 +48,7 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint64_t* tfull = bars + 2 * G_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + G_STAGES * G_STAGE_BYTES + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -170,14 +173,29 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = 0u;
                 }
-                if (m < prm.M) {
-                    if (vec && n0 + c0 + 32 <= prm.N) {
+                if (vec && n0 + c0 + 32 <= prm.N) {
+                    // a lane holds 32 consecutive columns of ITS row: stored directly, every 16-byte store of a warp lands in
+                    // a different 128-byte line.  Through a 32 x 32 shared-memory tile instead, eight lanes cover one row's
+                    // 128 bytes: full-sector, line-contiguous stores (the columns GEMM writes 6 GB per training step).
+                    float* st = epi_stage + q * 32 * G_EPI_PITCH;
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4)
-                            *reinterpret_cast<float4*>(drow + c0 + e) =
-                                make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
-                                            __uint_as_float(v[e + 3]));
-                    } else {
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(st + lane * G_EPI_PITCH + e) =
+                            make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                        __uint_as_float(v[e + 3]));
+                    __syncwarp();
+                    const int m_base = mt * G_BM + q * 32;
+                    float* dbase = prm.D + (long long)o * prm.d_stride + (long long)m_base * prm.ldd + n0 + c0;
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int row = rr * 4 + (lane >> 3), col = (lane & 7) * 4;
+                        if (m_base + row < prm.M)
+                            __stcs(reinterpret_cast<float4*>(dbase + (long long)row * prm.ldd + col),
+                                   *reinterpret_cast<const float4*>(st + row * G_EPI_PITCH + col));
+                    }
+                    __syncwarp();
+                } else if (m < prm.M) {
+                    {
 #pragma unroll
                         for (int e = 0; e < 32; ++e)
                             if (n0 + c0 + e < prm.N) drow[c0 + e] = __uint_as_float(v[e]);
