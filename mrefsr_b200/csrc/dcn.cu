@@ -329,7 +329,7 @@ dcn_bwd_coord_nhwc_kernel(const float* __restrict__ xt, const float* __restrict_
 // points, so when a backward wants both (grad_offset / grad_mask and grad_weight: every training step of MRefSR) one kernel
 // gathers them once.  Thread = (bl, deform group, position), taps as a loop; columns are written as planes
 // colT[bl][tap*C + c][p], rounded to tf32 (the grad_weight GEMM's B operand), exactly where dcn_im2col_planes_kernel puts them.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 dcn_bwd_coord_cols_kernel(const float* __restrict__ xt, const float* __restrict__ offset, const float* __restrict__ mask,
                           const float* __restrict__ gcol, float* __restrict__ goff, float* __restrict__ gmask,
                           float* __restrict__ colT, const DcnShape s, int b0, int nb) {
