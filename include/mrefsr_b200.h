@@ -74,6 +74,13 @@ enum {
 #define MREFSR_MATCH_FLAG_NO_DIAG 0x400       /* all nine taps as MMAs (round-1 kernel) instead of the diagonal form */
 #define MREFSR_MATCH_FLAG_NO_BSTRIP 0x800     /* diagonal form: reload the reference rows per tap row (no shared strip) */
 
+/* Introspection of the matcher's kernel choice and tiling for one pair (host logic only, no GPU work; tests/test_abi.py):
+ * meta[0] kernel: 0 CUDA-core fp32, 1 nine-tap one tap per stage, 2 nine-tap strip, 3 diagonal form, 4 diagonal form with
+ * the B strip;  meta[1], meta[2] M / N tiles;  meta[3], meta[4] output rows / columns owned by a tile;  meta[5], meta[6]
+ * pixel-linear rows of the input / reference grids that are computed (tensor-core kernels);  meta[7] pipeline stages;
+ * meta[8] dynamic shared memory in bytes;  meta[9] resolved mode.  meta must hold 10 ints. */
+MREFSR_API int mrefsr_match_plan(int C, int h_in, int w_in, int h_ref, int w_ref, int patch_size, int input_stride,
+                      int ref_stride, int mode, int* meta);
 MREFSR_API size_t mrefsr_match_workspace_bytes(int n_in, int n_pairs, int C, int h_in, int w_in, int h_ref, int w_ref,
                                     int mode);
 MREFSR_API int mrefsr_feature_match_batched(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div,

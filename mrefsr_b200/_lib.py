@@ -22,6 +22,7 @@ SIGNATURES = {
     'mrefsr_last_error': (ctypes.c_char_p, []),
     'mrefsr_sm_count': (c_int, []),
     'mrefsr_match_workspace_bytes': (c_size_t, [_I] * 8),
+    'mrefsr_match_plan': (c_int, [_I] * 9 + [_P]),
     'mrefsr_feature_match_batched': (c_int, [_P, _P] + [_I] * 15 + [_P, _P, _P, c_size_t, _P]),
     'mrefsr_pre_offsets': (c_int, [_P, _I, _I, _I, _P, _P, _P, _P]),
     'mrefsr_dcn_workspace_bytes': (c_size_t, [_I] * 17),

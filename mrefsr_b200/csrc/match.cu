@@ -1317,6 +1317,64 @@ size_t mrefsr_match_workspace_bytes(int n_in, int n_pairs, int C, int h_in, int 
     return best;
 }
 
+int mrefsr_match_plan(int C, int h_in, int w_in, int h_ref, int w_ref, int patch_size, int input_stride, int ref_stride,
+                      int mode, int* meta) {
+    MREFSR_CHECK(meta, ERR_BAD_ARG, "match_plan: null meta");
+    MREFSR_CHECK(patch_size >= 1 && input_stride >= 1 && ref_stride >= 1 && h_in >= patch_size && w_in >= patch_size &&
+                     h_ref >= patch_size && w_ref >= patch_size && C > 0,
+                 ERR_BAD_ARG, "match_plan: bad sizes");
+    MatchPlan pl;
+    int rc = make_plan(&pl, 1, 1, C, h_in, w_in, h_ref, w_ref, patch_size, input_stride, ref_stride, mode);
+    if (rc) return rc;
+    for (int i = 0; i < 10; ++i) meta[i] = 0;
+    const int x3 = pl.mode == MREFSR_MATCH_TC_BF16X3;
+    meta[9] = pl.mode;
+    if (pl.mode == MREFSR_MATCH_FP32) {       // CUDA-core kernel: 64 x 64 tiles over the patch grids
+        meta[0] = 0;
+        meta[1] = cdiv(pl.ho * pl.wo, ST);
+        meta[2] = cdiv(pl.ho_ref * pl.wo_ref, ST);
+        meta[3] = ST;
+        meta[4] = ST;
+        return 0;
+    }
+    const int rows_in = (pl.hw_in / w_in - 3) * w_in + (w_in - 2), rows_ref = (pl.hw_ref / w_ref - 3) * w_ref + (w_ref - 2);
+    meta[5] = rows_in;
+    meta[6] = rows_ref;
+    TcParams probe;
+    int smem = 0;
+    if (pl.diag && pl.bstrip && diag_strip_geometry(x3 ? 3 : 1, w_ref, &probe, &smem)) {
+        meta[0] = 4;
+        meta[1] = cdiv(rows_in, DG_MV);
+        meta[2] = cdiv(rows_ref, DG_NV);
+        meta[3] = DG_MV;
+        meta[4] = DG_NV;
+        meta[7] = probe.stages;
+        meta[8] = smem;
+    } else if (pl.diag) {
+        meta[0] = 3;
+        meta[1] = cdiv(rows_in, DG_MV);
+        meta[2] = cdiv(rows_ref, DG_NV);
+        meta[3] = DG_MV;
+        meta[4] = DG_NV;
+        meta[7] = x3 ? DgCfg<3>::STAGES : DgCfg<1>::STAGES;
+        meta[8] = x3 ? DgCfg<3>::SMEM_BYTES : DgCfg<1>::SMEM_BYTES;
+    } else {
+        meta[0] = pl.strip == 3 ? 2 : 1;
+        meta[1] = cdiv(rows_in, 128);
+        meta[2] = cdiv(rows_ref, 256);
+        meta[3] = 128;
+        meta[4] = 256;
+        if (pl.strip == 3) {
+            meta[7] = x3 ? TcCfg<3, 3>::STAGES : TcCfg<3, 1>::STAGES;
+            meta[8] = x3 ? TcCfg<3, 3>::SMEM_BYTES : TcCfg<3, 1>::SMEM_BYTES;
+        } else {
+            meta[7] = x3 ? TcCfg<1, 3>::STAGES : TcCfg<1, 1>::STAGES;
+            meta[8] = x3 ? TcCfg<1, 3>::SMEM_BYTES : TcCfg<1, 1>::SMEM_BYTES;
+        }
+    }
+    return 0;
+}
+
 int mrefsr_feature_match_batched(const float* feat_in, const float* feat_ref, int n_in, int n_pairs, int in_div, int C,
                                  int h_in, int w_in, int h_ref, int w_ref, int patch_size, int input_stride,
                                  int ref_stride, int is_norm, int norm_input, int normalize_pixels, int mode,

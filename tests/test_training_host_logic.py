@@ -62,3 +62,17 @@ def test_batched_reference_forward_is_selected_only_for_equal_shapes():
     except Exception:
         pass
     assert not called
+
+
+def test_dynagg_nodes_refuse_cpu_tensors():
+    """No CPU path behind the autograd nodes either: like the reference's extension (deform_conv_ext.cpp:124)."""
+    import pytest
+    from mrefsr_b200.dynagg import DynAgg
+    for fused in (True, False):
+        m = DynAgg(8, 8, 3, stride=1, padding=1, dilation=1, deform_groups=2, extra_offset_mask=True)
+        m.fused_autograd = fused
+        with pytest.raises(NotImplementedError):
+            m([torch.randn(1, 8, 5, 5), torch.randn(1, 8, 5, 5)], torch.zeros(1, 9, 5, 5, 2))
+    m = DynAgg(8, 8, 3, stride=2, padding=1, dilation=1, deform_groups=2, extra_offset_mask=False)
+    with pytest.raises(NotImplementedError):        # the folded activation needs the fused node's configuration
+        m(torch.randn(1, 8, 5, 5), torch.zeros(1, 9, 3, 3, 2), out_slope=0.1)
