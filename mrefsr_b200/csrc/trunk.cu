@@ -218,18 +218,22 @@ nchw_to_nhwc_conv_kernel(const float* __restrict__ src, float* __restrict__ dst,
 // and consume bf16 channels-last tensors, the alignment kernels fp32 planes): one pass instead of torch's cast followed
 // by the transpose.  bf16 side: 4 channels = 8 bytes per lane.
 // gate != NULL (same shape / layout as src): dst = src * (gate > 0 ? 1 : slope) -- the backward of a leaky ReLU whose output
-// is `gate`, folded into the conversion of the incoming gradient
+// is `gate`, folded into the conversion of the incoming gradient.  CT = channels per CTA tile (128, or 64 so that 64-channel
+// tensors -- the large scale -- keep every lane busy): CT / 4 lanes cover a pixel's channels, 8 bytes each.
+template <int CT>
 __global__ void __launch_bounds__(256)
 nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
                              const __nv_bfloat16* __restrict__ gate, float slope, int C, int HW) {
-    __shared__ float tile[128][33];
-    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    constexpr int LPP = CT / 4, PPW = 32 / LPP, IT = 32 / (8 * PPW);
+    __shared__ float tile[CT][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * CT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const __nv_bfloat16* s = src + (size_t)b * C * HW;
     float* d = dst + (size_t)b * C * HW;
+    const int cq = (lane % LPP) * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+    for (int j = 0; j < IT; ++j) {
+        const int pl = (warp * IT + j) * PPW + lane / LPP, pp = p0 + pl, c = c0 + cq;
         if (pp < HW && c < C) {
             const uint2 v = __ldcs(reinterpret_cast<const uint2*>(s + (size_t)pp * C + c));
             float f0 = __uint_as_float(v.x << 16), f1 = __uint_as_float(v.x & 0xffff0000u);
@@ -242,43 +246,46 @@ nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __res
                 f2 = ((g.y & 0x8000u) || !(g.y & 0x7fffu)) ? f2 * slope : f2;
                 f3 = ((g.y & 0x80000000u) || !(g.y & 0x7fff0000u)) ? f3 * slope : f3;
             }
-            tile[lane * 4][pl] = f0;
-            tile[lane * 4 + 1][pl] = f1;
-            tile[lane * 4 + 2][pl] = f2;
-            tile[lane * 4 + 3][pl] = f3;
+            tile[cq][pl] = f0;
+            tile[cq + 1][pl] = f1;
+            tile[cq + 2][pl] = f2;
+            tile[cq + 3][pl] = f3;
         }
     }
     __syncthreads();
     const int p = p0 + lane;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < CT / 8; ++i) {
         const int cl = warp + 8 * i, c = c0 + cl;
         if (c < C && p < HW) d[(size_t)c * HW + p] = tile[cl][lane];
     }
 }
 
 // slope != 1: a leaky ReLU applied on the way (dst = lrelu(src))
+template <int CT>
 __global__ void __launch_bounds__(256)
 nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, float slope, int C, int HW) {
-    __shared__ float tile[128][33];
-    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 128;
+    constexpr int LPP = CT / 4, PPW = 32 / LPP, IT = 32 / (8 * PPW);
+    __shared__ float tile[CT][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * CT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* s = src + (size_t)b * C * HW;
     __nv_bfloat16* d = dst + (size_t)b * C * HW;
     const int p = p0 + lane;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < CT / 8; ++i) {
         const int cl = warp + 8 * i, c = c0 + cl;
         float v = (c < C && p < HW) ? __ldcs(s + (size_t)c * HW + p) : 0.f;
         tile[cl][lane] = v > 0.f ? v : v * slope;
     }
     __syncthreads();
+    const int cq = (lane % LPP) * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int pl = warp * 4 + j, pp = p0 + pl, c = c0 + lane * 4;
+    for (int j = 0; j < IT; ++j) {
+        const int pl = (warp * IT + j) * PPW + lane / LPP, pp = p0 + pl, c = c0 + cq;
         if (pp < HW && c < C) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(tile[lane * 4][pl], tile[lane * 4 + 1][pl]);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(tile[lane * 4 + 2][pl], tile[lane * 4 + 3][pl]);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(tile[cq][pl], tile[cq + 1][pl]);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(tile[cq + 2][pl], tile[cq + 3][pl]);
             uint2 o;
             o.x = *reinterpret_cast<const uint32_t*>(&lo);
             o.y = *reinterpret_cast<const uint32_t*>(&hi);
@@ -548,13 +555,23 @@ int mrefsr_layout_convert_bf16_act(const void* src, void* dst, const void* gate,
     MREFSR_CHECK(B <= 65535 && cdiv(C, 128) <= 65535, ERR_BAD_ARG, "layout_convert_bf16: batch too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ScopedTiming tm(MREFSR_K_GLUE, st);
-    const dim3 grid(cdiv(HW, 32), cdiv(C, 128), B);
-    if (to_channels_last_bf16)
-        nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), slope,
-                                                           C, HW);
-    else
-        nhwc_bf16_to_nchw_f32_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst),
-                                                           static_cast<const __nv_bfloat16*>(gate), slope, C, HW);
+    const bool ct64 = C % 128 != 0 && C % 64 == 0;          // 64-channel tiles keep every lane busy at C = 64, 192, ...
+    const dim3 grid(cdiv(HW, 32), cdiv(C, ct64 ? 64 : 128), B);
+    if (to_channels_last_bf16) {
+        if (ct64)
+            nchw_f32_to_nhwc_bf16_kernel<64><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst),
+                                                                   slope, C, HW);
+        else
+            nchw_f32_to_nhwc_bf16_kernel<128><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst),
+                                                                    slope, C, HW);
+    } else {
+        if (ct64)
+            nhwc_bf16_to_nchw_f32_kernel<64><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst),
+                                                                   static_cast<const __nv_bfloat16*>(gate), slope, C, HW);
+        else
+            nhwc_bf16_to_nchw_f32_kernel<128><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst),
+                                                                    static_cast<const __nv_bfloat16*>(gate), slope, C, HW);
+    }
     MREFSR_LAUNCH_CHECK();
     count_launches(1);
     return 0;

@@ -270,7 +270,7 @@ def test_resblock_training_path_matches_torch():
         assert rel_err(res[True][1][k], res[False][1][k]) <= 1e-4, k
 
 
-@pytest.mark.parametrize('shape', [(2, 64, 9, 13), (1, 216, 16, 16), (3, 8, 5, 5), (2, 260, 4, 7)])
+@pytest.mark.parametrize('shape', [(2, 64, 9, 13), (1, 216, 16, 16), (3, 8, 5, 5), (2, 260, 4, 7), (1, 192, 6, 10)])
 def test_layout_convert_bf16_one_pass(shape):
     """bf16 channels-last <-> fp32 NCHW in one pass (training under autocast) against torch's two-step conversion:
     exact both ways (bf16 -> fp32 is exact; fp32 -> bf16 rounds to nearest even like torch)."""
