@@ -175,6 +175,46 @@ def test_dynagg_module_golden(golden):
         assert m.last_offset_abs_mean() is not None
 
 
+@pytest.mark.parametrize('fused', [True, False])
+def test_dynagg_module_gradients_golden(golden, fused):
+    """Backward of DynAgg.forward -- as one autograd node (default) and as the two operator Functions -- against the
+    gradients the REFERENCE module produced at the DCN boundary (tests/golden/make_golden.py::gen_dynagg: grad of input,
+    weight, bias, offset, mask for the same grad_output), pushed through the glue and the offset convolution in fp64 on
+    the host: grad_conv_out = [grad_offset, grad_mask * m * (1 - m)] (ref_mrapa_restoration_arch.py:55-68)."""
+    import torch.nn.functional as F
+    g = golden('dynagg')
+    for case in ('small', 'big_offsets'):
+        dg = int(g(f'{case}.dg'))
+        c = g(f'{case}.x').shape[1]
+        m = M.DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True).to(DEV)
+        m.load_state_dict({'weight': g(f'{case}.weight'), 'bias': g(f'{case}.bias'),
+                           'conv_offset_mask.weight': g(f'{case}.com_w'), 'conv_offset_mask.bias': g(f'{case}.com_b')})
+        m.fused_autograd = fused
+        x = g(f'{case}.x').to(DEV).requires_grad_(True)
+        feat = g(f'{case}.feat').to(DEV).requires_grad_(True)
+        # the offset convolution in exact fp32 like the CPU reference: with cuDNN's TF32 its 1e-3 noise moves a few sampling
+        # points across a pixel boundary, where the offset gradient is discontinuous
+        old_tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            y = m([x, feat], g(f'{case}.pre').to(DEV))
+            y.backward(g(f'{case}.go').to(DEV))
+        finally:
+            torch.backends.cudnn.allow_tf32 = old_tf32
+        assert rel_err(x.grad, g(f'{case}.gx')) <= TOL
+        assert rel_err(m.weight.grad, g(f'{case}.gweight')) <= TOL
+        assert rel_err(m.bias.grad, g(f'{case}.gbias')) <= TOL
+        mk = g(f'{case}.mask').double()
+        g_conv = torch.cat((g(f'{case}.goffset').double(), g(f'{case}.gmask').double() * mk * (1 - mk)), 1)
+        f64 = g(f'{case}.feat').double().requires_grad_(True)
+        w64 = g(f'{case}.com_w').double().requires_grad_(True)
+        b64 = g(f'{case}.com_b').double().requires_grad_(True)
+        F.conv2d(f64, w64, b64, 1, 1).backward(g_conv)
+        assert rel_err(feat.grad, f64.grad) <= TOL
+        assert rel_err(m.conv_offset_mask.weight.grad, w64.grad) <= TOL
+        assert rel_err(m.conv_offset_mask.bias.grad, b64.grad) <= TOL
+
+
 def _dynagg_module_run(fused, bf16, x, feat0, pre, gout, c, dg):
     torch.manual_seed(5)
     m = M.DynAgg(c, c, 3, stride=1, padding=1, dilation=1, deform_groups=dg, extra_offset_mask=True).to(DEV)
